@@ -1,0 +1,586 @@
+/*
+ * oracle.c -- CPU restatement of the pyarrowspace build-and-search hot path.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h for the scope statement, the reference
+ * file:line each function follows and the "parity unpinned" list).
+ *
+ * Build:  make -C oracle      (gcc -O3 -ffp-contract=off -fopenmp)
+ *
+ * Every reduction below is a left-to-right loop over the contracted index, the
+ * product rounded before the add.  OpenMP is only used on loops whose iterations
+ * own disjoint outputs, so the result does not depend on the thread count.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define TAU_FLOOR 1e-9   /* SURVEY.md Appendix A8 */
+
+struct orc_space {
+    int64_t n;
+    int32_t f;
+    double *items;    /* n x f, copied: helpers.rs:45 deep-copies the rows */
+    double *norms;    /* n */
+    double *lambdas;  /* n */
+};
+
+struct orc_graph {
+    int64_t  nnodes;
+    int64_t  nnz;
+    int64_t *indptr;
+    int32_t *indices;
+    double  *data;
+    orc_params   gp;
+    orc_switches sw;
+};
+
+void orc_default_switches(orc_switches *sw)
+{
+    sw->nodes = ORC_NODES_FEATURE_COLUMNS;
+    sw->kernel = ORC_KERNEL_INV_POWER;
+    sw->tau_mode = ORC_TAU_MEDIAN;
+    sw->lambda_form = ORC_LAMBDA_BOUNDED;
+    sw->tau_fixed = 0.0;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_set_num_threads(int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+}
+
+/* ---------------------------------------------------------------- dot products */
+
+/* acc[(a-a0)*m + b] = sum_t nt[t*m+a] * nt[t*m+b] for a in [a0,a1), b in [a,m): t ascending.
+ * Entries b < a are left at zero (callers mirror them: the product commutes and the
+ * order in t is the same, so G[b][a] is bit-identical to G[a][b]). */
+static void dots_block_upper(const double *nt, int64_t d, int64_t m, int64_t a0, int64_t a1,
+                             double *acc)
+{
+    memset(acc, 0, (size_t)((a1 - a0) * m) * sizeof(double));
+    for (int64_t t = 0; t < d; ++t) {
+        const double *row = nt + t * m;
+        for (int64_t a = a0; a < a1; ++a) {
+            const double va = row[a];
+            double *A = acc + (a - a0) * m;
+            for (int64_t b = a; b < m; ++b) A[b] += va * row[b];
+        }
+    }
+}
+
+/* Full rows (all b) for a in [a0,a1). */
+static void dots_block_full(const double *nt, int64_t d, int64_t m, int64_t a0, int64_t a1,
+                            double *acc)
+{
+    memset(acc, 0, (size_t)((a1 - a0) * m) * sizeof(double));
+    for (int64_t t = 0; t < d; ++t) {
+        const double *row = nt + t * m;
+        for (int64_t a = a0; a < a1; ++a) {
+            const double va = row[a];
+            double *A = acc + (a - a0) * m;
+            for (int64_t b = 0; b < m; ++b) A[b] += va * row[b];
+        }
+    }
+}
+
+void orc_gram_columns(const double *x, int64_t n, int64_t m, double *out)
+{
+    const int64_t blk = 8;
+    const int64_t nblk = (m + blk - 1) / blk;
+#pragma omp parallel
+    {
+        double *acc = (double *)malloc((size_t)(blk * m) * sizeof(double));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t ib = 0; ib < nblk; ++ib) {
+            const int64_t a0 = ib * blk, a1 = (a0 + blk < m) ? a0 + blk : m;
+            dots_block_upper(x, n, m, a0, a1, acc);
+            for (int64_t a = a0; a < a1; ++a)
+                for (int64_t b = a; b < m; ++b) out[a * m + b] = acc[(a - a0) * m + b];
+        }
+        free(acc);
+    }
+    for (int64_t a = 0; a < m; ++a)
+        for (int64_t b = 0; b < a; ++b) out[a * m + b] = out[b * m + a];
+}
+
+static double seq_dot(const double *a, const double *b, int64_t n)
+{
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+
+/* ---------------------------------------------------------------- neighbour selection */
+
+typedef struct { double d; int64_t b; } cand_t;
+
+static inline int cand_less(const cand_t *x, const cand_t *y)
+{
+    return (x->d < y->d) || (x->d == y->d && x->b < y->b);
+}
+
+/* max-heap on (d, b): the root is the worst kept candidate */
+static void heap_sift_down(cand_t *h, int64_t n, int64_t i)
+{
+    for (;;) {
+        int64_t l = 2 * i + 1, r = l + 1, w = i;
+        if (l < n && cand_less(&h[w], &h[l])) w = l;
+        if (r < n && cand_less(&h[w], &h[r])) w = r;
+        if (w == i) return;
+        cand_t t = h[i]; h[i] = h[w]; h[w] = t;
+        i = w;
+    }
+}
+
+static void heap_sift_up(cand_t *h, int64_t i)
+{
+    while (i > 0) {
+        int64_t p = (i - 1) / 2;
+        if (!cand_less(&h[p], &h[i])) return;
+        cand_t t = h[i]; h[i] = h[p]; h[p] = t;
+        i = p;
+    }
+}
+
+static int cand_cmp(const void *x, const void *y)
+{
+    const cand_t *a = (const cand_t *)x, *b = (const cand_t *)y;
+    if (cand_less(a, b)) return -1;
+    if (cand_less(b, a)) return 1;
+    return 0;
+}
+
+/* A3 + A4 for one node a given its dot products with every node.
+ * Writes up to kk (d, b) pairs, ascending by (d, b); returns the count. */
+static int64_t select_neighbours(const double *dots, const double *norm, int64_t m, int64_t a,
+                                 double eps, int64_t kk, cand_t *heap)
+{
+    int64_t cnt = 0;
+    if (kk <= 0) return 0;
+    const double na = norm[a];
+    for (int64_t b = 0; b < m; ++b) {
+        if (b == a) continue;
+        double c = 0.0;                                   /* A3: c := 0 if a norm is 0 */
+        if (na != 0.0 && norm[b] != 0.0) c = dots[b] / (na * norm[b]);
+        const double dist = 1.0 - (c > 0.0 ? c : 0.0);    /* GRAPH_VARIABLES.md:7,37 */
+        if (!(dist <= eps)) continue;                     /* GRAPH_VARIABLES.md:7 */
+        cand_t cd = { dist, b };
+        if (cnt < kk) {                                   /* GRAPH_VARIABLES.md:8: k-cap */
+            heap[cnt] = cd;
+            heap_sift_up(heap, cnt);
+            ++cnt;
+        } else if (cand_less(&cd, &heap[0])) {
+            heap[0] = cd;
+            heap_sift_down(heap, cnt, 0);
+        }
+    }
+    qsort(heap, (size_t)cnt, sizeof(cand_t), cand_cmp);
+    return cnt;
+}
+
+static inline double edge_weight(double dist, const orc_params *gp, int kernel)
+{
+    const double t = pow(dist / gp->sigma, gp->p);
+    if (kernel == ORC_KERNEL_GAUSSIAN) return exp(-t);
+    return 1.0 / (1.0 + t);                               /* GRAPH_VARIABLES.md:3,9 */
+}
+
+/* ---------------------------------------------------------------- CSR assembly */
+
+typedef struct { int64_t r; int64_t c; double w; } edge_t;
+
+static int edge_cmp(const void *x, const void *y)
+{
+    const edge_t *a = (const edge_t *)x, *b = (const edge_t *)y;
+    if (a->r != b->r) return a->r < b->r ? -1 : 1;
+    if (a->c != b->c) return a->c < b->c ? -1 : 1;
+    if (a->w != b->w) return a->w > b->w ? -1 : 1;       /* larger weight first: max rule */
+    return 0;
+}
+
+/* A6 + A7: symmetrise W = max(W, W^T), L = D - W, CSR with sorted columns and the diagonal. */
+static int assemble_laplacian(int64_t m, int64_t kk, const int64_t *cnt, const int64_t *nbr,
+                              const double *wgt, orc_graph *g)
+{
+    int64_t ne = 0;
+    for (int64_t a = 0; a < m; ++a) ne += cnt[a];
+    edge_t *e = (edge_t *)malloc((size_t)(2 * ne + 1) * sizeof(edge_t));
+    if (!e) return ORC_ERR_NOMEM;
+    int64_t q = 0;
+    for (int64_t a = 0; a < m; ++a)
+        for (int64_t j = 0; j < cnt[a]; ++j) {
+            const int64_t b = nbr[a * kk + j];
+            const double w = wgt[a * kk + j];
+            e[q].r = a; e[q].c = b; e[q].w = w; ++q;
+            e[q].r = b; e[q].c = a; e[q].w = w; ++q;
+        }
+    qsort(e, (size_t)q, sizeof(edge_t), edge_cmp);
+    int64_t u = 0;                                        /* dedupe, first (= max) wins */
+    for (int64_t i = 0; i < q; ++i)
+        if (u == 0 || e[i].r != e[u - 1].r || e[i].c != e[u - 1].c) e[u++] = e[i];
+    /* W entries that underflowed to 0 are not edges ("edge set" = W_ab > 0, A7) */
+    int64_t v = 0;
+    for (int64_t i = 0; i < u; ++i)
+        if (e[i].w > 0.0) e[v++] = e[i];
+    u = v;
+
+    g->nnodes = m;
+    g->nnz = u + m;
+    g->indptr = (int64_t *)malloc((size_t)(m + 1) * sizeof(int64_t));
+    g->indices = (int32_t *)malloc((size_t)(g->nnz) * sizeof(int32_t));
+    g->data = (double *)malloc((size_t)(g->nnz) * sizeof(double));
+    if (!g->indptr || !g->indices || !g->data) { free(e); return ORC_ERR_NOMEM; }
+    int64_t pos = 0, i = 0;
+    for (int64_t a = 0; a < m; ++a) {
+        g->indptr[a] = pos;
+        int64_t j = i;
+        double deg = 0.0;
+        while (j < u && e[j].r == a) { deg += e[j].w; ++j; }   /* ascending column order */
+        int diag_done = 0;
+        for (int64_t t = i; t < j; ++t) {
+            if (!diag_done && e[t].c > a) {
+                g->indices[pos] = (int32_t)a; g->data[pos] = deg; ++pos; diag_done = 1;
+            }
+            g->indices[pos] = (int32_t)e[t].c; g->data[pos] = -e[t].w; ++pos;
+        }
+        if (!diag_done) { g->indices[pos] = (int32_t)a; g->data[pos] = deg; ++pos; }
+        i = j;
+    }
+    g->indptr[m] = pos;
+    free(e);
+    return ORC_OK;
+}
+
+int orc_graph_from_nodes_t(const double *nt, int64_t d, int64_t m, const orc_params *gp,
+                           const orc_switches *sw_in, orc_graph **out_graph)
+{
+    if (!nt || !gp || !out_graph || d <= 0 || m <= 0) return ORC_ERR_ARG;
+    if (m > 2147483647LL) return ORC_ERR_ARG;
+    orc_switches sw;
+    if (sw_in) sw = *sw_in; else orc_default_switches(&sw);
+
+    int64_t kk = gp->k;
+    if (kk > m - 1) kk = m - 1;
+    if (kk < 0) kk = 0;
+    const int64_t kalloc = kk > 0 ? kk : 1;
+
+    double *norm = (double *)malloc((size_t)m * sizeof(double));
+    int64_t *cnt = (int64_t *)calloc((size_t)m, sizeof(int64_t));
+    int64_t *nbr = (int64_t *)malloc((size_t)(m * kalloc) * sizeof(int64_t));
+    double *wgt = (double *)malloc((size_t)(m * kalloc) * sizeof(double));
+    if (!norm || !cnt || !nbr || !wgt) { free(norm); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
+
+    /* A3: norms, sqrt of the sequential sum of squares */
+#pragma omp parallel for schedule(static)
+    for (int64_t a = 0; a < m; ++a) {
+        double s = 0.0;
+        for (int64_t t = 0; t < d; ++t) { const double v = nt[t * m + a]; s += v * v; }
+        norm[a] = sqrt(s);
+    }
+
+    const int64_t blk = 8;
+    const int64_t nblk = (m + blk - 1) / blk;
+#pragma omp parallel
+    {
+        double *acc = (double *)malloc((size_t)(blk * m) * sizeof(double));
+        cand_t *heap = (cand_t *)malloc((size_t)kalloc * sizeof(cand_t));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t ib = 0; ib < nblk; ++ib) {
+            const int64_t a0 = ib * blk, a1 = (a0 + blk < m) ? a0 + blk : m;
+            dots_block_full(nt, d, m, a0, a1, acc);
+            for (int64_t a = a0; a < a1; ++a) {
+                const int64_t c = select_neighbours(acc + (a - a0) * m, norm, m, a, gp->eps, kk, heap);
+                cnt[a] = c;
+                for (int64_t j = 0; j < c; ++j) {
+                    nbr[a * kalloc + j] = heap[j].b;
+                    wgt[a * kalloc + j] = edge_weight(heap[j].d, gp, sw.kernel);   /* A5 */
+                }
+            }
+        }
+        free(acc);
+        free(heap);
+    }
+
+    orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
+    if (!g) { free(norm); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
+    g->gp = *gp;
+    g->sw = sw;
+    int rc = assemble_laplacian(m, kalloc, cnt, nbr, wgt, g);
+    free(norm); free(cnt); free(nbr); free(wgt);
+    if (rc != ORC_OK) { orc_free_graph(g); return rc; }
+    *out_graph = g;
+    return ORC_OK;
+}
+
+/* ---------------------------------------------------------------- taumode lambda (A8) */
+
+static int dbl_cmp(const void *x, const void *y)
+{
+    const double a = *(const double *)x, b = *(const double *)y;
+    return (a < b) ? -1 : (a > b) ? 1 : 0;
+}
+
+static double median_of(const double *x, int64_t n, int use_abs, double *scratch)
+{
+    for (int64_t i = 0; i < n; ++i) scratch[i] = use_abs ? fabs(x[i]) : x[i];
+    qsort(scratch, (size_t)n, sizeof(double), dbl_cmp);
+    return (n & 1) ? scratch[n / 2] : 0.5 * (scratch[n / 2 - 1] + scratch[n / 2]);
+}
+
+static double tau_of(const double *x, int64_t n, const orc_switches *sw, double *scratch)
+{
+    double t;
+    switch (sw->tau_mode) {
+    case ORC_TAU_MEDIAN:     t = median_of(x, n, 0, scratch); break;
+    case ORC_TAU_MEDIAN_ABS: t = median_of(x, n, 1, scratch); break;
+    case ORC_TAU_MEAN: {
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += x[i];
+        t = s / (double)n;
+        break;
+    }
+    default: t = sw->tau_fixed; break;
+    }
+    return (t > TAU_FLOOR) ? t : TAU_FLOOR;
+}
+
+/* E = x^T L x / x^T x (TAUMODE.md:18,24); lambda = E/(E+tau) (TAUMODE.md:19,25). */
+static int taumode_one(const orc_graph *g, const orc_switches *sw, const double *x, double *scratch,
+                       double *out_e, double *out_tau, double *out_lambda)
+{
+    const int64_t m = g->nnodes;
+    double num = 0.0;
+    for (int64_t a = 0; a < m; ++a) {
+        double y = 0.0;
+        for (int64_t j = g->indptr[a]; j < g->indptr[a + 1]; ++j) y += g->data[j] * x[g->indices[j]];
+        num += x[a] * y;
+    }
+    const double den = seq_dot(x, x, m);
+    if (den == 0.0) return ORC_ERR_ZERO_VECTOR;           /* TAUMODE.md:13 */
+    const double e = num / den;
+    const double tau = tau_of(x, m, sw, scratch);
+    const double eb = e / (e + tau);
+    double lam = eb;
+    if (sw->lambda_form == ORC_LAMBDA_SYNTHETIC) {        /* TAUMODE.md:8,26-27 */
+        double tot = 0.0, sq = 0.0;
+        for (int64_t a = 0; a < m; ++a)
+            for (int64_t j = g->indptr[a]; j < g->indptr[a + 1]; ++j) {
+                const int64_t b = g->indices[j];
+                if (b <= a) continue;
+                const double df = x[a] - x[b];
+                const double en = -g->data[j] * (df * df);
+                tot += en;
+                sq += en * en;
+            }
+        double gd = (tot == 0.0) ? 0.0 : sq / (tot * tot);
+        if (gd < 0.0) gd = 0.0;
+        if (gd > 1.0) gd = 1.0;
+        lam = tau * eb + (1.0 - tau) * gd;
+    }
+    if (out_e) *out_e = e;
+    if (out_tau) *out_tau = tau;
+    if (out_lambda) *out_lambda = lam;
+    return ORC_OK;
+}
+
+int orc_taumode(const orc_graph *g, const orc_switches *sw_in, const double *x, int64_t nq,
+                double *out_energy, double *out_tau, double *out_lambda)
+{
+    if (!g || !x || nq < 0) return ORC_ERR_ARG;
+    orc_switches sw = sw_in ? *sw_in : g->sw;
+    const int64_t m = g->nnodes;
+    int rc = ORC_OK;
+#pragma omp parallel
+    {
+        double *scratch = (double *)malloc((size_t)m * sizeof(double));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < nq; ++i) {
+            double e = NAN, t = NAN, l = NAN;
+            const int r = taumode_one(g, &sw, x + i * m, scratch, &e, &t, &l);
+            if (r != ORC_OK) {
+#pragma omp atomic write
+                rc = r;
+            }
+            if (out_energy) out_energy[i] = e;
+            if (out_tau) out_tau[i] = t;
+            if (out_lambda) out_lambda[i] = l;
+        }
+        free(scratch);
+    }
+    return rc;
+}
+
+/* ---------------------------------------------------------------- build (A1-A8) */
+
+int orc_build(const double *items, int64_t n, int32_t f, const orc_params *gp,
+              const orc_switches *sw_in, orc_space **out_space, orc_graph **out_graph)
+{
+    if (!items || !gp || !out_space || !out_graph) return ORC_ERR_ARG;
+    if (n <= 0 || f <= 0) return ORC_ERR_EMPTY;           /* helpers.rs:27-29 */
+    orc_switches sw;
+    if (sw_in) sw = *sw_in; else orc_default_switches(&sw);
+
+    orc_space *s = (orc_space *)calloc(1, sizeof(orc_space));
+    if (!s) return ORC_ERR_NOMEM;
+    s->n = n; s->f = f;
+    s->items = (double *)malloc((size_t)(n * f) * sizeof(double));
+    s->norms = (double *)malloc((size_t)n * sizeof(double));
+    s->lambdas = (double *)malloc((size_t)n * sizeof(double));
+    if (!s->items || !s->norms || !s->lambdas) { orc_free_space(s); return ORC_ERR_NOMEM; }
+    memcpy(s->items, items, (size_t)(n * f) * sizeof(double));   /* A1: stored unchanged */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i)
+        s->norms[i] = sqrt(seq_dot(s->items + i * f, s->items + i * f, f));
+
+    orc_graph *g = NULL;
+    int rc;
+    if (sw.nodes == ORC_NODES_FEATURE_COLUMNS) {
+        /* A2: node a = column a of X; the transposed node matrix IS X (d = n, m = f). */
+        rc = orc_graph_from_nodes_t(s->items, n, f, gp, &sw, &g);
+        if (rc == ORC_OK) rc = orc_taumode(g, &sw, s->items, n, NULL, NULL, s->lambdas);
+    } else {
+        double *xt = (double *)malloc((size_t)(n * f) * sizeof(double));
+        if (!xt) { orc_free_space(s); return ORC_ERR_NOMEM; }
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t t = 0; t < f; ++t) xt[t * n + i] = s->items[i * f + t];
+        rc = orc_graph_from_nodes_t(xt, f, n, gp, &sw, &g);
+        free(xt);
+        for (int64_t i = 0; i < n; ++i) s->lambdas[i] = NAN;
+    }
+    if (rc != ORC_OK) { orc_free_space(s); orc_free_graph(g); return rc; }
+    *out_space = s;
+    *out_graph = g;
+    return ORC_OK;
+}
+
+/* ---------------------------------------------------------------- search (A9) */
+
+void orc_scores(const orc_space *s, const double *q, double lambda_q, double tau, double *out)
+{
+    const int64_t n = s->n, f = s->f;
+    const double nq = sqrt(seq_dot(q, q, f));
+    for (int64_t i = 0; i < n; ++i) {
+        const double den = nq * s->norms[i];
+        const double c = (den == 0.0) ? 0.0 : seq_dot(q, s->items + i * f, f) / den;   /* README KAT */
+        out[i] = tau * c + (1.0 - tau) * (1.0 / (1.0 + fabs(lambda_q - s->lambdas[i]))); /* TAUMODE.md:33 */
+    }
+}
+
+typedef struct { double s; int64_t i; } hit_t;
+
+/* "better" = larger score, ties -> smaller index */
+static inline int hit_better(const hit_t *x, const hit_t *y)
+{
+    return (x->s > y->s) || (x->s == y->s && x->i < y->i);
+}
+
+static int hit_cmp(const void *x, const void *y)
+{
+    const hit_t *a = (const hit_t *)x, *b = (const hit_t *)y;
+    if (hit_better(a, b)) return -1;
+    if (hit_better(b, a)) return 1;
+    return 0;
+}
+
+int orc_search(const orc_space *s, const orc_graph *g, const orc_switches *sw_in, const double *q,
+               int64_t nq, double tau, int64_t *out_idx, double *out_score, double *out_lambda_q)
+{
+    if (!s || !g || !q || nq < 0 || !out_idx || !out_score) return ORC_ERR_ARG;
+    if (g->nnodes != s->f) return ORC_ERR_ARG;
+    orc_switches sw = sw_in ? *sw_in : g->sw;
+    const int64_t n = s->n, f = s->f;
+    const int64_t topk = g->gp.topk;                      /* lib.rs:169 */
+    const int64_t kk = topk < n ? topk : n;
+    int rc = ORC_OK;
+#pragma omp parallel
+    {
+        double *scratch = (double *)malloc((size_t)f * sizeof(double));
+        double *sc = (double *)malloc((size_t)n * sizeof(double));
+        hit_t *heap = (hit_t *)malloc((size_t)(kk > 0 ? kk : 1) * sizeof(hit_t));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            const double *qv = q + qi * f;
+            for (int64_t j = 0; j < topk; ++j) { out_idx[qi * topk + j] = -1; out_score[qi * topk + j] = NAN; }
+            double lq = NAN;
+            int r = taumode_one(g, &sw, qv, scratch, NULL, NULL, &lq);   /* lib.rs:154 */
+            if (out_lambda_q) out_lambda_q[qi] = lq;
+            if (r == ORC_OK && lq == 0.0) r = ORC_ERR_LAMBDA_ZERO;       /* lib.rs:156-159 */
+            if (r != ORC_OK) {
+#pragma omp atomic write
+                rc = r;
+                continue;
+            }
+            orc_scores(s, qv, lq, tau, sc);
+            /* min-heap of the kk best: root = worst kept */
+            int64_t cnt = 0;
+            for (int64_t i = 0; i < n && kk > 0; ++i) {
+                hit_t h = { sc[i], i };
+                if (cnt < kk) {
+                    int64_t c = cnt++;
+                    heap[c] = h;
+                    while (c > 0) {
+                        int64_t p = (c - 1) / 2;
+                        if (!hit_better(&heap[p], &heap[c])) break;
+                        hit_t t = heap[p]; heap[p] = heap[c]; heap[c] = t; c = p;
+                    }
+                } else if (hit_better(&h, &heap[0])) {
+                    heap[0] = h;
+                    int64_t c = 0;
+                    for (;;) {
+                        int64_t l = 2 * c + 1, rr = l + 1, w = c;
+                        if (l < cnt && hit_better(&heap[w], &heap[l])) w = l;
+                        if (rr < cnt && hit_better(&heap[w], &heap[rr])) w = rr;
+                        if (w == c) break;
+                        hit_t t = heap[w]; heap[w] = heap[c]; heap[c] = t; c = w;
+                    }
+                }
+            }
+            qsort(heap, (size_t)cnt, sizeof(hit_t), hit_cmp);
+            for (int64_t j = 0; j < cnt; ++j) { out_idx[qi * topk + j] = heap[j].i; out_score[qi * topk + j] = heap[j].s; }
+        }
+        free(scratch); free(sc); free(heap);
+    }
+    return rc;
+}
+
+/* ---------------------------------------------------------------- accessors */
+
+int64_t orc_space_nitems(const orc_space *s) { return s->n; }
+int32_t orc_space_nfeatures(const orc_space *s) { return s->f; }
+const double *orc_space_items(const orc_space *s) { return s->items; }
+const double *orc_space_lambdas(const orc_space *s) { return s->lambdas; }
+const double *orc_space_norms(const orc_space *s) { return s->norms; }
+int64_t orc_graph_nnodes(const orc_graph *g) { return g->nnodes; }
+int64_t orc_graph_nnz(const orc_graph *g) { return g->nnz; }
+const int64_t *orc_graph_indptr(const orc_graph *g) { return g->indptr; }
+const int32_t *orc_graph_indices(const orc_graph *g) { return g->indices; }
+const double *orc_graph_data(const orc_graph *g) { return g->data; }
+void orc_graph_params(const orc_graph *g, orc_params *gp) { *gp = g->gp; }
+
+void orc_free_space(orc_space *s)
+{
+    if (!s) return;
+    free(s->items); free(s->norms); free(s->lambdas); free(s);
+}
+
+void orc_free_graph(orc_graph *g)
+{
+    if (!g) return;
+    free(g->indptr); free(g->indices); free(g->data); free(g);
+}
