@@ -1,0 +1,185 @@
+/*
+ * arrowspace_b200.h -- C ABI of the B200-native build-and-search hot path of pyarrowspace.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types.  Each entry
+ * point names the call of the reference binding it replaces (/root/reference, a pyo3 module
+ * whose numerics all live in the crate `arrowspace` 0.18.0, Cargo.lock:94-97).  The crate
+ * functions below are exactly the ones `src/lib.rs` imports (src/lib.rs:7-11) and calls.
+ *
+ * Conventions
+ *   - every function returns 0 (ASP_OK) or an ASP_ERR_* code; asp_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - `items`, `queries`, outputs may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes); inputs are copied (src/helpers.rs:45, src/lib.rs:139);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with ASP_ERR_CUDA;
+ *   - one asp_ctx per process and GPU; multi-GPU = one process per GPU, each owning a row
+ *     shard (asp_shard_rows); the host (torch.distributed / NCCL) moves the small exchange
+ *     buffers between the staged calls marked [exchange].
+ */
+#ifndef ARROWSPACE_B200_H
+#define ARROWSPACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASP_ABI_VERSION 1
+
+/* Fixed reduction geometry of the feature Gram (makes results independent of the GPU count):
+ * rows are cut into 32-row units, the units into ASP_GRAM_SEGMENTS contiguous segments (the
+ * sharding granularity) and every segment into ASP_GRAM_SLICES contiguous slices.  The Gram is
+ * sum_seg ( sum_slice ( in-order DMMA chain over the slice rows ) ), both sums in index order. */
+#define ASP_GRAM_SEGMENTS 8
+#define ASP_GRAM_SLICES   24
+#define ASP_ROW_UNIT      32
+
+enum {
+    ASP_OK = 0,
+    ASP_ERR_EMPTY = 1,        /* "items must be non-empty 2D array"            src/helpers.rs:27-29 */
+    ASP_ERR_ZERO_VECTOR = 2,  /* all-zero vector in the Rayleigh quotient      TAUMODE.md:13 */
+    ASP_ERR_LAMBDA_ZERO = 3,  /* "The lambdas are zero, check the magnitude of items and eps."  src/lib.rs:156-159 */
+    ASP_ERR_ARG = 4,
+    ASP_ERR_NOMEM = 5,
+    ASP_ERR_CUDA = 6,         /* no device / CUDA failure: there is no CPU fallback */
+    ASP_ERR_UNSUPPORTED = 7,
+    ASP_NEED_EXACT = 8        /* asp_graph_from_gram: decisions inside the rounding band, see below */
+};
+
+/* (eps, k, topk, p, sigma) as parsed by parse_graph_params, src/helpers.rs:48-77.
+ * has_sigma == 0  ->  sigma := eps * 0.5 (src/helpers.rs:68-72). */
+typedef struct {
+    double  eps;
+    int64_t k;
+    int64_t topk;
+    double  p;
+    double  sigma;
+    int32_t has_sigma;
+} asp_graph_params;
+
+/* Named switches for the choices the reference's tests cannot pin. */
+enum { ASP_KERNEL_INV_POWER = 0, ASP_KERNEL_GAUSSIAN = 1 };
+enum { ASP_TAU_MEDIAN = 0, ASP_TAU_MEDIAN_ABS = 1, ASP_TAU_MEAN = 2, ASP_TAU_FIXED = 3 };
+typedef struct {
+    int32_t kernel;      /* ASP_KERNEL_* : w = 1/(1+(d/sigma)^p)  |  exp(-(d/sigma)^p) */
+    int32_t tau_mode;    /* ASP_TAU_*    : tau of a vector (floored at 1e-9) */
+    double  tau_fixed;
+} asp_switches;
+
+typedef struct asp_ctx   asp_ctx;    /* device, streams, scratch */
+typedef struct asp_space asp_space;  /* replaces arrowspace::core::ArrowSpace   (src/lib.rs:64-67)  */
+typedef struct asp_graph asp_graph;  /* replaces arrowspace::graph::GraphLaplacian (src/lib.rs:26-29) */
+
+const char *asp_last_error(void);
+int  asp_abi_version(void);
+void asp_default_switches(asp_switches *sw);
+
+int  asp_ctx_create(int device, asp_ctx **out);
+void asp_ctx_destroy(asp_ctx *ctx);
+int  asp_ctx_device(const asp_ctx *ctx);
+/* Adopt a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream. */
+int  asp_ctx_set_stream(asp_ctx *ctx, void *cuda_stream);
+int  asp_ctx_synchronize(asp_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t asp_ctx_launch_count(const asp_ctx *ctx);
+
+/* ---- one-call single-GPU path --------------------------------------------------------------
+ * Replaces RustBuilder::new().with_lambda_graph(eps,k,topk,p,sigma)...build(rows)
+ * (src/lib.rs:278-289): feature graph (nodes = columns of items), Laplacian CSR, per-item lambda. */
+int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f,
+              const asp_graph_params *gp, const asp_switches *sw,
+              asp_space **out_space, asp_graph **out_graph);
+
+/* ---- staged path (what asp_build does; the multi-GPU host calls the stages itself) --------- */
+
+/* Row range [row0,row1) owned by `rank` of `world` (world in {1,2,4,8}): whole Gram segments. */
+int asp_shard_rows(int64_t n_total, int world, int rank, int64_t *row0, int64_t *row1);
+
+/* Upload (copy) the row shard of `rank` (of `world`): items_shard is n_local x f row-major f64 and
+ * must hold exactly the rows asp_shard_rows(n_total, world, rank) names.  Replaces
+ * pyarray2_to_vecvec + ArrowSpace construction (src/helpers.rs:24-46, src/lib.rs:277). */
+int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, int32_t f,
+                     int64_t n_total, int world, int rank, asp_space **out);
+
+/* K1 (API orientation): per-segment partial Gram X_s^T X_s of the owned segments, FP64 DMMA fed
+ * by TMA.  out_dev: DEVICE buffer [ASP_GRAM_SEGMENTS][f][f] f64; only the owned segments'
+ * blocks are written (the others are left untouched).  [exchange]: all-gather the blocks. */
+int asp_space_gram_partials(asp_space *s, double *out_dev);
+
+/* K1 selection + K2: graph from the complete set of segment partials.
+ * gram_segments_dev: DEVICE [ASP_GRAM_SEGMENTS][f][f].  Distances d = 1 - max(0, cos) between
+ * feature columns, eps-radius, k smallest by (d, index), weights, W = max(W, W^T), L = D - W as
+ * CSR (GRAPH_VARIABLES.md:3,7-10).  Decisions (d <= eps, k-th neighbour) are guaranteed equal to
+ * the ones made on left-to-right f64 sums: any comparison inside the rounding band of the DMMA
+ * Gram is listed in need_pairs (pairs a<b, 2 int32 each, at most need_cap pairs) and the call
+ * returns ASP_NEED_EXACT; resolve them with asp_space_exact_pairs and call again.
+ * exact_pairs/exact_sums (n_exact pairs, 3 sums each: <a,b>, <a,a>, <b,b>) may be NULL/0. */
+int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f, int64_t n_total,
+                        const asp_graph_params *gp, const asp_switches *sw,
+                        const int32_t *exact_pairs, const double *exact_sums, int64_t n_exact,
+                        int32_t *need_pairs, int64_t need_cap, int64_t *n_need,
+                        asp_graph **out_graph);
+
+/* Continue the left-to-right sums of the listed column pairs over this shard's rows:
+ * sums[3*i+0] += sum_r x[r][a]*x[r][b], [1] += x[r][a]^2, [2] += x[r][b]^2 (r ascending, product
+ * rounded then added).  [exchange]: rank r+1 continues from rank r's sums.  HOST arrays. */
+int asp_space_exact_pairs(asp_space *s, const int32_t *pairs, int64_t n_pairs, double *sums);
+
+/* K3: per-item taumode lambda (Rayleigh quotient on the feature Laplacian, median tau, bounded
+ * transform: TAUMODE.md:18-19,24-25) for the shard's rows.  Replaces the lambda computation inside
+ * ArrowSpaceBuilder::build (read back by lambdas(), src/lib.rs:122-124). */
+int asp_space_compute_lambdas(asp_space *s, const asp_graph *g);
+
+/* ---- accessors (src/lib.rs:40-61, 78-124) -------------------------------------------------- */
+int asp_space_dims(const asp_space *s, int64_t *n_local, int32_t *f, int64_t *row0, int64_t *n_total);
+int asp_space_lambdas(const asp_space *s, double *out /* n_local, host or device */);
+int asp_space_norms(const asp_space *s, double *out /* n_local */);
+int asp_space_get_item(const asp_space *s, int64_t local_idx, double *out_features /* f */, double *out_lambda);
+int asp_graph_info(const asp_graph *g, int64_t *nnodes, int64_t *nnz, asp_graph_params *gp);
+int asp_graph_csr(const asp_graph *g, int64_t *indptr /* nnodes+1 */, int32_t *indices /* nnz */, double *data /* nnz */);
+
+/* ---- search -------------------------------------------------------------------------------- */
+
+/* lambda of nq query vectors (nq x f).  Replaces ArrowSpace::prepare_query_item (src/lib.rs:154).
+ * Any of out_energy / out_tau / out_lambda may be NULL. */
+int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const double *queries,
+                     int64_t nq, double *out_energy, double *out_tau, double *out_lambda);
+
+/* K4: batched lambda-aware search of nq queries against this shard.  Replaces prepare_query_item +
+ * search_lambda_aware(&query, gl.graph_params.topk, tau) (src/lib.rs:154-173), batched.
+ * score_i = tau*cos(q,x_i) + (1-tau)/(1+|lambda_q-lambda_i|)   (TAUMODE.md:33)
+ * Returns per query min(topk, n_local) hits, best first, ties by smaller index, GLOBAL row indices;
+ * rows are padded to topk with index -1 / score NaN.  Scores of the returned hits are evaluated
+ * in the reference order (left-to-right f64 dot); the candidate set is proven complete against the
+ * rounding band of the tensor-core pass, otherwise the query is re-scanned exactly.
+ * Fails with ASP_ERR_LAMBDA_ZERO if some lambda_q == 0.0 (src/lib.rs:156-159).
+ * out_lambda_q (nq) may be NULL.  [exchange]: all-gather (idx, score) and asp_topk_merge. */
+int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq,
+                     double tau, int64_t *out_idx, double *out_score, double *out_lambda_q);
+
+/* K5: merge `parts` candidate lists per query ([parts][nq][topk], as produced by
+ * asp_search_batch on each shard) into the global top-k by (score desc, index asc). */
+int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int parts, int64_t nq,
+                   int64_t topk, int64_t *out_idx, double *out_score);
+
+/* ---- item graph (nodes = items; the graph-build workload of configs C4/C5) ------------------ */
+
+/* K1 (item orientation) + K2 for the shard's rows against `all_items` (n_total x f, host or
+ * device; NULL = the shard itself, single GPU): eps / k-NN graph on rectified-cosine distance,
+ * weights, symmetrised Laplacian CSR over n_total nodes.  Single-GPU in this round. */
+int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
+
+/* ---- teardown / stats ---------------------------------------------------------------------- */
+void asp_free_space(asp_space *s);
+void asp_free_graph(asp_graph *g);
+
+/* Last-call statistics (diagnostics; -1 = not applicable).  keys: "gram_ms", "graph_ms",
+ * "lambda_ms", "search_gemm_ms", "search_rescore_ms", "search_slow_queries", "need_exact_pairs". */
+double asp_ctx_stat(const asp_ctx *ctx, const char *key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+"""ctypes binding of ``libarrowspace_b200.so`` (the C ABI in ``include/arrowspace_b200.h``).
+
+The library is the product: hand-written sm_100a CUDA behind ``extern "C"`` entry points.
+If it is missing or there is no CUDA device every compute call raises -- there is no CPU
+fallback and nothing here imports ``oracle/``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarrowspace_b200.so")
+
+ASP_OK = 0
+ASP_ERR_EMPTY = 1
+ASP_ERR_ZERO_VECTOR = 2
+ASP_ERR_LAMBDA_ZERO = 3
+ASP_ERR_ARG = 4
+ASP_ERR_NOMEM = 5
+ASP_ERR_CUDA = 6
+ASP_ERR_UNSUPPORTED = 7
+ASP_NEED_EXACT = 8
+
+GRAM_SEGMENTS = 8
+GRAM_SLICES = 24
+ROW_UNIT = 32
+
+KERNEL = {"inv_power": 0, "gaussian": 1}
+TAU_MODE = {"median": 0, "median_abs": 1, "mean": 2, "fixed": 3}
+
+
+class GraphParams(C.Structure):
+    _fields_ = [("eps", C.c_double), ("k", C.c_int64), ("topk", C.c_int64), ("p", C.c_double),
+                ("sigma", C.c_double), ("has_sigma", C.c_int32)]
+
+
+class Switches(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("tau_mode", C.c_int32), ("tau_fixed", C.c_double)]
+
+
+class LibraryError(RuntimeError):
+    """A call into libarrowspace_b200.so failed (code + the library's message)."""
+
+    def __init__(self, code, message):
+        super().__init__("%s (arrowspace_b200 error %d)" % (message, code))
+        self.code = code
+        self.message = message
+
+
+# name -> (restype, argtypes); every symbol include/arrowspace_b200.h declares
+_vp, _i64, _i32, _dbl, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int
+SYMBOLS = {
+    "asp_last_error": (C.c_char_p, []),
+    "asp_abi_version": (_int, []),
+    "asp_default_switches": (None, [C.POINTER(Switches)]),
+    "asp_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "asp_ctx_destroy": (None, [_vp]),
+    "asp_ctx_device": (_int, [_vp]),
+    "asp_ctx_set_stream": (_int, [_vp, _vp]),
+    "asp_ctx_synchronize": (_int, [_vp]),
+    "asp_ctx_launch_count": (_i64, [_vp]),
+    "asp_build": (_int, [_vp, _vp, _i64, _i32, C.POINTER(GraphParams), C.POINTER(Switches),
+                         C.POINTER(_vp), C.POINTER(_vp)]),
+    "asp_shard_rows": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
+    "asp_space_create": (_int, [_vp, _vp, _i64, _i32, _i64, _int, _int, C.POINTER(_vp)]),
+    "asp_space_gram_partials": (_int, [_vp, _vp]),
+    "asp_graph_from_gram": (_int, [_vp, _vp, _i32, _i64, C.POINTER(GraphParams), C.POINTER(Switches),
+                                   _vp, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_vp)]),
+    "asp_space_exact_pairs": (_int, [_vp, _vp, _i64, _vp]),
+    "asp_space_compute_lambdas": (_int, [_vp, _vp]),
+    "asp_space_dims": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
+    "asp_space_lambdas": (_int, [_vp, _vp]),
+    "asp_space_norms": (_int, [_vp, _vp]),
+    "asp_space_get_item": (_int, [_vp, _i64, _vp, _vp]),
+    "asp_graph_info": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(GraphParams)]),
+    "asp_graph_csr": (_int, [_vp, _vp, _vp, _vp]),
+    "asp_query_lambda": (_int, [_vp, _vp, C.POINTER(Switches), _vp, _i64, _vp, _vp, _vp]),
+    "asp_search_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
+    "asp_topk_merge": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp]),
+    "asp_item_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
+    "asp_free_space": (None, [_vp]),
+    "asp_free_graph": (None, [_vp]),
+    "asp_ctx_stat": (_dbl, [_vp, C.c_char_p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and type every entry point.  Raises if the .so is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libarrowspace_b200.so is not built (run `python -m pyarrowspace_b200.build`); "
+                "arrowspace_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != ASP_OK:
+        msg = load().asp_last_error()
+        raise LibraryError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+_contexts = {}
+
+
+def context(device=None):
+    """One asp_ctx per (process, device).  Fails loudly without a CUDA device."""
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _contexts:
+        h = _vp()
+        check(lib.asp_ctx_create(int(device), C.byref(h)))
+        _contexts[device] = h
+    return _contexts[device]
+
+
+def make_params(eps, k, topk, p, sigma):
+    return GraphParams(float(eps), int(k), int(topk), float(p), float(sigma if sigma is not None else 0.0),
+                       0 if sigma is None else 1)
+
+
+def make_switches(kernel="inv_power", tau_mode="median", tau_fixed=0.0):
+    return Switches(KERNEL[kernel], TAU_MODE[tau_mode], float(tau_fixed))

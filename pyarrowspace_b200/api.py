@@ -1,0 +1,382 @@
+"""Host-side mirror of the reference's Python surface, over the C ABI.
+
+Mirrors /root/reference/src/lib.rs (pyo3 module ``arrowspace``): same class names, method
+names, argument order / keyword names, return shapes and error behaviour.
+
+    ArrowSpaceBuilder.build(graph_params, items) -> (ArrowSpace, GraphLaplacian)   src/lib.rs:270-300
+    ArrowSpace.search(item, gl, tau) -> [(index, score)]                           src/lib.rs:132-174
+    ArrowSpace.nitems / nfeatures / get_item(idx) / lambdas()                      src/lib.rs:78-124
+    GraphLaplacian.nnodes / shape() / graph_params                                 src/lib.rs:40-61
+    set_debug(enabled)                                                             src/helpers.rs:12-21
+
+Extensions (not in the reference): ``ArrowSpace.search_batch``, ``ArrowSpaceBuilder.build_sharded``
+and device-tensor inputs (anything exposing ``data_ptr()``), used by bench.py.
+
+Every numeric step runs in libarrowspace_b200.so (hand-written sm_100a CUDA).  There is no CPU
+path: without the library or without a GPU the calls raise.
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import LibraryError
+
+_DEBUG = False
+
+# crate defaults when graph_params is None (GRAPH_VARIABLES.md:15: eps~1e-3, k~6, p=2, sigma=eps).
+# topk has no documented default; 3 is the binding's doc-comment default (src/lib.rs:131).  [UNPINNED]
+DEFAULT_GRAPH_PARAMS = {"eps": 1e-3, "k": 6, "topk": 3, "p": 2.0, "sigma": 1e-3}
+
+
+class PanicException(BaseException):
+    """Stand-in for pyo3_runtime.PanicException: the reference `.unwrap()`s / `assert_ne!`s inside
+    build and search (src/lib.rs:156-159,277,279), which surfaces as a BaseException subclass."""
+
+
+def set_debug(enabled):
+    """Process-global debug flag; messages go to stderr with the reference's prefix (src/helpers.rs:12-21)."""
+    global _DEBUG
+    _DEBUG = bool(enabled)
+
+
+def dbg_println(msg):
+    if _DEBUG:
+        sys.stderr.write("[pyarrowspace] %s\n" % msg)
+        sys.stderr.flush()
+
+
+def _is_device_tensor(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _unwrap(exc):
+    """What `Result::unwrap()` on a PyErr looks like from Python."""
+    return PanicException(
+        "called `Result::unwrap()` on an `Err` value: PyErr { type: <class '%s'>, value: %s(%r), traceback: None }"
+        % (type(exc).__name__, type(exc).__name__, str(exc)))
+
+
+def parse_graph_params(graph_params):
+    """src/helpers.rs:48-77: eps, k, topk, p required; sigma missing/None -> eps * 0.5."""
+    if graph_params is None:
+        return None
+    if not isinstance(graph_params, dict):
+        raise TypeError("argument 'graph_params': 'dict' object expected")
+    out = {}
+    for key, conv in (("eps", float), ("k", int), ("topk", int), ("p", float)):
+        if key not in graph_params:
+            raise ValueError("graph_params['%s'] is required" % key)
+        v = graph_params[key]
+        if conv is int:
+            if isinstance(v, bool) or not isinstance(v, (int, np.integer)):
+                raise TypeError("'%s' object cannot be interpreted as an integer" % type(v).__name__)
+            if v < 0:
+                raise OverflowError("can't convert negative int to unsigned")
+            out[key] = int(v)
+        else:
+            if not isinstance(v, (int, float, np.integer, np.floating)) or isinstance(v, bool):
+                raise TypeError("argument '%s': must be real number, not %s" % (key, type(v).__name__))
+            out[key] = float(v)
+    sigma = graph_params.get("sigma")
+    out["sigma"] = out["eps"] * 0.5 if sigma is None else float(sigma)
+    return out
+
+
+class GraphLaplacian:
+    """Opaque handle of the feature-graph Laplacian (CSR on the device) + its parameters."""
+
+    def __new__(cls, *a, **k):
+        raise ValueError("GraphLaplacian cannot be constructed directly; use ArrowSpaceBuilder.build_with_graph")
+
+    @classmethod
+    def _wrap(cls, handle):
+        self = object.__new__(cls)
+        self._h = handle
+        return self
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.asp_free_graph(h)
+            self._h = None
+
+    def _info(self):
+        n, nnz, gp = C.c_int64(), C.c_int64(), _lib.GraphParams()
+        _lib.check(_lib.load().asp_graph_info(self._h, C.byref(n), C.byref(nnz), C.byref(gp)))
+        return n.value, nnz.value, gp
+
+    @property
+    def nnodes(self):
+        return self._info()[0]
+
+    def shape(self):
+        n = self._info()[0]
+        return (n, n)
+
+    @property
+    def graph_params(self):
+        gp = self._info()[2]
+        return {"eps": gp.eps, "k": gp.k, "topk": gp.topk, "p": gp.p, "sigma": gp.sigma}
+
+    # -- extension: parity export
+    @property
+    def nnz(self):
+        return self._info()[1]
+
+    def csr(self):
+        """(indptr int64[nnodes+1], indices int32[nnz], data f64[nnz]) of L = D - W."""
+        n, nnz, _ = self._info()
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(nnz, dtype=np.int32)
+        data = np.empty(nnz, dtype=np.float64)
+        _lib.check(_lib.load().asp_graph_csr(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data))
+        return indptr, indices, data
+
+    def edges(self):
+        """Sorted (a, b), a < b, W_ab > 0."""
+        indptr, indices, data = self.csr()
+        rows = np.repeat(np.arange(len(indptr) - 1, dtype=np.int64), np.diff(indptr))
+        keep = (indices > rows) & (data < 0.0)
+        return np.stack([rows[keep], indices[keep].astype(np.int64)], axis=1)
+
+
+class ArrowSpace:
+    """Device-resident items (row shard) + per-item taumode lambdas."""
+
+    def __new__(cls, *a, **k):
+        raise ValueError("ArrowSpace cannot be constructed directly; use ArrowSpaceBuilder.build")
+
+    @classmethod
+    def _wrap(cls, handle, ctx, group=None):
+        self = object.__new__(cls)
+        self._h = handle
+        self._ctx = ctx
+        self._group = group          # torch.distributed group for sharded spaces, else None
+        return self
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib._lib is not None:
+            _lib._lib.asp_free_space(h)
+            self._h = None
+
+    def _dims(self):
+        n, f, r0, nt = C.c_int64(), C.c_int32(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().asp_space_dims(self._h, C.byref(n), C.byref(f), C.byref(r0), C.byref(nt)))
+        return n.value, f.value, r0.value, nt.value
+
+    @property
+    def nitems(self):
+        return self._dims()[3]
+
+    @property
+    def nfeatures(self):
+        return self._dims()[1]
+
+    @property
+    def nitems_local(self):
+        return self._dims()[0]
+
+    @property
+    def row_offset(self):
+        return self._dims()[2]
+
+    def get_item(self, idx):
+        """(features ndarray[f64, F], lambda) -- src/lib.rs:100-120.  Sharded spaces: local rows only."""
+        if isinstance(idx, bool) or not isinstance(idx, (int, np.integer)):
+            raise TypeError("argument 'idx': '%s' object cannot be interpreted as an integer" % type(idx).__name__)
+        if idx < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+        n_local, f, row0, n_total = self._dims()
+        if idx >= n_total:
+            raise ValueError("index %d out of range [0, %d)" % (idx, n_total))
+        local = idx - row0
+        if local < 0 or local >= n_local:
+            raise ValueError("index %d is not on this rank (rows [%d, %d))" % (idx, row0, row0 + n_local))
+        feats = np.empty(f, dtype=np.float64)
+        lam = C.c_double()
+        _lib.check(_lib.load().asp_space_get_item(self._h, local, feats.ctypes.data, C.byref(lam)))
+        return feats, lam.value
+
+    def lambdas(self):
+        """New ndarray[f64] of the per-item lambdas (src/lib.rs:122-124); sharded: this rank's rows."""
+        out = np.empty(self._dims()[0], dtype=np.float64)
+        _lib.check(_lib.load().asp_space_lambdas(self._h, out.ctypes.data))
+        return out
+
+    def norms(self):
+        out = np.empty(self._dims()[0], dtype=np.float64)
+        _lib.check(_lib.load().asp_space_norms(self._h, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ search
+    def search(self, item, gl, tau):
+        """list[(index, score)], best first, length min(topk, nitems) -- src/lib.rs:132-174."""
+        if not isinstance(gl, GraphLaplacian):
+            raise TypeError("argument 'gl': 'GraphLaplacian' object expected")
+        if not isinstance(item, np.ndarray) or item.dtype != np.float64 or item.ndim != 1:
+            raise TypeError("argument 'item': expected 1-D numpy.ndarray of float64")
+        if not item.flags.c_contiguous:
+            raise ValueError("The given array is not contiguous")           # as_slice()? src/lib.rs:139
+        if item.shape[0] != self.nfeatures:
+            raise ValueError("query length %d must match nfeatures %d" % (item.shape[0], self.nfeatures))
+        tau = float(tau)
+        idx, score, lam_q = self._search_batch(item.reshape(1, -1), gl, tau, want_lambda=True)
+        dbg_println("search: qlen=%d, lambda_q=%.6f" % (item.shape[0], lam_q[0]))
+        return [(int(i), float(s)) for i, s in zip(idx[0], score[0]) if i >= 0]
+
+    def search_batch(self, queries, gl, tau):
+        """Extension: (idx int64[Q, topk], score f64[Q, topk]); rows padded with -1 / NaN."""
+        idx, score, _ = self._search_batch(queries, gl, float(tau), want_lambda=False)
+        return idx, score
+
+    def _search_batch(self, queries, gl, tau, want_lambda):
+        lib = _lib.load()
+        f = self.nfeatures
+        topk = gl.graph_params["topk"]
+        if _is_device_tensor(queries):
+            if queries.dim() != 2 or queries.shape[1] != f:
+                raise ValueError("query length %d must match nfeatures %d" % (queries.shape[-1], f))
+            import torch
+            q = queries.contiguous()
+            if q.dtype != torch.float64:
+                raise TypeError("queries must be float64")
+            nq = q.shape[0]
+            idx = torch.empty((nq, topk), dtype=torch.int64, device=q.device)
+            score = torch.empty((nq, topk), dtype=torch.float64, device=q.device)
+            lam = torch.empty(nq, dtype=torch.float64, device=q.device)
+            qp, ip, sp, lp = q.data_ptr(), idx.data_ptr(), score.data_ptr(), lam.data_ptr()
+        else:
+            q = np.ascontiguousarray(queries, dtype=np.float64)
+            if q.ndim != 2 or q.shape[1] != f:
+                raise ValueError("query length %d must match nfeatures %d" % (q.shape[-1], f))
+            nq = q.shape[0]
+            idx = np.empty((nq, topk), dtype=np.int64)
+            score = np.empty((nq, topk), dtype=np.float64)
+            lam = np.empty(nq, dtype=np.float64)
+            qp, ip, sp, lp = q.ctypes.data, idx.ctypes.data, score.ctypes.data, lam.ctypes.data
+        try:
+            _lib.check(lib.asp_search_batch(self._h, gl._h, qp, nq, tau, ip, sp, lp))
+        except LibraryError as e:
+            if e.code == _lib.ASP_ERR_LAMBDA_ZERO:                          # src/lib.rs:156-159
+                raise PanicException("assertion `left != right` failed: %s\n  left: 0.0\n right: 0.0" % e.message)
+            if e.code == _lib.ASP_ERR_ZERO_VECTOR:
+                raise PanicException(e.message)
+            raise
+        if self._group is not None:
+            idx, score = _merge_across_ranks(self, idx, score, nq, topk)
+        return idx, score, lam
+
+    # ------------------------------------------------------------------ out of scope
+    def search_hybrid(self, item, gl, tau):
+        raise NotImplementedError("search_hybrid is outside the build-and-search hot path (src/lib.rs:182-219)")
+
+    def search_energy(self, item, gl, k, w_lambda=None, w_dirichlet=None):
+        raise NotImplementedError("search_energy belongs to the energy pipeline (src/lib.rs:232-262)")
+
+
+def _merge_across_ranks(space, idx, score, nq, topk):
+    """K5 host side: all-gather the per-shard (idx, score) lists, merge on the device."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    group = space._group
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", _lib.load().asp_ctx_device(space._ctx))
+    was_numpy = isinstance(idx, np.ndarray)
+    t_idx = torch.from_numpy(idx).to(dev) if was_numpy else idx
+    t_sc = torch.from_numpy(score).to(dev) if was_numpy else score
+    all_idx = torch.empty((world, nq, topk), dtype=torch.int64, device=dev)
+    all_sc = torch.empty((world, nq, topk), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(all_idx, t_idx.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_sc, t_sc.contiguous(), group=group)
+    out_idx = torch.empty((nq, topk), dtype=torch.int64, device=dev)
+    out_sc = torch.empty((nq, topk), dtype=torch.float64, device=dev)
+    torch.cuda.current_stream(dev).synchronize()
+    _lib.check(lib.asp_topk_merge(space._ctx, all_idx.data_ptr(), all_sc.data_ptr(), world, nq, topk,
+                                  out_idx.data_ptr(), out_sc.data_ptr()))
+    _lib.check(lib.asp_ctx_synchronize(space._ctx))
+    if was_numpy:
+        return out_idx.cpu().numpy(), out_sc.cpu().numpy()
+    return out_idx, out_sc
+
+
+class ArrowSpaceBuilder:
+    @staticmethod
+    def build(graph_params, items, **extras):
+        """Feature graph + Laplacian + per-item lambdas.  src/lib.rs:270-300.
+
+        keyword-only extras (never positional): device=int, kernel=, tau_mode=, tau_fixed=.
+        """
+        lib = _lib.load()
+        dbg_println("Convert pyarray2 and Vec<Vec>")
+        device_in = _is_device_tensor(items)
+        if device_in:
+            import torch
+            if items.dtype != torch.float64 or items.dim() != 2:
+                raise TypeError("argument 'items': expected a 2-D float64 tensor")
+            x = items.contiguous()
+            n, f = x.shape
+            ptr = x.data_ptr()
+        else:
+            if not isinstance(items, np.ndarray) or items.dtype != np.float64 or items.ndim != 2:
+                raise TypeError("argument 'items': expected 2-D numpy.ndarray of float64")
+            n, f = items.shape
+            x = np.ascontiguousarray(items)          # any strides accepted (as_array()), src/helpers.rs:25
+            ptr = x.ctypes.data
+        if n == 0 or f == 0:
+            raise _unwrap(ValueError("items must be non-empty 2D array"))        # src/helpers.rs:27-29 + .unwrap()
+        dbg_println("items shape: (%d, %d)" % (n, f))
+        if _DEBUG and not device_in:
+            dbg_println("items[0][:5]: %s" % list(x[0, :5]))
+            dbg_println("NaNs: %d, Infs: %d" % (int(np.isnan(x).sum()), int(np.isinf(x).sum())))
+        try:
+            gp = parse_graph_params(graph_params)
+        except (ValueError, TypeError, OverflowError) as e:
+            raise _unwrap(e)                                                     # src/lib.rs:279 .unwrap()
+        if gp is None:
+            gp = dict(DEFAULT_GRAPH_PARAMS)
+        cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+        sw = _lib.make_switches(extras.get("kernel", "inv_power"), extras.get("tau_mode", "median"),
+                                extras.get("tau_fixed", 0.0))
+        ctx = _lib.context(extras.get("device"))
+        dbg_println("Building from rows")
+        hs, hg = C.c_void_p(), C.c_void_p()
+        try:
+            _lib.check(lib.asp_build(ctx, ptr, n, f, C.byref(cgp), C.byref(sw), C.byref(hs), C.byref(hg)))
+        except LibraryError as e:
+            if e.code in (_lib.ASP_ERR_ZERO_VECTOR, _lib.ASP_ERR_EMPTY):
+                raise PanicException(e.message)
+            raise
+        aspace, gl = ArrowSpace._wrap(hs, ctx), GraphLaplacian._wrap(hg)
+        dbg_println("built ArrowSpace: nitems=%d, nfeatures=%d, lambdas_len=%d" % (n, f, n))
+        return aspace, gl
+
+    @staticmethod
+    def build_sharded(graph_params, items_shard, n_total, group=None, **extras):
+        """Extension: one process per GPU, each passing ITS rows (see shard_rows).  Collectives:
+        all-gather of the Gram segment partials (8 x F x F f64), rank-ordered continuation of the
+        exact column sums (rare), nothing else.  Returns (ArrowSpace shard, GraphLaplacian replica)."""
+        from . import distributed
+        return distributed.build_sharded(graph_params, items_shard, n_total, group, **extras)
+
+    @staticmethod
+    def build_energy(items, energy_params=None, graph_params=None):
+        raise NotImplementedError("build_energy belongs to the energy pipeline (src/lib.rs:333-376)")
+
+
+def shard_rows(n_total, world, rank):
+    """Rows [row0, row1) of `rank`: whole Gram segments (see ASP_GRAM_SEGMENTS)."""
+    r0, r1 = C.c_int64(), C.c_int64()
+    _lib.check(_lib.load().asp_shard_rows(int(n_total), int(world), int(rank), C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+def stat(key, device=None):
+    return _lib.load().asp_ctx_stat(_lib.context(device), key.encode())
+
+
+def launch_count(device=None):
+    return _lib.load().asp_ctx_launch_count(_lib.context(device))

@@ -1,0 +1,656 @@
+// api.cu -- the C ABI declared in include/arrowspace_b200.h (extern "C", plain pointers).
+// Host-side orchestration only; every numeric step is a kernel in gram.cu / graph_select.cu /
+// csr.cu / taumode.cu / search.cu / knn.cu.  There is no CPU fallback anywhere in this file.
+#include "common.cuh"
+
+#include <algorithm>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+void asp_set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+bool asp_is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int asp_copy_in(asp_ctx *ctx, void *dst_dev, const void *src, size_t bytes)
+{
+    if (bytes == 0) return ASP_OK;
+    ASP_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return ASP_OK;
+}
+
+int asp_copy_out(asp_ctx *ctx, void *dst, const void *src_dev, size_t bytes)
+{
+    if (bytes == 0) return ASP_OK;
+    ASP_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    if (!asp_is_device_ptr(dst)) ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ASP_OK;
+}
+
+namespace {
+
+struct StageTimer {
+    asp_ctx *ctx;
+    const char *key;
+    cudaEvent_t a, b;
+    StageTimer(asp_ctx *c, const char *k) : ctx(c), key(k)
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    void stop()
+    {
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        ctx->stats[key] = ms;
+    }
+    ~StageTimer()
+    {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+__global__ void zero_lambda_check_kernel(const double *lam, int64_t n, int *flag)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (lam[i] == 0.0) atomicExch(flag, 1);
+}
+
+// upload an n x f row-major matrix (host or device) into a pitched, zero padded device buffer
+int upload_pitched(asp_ctx *ctx, const double *src, int64_t n, int32_t f, int32_t pitch, double *dst)
+{
+    if (pitch != f) ASP_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)n * pitch, ctx->stream));
+    ASP_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * pitch, src, sizeof(double) * f, sizeof(double) * f, (size_t)n,
+                               cudaMemcpyDefault, ctx->stream));
+    return ASP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *asp_last_error(void) { return g_last_error.c_str(); }
+int asp_abi_version(void) { return ASP_ABI_VERSION; }
+
+void asp_default_switches(asp_switches *sw)
+{
+    sw->kernel = ASP_KERNEL_INV_POWER;
+    sw->tau_mode = ASP_TAU_MEDIAN;
+    sw->tau_fixed = 0.0;
+}
+
+int asp_ctx_create(int device, asp_ctx **out)
+{
+    if (!out) ASP_FAIL(ASP_ERR_ARG, "asp_ctx_create: out is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        ASP_FAIL(ASP_ERR_CUDA, "no CUDA device: arrowspace_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) ASP_FAIL(ASP_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+    ASP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ASP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        ASP_FAIL(ASP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    asp_ctx *ctx = new asp_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ASP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ASP_CUDA(cudaEventCreate(&ctx->ev0));
+    ASP_CUDA(cudaEventCreate(&ctx->ev1));
+    const char *no_tma = getenv("ASP_NO_TMA");
+    ctx->use_tma = !(no_tma && no_tma[0] == '1');
+    *out = ctx;
+    return ASP_OK;
+}
+
+void asp_ctx_destroy(asp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+int asp_ctx_device(const asp_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int asp_ctx_set_stream(asp_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) ASP_FAIL(ASP_ERR_ARG, "ctx is NULL");
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+        ctx->own_stream = false;
+    } else {
+        ASP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return ASP_OK;
+}
+
+int asp_ctx_synchronize(asp_ctx *ctx)
+{
+    if (!ctx) ASP_FAIL(ASP_ERR_ARG, "ctx is NULL");
+    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ASP_OK;
+}
+
+int64_t asp_ctx_launch_count(const asp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+double asp_ctx_stat(const asp_ctx *ctx, const char *key)
+{
+    if (!ctx || !key) return -1.0;
+    auto it = ctx->stats.find(key);
+    return it == ctx->stats.end() ? -1.0 : it->second;
+}
+
+// ------------------------------------------------------------------ sharding
+int asp_shard_rows(int64_t n_total, int world, int rank, int64_t *row0, int64_t *row1)
+{
+    if (n_total <= 0 || world <= 0 || rank < 0 || rank >= world || ASP_GRAM_SEGMENTS % world != 0)
+        ASP_FAIL(ASP_ERR_ARG, "asp_shard_rows: world must divide %d and 0 <= rank < world (got world=%d rank=%d)",
+                 ASP_GRAM_SEGMENTS, world, rank);
+    const int64_t units = asp_ceil_div(n_total, ASP_ROW_UNIT);
+    const int seg0 = rank * (ASP_GRAM_SEGMENTS / world), seg1 = (rank + 1) * (ASP_GRAM_SEGMENTS / world);
+    int64_t r0 = (units * seg0) / ASP_GRAM_SEGMENTS * ASP_ROW_UNIT;
+    int64_t r1 = (units * seg1) / ASP_GRAM_SEGMENTS * ASP_ROW_UNIT;
+    if (r0 > n_total) r0 = n_total;
+    if (r1 > n_total) r1 = n_total;
+    if (row0) *row0 = r0;
+    if (row1) *row1 = r1;
+    return ASP_OK;
+}
+
+int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, int32_t f, int64_t n_total, int world,
+                     int rank, asp_space **out)
+{
+    if (!ctx || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_create: NULL argument");
+    if (!items_shard || n_local <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    int64_t r0 = 0, r1 = 0;
+    ASP_CHECK(asp_shard_rows(n_total, world, rank, &r0, &r1));
+    if (r1 - r0 != n_local)
+        ASP_FAIL(ASP_ERR_ARG, "rank %d of %d owns rows [%lld,%lld) of %lld, got %lld rows", rank, world, (long long)r0,
+                 (long long)r1, (long long)n_total, (long long)n_local);
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_space *s = new asp_space();
+    s->ctx = ctx;
+    s->n_local = n_local;
+    s->row0 = r0;
+    s->n_total = n_total;
+    s->f = f;
+    s->fp = (f + 3) & ~3;
+    s->world = world;
+    s->rank = rank;
+    ASP_CUDA(cudaMalloc(&s->items, sizeof(double) * (size_t)n_local * s->fp));
+    ASP_CUDA(cudaMalloc(&s->norms, sizeof(double) * n_local));
+    ASP_CUDA(cudaMalloc(&s->inv_norms, sizeof(double) * n_local));
+    ASP_CUDA(cudaMalloc(&s->lambdas, sizeof(double) * n_local));
+    int rc = upload_pitched(ctx, items_shard, n_local, f, s->fp, s->items);
+    if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_gram, s->items, n_local, s->fp, ASP_ROW_UNIT, 32);
+    if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n_local, s->fp, 128, 4);
+    if (rc == ASP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        asp_set_error("upload of the item shard failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = ASP_ERR_CUDA;
+    }
+    if (rc != ASP_OK) { asp_free_space(s); return rc; }
+    *out = s;
+    return ASP_OK;
+}
+
+void asp_free_space(asp_space *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->items);
+    cudaFree(s->norms);
+    cudaFree(s->inv_norms);
+    cudaFree(s->lambdas);
+    delete s;
+}
+
+void asp_free_graph(asp_graph *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaFree(g->d_indptr);
+    cudaFree(g->d_indices);
+    cudaFree(g->d_data);
+    cudaFree(g->d_uptr);
+    cudaFree(g->d_ucol);
+    cudaFree(g->d_uval);
+    cudaFree(g->d_deg);
+    delete g;
+}
+
+// ------------------------------------------------------------------ build stages
+int asp_space_gram_partials(asp_space *s, double *out_dev)
+{
+    if (!s || !out_dev) ASP_FAIL(ASP_ERR_ARG, "asp_space_gram_partials: NULL argument");
+    if (!asp_is_device_ptr(out_dev)) ASP_FAIL(ASP_ERR_ARG, "asp_space_gram_partials: out_dev must be device memory");
+    ASP_CUDA(cudaSetDevice(s->ctx->device));
+    return asp_launch_gram_partials(s, out_dev);
+}
+
+int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f, int64_t n_total,
+                        const asp_graph_params *gp, const asp_switches *sw_in, const int32_t *exact_pairs,
+                        const double *exact_sums, int64_t n_exact, int32_t *need_pairs, int64_t need_cap, int64_t *n_need,
+                        asp_graph **out_graph)
+{
+    if (!ctx || !gram_segments_dev || !gp || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_graph_from_gram: NULL argument");
+    if (!asp_is_device_ptr(gram_segments_dev)) ASP_FAIL(ASP_ERR_ARG, "gram_segments_dev must be device memory");
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_switches sw;
+    if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    cudaStream_t st = ctx->stream;
+    if (n_need) *n_need = 0;
+
+    double *gram = nullptr;
+    ASP_CUDA(cudaMallocAsync(&gram, sizeof(double) * (size_t)f * f, st));
+    ASP_CHECK(asp_launch_gram_reduce(ctx, gram_segments_dev, f, gram));
+
+    // exact pairs, sorted by (a, b) for the device binary search
+    int32_t *d_pairs = nullptr;
+    double *d_sums = nullptr;
+    if (n_exact > 0) {
+        std::vector<int64_t> order(n_exact);
+        for (int64_t i = 0; i < n_exact; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+            if (exact_pairs[2 * x] != exact_pairs[2 * y]) return exact_pairs[2 * x] < exact_pairs[2 * y];
+            return exact_pairs[2 * x + 1] < exact_pairs[2 * y + 1];
+        });
+        std::vector<int32_t> hp(2 * n_exact);
+        std::vector<double> hs(3 * n_exact);
+        for (int64_t i = 0; i < n_exact; ++i) {
+            hp[2 * i] = exact_pairs[2 * order[i]];
+            hp[2 * i + 1] = exact_pairs[2 * order[i] + 1];
+            for (int c = 0; c < 3; ++c) hs[3 * i + c] = exact_sums[3 * order[i] + c];
+        }
+        ASP_CUDA(cudaMallocAsync(&d_pairs, sizeof(int32_t) * 2 * n_exact, st));
+        ASP_CUDA(cudaMallocAsync(&d_sums, sizeof(double) * 3 * n_exact, st));
+        ASP_CUDA(cudaMemcpyAsync(d_pairs, hp.data(), sizeof(int32_t) * 2 * n_exact, cudaMemcpyHostToDevice, st));
+        ASP_CUDA(cudaMemcpyAsync(d_sums, hs.data(), sizeof(double) * 3 * n_exact, cudaMemcpyHostToDevice, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+
+    const int64_t dev_cap = 1 << 16;
+    int32_t *d_need = nullptr, *d_need_count = nullptr;
+    ASP_CUDA(cudaMallocAsync(&d_need, sizeof(int32_t) * 2 * dev_cap, st));
+    ASP_CUDA(cudaMallocAsync(&d_need_count, sizeof(int32_t), st));
+    ASP_CUDA(cudaMemsetAsync(d_need_count, 0, sizeof(int32_t), st));
+
+    asp_knn_lists lists;
+    int rc = asp_feature_select(ctx, gram, f, n_total, gp, d_pairs, d_sums, n_exact, &lists, d_need, dev_cap, d_need_count);
+    int32_t need_count = 0;
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(&need_count, d_need_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    asp_graph *g = nullptr;
+    if (rc == ASP_OK && need_count > 0) {
+        const int64_t got = need_count < dev_cap ? need_count : dev_cap;
+        std::vector<int32_t> hp(2 * got);
+        ASP_CUDA(cudaMemcpyAsync(hp.data(), d_need, sizeof(int32_t) * 2 * got, cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+        std::vector<std::pair<int32_t, int32_t>> uniq(got);
+        for (int64_t i = 0; i < got; ++i) uniq[i] = {hp[2 * i], hp[2 * i + 1]};
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        if (n_need) *n_need = (int64_t)uniq.size();
+        ctx->stats["need_exact_pairs"] = (double)uniq.size();
+        if (!need_pairs || (int64_t)uniq.size() > need_cap) {
+            rc = ASP_ERR_ARG;
+            asp_set_error("%lld column pairs fall inside the rounding band; need_pairs has room for %lld",
+                          (long long)uniq.size(), (long long)need_cap);
+        } else {
+            for (size_t i = 0; i < uniq.size(); ++i) { need_pairs[2 * i] = uniq[i].first; need_pairs[2 * i + 1] = uniq[i].second; }
+            rc = ASP_NEED_EXACT;
+            asp_set_error("%lld column pairs need exact sums", (long long)uniq.size());
+        }
+    } else if (rc == ASP_OK) {
+        g = new asp_graph();
+        g->ctx = ctx;
+        g->gp = *gp;
+        if (!g->gp.has_sigma) { g->gp.sigma = gp->eps * 0.5; g->gp.has_sigma = 1; }   // src/helpers.rs:68-72
+        g->sw = sw;
+        rc = asp_assemble_laplacian(ctx, &lists, gp, &sw, g);
+        if (rc == ASP_OK) rc = asp_graph_upload_upper(g);
+        if (rc != ASP_OK) { asp_free_graph(g); g = nullptr; }
+    }
+    cudaFreeAsync(lists.idx, st);
+    cudaFreeAsync(lists.dist, st);
+    cudaFreeAsync(lists.cnt, st);
+    cudaFreeAsync(d_need, st);
+    cudaFreeAsync(d_need_count, st);
+    if (d_pairs) cudaFreeAsync(d_pairs, st);
+    if (d_sums) cudaFreeAsync(d_sums, st);
+    cudaFreeAsync(gram, st);
+    if (rc == ASP_OK) *out_graph = g;
+    return rc;
+}
+
+int asp_space_exact_pairs(asp_space *s, const int32_t *pairs, int64_t n_pairs, double *sums)
+{
+    if (!s || (n_pairs > 0 && (!pairs || !sums))) ASP_FAIL(ASP_ERR_ARG, "asp_space_exact_pairs: NULL argument");
+    if (n_pairs == 0) return ASP_OK;
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int32_t *d_pairs = nullptr;
+    double *d_sums = nullptr;
+    ASP_CUDA(cudaMallocAsync(&d_pairs, sizeof(int32_t) * 2 * n_pairs, st));
+    ASP_CUDA(cudaMallocAsync(&d_sums, sizeof(double) * 3 * n_pairs, st));
+    ASP_CUDA(cudaMemcpyAsync(d_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDefault, st));
+    ASP_CUDA(cudaMemcpyAsync(d_sums, sums, sizeof(double) * 3 * n_pairs, cudaMemcpyDefault, st));
+    int rc = asp_launch_exact_pairs(s, d_pairs, n_pairs, d_sums);
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(sums, d_sums, sizeof(double) * 3 * n_pairs, cudaMemcpyDefault, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    cudaFreeAsync(d_pairs, st);
+    cudaFreeAsync(d_sums, st);
+    return rc;
+}
+
+int asp_space_compute_lambdas(asp_space *s, const asp_graph *g)
+{
+    if (!s || !g) ASP_FAIL(ASP_ERR_ARG, "asp_space_compute_lambdas: NULL argument");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    int *flag = nullptr;
+    ASP_CUDA(cudaMallocAsync(&flag, sizeof(int), ctx->stream));
+    ASP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    int rc = asp_launch_taumode(ctx, g, &g->sw, s->items, s->n_local, s->f, s->fp, nullptr, nullptr, s->lambdas, s->norms,
+                                s->inv_norms, flag);
+    int h = 0;
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFreeAsync(flag, ctx->stream);
+    if (rc != ASP_OK) return rc;
+    if (h) ASP_FAIL(ASP_ERR_ZERO_VECTOR, "an item vector is all zeros: its Rayleigh quotient is undefined");
+    s->have_lambdas = true;
+    return ASP_OK;
+}
+
+int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp_graph_params *gp, const asp_switches *sw,
+              asp_space **out_space, asp_graph **out_graph)
+{
+    if (!ctx || !gp || !out_space || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_build: NULL argument");
+    if (!items || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    asp_space *s = nullptr;
+    {
+        StageTimer t(ctx, "upload_ms");
+        ASP_CHECK(asp_space_create(ctx, items, n, f, n, 1, 0, &s));
+        t.stop();
+    }
+    double *segs = nullptr;
+    asp_graph *g = nullptr;
+    int rc = ASP_OK;
+    if (cudaMalloc(&segs, sizeof(double) * (size_t)ASP_GRAM_SEGMENTS * f * f) != cudaSuccess) {
+        asp_set_error("out of device memory for the Gram segments");
+        rc = ASP_ERR_NOMEM;
+    }
+    if (rc == ASP_OK) {
+        StageTimer t(ctx, "gram_ms");
+        rc = asp_space_gram_partials(s, segs);
+        t.stop();
+    }
+    if (rc == ASP_OK) {
+        StageTimer t(ctx, "graph_ms");
+        std::vector<int32_t> pairs;
+        std::vector<double> sums;
+        const int64_t cap = 1 << 16;
+        std::vector<int32_t> need(2 * cap);
+        for (int pass = 0; pass < 4; ++pass) {
+            int64_t n_need = 0;
+            rc = asp_graph_from_gram(ctx, segs, f, n, gp, sw, pairs.data(), sums.data(), (int64_t)(pairs.size() / 2),
+                                     need.data(), cap, &n_need, &g);
+            if (rc != ASP_NEED_EXACT) break;
+            std::vector<double> add(3 * n_need, 0.0);
+            rc = asp_space_exact_pairs(s, need.data(), n_need, add.data());
+            if (rc != ASP_OK) break;
+            pairs.insert(pairs.end(), need.begin(), need.begin() + 2 * n_need);
+            sums.insert(sums.end(), add.begin(), add.end());
+            rc = ASP_NEED_EXACT;
+        }
+        if (rc == ASP_NEED_EXACT) { asp_set_error("exact-pair resolution did not converge"); rc = ASP_ERR_CUDA; }
+        t.stop();
+    }
+    if (rc == ASP_OK) {
+        StageTimer t(ctx, "lambda_ms");
+        rc = asp_space_compute_lambdas(s, g);
+        t.stop();
+    }
+    cudaFree(segs);
+    if (rc != ASP_OK) { asp_free_space(s); asp_free_graph(g); return rc; }
+    *out_space = s;
+    *out_graph = g;
+    return ASP_OK;
+}
+
+// ------------------------------------------------------------------ accessors
+int asp_space_dims(const asp_space *s, int64_t *n_local, int32_t *f, int64_t *row0, int64_t *n_total)
+{
+    if (!s) ASP_FAIL(ASP_ERR_ARG, "space is NULL");
+    if (n_local) *n_local = s->n_local;
+    if (f) *f = s->f;
+    if (row0) *row0 = s->row0;
+    if (n_total) *n_total = s->n_total;
+    return ASP_OK;
+}
+
+int asp_space_lambdas(const asp_space *s, double *out)
+{
+    if (!s || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_lambdas: NULL argument");
+    if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "lambdas have not been computed yet");
+    ASP_CUDA(cudaSetDevice(s->ctx->device));
+    return asp_copy_out(s->ctx, out, s->lambdas, sizeof(double) * s->n_local);
+}
+
+int asp_space_norms(const asp_space *s, double *out)
+{
+    if (!s || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_norms: NULL argument");
+    if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "norms are computed together with the lambdas");
+    ASP_CUDA(cudaSetDevice(s->ctx->device));
+    return asp_copy_out(s->ctx, out, s->norms, sizeof(double) * s->n_local);
+}
+
+int asp_space_get_item(const asp_space *s, int64_t local_idx, double *out_features, double *out_lambda)
+{
+    if (!s) ASP_FAIL(ASP_ERR_ARG, "space is NULL");
+    if (local_idx < 0 || local_idx >= s->n_local)
+        ASP_FAIL(ASP_ERR_ARG, "index %lld out of range [0, %lld)", (long long)local_idx, (long long)s->n_local);
+    ASP_CUDA(cudaSetDevice(s->ctx->device));
+    if (out_features) ASP_CHECK(asp_copy_out(s->ctx, out_features, s->items + local_idx * s->fp, sizeof(double) * s->f));
+    if (out_lambda) {
+        if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "lambdas have not been computed yet");
+        ASP_CHECK(asp_copy_out(s->ctx, out_lambda, s->lambdas + local_idx, sizeof(double)));
+    }
+    return ASP_OK;
+}
+
+int asp_graph_info(const asp_graph *g, int64_t *nnodes, int64_t *nnz, asp_graph_params *gp)
+{
+    if (!g) ASP_FAIL(ASP_ERR_ARG, "graph is NULL");
+    if (nnodes) *nnodes = g->nnodes;
+    if (nnz) *nnz = g->nnz;
+    if (gp) *gp = g->gp;
+    return ASP_OK;
+}
+
+int asp_graph_csr(const asp_graph *g, int64_t *indptr, int32_t *indices, double *data)
+{
+    if (!g) ASP_FAIL(ASP_ERR_ARG, "graph is NULL");
+    ASP_CUDA(cudaSetDevice(g->ctx->device));
+    if (indptr) ASP_CHECK(asp_copy_out(g->ctx, indptr, g->d_indptr, sizeof(int64_t) * (g->nnodes + 1)));
+    if (indices) ASP_CHECK(asp_copy_out(g->ctx, indices, g->d_indices, sizeof(int32_t) * g->nnz));
+    if (data) ASP_CHECK(asp_copy_out(g->ctx, data, g->d_data, sizeof(double) * g->nnz));
+    return ASP_OK;
+}
+
+// ------------------------------------------------------------------ search
+int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw_in, const double *queries, int64_t nq,
+                     double *out_energy, double *out_tau, double *out_lambda)
+{
+    if (!ctx || !g || (nq > 0 && !queries)) ASP_FAIL(ASP_ERR_ARG, "asp_query_lambda: NULL argument");
+    if (nq == 0) return ASP_OK;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    const asp_switches sw = sw_in ? *sw_in : g->sw;
+    const int32_t f = (int32_t)g->nnodes;
+    cudaStream_t st = ctx->stream;
+    double *dq = nullptr, *de = nullptr;
+    int *flag = nullptr;
+    ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * f, st));
+    ASP_CUDA(cudaMallocAsync(&de, sizeof(double) * 3 * nq, st));
+    ASP_CUDA(cudaMallocAsync(&flag, sizeof(int), st));
+    ASP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    ASP_CUDA(cudaMemcpyAsync(dq, queries, sizeof(double) * (size_t)nq * f, cudaMemcpyDefault, st));
+    int rc = asp_launch_taumode(ctx, g, &sw, dq, nq, f, f, de, de + nq, de + 2 * nq, nullptr, nullptr, flag);
+    int h = 0;
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (out_energy) rc = asp_copy_out(ctx, out_energy, de, sizeof(double) * nq);
+        if (rc == ASP_OK && out_tau) rc = asp_copy_out(ctx, out_tau, de + nq, sizeof(double) * nq);
+        if (rc == ASP_OK && out_lambda) rc = asp_copy_out(ctx, out_lambda, de + 2 * nq, sizeof(double) * nq);
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    cudaFreeAsync(dq, st);
+    cudaFreeAsync(de, st);
+    cudaFreeAsync(flag, st);
+    if (rc != ASP_OK) return rc;
+    if (h) ASP_FAIL(ASP_ERR_ZERO_VECTOR, "a query vector is all zeros: its Rayleigh quotient is undefined");
+    return ASP_OK;
+}
+
+int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq, double tau,
+                     int64_t *out_idx, double *out_score, double *out_lambda_q)
+{
+    if (!s || !g || (nq > 0 && (!queries || !out_idx || !out_score))) ASP_FAIL(ASP_ERR_ARG, "asp_search_batch: NULL argument");
+    if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "asp_search_batch: item lambdas have not been computed");
+    if (g->nnodes != s->f)
+        ASP_FAIL(ASP_ERR_ARG, "graph has %lld nodes but items have %d features", (long long)g->nnodes, s->f);
+    if (nq == 0) return ASP_OK;
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t topk = g->gp.topk;                              // src/lib.rs:169
+    const int32_t f = s->f, fp = s->fp;
+
+    double *dq = nullptr, *dlam = nullptr, *dnorm = nullptr, *dscore = nullptr;
+    int64_t *didx = nullptr;
+    int *flags = nullptr;
+    ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * fp, st));
+    ASP_CUDA(cudaMallocAsync(&dlam, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&dnorm, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&flags, sizeof(int) * 2, st));
+    ASP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, st));
+    int rc = upload_pitched(ctx, queries, nq, f, fp, dq);
+    if (rc == ASP_OK)
+        rc = asp_launch_taumode(ctx, g, &g->sw, dq, nq, f, fp, nullptr, nullptr, dlam, dnorm, nullptr, flags);   // src/lib.rs:154
+    if (rc == ASP_OK) {
+        zero_lambda_check_kernel<<<64, 256, 0, st>>>(dlam, nq, flags + 1);
+        ASP_LAUNCHED(ctx);
+        int h[2] = {0, 0};
+        ASP_CUDA(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+        if (h[0]) { asp_set_error("a query vector is all zeros: its Rayleigh quotient is undefined"); rc = ASP_ERR_ZERO_VECTOR; }
+        else if (h[1]) { asp_set_error("The lambdas are zero, check the magnitude of items and eps."); rc = ASP_ERR_LAMBDA_ZERO; }   // src/lib.rs:156-159
+    }
+    if (rc == ASP_OK && out_lambda_q) rc = asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq);
+    if (rc == ASP_OK && topk > 0) {
+        ASP_CUDA(cudaMallocAsync(&didx, sizeof(int64_t) * (size_t)nq * topk, st));
+        ASP_CUDA(cudaMallocAsync(&dscore, sizeof(double) * (size_t)nq * topk, st));
+        rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
+        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
+        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    cudaFreeAsync(dq, st);
+    cudaFreeAsync(dlam, st);
+    cudaFreeAsync(dnorm, st);
+    cudaFreeAsync(flags, st);
+    if (didx) cudaFreeAsync(didx, st);
+    if (dscore) cudaFreeAsync(dscore, st);
+    return rc;
+}
+
+int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int parts, int64_t nq, int64_t topk,
+                   int64_t *out_idx, double *out_score)
+{
+    if (!ctx || !idx || !score || !out_idx || !out_score || parts <= 0) ASP_FAIL(ASP_ERR_ARG, "asp_topk_merge: bad argument");
+    if (nq == 0 || topk == 0) return ASP_OK;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n_in = (size_t)parts * nq * topk, n_out = (size_t)nq * topk;
+    int64_t *d_idx = nullptr, *d_oidx = nullptr;
+    double *d_sc = nullptr, *d_osc = nullptr;
+    ASP_CUDA(cudaMallocAsync(&d_idx, sizeof(int64_t) * n_in, st));
+    ASP_CUDA(cudaMallocAsync(&d_sc, sizeof(double) * n_in, st));
+    ASP_CUDA(cudaMallocAsync(&d_oidx, sizeof(int64_t) * n_out, st));
+    ASP_CUDA(cudaMallocAsync(&d_osc, sizeof(double) * n_out, st));
+    ASP_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int64_t) * n_in, cudaMemcpyDefault, st));
+    ASP_CUDA(cudaMemcpyAsync(d_sc, score, sizeof(double) * n_in, cudaMemcpyDefault, st));
+    int rc = asp_topk_merge_impl(ctx, d_idx, d_sc, parts, nq, topk, d_oidx, d_osc);
+    if (rc == ASP_OK) rc = asp_copy_out(ctx, out_idx, d_oidx, sizeof(int64_t) * n_out);
+    if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, d_osc, sizeof(double) * n_out);
+    ASP_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_idx, st);
+    cudaFreeAsync(d_sc, st);
+    cudaFreeAsync(d_oidx, st);
+    cudaFreeAsync(d_osc, st);
+    return rc;
+}
+
+int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw_in, asp_graph **out_graph)
+{
+    if (!s || !gp || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_item_graph: NULL argument");
+    if (s->world != 1) ASP_FAIL(ASP_ERR_UNSUPPORTED, "asp_item_graph is single-GPU in this version");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_switches sw;
+    if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    asp_knn_lists lists;
+    ASP_CHECK(asp_item_knn(s, gp, &lists));
+    asp_graph *g = new asp_graph();
+    g->ctx = ctx;
+    g->gp = *gp;
+    if (!g->gp.has_sigma) { g->gp.sigma = gp->eps * 0.5; g->gp.has_sigma = 1; }
+    g->sw = sw;
+    int rc = asp_assemble_laplacian(ctx, &lists, gp, &sw, g);
+    cudaFreeAsync(lists.idx, ctx->stream);
+    cudaFreeAsync(lists.dist, ctx->stream);
+    cudaFreeAsync(lists.cnt, ctx->stream);
+    if (rc != ASP_OK) { asp_free_graph(g); return rc; }
+    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_graph = g;
+    return ASP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""Multi-GPU host logic: one process per GPU, ``torch.distributed`` (NCCL over NVLink) for the plumbing.
+
+The path shards by rows: rank r owns the rows of Gram segments
+[r*8/world, (r+1)*8/world).  Exchange steps, and nothing else:
+
+  build   1. all-gather of the per-segment partial Grams (8 x F x F f64: 9.4 MB at F = 384)
+          2. (rare) rank-ordered continuation of left-to-right column sums for the pairs whose
+             distance falls inside the rounding band: rank r continues rank r-1's sums
+  search  3. all-gather of the per-shard top-k lists (16 * Q * topk bytes per rank) + merge kernel
+
+The summation tree of the Gram is fixed (segments -> slices), so every world size produces
+bit-identical graphs, lambdas and result lists.
+
+`sharded_build` / `sharded_search` take an *engine* (the calls into the C ABI) so that the
+orchestration can be exercised on CPU with gloo in tests; the product engine is `CudaEngine`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def shard_rows(n_total, world, rank):
+    r0, r1 = C.c_int64(), C.c_int64()
+    _lib.check(_lib.load().asp_shard_rows(int(n_total), int(world), int(rank), C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+class CudaEngine:
+    """The product engine: every method is one call into libarrowspace_b200.so."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.ctx = _lib.context(device)
+        self.device = torch.device("cuda", self.lib.asp_ctx_device(self.ctx))
+
+    def _ptr(self, x):
+        return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+
+    def space_create(self, shard, n_total, world, rank):
+        n_local, f = shard.shape
+        h = C.c_void_p()
+        _lib.check(self.lib.asp_space_create(self.ctx, self._ptr(shard), n_local, f, n_total, world, rank, C.byref(h)))
+        return h
+
+    def gram_partials(self, space, f):
+        segs = self.torch.zeros((_lib.GRAM_SEGMENTS, f, f), dtype=self.torch.float64, device=self.device)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_space_gram_partials(space, segs.data_ptr()))
+        _lib.check(self.lib.asp_ctx_synchronize(self.ctx))
+        return segs
+
+    def graph_from_gram(self, segs, f, n_total, cgp, sw, pairs, sums):
+        """-> (graph handle | None, need_pairs int32[m, 2])"""
+        cap = 1 << 16
+        need = np.empty((cap, 2), dtype=np.int32)
+        n_need = C.c_int64(0)
+        hg = C.c_void_p()
+        n_exact = 0 if pairs is None else len(pairs)
+        pp = pairs.ctypes.data if n_exact else None
+        sp = sums.ctypes.data if n_exact else None
+        rc = self.lib.asp_graph_from_gram(self.ctx, segs.data_ptr(), f, n_total, C.byref(cgp), C.byref(sw), pp, sp,
+                                          n_exact, need.ctypes.data, cap, C.byref(n_need), C.byref(hg))
+        if rc == _lib.ASP_NEED_EXACT:
+            return None, need[: n_need.value].copy()
+        _lib.check(rc)
+        return hg, need[:0]
+
+    def exact_pairs(self, space, pairs, sums):
+        _lib.check(self.lib.asp_space_exact_pairs(space, pairs.ctypes.data, len(pairs), sums.ctypes.data))
+        return sums
+
+    def compute_lambdas(self, space, graph):
+        _lib.check(self.lib.asp_space_compute_lambdas(space, graph))
+
+    def to_comm(self, arr):
+        return self.torch.from_numpy(arr).to(self.device)
+
+    def from_comm(self, t):
+        return t.cpu().numpy()
+
+
+def _all_gather_blocks(t_local, world, group):
+    """all-gather equal-size blocks; returns a tensor [world, *t_local.shape]."""
+    dist = _dist()
+    import torch
+    out = torch.empty((world,) + tuple(t_local.shape), dtype=t_local.dtype, device=t_local.device)
+    try:
+        dist.all_gather_into_tensor(out, t_local.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):
+        parts = [torch.empty_like(t_local) for _ in range(world)]
+        dist.all_gather(parts, t_local.contiguous(), group=group)
+        out = torch.stack(parts)
+    return out
+
+
+def sharded_build(engine, shard, n_total, cgp, sw, group=None):
+    """Steps 1-2 above + lambdas.  Returns (space handle, graph handle)."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if _lib.GRAM_SEGMENTS % world != 0:
+        raise ValueError("world size %d must divide %d" % (world, _lib.GRAM_SEGMENTS))
+    f = shard.shape[1]
+    space = engine.space_create(shard, n_total, world, rank)
+    segs = engine.gram_partials(space, f)                        # [8, f, f], own blocks filled
+    per = _lib.GRAM_SEGMENTS // world
+    if world > 1:
+        own = segs[rank * per:(rank + 1) * per]
+        gathered = _all_gather_blocks(own, world, group)         # [world, per, f, f] == [8, f, f] in order
+        segs = gathered.reshape(_lib.GRAM_SEGMENTS, f, f)
+    pairs = np.empty((0, 2), dtype=np.int32)
+    sums = np.empty((0, 3), dtype=np.float64)
+    graph = None
+    for _ in range(4):
+        graph, need = engine.graph_from_gram(segs, f, n_total, cgp, sw, pairs if len(pairs) else None,
+                                             sums if len(sums) else None)
+        if graph is not None:
+            break
+        # left-to-right sums continue from rank to rank (every rank sees the same `need`)
+        add = np.zeros((len(need), 3), dtype=np.float64)
+        for r in range(world):
+            if rank == r:
+                add = engine.exact_pairs(space, np.ascontiguousarray(need), add)
+            if world > 1:
+                t = engine.to_comm(add)
+                dist.broadcast(t, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                add = np.ascontiguousarray(engine.from_comm(t))
+        pairs = np.ascontiguousarray(np.concatenate([pairs, need]))
+        sums = np.ascontiguousarray(np.concatenate([sums, add]))
+    if graph is None:
+        raise RuntimeError("exact-pair resolution did not converge")
+    engine.compute_lambdas(space, graph)
+    return space, graph
+
+
+def build_sharded(graph_params, items_shard, n_total, group=None, **extras):
+    from . import api
+    gp = api.parse_graph_params(graph_params) or dict(api.DEFAULT_GRAPH_PARAMS)
+    cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+    sw = _lib.make_switches(extras.get("kernel", "inv_power"), extras.get("tau_mode", "median"),
+                            extras.get("tau_fixed", 0.0))
+    engine = CudaEngine(extras.get("device"))
+    if not (hasattr(items_shard, "data_ptr") and items_shard.is_cuda):
+        items_shard = np.ascontiguousarray(items_shard, dtype=np.float64)
+    dist = _dist()
+    if group is None:
+        group = dist.group.WORLD
+    space, graph = sharded_build(engine, items_shard, int(n_total), cgp, sw, group)
+    return api.ArrowSpace._wrap(space, engine.ctx, group), api.GraphLaplacian._wrap(graph)

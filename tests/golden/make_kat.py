@@ -1,0 +1,50 @@
+"""Regenerates tests/golden/oracle_vectors.npz: oracle outputs on the reference's two KAT inputs and on
+two small seeded synthetic cases.  kat.json itself is transcribed from the reference's README.md:37-69
+and tests/test_0.py:4-61 (the reference engine -- crate arrowspace 0.18.0 -- is not vendored and cannot
+be imported here, so there is no reference run to record).
+
+    python tests/golden/make_kat.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+import oracle  # noqa: E402
+from pyarrowspace_b200 import synth  # noqa: E402
+
+
+def run_case(items, gp, queries, tau):
+    s, g = oracle.build(gp, items)
+    indptr, indices, data = g.csr()
+    idx, sc, lq = s.search_batch(queries, g, tau)
+    return dict(indptr=indptr, indices=indices, data=data, lambdas=s.lambdas(), idx=idx, score=sc, lambda_q=lq)
+
+
+def main():
+    kat = json.load(open(os.path.join(HERE, "kat.json")))
+    out = {}
+    r = kat["readme"]
+    for k, v in run_case(np.array(r["items"]), r["graph_params"], np.array([r["query"]]), r["tau"]).items():
+        out["readme_" + k] = v
+    t = kat["test_0"]
+    it = np.array(t["items"])
+    q = (it[t["query_item"]] * t["query_scale"]).reshape(1, -1)
+    for tau in t["expected_top3"]:
+        for k, v in run_case(it, t["graph_params"], q, float(tau)).items():
+            out["test0_%s_%s" % (tau, k)] = v
+    for name, (n, f, seed, gp, nq) in {"synthA": (600, 48, 5, {"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}, 16),
+                                       "synthB": (1500, 100, 6, {"eps": 1.0, "k": 12, "topk": 5, "p": 2.0, "sigma": None}, 16)}.items():
+        x = synth.make_items(n, f, seed, scale=100.0, n_clusters=16)
+        qs, _ = synth.make_queries(x, nq, seed)
+        for k, v in run_case(x, gp, qs, 0.62).items():
+            out["%s_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,419 @@
+"""GPU parity: the sm_100a path (through the C ABI / the drop-in Python surface) against the CPU
+oracle on the same seeded inputs.  Integer outputs (edge sets, CSR structure, top-k index lists) must
+be identical; lambda and scores within 1e-9 relative (BASELINE.json north_star).  Run with -m gpu."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-9          # tolerance stated by BASELINE.json for f64 outputs
+
+
+def _build_both(oracle_mod, gp, x, **sw):
+    from arrowspace import ArrowSpaceBuilder
+    aspace, gl = ArrowSpaceBuilder.build(gp, x, **sw)
+    s, g = oracle_mod.build(gp, x, **sw)
+    return aspace, gl, s, g
+
+
+def _assert_graph_equal(gl, g):
+    ip, ix, dt = gl.csr()
+    oip, oix, odt = g.csr()
+    assert gl.nnodes == g.nnodes
+    assert np.array_equal(ip, oip), "CSR row pointers differ"
+    assert np.array_equal(ix, oix), "CSR column indices differ"
+    assert np.array_equal(gl.edges(), g.edges()), "edge sets differ"
+    np.testing.assert_allclose(dt, odt, rtol=RTOL, atol=0)
+
+
+def _assert_hits_equal(idx, sc, oidx, osc):
+    assert np.array_equal(idx, oidx), "top-k index lists differ at rows %s" % np.where((idx != oidx).any(axis=1))[0][:10]
+    m = oidx >= 0
+    np.testing.assert_allclose(sc[m], osc[m], rtol=RTOL, atol=0)
+    assert np.isnan(sc[~m]).all()
+
+
+# ----------------------------------------------------------------------------- reference KATs
+
+def test_readme_example_bit_exact(kat):
+    """README.md:33-70 through the drop-in API; scores are evaluated in the reference order -> bit exact."""
+    from arrowspace import ArrowSpaceBuilder
+    r = kat["readme"]
+    aspace, gl = ArrowSpaceBuilder.build(r["graph_params"], np.array(r["items"], dtype=np.float64))
+    hits = aspace.search(np.array(r["query"], dtype=np.float64), gl, r["tau"])
+    assert hits == [(i, s) for i, s in r["hits"]]
+    assert aspace.nitems == 3 and aspace.nfeatures == 3
+    assert gl.nnodes == 3 and gl.shape() == (3, 3)
+    assert gl.graph_params == {"eps": 1.0, "k": 6, "topk": 3, "p": 2.0, "sigma": 1.0}
+
+
+@pytest.mark.parametrize("tau", ["1.0", "0.9", "0.6", "0.55"])
+def test_test0_script(kat, oracle_mod, tau):
+    """tests/test_0.py: same calls, same assertions (tau=0.9 third place: documented deviation, checked
+    against the oracle instead of the reference value)."""
+    from arrowspace import ArrowSpaceBuilder
+    t = kat["test_0"]
+    items = np.array(t["items"], dtype=np.float64)
+    aspace, gl = ArrowSpaceBuilder.build(t["graph_params"], items)
+    q = np.array(items[t["query_item"]] * t["query_scale"], dtype=np.float64)
+    hits = aspace.search(q, gl, float(tau))
+    assert len(hits) == 3
+    want = list(t["expected_top3"][tau])
+    if tau == t["known_deviation"]["tau"]:
+        want[t["known_deviation"]["position"]] = t["known_deviation"]["oracle"]
+    assert [i for i, _ in hits] == want
+    s, g = oracle_mod.build(t["graph_params"], items)
+    assert hits == s.search(q, g, float(tau))
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL)
+    feats, lam = aspace.get_item(2)
+    assert np.array_equal(feats, items[2]) and lam == aspace.lambdas()[2]
+    with pytest.raises(ValueError, match=r"index 5 out of range \[0, 5\)"):
+        aspace.get_item(5)
+
+
+def test_golden_fixture(golden):
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(1500, 100, 6, scale=100.0, n_clusters=16)
+    q, _ = synth.make_queries(x, 16, 6)
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 1.0, "k": 12, "topk": 5, "p": 2.0, "sigma": None}, x)
+    ip, ix, dt = gl.csr()
+    assert np.array_equal(ip, golden["synthB_indptr"]) and np.array_equal(ix, golden["synthB_indices"])
+    np.testing.assert_allclose(dt, golden["synthB_data"], rtol=RTOL)
+    np.testing.assert_allclose(aspace.lambdas(), golden["synthB_lambdas"], rtol=RTOL)
+    idx, sc = aspace.search_batch(q, gl, 0.62)
+    _assert_hits_equal(idx, sc, golden["synthB_idx"], golden["synthB_score"])
+
+
+# ----------------------------------------------------------------------------- stage by stage
+
+@pytest.mark.parametrize("n,f", [(5, 3), (33, 24), (1000, 50), (4097, 130), (20000, 384)])
+def test_gram_partials_vs_oracle(oracle_mod, n, f):
+    """K1: sum of the DMMA segment partials == left-to-right Gram up to the rounding band."""
+    import torch
+    from pyarrowspace_b200 import _lib, synth
+    x = synth.make_items(n, f, 21, n_clusters=8)
+    lib = _lib.load()
+    ctx = _lib.context()
+    hs = C.c_void_p()
+    _lib.check(lib.asp_space_create(ctx, x.ctypes.data, n, f, n, 1, 0, C.byref(hs)))
+    segs = torch.zeros((8, f, f), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    _lib.check(lib.asp_space_gram_partials(hs, segs.data_ptr()))
+    _lib.check(lib.asp_ctx_synchronize(ctx))
+    g = segs.cpu().numpy().sum(axis=0)
+    lib.asp_free_space(hs)
+    ref = oracle_mod.gram_columns(x)
+    assert np.array_equal(g, g.T), "Gram must be bitwise symmetric"
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+    assert (np.abs(g - ref) / scale).max() < 4 * n * 1.2e-16 + 1e-15
+
+
+@pytest.mark.parametrize("n,f,gp", [
+    (300, 24, {"eps": 0.5, "k": 4, "topk": 10, "p": 2.0, "sigma": 0.25}),
+    (2000, 50, {"eps": 0.05, "k": 7, "topk": 3, "p": 2.0, "sigma": None}),
+    (5000, 130, {"eps": 1.31, "k": 25, "topk": 10, "p": 2.0, "sigma": 0.535}),
+    (3000, 384, {"eps": 10.0, "k": 25, "topk": 10, "p": 2.0, "sigma": None}),
+    (1200, 768, {"eps": 0.2, "k": 3, "topk": 15, "p": 3.0, "sigma": 0.1}),
+    (700, 96, {"eps": 0.8, "k": 200, "topk": 2, "p": 1.0, "sigma": 0.4}),
+])
+def test_build_and_search_parity(oracle_mod, n, f, gp):
+    """K1+K2+K3+K4 end to end through the drop-in API on seeded data."""
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(n, f, 100 + f, n_clusters=12)
+    q, _ = synth.make_queries(x, 200, 100 + f)
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+    _assert_graph_equal(gl, g)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+    np.testing.assert_array_equal(aspace.norms(), s.norms())          # left-to-right on both sides
+    for tau in (1.0, 0.62):
+        idx, sc = aspace.search_batch(q, gl, tau)
+        oidx, osc, olq = s.search_batch(q, g, tau)
+        _assert_hits_equal(idx, sc, oidx, osc)
+    # the reference's one-query-per-call shape goes through the HBM-bound GEMV kernel
+    for j in (0, 7, 199):
+        assert aspace.search(q[j], gl, 0.62) == [(int(i), float(v)) for i, v in zip(oidx[j], sc[j]) if i >= 0]
+
+
+@pytest.mark.parametrize("kernel,tau_mode", [("gaussian", "median"), ("inv_power", "median_abs"),
+                                             ("inv_power", "mean"), ("gaussian", "fixed")])
+def test_switches(oracle_mod, kernel, tau_mode):
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(900, 64, 31, n_clusters=6) - 20.0       # mixed signs: median vs median_abs differ
+    q, _ = synth.make_queries(x, 40, 31)
+    gp = {"eps": 1.0, "k": 6, "topk": 8, "p": 2.0, "sigma": 0.05}
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x, kernel=kernel, tau_mode=tau_mode, tau_fixed=0.3)
+    _assert_graph_equal(gl, g)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+    idx, sc = aspace.search_batch(q, gl, 0.5)
+    oidx, osc, _ = s.search_batch(q, g, 0.5)
+    _assert_hits_equal(idx, sc, oidx, osc)
+
+
+def test_query_lambda_entry_point(oracle_mod):
+    from pyarrowspace_b200 import _lib, synth
+    x = synth.make_items(800, 48, 8, n_clusters=6)
+    q, _ = synth.make_queries(x, 33, 8)
+    aspace, gl, s, g = _build_both(oracle_mod, {"eps": 0.5, "k": 5, "topk": 4, "p": 2.0, "sigma": 0.2}, x)
+    e, t, lam = (np.empty(33) for _ in range(3))
+    _lib.check(_lib.load().asp_query_lambda(_lib.context(), gl._h, None, q.ctypes.data, 33, e.ctypes.data,
+                                            t.ctypes.data, lam.ctypes.data))
+    oe, ot, ol = g.taumode(q)
+    np.testing.assert_allclose(e, oe, rtol=RTOL)
+    np.testing.assert_array_equal(t, ot)                                # medians are selections: exact
+    np.testing.assert_allclose(lam, ol, rtol=RTOL)
+
+
+# ----------------------------------------------------------------------------- edge cases
+
+def test_duplicate_items_tie_break_by_index(oracle_mod):
+    from pyarrowspace_b200 import synth
+    base = synth.make_items(64, 40, 4, n_clusters=4)
+    x = np.concatenate([base, base[:20], base[5:9]])                    # exact duplicates -> exact score ties
+    aspace, gl, s, g = _build_both(oracle_mod, {"eps": 0.5, "k": 3, "topk": 12, "p": 2.0, "sigma": 0.2}, x)
+    q = np.ascontiguousarray(base[:30] / 100.0)
+    idx, sc = aspace.search_batch(q, gl, 0.7)
+    oidx, osc, _ = s.search_batch(q, g, 0.7)
+    _assert_hits_equal(idx, sc, oidx, osc)
+    assert (idx[6][:3] == [6, 70, 85]).all()                            # item 6 and its two copies, index order
+
+
+def test_many_near_ties_take_the_exact_scan(oracle_mod):
+    """More equal-score items than the candidate list holds: the completeness test fails and the
+    query is re-scanned exactly; the answer is still the oracle's."""
+    from pyarrowspace_b200 import api, synth
+    base = synth.make_items(4, 32, 12, n_clusters=2)
+    x = np.repeat(base, 60, axis=0)                                     # 4 distinct rows x 60 copies
+    aspace, gl, s, g = _build_both(oracle_mod, {"eps": 0.5, "k": 3, "topk": 10, "p": 2.0, "sigma": 0.2}, x)
+    q = np.ascontiguousarray(np.repeat(base / 100.0, 5, axis=0))        # 20 queries -> GEMM path
+    idx, sc = aspace.search_batch(q, gl, 0.8)
+    oidx, osc, _ = s.search_batch(q, g, 0.8)
+    _assert_hits_equal(idx, sc, oidx, osc)
+    assert api.stat("search_slow_queries") == 20
+    hits = aspace.search(q[0], gl, 0.8)                                 # GEMV path, same fallback
+    assert [i for i, _ in hits] == list(oidx[0])
+
+
+def test_duplicate_feature_columns_resolve_exactly(oracle_mod):
+    """Duplicate / proportional feature columns put distances exactly on the k-th boundary: the pairs
+    inside the rounding band are recomputed in the oracle's order and the edge set still matches."""
+    from pyarrowspace_b200 import api
+    rng = np.random.default_rng(5)
+    a = np.abs(rng.normal(size=(500, 6))) + 0.2
+    x = np.concatenate([a, a[:, :4], 2.0 * a[:, 1:3], a[:, :2] + 1e-13], axis=1)     # 14 columns, many ties
+    x = np.ascontiguousarray(x)
+    for k in (1, 2, 3):
+        gp = {"eps": 1.0, "k": k, "topk": 3, "p": 2.0, "sigma": 0.3}
+        aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+        _assert_graph_equal(gl, g)
+    assert api.stat("need_exact_pairs") > 0
+
+
+def test_eps_boundary_resolves_exactly(oracle_mod):
+    """eps set exactly to an occurring distance: `d <= eps` must be decided on the oracle's value."""
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(3000, 20, 77, n_clusters=5)
+    ref = oracle_mod.gram_columns(x)
+    nrm = np.sqrt(np.diag(ref))
+    d = 1.0 - np.maximum(0.0, ref / np.outer(nrm, nrm))
+    vals = np.sort(d[np.triu_indices(20, 1)])
+    for eps in (vals[10], vals[57], np.nextafter(vals[57], 0)):
+        gp = {"eps": float(eps), "k": 19, "topk": 3, "p": 2.0, "sigma": 0.01}
+        aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+        _assert_graph_equal(gl, g)
+
+
+def test_small_and_ragged_shapes(oracle_mod):
+    rng = np.random.default_rng(1)
+    for n, f, k, topk in [(1, 1, 1, 1), (2, 2, 1, 5), (3, 5, 4, 2), (7, 3, 2, 30), (129, 17, 16, 13), (31, 33, 40, 29)]:
+        x = np.abs(rng.normal(size=(n, f))) + 0.1
+        gp = {"eps": 1.0, "k": k, "topk": topk, "p": 2.0, "sigma": 0.5}
+        from arrowspace import ArrowSpaceBuilder, PanicException
+        aspace, gl = ArrowSpaceBuilder.build(gp, x)
+        s, g = oracle_mod.build(gp, x)
+        _assert_graph_equal(gl, g)
+        np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+        q = np.ascontiguousarray(x[:3] * 0.7 + 0.01)
+        if (s.lambdas() == 0).all():                                       # f == 1: no edges, lambda == 0
+            with pytest.raises(PanicException, match="The lambdas are zero"):
+                aspace.search(q[0], gl, 0.5)
+            continue
+        idx, sc = aspace.search_batch(q, gl, 0.5)
+        oidx, osc, _ = s.search_batch(q, g, 0.5)
+        _assert_hits_equal(idx, sc, oidx, osc)
+        assert len(aspace.search(q[0], gl, 0.5)) == min(topk, n)
+
+
+def test_error_behaviour():
+    from arrowspace import ArrowSpaceBuilder, PanicException
+    x = np.abs(np.random.default_rng(2).normal(size=(10, 6))) + 0.1
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 1.0, "k": 3, "topk": 2, "p": 2.0}, x)
+    with pytest.raises(ValueError, match="query length 5 must match nfeatures 6"):
+        aspace.search(np.ones(5), gl, 0.5)
+    with pytest.raises(ValueError, match="not contiguous"):
+        aspace.search(np.ones(12)[::2], gl, 0.5)
+    with pytest.raises(TypeError):
+        aspace.search(np.ones(6, dtype=np.float32), gl, 0.5)
+    # k = 0: no edges, all lambdas 0 -> the reference's assert_ne! fires (src/lib.rs:156-159)
+    a0, g0 = ArrowSpaceBuilder.build({"eps": 1.0, "k": 0, "topk": 2, "p": 2.0}, x)
+    assert (a0.lambdas() == 0).all() and g0.nnz == 6
+    with pytest.raises(PanicException, match="The lambdas are zero, check the magnitude of items and eps."):
+        a0.search(x[0].copy(), g0, 0.5)
+    # an all-zero item: Rayleigh quotient undefined (TAUMODE.md:13)
+    z = x.copy()
+    z[3] = 0.0
+    with pytest.raises(PanicException, match="all zeros"):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 3, "topk": 2, "p": 2.0}, z)
+    # strided input is accepted (as_array(), src/helpers.rs:25) and copied
+    big = np.abs(np.random.default_rng(3).normal(size=(20, 12))) + 0.1
+    a1, g1 = ArrowSpaceBuilder.build({"eps": 1.0, "k": 3, "topk": 2, "p": 2.0}, big[::2, ::2])
+    a2, g2 = ArrowSpaceBuilder.build({"eps": 1.0, "k": 3, "topk": 2, "p": 2.0}, np.ascontiguousarray(big[::2, ::2]))
+    assert np.array_equal(a1.lambdas(), a2.lambdas())
+
+
+# ----------------------------------------------------------------------------- loaders, merge, shards
+
+def test_cp_async_loader_matches_tma_bitwise(tmp_path):
+    """ASP_NO_TMA=1 swaps the TMA operand loads for cp.async into the same shared-memory layout: both
+    feed identical DMMA chains, so every output must be bit-identical."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from arrowspace import ArrowSpaceBuilder
+from pyarrowspace_b200 import synth
+x = synth.make_items(3000, 200, 3, n_clusters=10)
+q, _ = synth.make_queries(x, 150, 3)
+a, g = ArrowSpaceBuilder.build({"eps": 0.7, "k": 9, "topk": 10, "p": 2.0, "sigma": None}, x)
+idx, sc = a.search_batch(q, g, 0.62)
+np.savez(sys.argv[1], lam=a.lambdas(), data=g.csr()[2], idx=idx, sc=sc)
+""" % ROOT
+    outs = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / ("r%s.npz" % flag))
+        env = dict(os.environ, ASP_NO_TMA=flag)
+        subprocess.check_call([sys.executable, "-c", code, out], env=env, timeout=600)
+        outs.append(np.load(out))
+    for key in ("lam", "data", "idx", "sc"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
+def test_topk_merge_kernel():
+    from pyarrowspace_b200 import _lib
+    rng = np.random.default_rng(9)
+    parts, nq, topk = 4, 300, 10
+    sc = np.round(rng.normal(size=(parts, nq, topk)), 1)                 # rounded -> plenty of ties
+    sc = -np.sort(-sc, axis=2)
+    idx = rng.permutation(parts * nq * topk).reshape(parts, nq, topk).astype(np.int64)
+    idx[1, :, 7:] = -1
+    sc[1, :, 7:] = np.nan
+    out_idx = np.empty((nq, topk), dtype=np.int64)
+    out_sc = np.empty((nq, topk))
+    _lib.check(_lib.load().asp_topk_merge(_lib.context(), idx.ctypes.data, sc.ctypes.data, parts, nq, topk,
+                                          out_idx.ctypes.data, out_sc.ctypes.data))
+    for qi in range(nq):
+        cand = [(-sc[p, qi, j], idx[p, qi, j]) for p in range(parts) for j in range(topk) if idx[p, qi, j] >= 0]
+        cand.sort()
+        assert [c[1] for c in cand[:topk]] == list(out_idx[qi])
+        assert [-c[0] for c in cand[:topk]] == list(out_sc[qi])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shards_on_one_gpu_equal_single(oracle_mod, world):
+    """Multi-GPU path emulated as `world` shards living on one device: the staged C ABI (segment Grams,
+    graph from the gathered segments, per-shard lambdas, per-shard search + merge) gives bit-identical
+    results to the single-shard build, for every world size."""
+    import torch
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import _lib, synth
+    from pyarrowspace_b200.distributed import CudaEngine, shard_rows
+    n, f = 5000, 72
+    x = synth.make_items(n, f, 55, n_clusters=10)
+    q, _ = synth.make_queries(x, 64, 55)
+    gp = {"eps": 0.6, "k": 8, "topk": 10, "p": 2.0, "sigma": 0.3}
+    a1, g1 = ArrowSpaceBuilder.build(gp, x)
+    idx1, sc1 = a1.search_batch(q, g1, 0.62)
+
+    eng = CudaEngine()
+    lib = _lib.load()
+    cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+    sw = _lib.make_switches()
+    spaces, segs = [], torch.zeros((8, f, f), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        r0, r1 = shard_rows(n, world, r)
+        sp = eng.space_create(np.ascontiguousarray(x[r0:r1]), n, world, r)
+        part = eng.gram_partials(sp, f)
+        per = 8 // world
+        segs[r * per:(r + 1) * per] = part[r * per:(r + 1) * per]
+        spaces.append((sp, r0, r1))
+    graph, need = eng.graph_from_gram(segs, f, n, cgp, sw, None, None)
+    assert graph is not None and len(need) == 0
+    from pyarrowspace_b200.api import GraphLaplacian
+    gl = GraphLaplacian._wrap(graph)
+    for a, b in zip(gl.csr(), g1.csr()):
+        assert np.array_equal(a, b)
+    lam, all_idx, all_sc = [], [], []
+    for sp, r0, r1 in spaces:
+        eng.compute_lambdas(sp, graph)
+        out = np.empty(r1 - r0)
+        _lib.check(lib.asp_space_lambdas(sp, out.ctypes.data))
+        lam.append(out)
+        idx = np.empty((64, 10), dtype=np.int64)
+        sc = np.empty((64, 10))
+        _lib.check(lib.asp_search_batch(sp, graph, q.ctypes.data, 64, 0.62, idx.ctypes.data, sc.ctypes.data, None))
+        all_idx.append(idx)
+        all_sc.append(sc)
+    assert np.array_equal(np.concatenate(lam), a1.lambdas())
+    m_idx = np.empty((64, 10), dtype=np.int64)
+    m_sc = np.empty((64, 10))
+    ai, asc = np.ascontiguousarray(np.stack(all_idx)), np.ascontiguousarray(np.stack(all_sc))
+    _lib.check(lib.asp_topk_merge(eng.ctx, ai.ctypes.data, asc.ctypes.data, world, 64, 10, m_idx.ctypes.data,
+                                  m_sc.ctypes.data))
+    assert np.array_equal(m_idx, idx1) and np.array_equal(m_sc, sc1)
+    for sp, _, _ in spaces:
+        lib.asp_free_space(sp)
+
+
+def test_device_resident_inputs(oracle_mod):
+    """Tensor hand-off: items / queries already in HBM (torch tensors) give the same answers."""
+    import torch
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(4000, 96, 14, n_clusters=10)
+    q, _ = synth.make_queries(x, 300, 14)
+    gp = {"eps": 0.5, "k": 4, "topk": 10, "p": 2.0, "sigma": 0.25}
+    a_h, g_h = ArrowSpaceBuilder.build(gp, x)
+    a_d, g_d = ArrowSpaceBuilder.build(gp, torch.from_numpy(x).cuda())
+    assert np.array_equal(a_h.lambdas(), a_d.lambdas())
+    idx_h, sc_h = a_h.search_batch(q, g_h, 0.62)
+    idx_d, sc_d = a_d.search_batch(torch.from_numpy(q).cuda(), g_d, 0.62)
+    assert np.array_equal(idx_h, idx_d.cpu().numpy()) and np.array_equal(sc_h, sc_d.cpu().numpy())
+
+
+# ----------------------------------------------------------------------------- BASELINE-size cases
+
+def test_c2_shape_parity(oracle_mod):
+    """BASELINE.json configs[1] (Quora-shaped 100k x 384, 10k queries, top-10): full parity against the
+    oracle on the graph and the lambdas, and on a 512-query sample of the searches."""
+    from pyarrowspace_b200 import synth
+    c = synth.config("C2")
+    x = synth.make_items(c["n"], c["f"], c["seed"], c["scale"])
+    q, sel = synth.make_queries(x, c["nq"], c["seed"], c["scale"])
+    aspace, gl, s, g = _build_both(oracle_mod, c["graph_params"], x)
+    _assert_graph_equal(gl, g)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+    idx, sc = aspace.search_batch(q, gl, c["tau"])
+    oidx, osc, _ = s.search_batch(q[:512], g, c["tau"])
+    _assert_hits_equal(idx[:512], sc[:512], oidx, osc)
+    # size-independent properties on all 10k queries
+    assert (np.diff(sc, axis=1) <= 0).all()                             # sorted best first
+    assert (idx[:, 0] == sel).mean() > 0.99                             # a perturbed copy finds its source
+    assert all(len(set(r)) == len(r) for r in idx[:2000])               # no duplicates in a result list
+    idx1, sc1 = aspace.search_batch(q, gl, 1.0)                         # tau = 1: pure cosine order
+    cos = (x[idx1[:50, 0]] * q[:50]).sum(1) / (np.linalg.norm(x[idx1[:50, 0]], axis=1) * np.linalg.norm(q[:50], axis=1))
+    np.testing.assert_allclose(sc1[:50, 0], cos, rtol=1e-12)

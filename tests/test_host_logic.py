@@ -1,0 +1,154 @@
+"""Host side of the drop-in boundary, no GPU needed: the C-ABI library loads and exports every symbol
+include/arrowspace_b200.h declares, the Python surface mirrors src/lib.rs / src/helpers.rs, the product
+never touches oracle/, and compute calls fail loudly without a device."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "arrowspace_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(asp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyarrowspace_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "libarrowspace_b200.so lacks %s" % name
+    assert sorted(_lib.SYMBOLS) == declared, "ctypes table and header disagree"
+    assert lib.asp_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (asp_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_library_is_built_for_sm_100a_only():
+    from pyarrowspace_b200 import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_sass_has_dmma_and_tma():
+    """FP64 tensor-core instructions and TMA tile loads are really in the binary."""
+    from pyarrowspace_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") > 500
+    assert "UTMALDG" in sass
+
+
+def test_module_surface_matches_reference():
+    import arrowspace
+    assert set(arrowspace.__all__) == {"ArrowSpaceBuilder", "ArrowSpace", "GraphLaplacian", "set_debug"}
+    from arrowspace import ArrowSpace, ArrowSpaceBuilder, GraphLaplacian
+    with pytest.raises(ValueError, match="ArrowSpace cannot be constructed directly; use ArrowSpaceBuilder.build"):
+        ArrowSpace()
+    with pytest.raises(ValueError, match="use ArrowSpaceBuilder.build_with_graph"):
+        GraphLaplacian()
+    for name in ("nitems", "nfeatures", "get_item", "lambdas", "search", "search_hybrid", "search_energy"):
+        assert hasattr(ArrowSpace, name)
+    for name in ("nnodes", "shape", "graph_params"):
+        assert hasattr(GraphLaplacian, name)
+    assert isinstance(ArrowSpaceBuilder.__dict__["build"], staticmethod)
+    assert isinstance(ArrowSpaceBuilder.__dict__["build_energy"], staticmethod)
+    import inspect
+    assert list(inspect.signature(ArrowSpace.search).parameters)[1:] == ["item", "gl", "tau"]
+    assert list(inspect.signature(ArrowSpaceBuilder.build).parameters)[:2] == ["graph_params", "items"]
+
+
+def test_parse_graph_params():
+    from pyarrowspace_b200.api import parse_graph_params
+    assert parse_graph_params(None) is None
+    gp = parse_graph_params({"eps": 1, "k": 6, "topk": 3, "p": 2})
+    assert gp == {"eps": 1.0, "k": 6, "topk": 3, "p": 2.0, "sigma": 0.5}          # helpers.rs:68-72
+    assert parse_graph_params({"eps": 0.2, "k": 1, "topk": 1, "p": 2.0, "sigma": None})["sigma"] == 0.1
+    assert parse_graph_params({"eps": 0.2, "k": 1, "topk": 1, "p": 2.0, "sigma": 0.7})["sigma"] == 0.7
+    for key in ("eps", "k", "topk", "p"):
+        d = {"eps": 1.0, "k": 6, "topk": 3, "p": 2.0}
+        del d[key]
+        with pytest.raises(ValueError, match=re.escape("graph_params['%s'] is required" % key)):
+            parse_graph_params(d)
+    with pytest.raises(OverflowError):
+        parse_graph_params({"eps": 1.0, "k": -1, "topk": 3, "p": 2.0})
+    with pytest.raises(TypeError):
+        parse_graph_params({"eps": 1.0, "k": 2.5, "topk": 3, "p": 2.0})
+
+
+def test_build_argument_errors_surface_as_panics():
+    """.unwrap() in src/lib.rs:277,279 turns ValueErrors into PanicException (a BaseException)."""
+    from arrowspace import ArrowSpaceBuilder, PanicException
+    assert issubclass(PanicException, BaseException) and not issubclass(PanicException, Exception)
+    with pytest.raises(PanicException, match="items must be non-empty 2D array"):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 1, "topk": 1, "p": 2.0}, np.zeros((0, 4)))
+    with pytest.raises(PanicException, match=r"graph_params\[\\?'topk\\?'\] is required"):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 1, "p": 2.0}, np.ones((2, 4)))
+    with pytest.raises(TypeError):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 1, "topk": 1, "p": 2.0}, np.ones((2, 4), dtype=np.float32))
+    with pytest.raises(TypeError):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 1, "topk": 1, "p": 2.0}, np.ones(4))
+    with pytest.raises(NotImplementedError):
+        ArrowSpaceBuilder.build_energy(np.ones((2, 2)))
+
+
+def test_set_debug_prefix(capsys):
+    from pyarrowspace_b200 import api
+    api.set_debug(True)
+    api.dbg_println("items shape: (3, 3)")
+    api.set_debug(False)
+    api.dbg_println("silent")
+    err = capsys.readouterr().err
+    assert err == "[pyarrowspace] items shape: (3, 3)\n"
+
+
+def test_shard_rows_cover_and_align():
+    from pyarrowspace_b200 import shard_rows
+    for n in (1, 5, 31, 32, 33, 255, 256, 257, 1000, 99_999, 1_000_000, 8_800_000):
+        for world in (1, 2, 4, 8):
+            prev = 0
+            for r in range(world):
+                r0, r1 = shard_rows(n, world, r)
+                assert r0 == prev and r0 <= r1 <= n
+                assert r0 % 32 == 0 or r0 == n
+                prev = r1
+            assert prev == n
+        # world sizes nest: a rank of world 2 is the union of two ranks of world 4
+        a0, a1 = shard_rows(n, 2, 1)
+        assert a0 == shard_rows(n, 4, 2)[0] and a1 == shard_rows(n, 4, 3)[1]
+    with pytest.raises(Exception):
+        shard_rows(100, 3, 0)
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly when there is no device -- never compute on the CPU."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200._lib import LibraryError
+    with pytest.raises(LibraryError, match="no CUDA device"):
+        ArrowSpaceBuilder.build({"eps": 1.0, "k": 6, "topk": 3, "p": 2.0, "sigma": 1.0},
+                                np.array([[0.1, 0.2, 0.3], [0.0, 0.5, 0.1], [0.9, 0.1, 0.0]]))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under pyarrowspace_b200/ or arrowspace/ may reference it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|oracle_np|orc_[a-z_]+\(", re.M)
+    for pkg in ("pyarrowspace_b200", "arrowspace"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            if "_obj" in dirpath:
+                continue
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, fn)).read()
+                    assert not pat.search(text), "%s references the oracle" % os.path.join(dirpath, fn)
+    code = ("import sys; import arrowspace, pyarrowspace_b200, pyarrowspace_b200.distributed; "
+            "assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
