@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric   : search queries/s (top-10) on the BEIR/MS MARCO-shaped synthetic 1M x 384 f64 workload (C4),
+           with the build (feature graph + Laplacian + lambda) timed beside it as items/s.
+step     : one pass of the search hot path over one batch of Q synthetic queries (default 16384)
+           against all N items (row-sharded over the ranks when --gpus > 1, results merged).
+value    : whole-job queries/s with items and queries resident in HBM.
+e2e      : the same through the public API (ArrowSpace.search_batch) with HOST buffers: pinned
+           host -> device copy of the batch and device -> host read of (idx, score) inside the timed region.
+roofline : dominant kernel = search_gemm_kernel (FP64 DMMA): 2*Q*N_local*F algorithmic FLOP per launch /
+           its CUDA-event duration; peak = cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no
+           FP64 figure).  The build's kernels are reported under "build".
+cpu_baseline / --impl reference : the CPU oracle (oracle/, a restatement: the reference's Rust engine is not
+           vendored and cannot be built here) timed on this box's host cores.
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1 under torchrun, one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLAGSHIP = "C4"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--items", type=int, default=None, help="override N (default: the C4 shape, 1,000,000)")
+    ap.add_argument("--features", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=16384, help="queries per step")
+    ap.add_argument("--build-reps", type=int, default=3)
+    ap.add_argument("--cpu-sample-items", type=int, default=100_000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=64)
+    ap.add_argument("--ref-queries", type=int, default=256, help="--impl reference: queries per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        # median over the samples taken under load (>= 60 % of the highest draw seen)
+        load = [s for s, p in zip(sm, pw) if pw and p >= 0.6 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU oracle legs
+def cpu_oracle_run(cfg, n_items, nq, reps, label):
+    """Oracle build on n_items rows of the workload + `reps` search batches of nq queries, all host threads."""
+    import oracle
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(cfg["n"], cfg["f"], cfg["seed"], cfg["scale"], rows=(0, n_items))
+    q, _ = synth.make_queries(x, nq, cfg["seed"], cfg["scale"])
+    t0 = time.perf_counter()
+    s, g = oracle.build(cfg["graph_params"], x)
+    t_build = time.perf_counter() - t0
+    s.search_batch(q[: max(1, nq // 8)], g, cfg["tau"])              # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        s.search_batch(q, g, cfg["tau"])
+        ts.append(time.perf_counter() - t0)
+    return {"build_s": t_build, "search_s": ts, "threads": oracle.num_threads(), "n_items": n_items, "nq": nq}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU implementation of the path (the oracle port) on the host cores, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.items or cfg["n"]
+    cfg = dict(cfg, n=n)
+    nq = args.ref_queries
+    r = cpu_oracle_run(cfg, n, nq, args.warmup + args.steps, "reference")
+    ts = r["search_s"][args.warmup:]
+    total = sum(ts)
+    val = nq * len(ts) / total
+    line = {
+        "impl": "reference", "metric": "search queries/s (top-10, 1M x 384 f64)", "value": val, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 BEIR/MS MARCO-shaped synthetic %d x %d f64, top-%d, tau %.2f" % (n, cfg["f"], cfg["graph_params"]["topk"], cfg["tau"]),
+                   "queries_per_step": nq, "graph_params": cfg["graph_params"]},
+        "cpu_baseline": {"value": val, "unit": "queries/s", "cores": r["threads"], "kind": "port",
+                         "sample": "oracle (C + OpenMP) search of %d queries per step against all %d items; build %.1f s (%.0f items/s) untimed"
+                                   % (nq, n, r["build_s"], n / r["build_s"])},
+        "build": {"items_per_s": n / r["build_s"], "seconds": r["build_s"]},
+        "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse_args()
+    from pyarrowspace_b200 import synth
+    cfg = synth.config(FLAGSHIP)
+    if args.features:
+        cfg["f"] = args.features
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+    from pyarrowspace_b200 import _lib, api
+    from pyarrowspace_b200.api import ArrowSpaceBuilder, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.items or cfg["n"]
+    f, gp, tau, Q = cfg["f"], cfg["graph_params"], cfg["tau"], args.queries
+    topk = gp["topk"]
+    lib = _lib.load()
+    ctx = _lib.context(local)
+    stream = torch.cuda.Stream(device=dev)
+    _lib.check(lib.asp_ctx_set_stream(ctx, stream.cuda_stream))       # the library's kernels go on this stream
+
+    def barrier_sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- FP64 tensor peak on this GPU (cuBLAS DGEMM), the roofline denominator for the DMMA kernels
+    with torch.cuda.stream(stream):
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        best = 1e9
+        for i in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); torch.matmul(a, b); e1.record(stream); e1.synchronize()
+            if i:
+                best = min(best, e0.elapsed_time(e1))
+        fp64_peak_tflops = 2 * 4096 ** 3 / best / 1e9
+        del a, b
+
+    # ---- synthetic inputs: this rank's row shard (identical bytes to what the oracle sees)
+    r0, r1 = shard_rows(n, world, rank)
+    x_host = torch.from_numpy(synth.make_items(n, f, cfg["seed"], cfg["scale"], rows=(r0, r1))).pin_memory()
+    nbatch = 2
+    qrng_src = synth.make_items(n, f, cfg["seed"], cfg["scale"], rows=(0, min(n, 65536)))
+    q_host = [torch.from_numpy(synth.make_queries(qrng_src, Q, cfg["seed"] + b_, cfg["scale"])[0]).pin_memory()
+              for b_ in range(nbatch)]
+    with torch.cuda.stream(stream):
+        x_dev = x_host.to(dev, non_blocking=True)
+        q_dev = [q.to(dev, non_blocking=True) for q in q_host]
+    stream.synchronize()
+
+    def build(items):
+        if world == 1:
+            return ArrowSpaceBuilder.build(gp, items, device=local)
+        return ArrowSpaceBuilder.build_sharded(gp, items, n, device=local)
+
+    # ---- build: items resident in HBM (value) and from pinned host memory (e2e)
+    launches0 = lib.asp_ctx_launch_count(ctx)
+    build_ms, build_e2e_ms, stages = [], [], {}
+    with torch.cuda.stream(stream):
+        for rep in range(1 + args.build_reps):
+            barrier_sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            aspace, gl = build(x_dev)
+            e1.record(stream)
+            barrier_sync()
+            if rep:
+                build_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+                for k in ("gram_ms", "graph_ms", "lambda_ms"):
+                    stages.setdefault(k, []).append(api.stat(k, local))
+            del aspace, gl
+        for rep in range(2):
+            barrier_sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            aspace, gl = build(x_host.numpy())
+            e1.record(stream)
+            barrier_sync()
+            build_e2e_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+            if rep == 0:
+                del aspace, gl
+    build_launches = (lib.asp_ctx_launch_count(ctx) - launches0) // (3 + args.build_reps)
+
+    # ---- search: W warm-up steps, then exactly K timed steps
+    clocks = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        for w in range(args.warmup):
+            aspace.search_batch(q_dev[w % nbatch], gl, tau)
+        barrier_sync()
+        if rank == 0:
+            clocks.start()
+        l0 = lib.asp_ctx_launch_count(ctx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage1 = []
+        e0.record(stream)
+        for k in range(args.steps):
+            idx, sc = aspace.search_batch(q_dev[k % nbatch], gl, tau)
+            stage1.append(api.stat("search_stage1_ms", local))
+        e1.record(stream)
+        barrier_sync()
+        step_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        launches = lib.asp_ctx_launch_count(ctx) - l0
+        slow = api.stat("search_slow_queries", local)
+        # end to end: pinned host queries in, host results out, every step
+        for w in range(2):
+            aspace.search_batch(q_host[w % nbatch].numpy(), gl, tau)
+        barrier_sync()
+        e0.record(stream)
+        for k in range(args.steps):
+            idx_h, sc_h = aspace.search_batch(q_host[k % nbatch].numpy(), gl, tau)
+        e1.record(stream)
+        barrier_sync()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # sanity: a perturbed copy must find its source item (size-independent property)
+    stage1_ms = max_over_ranks(float(np.mean(stage1)))
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    n_local = r1 - r0
+    gemm_flop = 2.0 * Q * n_local * f
+    achieved = gemm_flop / (stage1_ms * 1e-3) / 1e12
+    gram_ms = float(np.mean(stages["gram_ms"]))
+    lam_ms = float(np.mean(stages["lambda_ms"]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+    except Exception:
+        pass
+
+    line = {
+        "metric": "search queries/s (top-10, 1M x 384 f64)",
+        "value": Q / (step_ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 BEIR/MS MARCO-shaped synthetic %d x %d f64 items (seed %d, x%g), %d queries per step, top-%d, tau %.2f"
+                               % (n, f, cfg["seed"], cfg["scale"], Q, topk, tau),
+                   "graph_params": gp, "queries_per_step": Q, "sharding": "rows over %d rank(s)" % world,
+                   "l2": "inputs larger than L2 (item shard %.2f GB)" % (n_local * f * 8 / 1e9),
+                   "exact_rescan_queries_last_step": slow},
+        "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": Q * f * 8, "d2h_bytes_per_step": Q * topk * 16},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "search_gemm_kernel (FP64 DMMA.8x8x4, TMA fed, fused score/top-k epilogue)",
+                     "bound": "tensor", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak_tflops, "traffic": prof.get("search_gemm_dram_bytes_per_launch"),
+                     "algorithmic": "2*Q*N_local*F = %.3e FLOP per launch" % gemm_flop,
+                     "kernel_ms": stage1_ms, "share_of_step": stage1_ms / step_ms,
+                     "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+        "build": {"items_per_s": n / (float(np.mean(build_ms)) * 1e-3), "ms": float(np.mean(build_ms)),
+                  "e2e_items_per_s": n / (min(build_e2e_ms) * 1e-3), "e2e_ms": min(build_e2e_ms),
+                  "h2d_bytes": n_local * f * 8, "gpu_launches": int(build_launches),
+                  "gram": {"ms": gram_ms, "bound": "tensor", "achieved_tflops": 2.0 * n_local * f * f / (gram_ms * 1e-3) / 1e12,
+                           "frac": 2.0 * n_local * f * f / (gram_ms * 1e-3) / 1e12 / fp64_peak_tflops},
+                  "graph_ms": float(np.mean(stages["graph_ms"])),
+                  "lambda": {"ms": lam_ms, "bound": "hbm", "achieved_gbs": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9,
+                             "frac": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak}},
+        "clocks": clk,
+    }
+    if not args.no_cpu_baseline:
+        ns = min(n, args.cpu_sample_items)
+        r = cpu_oracle_run(dict(cfg, n=n), ns, args.cpu_sample_queries, 3, "sample")
+        per_q = min(r["search_s"]) / r["nq"] * (n / ns)           # a scan is linear in the item count
+        line["cpu_baseline"] = {
+            "value": 1.0 / per_q, "unit": "queries/s", "cores": r["threads"], "kind": "port",
+            "sample": "oracle (C + OpenMP) on the first %d items and %d queries of the workload; search time scaled x%.0f "
+                      "to %d items (linear scan); oracle build of the sample %.2f s = %.0f items/s"
+                      % (ns, r["nq"], n / ns, n, r["build_s"], ns / r["build_s"]),
+            "build_items_per_s": ns / r["build_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

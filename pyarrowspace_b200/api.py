@@ -248,6 +248,7 @@ class ArrowSpace:
             score = torch.empty((nq, topk), dtype=torch.float64, device=q.device)
             lam = torch.empty(nq, dtype=torch.float64, device=q.device)
             qp, ip, sp, lp = q.data_ptr(), idx.data_ptr(), score.data_ptr(), lam.data_ptr()
+            torch.cuda.current_stream(q.device).synchronize()      # the library runs on its own stream
         else:
             q = np.ascontiguousarray(queries, dtype=np.float64)
             if q.ndim != 2 or q.shape[1] != f:
@@ -320,6 +321,7 @@ class ArrowSpaceBuilder:
             x = items.contiguous()
             n, f = x.shape
             ptr = x.data_ptr()
+            torch.cuda.current_stream(x.device).synchronize()      # the library runs on its own stream
         else:
             if not isinstance(items, np.ndarray) or items.dtype != np.float64 or items.ndim != 2:
                 raise TypeError("argument 'items': expected 2-D numpy.ndarray of float64")

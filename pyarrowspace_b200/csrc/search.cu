@@ -79,7 +79,7 @@ search_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                    const double *__restrict__ q, const double *__restrict__ items, int64_t nq, int64_t n_local, int fp,
                    const double *__restrict__ inv_nx, const double *__restrict__ lam_x,
                    const double *__restrict__ inv_nq, const double *__restrict__ lam_q, double tau,
-                   int tiles_per_chunk, int nchunks, double *__restrict__ cand_score, int32_t *__restrict__ cand_idx)
+                   int nchunks, double *__restrict__ cand_score, int32_t *__restrict__ cand_idx)
 {
     constexpr int CAP = 2 * LIST;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -91,10 +91,8 @@ search_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, chunk = blockIdx.y;
     const int64_t tiles_total = (n_local + IT - 1) / IT;
-    const int64_t tile0 = (int64_t)chunk * tiles_per_chunk;
-    int64_t ntiles = tiles_total - tile0;
-    if (ntiles > tiles_per_chunk) ntiles = tiles_per_chunk;
-    if (ntiles < 0) ntiles = 0;
+    const int64_t tile0 = (tiles_total * chunk) / nchunks;               // even split of the item tiles
+    const int64_t ntiles = (tiles_total * (chunk + 1)) / nchunks - tile0;
     const int ksteps = (fp + KSTEP - 1) / KSTEP;
     const int64_t total_it = ntiles * ksteps;
 
@@ -624,7 +622,7 @@ __global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double 
 
 template <int LIST>
 int launch_gemm(const asp_space *s, const CUtensorMap &tmap_q, const double *q_dev, int64_t nq, const double *inv_nq,
-                const double *lam_q, double tau, int tiles_per_chunk, int nchunks, double *cand_score, int32_t *cand_idx)
+                const double *lam_q, double tau, int nchunks, double *cand_score, int32_t *cand_idx)
 {
     asp_ctx *ctx = s->ctx;
     constexpr int STAGES = (LIST == 16) ? 4 : 3;
@@ -634,14 +632,14 @@ int launch_gemm(const asp_space *s, const CUtensorMap &tmap_q, const double *q_d
         auto k = search_gemm_kernel<LIST, STAGES, true>;
         ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, MMA_WARPS * 32, smem, ctx->stream>>>(tmap_q, s->tmap_rows, q_dev, s->items, nq, s->n_local, s->fp,
-                                                           s->inv_norms, s->lambdas, inv_nq, lam_q, tau, tiles_per_chunk,
-                                                           nchunks, cand_score, cand_idx);
+                                                           s->inv_norms, s->lambdas, inv_nq, lam_q, tau, nchunks, cand_score,
+                                                           cand_idx);
     } else {
         auto k = search_gemm_kernel<LIST, STAGES, false>;
         ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, MMA_WARPS * 32, smem, ctx->stream>>>(tmap_q, s->tmap_rows, q_dev, s->items, nq, s->n_local, s->fp,
-                                                     s->inv_norms, s->lambdas, inv_nq, lam_q, tau, tiles_per_chunk,
-                                                     nchunks, cand_score, cand_idx);
+                                                     s->inv_norms, s->lambdas, inv_nq, lam_q, tau, nchunks, cand_score,
+                                                     cand_idx);
     }
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
@@ -720,17 +718,26 @@ int asp_search_impl(const asp_space *s, const asp_graph *g, const double *q_dev,
     } else {
         const int64_t tiles_total = asp_ceil_div(s->n_local, IT);
         const int64_t qblocks = asp_ceil_div(nq, QT);
-        int64_t want_chunks = asp_ceil_div((int64_t)ctx->num_sms * 2, qblocks);
-        if (want_chunks > tiles_total) want_chunks = tiles_total;
-        if (want_chunks < 1) want_chunks = 1;
-        const int tiles_per_chunk = (int)asp_ceil_div(tiles_total, want_chunks);
-        nparts = (int)asp_ceil_div(tiles_total, tiles_per_chunk);
+        // CTAs = qblocks x chunks; pick the chunk count whose CTA total fills whole waves of SMs
+        // (1 CTA per SM): smallest wave count w with >= 97 % of w * num_sms CTAs, else the best seen.
+        int64_t best_chunks = 1;
+        double best_eff = 0.0;
+        for (int w = 1; w <= 16; ++w) {
+            int64_t c = ((int64_t)w * ctx->num_sms) / qblocks;
+            if (c < 1) continue;
+            if (c > tiles_total) c = tiles_total;
+            const int64_t ctas = c * qblocks;
+            const double eff = (double)ctas / (double)(asp_ceil_div(ctas, ctx->num_sms) * ctx->num_sms);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = c; }
+            if (eff >= 0.97 || c == tiles_total) break;
+        }
+        nparts = (int)best_chunks;
         CUtensorMap tmap_q;
         ASP_CHECK(asp_make_items_tmap(&tmap_q, q_dev, nq, qpitch, QT, KSTEP / 4));
         ASP_CUDA(cudaMallocAsync(&cand_score, sizeof(double) * (size_t)nq * nparts * LISTSEL, st));
         ASP_CUDA(cudaMallocAsync(&cand_idx, sizeof(int32_t) * (size_t)nq * nparts * LISTSEL, st));
-        if (LISTSEL == 16) ASP_CHECK(launch_gemm<16>(s, tmap_q, q_dev, nq, inv_nq, lambda_q_dev, tau, tiles_per_chunk, nparts, cand_score, cand_idx));
-        else ASP_CHECK(launch_gemm<32>(s, tmap_q, q_dev, nq, inv_nq, lambda_q_dev, tau, tiles_per_chunk, nparts, cand_score, cand_idx));
+        if (LISTSEL == 16) ASP_CHECK(launch_gemm<16>(s, tmap_q, q_dev, nq, inv_nq, lambda_q_dev, tau, nparts, cand_score, cand_idx));
+        else ASP_CHECK(launch_gemm<32>(s, tmap_q, q_dev, nq, inv_nq, lambda_q_dev, tau, nparts, cand_score, cand_idx));
     }
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));
 

@@ -1,0 +1,140 @@
+"""world_size-2 (and 4) gloo runs of the multi-GPU host logic on CPU.
+
+`pyarrowspace_b200.distributed.sharded_build` is the orchestration the GPU ranks run (segment
+all-gather, rank-ordered continuation of exact column sums, per-shard lambdas).  Here it is driven with
+an oracle-backed engine (test infrastructure, lives in this file) over gloo, and must reproduce the
+single-process oracle: same edges, same lambdas, and left-to-right sums that continue across ranks
+bit-exactly."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class OracleEngine:
+    """Stands in for CudaEngine: same methods, numpy/oracle arithmetic, CPU tensors for the collectives."""
+
+    def __init__(self, force_need):
+        import torch
+        self.torch = torch
+        self.force_need = force_need       # ask for these pairs once, to exercise the rank-ordered chain
+        self.asked = False
+        self.exact = None
+
+    def space_create(self, shard, n_total, world, rank):
+        from pyarrowspace_b200 import shard_rows
+        r0, r1 = shard_rows(n_total, world, rank)
+        assert shard.shape[0] == r1 - r0
+        return {"x": np.ascontiguousarray(shard), "world": world, "rank": rank, "n_total": n_total}
+
+    def gram_partials(self, space, f):
+        from pyarrowspace_b200 import shard_rows
+        x, world, rank, n = space["x"], space["world"], space["rank"], space["n_total"]
+        segs = np.zeros((8, f, f))
+        r0, _ = shard_rows(n, world, rank)
+        for e in range(rank * 8 // world, (rank + 1) * 8 // world):
+            e0, e1 = shard_rows(n, 8, e)
+            blk = x[e0 - r0:e1 - r0]
+            segs[e] = blk.T @ blk if len(blk) else 0.0
+        return self.torch.from_numpy(segs)
+
+    def graph_from_gram(self, segs, f, n_total, cgp, sw, pairs, sums):
+        if self.force_need is not None and not self.asked:
+            self.asked = True
+            return None, np.asarray(self.force_need, dtype=np.int32)
+        self.exact = (pairs, sums)
+        return {"gram": segs.numpy().sum(0)}, np.empty((0, 2), dtype=np.int32)
+
+    def exact_pairs(self, space, pairs, sums):
+        x = space["x"]
+        for i, (a, b) in enumerate(pairs):
+            s = sums[i].copy()
+            for r in range(x.shape[0]):
+                s[0] = s[0] + x[r, a] * x[r, b]
+                s[1] = s[1] + x[r, a] * x[r, a]
+                s[2] = s[2] + x[r, b] * x[r, b]
+            sums[i] = s
+        return sums
+
+    def compute_lambdas(self, space, graph):
+        space["gram"] = graph["gram"]
+
+    def to_comm(self, arr):
+        return self.torch.from_numpy(np.ascontiguousarray(arr))
+
+    def from_comm(self, t):
+        return t.numpy()
+
+
+def _worker(rank, world, port, n, f, q):
+    import torch.distributed as dist
+    try:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        from pyarrowspace_b200 import _lib, shard_rows, synth
+        from pyarrowspace_b200.distributed import sharded_build
+        r0, r1 = shard_rows(n, world, rank)
+        shard = synth.make_items(n, f, 3, n_clusters=4, rows=(r0, r1))
+        eng = OracleEngine(force_need=[(0, 1), (2, 5)])
+        cgp = _lib.make_params(0.5, 3, 4, 2.0, None)
+        space, graph = sharded_build(eng, shard, n, cgp, _lib.make_switches(), None)
+        q.put((rank, r0, r1, graph["gram"], eng.exact[0], eng.exact[1]))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:                                              # pragma: no cover
+        q.put((rank, "error", repr(e)))
+        raise
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_build_over_gloo(world, oracle_mod):
+    import torch.multiprocessing as mp
+    from pyarrowspace_b200 import synth
+    n, f = 1000, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, f, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda t: t[0])
+    assert all(r[1] != "error" for r in res), res
+    x = synth.make_items(n, f, 3, n_clusters=4)
+    # shards tile the matrix and every rank ends with the same, complete Gram
+    assert res[0][1] == 0 and res[-1][2] == n and all(res[i][2] == res[i + 1][1] for i in range(world - 1))
+    ref = oracle_mod.gram_columns(x)
+    for r in res:
+        assert np.array_equal(r[3], res[0][3])
+        np.testing.assert_allclose(r[3], ref, rtol=1e-12)
+        # the exact sums were continued rank after rank: identical to ONE left-to-right pass over all rows
+        pairs, sums = r[4], r[5]
+        assert [tuple(p) for p in pairs] == [(0, 1), (2, 5)]
+        assert sums[0][0] == ref[0, 1] and sums[0][1] == ref[0, 0] and sums[0][2] == ref[1, 1]
+        assert sums[1][0] == ref[2, 5] and sums[1][1] == ref[2, 2] and sums[1][2] == ref[5, 5]
+
+
+def test_synthetic_shards_are_consistent():
+    """Rows generated per shard equal the rows of the whole matrix (ranks generate their own shard)."""
+    from pyarrowspace_b200 import shard_rows, synth
+    n, f = 200_000, 8
+    full = synth.make_items(n, f, 44)
+    for world in (2, 8):
+        for r in (0, world - 1):
+            r0, r1 = shard_rows(n, world, r)
+            assert np.array_equal(synth.make_items(n, f, 44, rows=(r0, r1)), full[r0:r1])
