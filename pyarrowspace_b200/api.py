@@ -365,6 +365,33 @@ class ArrowSpaceBuilder:
         return distributed.build_sharded(graph_params, items_shard, n_total, group, **extras)
 
     @staticmethod
+    def build_item_graph(graph_params, items, **extras):
+        """Extension (`nodes = items`): the eps / k-NN graph whose nodes are the ITEMS
+        (the graph-build workload of BASELINE.json configs C4/C5).  Returns (ArrowSpace without lambdas,
+        GraphLaplacian over nitems nodes).  Single GPU."""
+        lib = _lib.load()
+        if _is_device_tensor(items):
+            import torch
+            x = items.contiguous()
+            ptr = x.data_ptr()
+            torch.cuda.current_stream(x.device).synchronize()
+        else:
+            if not isinstance(items, np.ndarray) or items.dtype != np.float64 or items.ndim != 2:
+                raise TypeError("argument 'items': expected 2-D numpy.ndarray of float64")
+            x = np.ascontiguousarray(items)
+            ptr = x.ctypes.data
+        n, f = x.shape
+        gp = parse_graph_params(graph_params) or dict(DEFAULT_GRAPH_PARAMS)
+        cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+        sw = _lib.make_switches(extras.get("kernel", "inv_power"))
+        ctx = _lib.context(extras.get("device"))
+        hs, hg = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.asp_space_create(ctx, ptr, n, f, n, 1, 0, C.byref(hs)))
+        aspace = ArrowSpace._wrap(hs, ctx)
+        _lib.check(lib.asp_item_graph(hs, C.byref(cgp), C.byref(sw), C.byref(hg)))
+        return aspace, GraphLaplacian._wrap(hg)
+
+    @staticmethod
     def build_energy(items, energy_params=None, graph_params=None):
         raise NotImplementedError("build_energy belongs to the energy pipeline (src/lib.rs:333-376)")
 

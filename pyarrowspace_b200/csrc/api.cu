@@ -124,6 +124,13 @@ int asp_ctx_create(int device, asp_ctx **out)
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ASP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // keep freed blocks in the stream-ordered pool: every build/search reuses its scratch instead of
+        // going back to the driver (cudaMalloc/cudaFree of GB-sized buffers cost milliseconds and synchronise)
+        cudaMemPool_t pool;
+        ASP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        ASP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     ASP_CUDA(cudaEventCreate(&ctx->ev0));
     ASP_CUDA(cudaEventCreate(&ctx->ev1));
     const char *no_tma = getenv("ASP_NO_TMA");
@@ -211,10 +218,10 @@ int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, i
     s->fp = (f + 3) & ~3;
     s->world = world;
     s->rank = rank;
-    ASP_CUDA(cudaMalloc(&s->items, sizeof(double) * (size_t)n_local * s->fp));
-    ASP_CUDA(cudaMalloc(&s->norms, sizeof(double) * n_local));
-    ASP_CUDA(cudaMalloc(&s->inv_norms, sizeof(double) * n_local));
-    ASP_CUDA(cudaMalloc(&s->lambdas, sizeof(double) * n_local));
+    ASP_CUDA(cudaMallocAsync(&s->items, sizeof(double) * (size_t)n_local * s->fp, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->norms, sizeof(double) * n_local, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->inv_norms, sizeof(double) * n_local, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->lambdas, sizeof(double) * n_local, ctx->stream));
     int rc = upload_pitched(ctx, items_shard, n_local, f, s->fp, s->items);
     if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_gram, s->items, n_local, s->fp, ASP_ROW_UNIT, 32);
     if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n_local, s->fp, 128, 4);
@@ -231,10 +238,11 @@ void asp_free_space(asp_space *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->items);
-    cudaFree(s->norms);
-    cudaFree(s->inv_norms);
-    cudaFree(s->lambdas);
+    cudaStream_t st = s->ctx->stream;
+    if (s->items) cudaFreeAsync(s->items, st);
+    if (s->norms) cudaFreeAsync(s->norms, st);
+    if (s->inv_norms) cudaFreeAsync(s->inv_norms, st);
+    if (s->lambdas) cudaFreeAsync(s->lambdas, st);
     delete s;
 }
 
@@ -242,13 +250,10 @@ void asp_free_graph(asp_graph *g)
 {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
-    cudaFree(g->d_indptr);
-    cudaFree(g->d_indices);
-    cudaFree(g->d_data);
-    cudaFree(g->d_uptr);
-    cudaFree(g->d_ucol);
-    cudaFree(g->d_uval);
-    cudaFree(g->d_deg);
+    cudaStream_t st = g->ctx->stream;
+    void *bufs[] = {g->d_indptr, g->d_indices, g->d_data, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg};
+    for (void *b : bufs)
+        if (b) cudaFreeAsync(b, st);
     delete g;
 }
 
@@ -417,7 +422,7 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
     double *segs = nullptr;
     asp_graph *g = nullptr;
     int rc = ASP_OK;
-    if (cudaMalloc(&segs, sizeof(double) * (size_t)ASP_GRAM_SEGMENTS * f * f) != cudaSuccess) {
+    if (cudaMallocAsync(&segs, sizeof(double) * (size_t)ASP_GRAM_SEGMENTS * f * f, ctx->stream) != cudaSuccess) {
         asp_set_error("out of device memory for the Gram segments");
         rc = ASP_ERR_NOMEM;
     }
@@ -452,7 +457,7 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
         rc = asp_space_compute_lambdas(s, g);
         t.stop();
     }
-    cudaFree(segs);
+    if (segs) cudaFreeAsync(segs, ctx->stream);
     if (rc != ASP_OK) { asp_free_space(s); asp_free_graph(g); return rc; }
     *out_space = s;
     *out_graph = g;

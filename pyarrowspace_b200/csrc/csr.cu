@@ -297,10 +297,10 @@ int asp_graph_upload_upper(asp_graph *g)
     build_upper(g, uptr, ucol, uval, deg);
     g->unnz = (int64_t)ucol.size();
     const size_t un = ucol.size() > 0 ? ucol.size() : 1;
-    ASP_CUDA(cudaMalloc(&g->d_uptr, sizeof(int32_t) * (g->nnodes + 1)));
-    ASP_CUDA(cudaMalloc(&g->d_ucol, sizeof(int32_t) * un));
-    ASP_CUDA(cudaMalloc(&g->d_uval, sizeof(double) * un));
-    ASP_CUDA(cudaMalloc(&g->d_deg, sizeof(double) * g->nnodes));
+    ASP_CUDA(cudaMallocAsync(&g->d_uptr, sizeof(int32_t) * (g->nnodes + 1), ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&g->d_ucol, sizeof(int32_t) * un, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&g->d_uval, sizeof(double) * un, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&g->d_deg, sizeof(double) * g->nnodes, ctx->stream));
     ASP_CUDA(cudaMemcpyAsync(g->d_uptr, uptr.data(), sizeof(int32_t) * (g->nnodes + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (!ucol.empty()) {
         ASP_CUDA(cudaMemcpyAsync(g->d_ucol, ucol.data(), sizeof(int32_t) * ucol.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -339,7 +339,7 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
     count_mirror_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->cnt, extra);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
 
-    ASP_CUDA(cudaMalloc(&g->d_indptr, sizeof(int64_t) * (m + 1)));
+    ASP_CUDA(cudaMallocAsync(&g->d_indptr, sizeof(int64_t) * (m + 1), st));
     scan_blocks_kernel<<<(unsigned)nblocks, SCAN_BLOCK, 0, st>>>(m, lists->cnt, extra, g->d_indptr, block_sums);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     scan_sums_kernel<<<1, SCAN_BLOCK, 0, st>>>(nblocks, block_sums, total);
@@ -352,8 +352,8 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
     ASP_CUDA(cudaStreamSynchronize(st));
     g->nnodes = m;
     g->nnz = nnz;
-    ASP_CUDA(cudaMalloc(&g->d_indices, sizeof(int32_t) * nnz));
-    ASP_CUDA(cudaMalloc(&g->d_data, sizeof(double) * nnz));
+    ASP_CUDA(cudaMallocAsync(&g->d_indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1), st));
+    ASP_CUDA(cudaMallocAsync(&g->d_data, sizeof(double) * (nnz > 0 ? nnz : 1), st));
 
     fill_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->dist, lists->cnt, g->d_indptr, cursor, g->d_indices,
                                       g->d_data);

@@ -8,10 +8,12 @@
 // Bound: HBM (8*n*f bytes, X read once) while nnz(L)/f is small; for k = 25 the gathers from the
 // shared-memory X tile dominate (8 bytes per nonzero per item) -- see DESIGN.md.
 //
-// CTA = 256 threads, one tile of T = 16*R items at a time, grid-stride (persistent):
-//   A. warp w loads item rows (coalesced), keeps them in registers, finds the median by a
-//      warp-cooperative quickselect (ballot-free: counts via __reduce_add_sync), and stores the
-//      values transposed into shared memory xs[feature][item] (row stride T+1: conflict free both ways)
+// Two kernels:
+//  median_kernel   one warp per vector, values in registers, warp-cooperative quickselect (counts through
+//                  __reduce_add_sync); streaming, high occupancy
+//  taumode_kernel  CTA = 256 threads, one tile of T = 16*R items at a time, grid-stride (persistent):
+//   A. warp w loads item rows (coalesced) and stores them transposed into shared memory
+//      xs[feature][item] (row stride T+1: conflict free both ways)
 //   A' thread t < T: left-to-right sum of squares (the norm the search kernel divides by; same
 //      order as the oracle) and, for tau_mode = mean, the left-to-right sum
 //   B. thread (part p = tid/16, lane-group g = tid%16) owns items g+16r (r < R) and the graph rows
@@ -58,6 +60,7 @@ __device__ double warp_select(const double (&v)[FPL], int rank, int lane, uint32
             if (lane >= off) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total <= 0) { *count_le = nbelow; return NAN; }       // only with NaN / inf data
         const int pick = (int)(hash32(seed + iter) % (uint32_t)total);
         const unsigned ballot = __ballot_sync(0xffffffffu, incl > pick);
         const int owner = __ffs(ballot) - 1;
@@ -114,12 +117,36 @@ __device__ double warp_median(const double (&v)[FPL], int n, int lane, uint32_t 
     return 0.5 * (vlo + vhi);            // oracle.c median_of: 0.5 * (s[n/2-1] + s[n/2])
 }
 
+// K3a: per-vector median (tau before flooring), one warp per vector, grid-stride.  A pure streaming pass with
+// small footprint (no shared memory, FPL f64 registers per lane): many resident warps hide the shuffle latency
+// of the selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
+template <int FPL>
+__global__ void __launch_bounds__(256)
+median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use_abs, double *__restrict__ out_median)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t item = warp; item < n; item += nwarps) {
+        const double *row = x + item * pitch;
+        double v[FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+            const int ff = lane + 32 * j;
+            v[j] = (ff < f) ? row[ff] : INFINITY;
+            if (use_abs && ff < f) v[j] = fabs(v[j]);
+        }
+        const double med = warp_median<FPL>(v, f, lane, (uint32_t)(item * 2654435761ULL));
+        if (lane == 0) out_median[item] = med;
+    }
+}
+
 template <int FPL, int R>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
                const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ deg,
                const TmChunk *__restrict__ chunks, int nchunks, int tau_mode, double tau_fixed,
-               double *__restrict__ out_energy, double *__restrict__ out_tau, double *__restrict__ out_lambda,
+               const double *__restrict__ medians, double *__restrict__ out_energy, double *__restrict__ out_tau, double *__restrict__ out_lambda,
                double *__restrict__ out_norm, double *__restrict__ out_inv_norm, int *zero_flag)
 {
     constexpr int T = 16 * R;
@@ -142,7 +169,7 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
         const int64_t item0 = tile * T;
         __syncthreads();                                               // previous tile fully consumed
 
-        // ---- A: load, median, transpose into shared memory
+        // ---- A: load, transpose into shared memory
         for (int t = warp; t < T; t += TM_THREADS / 32) {
             const int64_t item = item0 + t;
             double v[FPL];
@@ -162,14 +189,6 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
                 const int ff = lane + 32 * j;
                 if (ff < f) xs[ff * XS + t] = v[j];
             }
-            if (tau_mode == ASP_TAU_MEDIAN || tau_mode == ASP_TAU_MEDIAN_ABS) {
-                if (tau_mode == ASP_TAU_MEDIAN_ABS) {
-#pragma unroll
-                    for (int j = 0; j < FPL; ++j) v[j] = fabs(v[j]);
-                }
-                const double med = warp_median<FPL>(v, f, lane, (uint32_t)(item * 2654435761ULL));
-                if (lane == 0) s_tau[t] = med;
-            }
         }
         __syncthreads();
 
@@ -186,7 +205,7 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
             double tau;
             if (tau_mode == ASP_TAU_MEAN) tau = sm / (double)f;
             else if (tau_mode == ASP_TAU_FIXED) tau = tau_fixed;
-            else tau = s_tau[t];
+            else tau = (item0 + t < n) ? medians[item0 + t] : 1.0;
             s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
         }
 
@@ -252,6 +271,15 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
               int *zero_flag)
 {
     constexpr int T = 16 * R;
+    double *medians = nullptr;
+    if (sw->tau_mode == ASP_TAU_MEDIAN || sw->tau_mode == ASP_TAU_MEDIAN_ABS) {
+        ASP_CUDA(cudaMallocAsync(&medians, sizeof(double) * n, ctx->stream));
+        const int64_t want = asp_ceil_div(n, 8);
+        const int mgrid = (int)(want < (int64_t)ctx->num_sms * 8 ? want : (int64_t)ctx->num_sms * 8);
+        median_kernel<FPL><<<mgrid, 256, 0, ctx->stream>>>(x, n, f, pitch, sw->tau_mode == ASP_TAU_MEDIAN_ABS ? 1 : 0, medians);
+        ASP_CUDA(cudaGetLastError());
+        ASP_LAUNCHED(ctx);
+    }
     const size_t smem = (size_t)f * (T + 1) * 8 + (size_t)CH_NNZ * 12 + (CH_ROWS + 2) * 4 + (size_t)CH_ROWS * 8 +
                         (size_t)T * 16 + 64;
     if (smem > 227 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "taumode kernel: %d features do not fit in shared memory", f);
@@ -260,9 +288,10 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
     const int64_t ntiles = (n + T - 1) / T;
     const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
     kern<<<grid, TM_THREADS, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
-                                                  nchunks, sw->tau_mode, sw->tau_fixed, oe, ot, ol, on, oi, zero_flag);
+                                                  nchunks, sw->tau_mode, sw->tau_fixed, medians, oe, ot, ol, on, oi, zero_flag);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
+    if (medians) ASP_CUDA(cudaFreeAsync(medians, ctx->stream));
     return ASP_OK;
 }
 
