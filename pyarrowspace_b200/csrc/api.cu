@@ -263,7 +263,10 @@ int asp_space_gram_partials(asp_space *s, double *out_dev)
     if (!s || !out_dev) ASP_FAIL(ASP_ERR_ARG, "asp_space_gram_partials: NULL argument");
     if (!asp_is_device_ptr(out_dev)) ASP_FAIL(ASP_ERR_ARG, "asp_space_gram_partials: out_dev must be device memory");
     ASP_CUDA(cudaSetDevice(s->ctx->device));
-    return asp_launch_gram_partials(s, out_dev);
+    StageTimer t(s->ctx, "gram_ms");
+    const int rc = asp_launch_gram_partials(s, out_dev);
+    t.stop();
+    return rc;
 }
 
 int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f, int64_t n_total,
@@ -278,6 +281,7 @@ int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f
     if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
     cudaStream_t st = ctx->stream;
     if (n_need) *n_need = 0;
+    StageTimer timer(ctx, "graph_ms");
 
     double *gram = nullptr;
     ASP_CUDA(cudaMallocAsync(&gram, sizeof(double) * (size_t)f * f, st));
@@ -359,6 +363,7 @@ int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f
     if (d_pairs) cudaFreeAsync(d_pairs, st);
     if (d_sums) cudaFreeAsync(d_sums, st);
     cudaFreeAsync(gram, st);
+    timer.stop();
     if (rc == ASP_OK) *out_graph = g;
     return rc;
 }
@@ -394,8 +399,10 @@ int asp_space_compute_lambdas(asp_space *s, const asp_graph *g)
     int *flag = nullptr;
     ASP_CUDA(cudaMallocAsync(&flag, sizeof(int), ctx->stream));
     ASP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    StageTimer timer(ctx, "lambda_ms");
     int rc = asp_launch_taumode(ctx, g, &g->sw, s->items, s->n_local, s->f, s->fp, nullptr, nullptr, s->lambdas, s->norms,
                                 s->inv_norms, flag);
+    timer.stop();
     int h = 0;
     if (rc == ASP_OK) {
         ASP_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -426,13 +433,9 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
         asp_set_error("out of device memory for the Gram segments");
         rc = ASP_ERR_NOMEM;
     }
+    if (rc == ASP_OK) rc = asp_space_gram_partials(s, segs);
     if (rc == ASP_OK) {
-        StageTimer t(ctx, "gram_ms");
-        rc = asp_space_gram_partials(s, segs);
-        t.stop();
-    }
-    if (rc == ASP_OK) {
-        StageTimer t(ctx, "graph_ms");
+        double graph_ms = 0.0;
         std::vector<int32_t> pairs;
         std::vector<double> sums;
         const int64_t cap = 1 << 16;
@@ -441,6 +444,7 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
             int64_t n_need = 0;
             rc = asp_graph_from_gram(ctx, segs, f, n, gp, sw, pairs.data(), sums.data(), (int64_t)(pairs.size() / 2),
                                      need.data(), cap, &n_need, &g);
+            graph_ms += ctx->stats["graph_ms"];
             if (rc != ASP_NEED_EXACT) break;
             std::vector<double> add(3 * n_need, 0.0);
             rc = asp_space_exact_pairs(s, need.data(), n_need, add.data());
@@ -450,13 +454,9 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
             rc = ASP_NEED_EXACT;
         }
         if (rc == ASP_NEED_EXACT) { asp_set_error("exact-pair resolution did not converge"); rc = ASP_ERR_CUDA; }
-        t.stop();
+        ctx->stats["graph_ms"] = graph_ms;
     }
-    if (rc == ASP_OK) {
-        StageTimer t(ctx, "lambda_ms");
-        rc = asp_space_compute_lambdas(s, g);
-        t.stop();
-    }
+    if (rc == ASP_OK) rc = asp_space_compute_lambdas(s, g);
     if (segs) cudaFreeAsync(segs, ctx->stream);
     if (rc != ASP_OK) { asp_free_space(s); asp_free_graph(g); return rc; }
     *out_space = s;
