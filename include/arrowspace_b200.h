@@ -154,10 +154,17 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, c
  * rows are padded to topk with index -1 / score NaN.  Scores of the returned hits are evaluated
  * in the reference order (left-to-right f64 dot); the candidate set is proven complete against the
  * rounding band of the tensor-core pass, otherwise the query is re-scanned exactly.
+ * Stage 1 runs on tcgen05 (bf16 two-term split) for nq >= 256 and topk <= 16, on FP64 DMMA for smaller
+ * batches, on the HBM-bound GEMV kernel for nq <= 8; env ASP_SEARCH_STAGE1=fp64|tc forces one.  The answers
+ * are bit-identical whichever stage 1 produced the candidates.
  * Fails with ASP_ERR_LAMBDA_ZERO if some lambda_q == 0.0 (src/lib.rs:156-159).
  * out_lambda_q (nq) may be NULL.  [exchange]: all-gather (idx, score) and asp_topk_merge. */
 int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq,
                      double tau, int64_t *out_idx, double *out_score, double *out_lambda_q);
+
+/* Test hook of the tcgen05 candidate pass: raw approximate dot products q.x (bf16 two-term split, f32
+ * accumulation in TMEM) of nq queries against every item of the shard, out[nq][n_local] f32 (host or device). */
+int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, float *out);
 
 /* K5: merge `parts` candidate lists per query ([parts][nq][topk], as produced by
  * asp_search_batch on each shard) into the global top-k by (score desc, index asc). */

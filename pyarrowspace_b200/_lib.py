@@ -75,6 +75,7 @@ SYMBOLS = {
     "asp_graph_csr": (_int, [_vp, _vp, _vp, _vp]),
     "asp_query_lambda": (_int, [_vp, _vp, C.POINTER(Switches), _vp, _i64, _vp, _vp, _vp]),
     "asp_search_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
+    "asp_debug_tc_dots": (_int, [_vp, _vp, _i64, _vp]),
     "asp_topk_merge": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp]),
     "asp_item_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
     "asp_free_space": (None, [_vp]),

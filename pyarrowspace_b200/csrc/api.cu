@@ -239,6 +239,7 @@ void asp_free_space(asp_space *s)
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStream_t st = s->ctx->stream;
+    asp_free_tc_cache(s);
     if (s->items) cudaFreeAsync(s->items, st);
     if (s->norms) cudaFreeAsync(s->norms, st);
     if (s->inv_norms) cudaFreeAsync(s->inv_norms, st);
@@ -596,7 +597,14 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     if (rc == ASP_OK && topk > 0) {
         ASP_CUDA(cudaMallocAsync(&didx, sizeof(int64_t) * (size_t)nq * topk, st));
         ASP_CUDA(cudaMallocAsync(&dscore, sizeof(double) * (size_t)nq * topk, st));
-        rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
+        // stage 1 on tcgen05 (bf16 split) for batches, FP64 DMMA / GEMV otherwise; same exact stage 2, same answers
+        const char *force = getenv("ASP_SEARCH_STAGE1");
+        const bool want_fp64 = force && force[0] == 'f';
+        const bool want_tc = force && force[0] == 't';
+        if (!want_fp64 && asp_search_tc_supported(s, nq, topk) && (want_tc || nq >= 256))
+            rc = asp_search_tc_impl(s, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore, nullptr);
+        else
+            rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
         if (rc == ASP_OK) rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
         if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
         ASP_CUDA(cudaStreamSynchronize(st));
@@ -607,6 +615,28 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     cudaFreeAsync(flags, st);
     if (didx) cudaFreeAsync(didx, st);
     if (dscore) cudaFreeAsync(dscore, st);
+    return rc;
+}
+
+int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, float *out)
+{
+    if (!s || !queries || !out || nq <= 0) ASP_FAIL(ASP_ERR_ARG, "asp_debug_tc_dots: bad argument");
+    if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "asp_debug_tc_dots: build the space first");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *dq = nullptr, *dz = nullptr;
+    float *dd = nullptr;
+    ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * s->fp, st));
+    ASP_CUDA(cudaMallocAsync(&dz, sizeof(double) * 2 * nq, st));
+    ASP_CUDA(cudaMallocAsync(&dd, sizeof(float) * (size_t)nq * s->n_local, st));
+    ASP_CUDA(cudaMemsetAsync(dz, 0, sizeof(double) * 2 * nq, st));
+    ASP_CUDA(cudaMemsetAsync(dd, 0, sizeof(float) * (size_t)nq * s->n_local, st));
+    int rc = upload_pitched(ctx, queries, nq, s->f, s->fp, dq);
+    if (rc == ASP_OK) rc = asp_search_tc_impl(s, dq, nq, s->fp, dz, dz + nq, 1.0, 1, nullptr, nullptr, dd);
+    if (rc == ASP_OK) rc = asp_copy_out(ctx, out, dd, sizeof(float) * (size_t)nq * s->n_local);
+    ASP_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(dq, st); cudaFreeAsync(dz, st); cudaFreeAsync(dd, st);
     return rc;
 }
 

@@ -206,22 +206,9 @@ int asp_launch_gram_partials(asp_space *s, double *out_dev)
 {
     asp_ctx *ctx = s->ctx;
     const int64_t units_total = asp_ceil_div(s->n_total, ASP_ROW_UNIT);
-    // owned segments: those whose unit range starts inside the shard (shards are whole segments)
+    // owned segments: rank r of `world` holds segments [r*8/world, (r+1)*8/world)  (asp_shard_rows)
     const int64_t unit0 = s->row0 / ASP_ROW_UNIT;
-    const int64_t unit1 = asp_ceil_div(s->row0 + s->n_local, ASP_ROW_UNIT);
-    int seg0 = -1, seg1 = -1;
-    for (int e = 0; e < ASP_GRAM_SEGMENTS; ++e) {
-        const int64_t b = seg_unit_begin(units_total, e), en = seg_unit_begin(units_total, e + 1);
-        if (b >= unit0 && en <= unit1 && !(b == en && (b < unit0 || b > unit1))) {
-            if (seg0 < 0) seg0 = e;
-            seg1 = e + 1;
-        }
-    }
-    if (seg0 < 0) ASP_FAIL(ASP_ERR_ARG, "shard [%lld,%lld) owns no Gram segment", (long long)s->row0,
-                           (long long)(s->row0 + s->n_local));
-    if (seg_unit_begin(units_total, seg0) != unit0 || seg_unit_begin(units_total, seg1) != unit1)
-        ASP_FAIL(ASP_ERR_ARG, "shard rows [%lld,%lld) are not whole Gram segments; use asp_shard_rows",
-                 (long long)s->row0, (long long)(s->row0 + s->n_local));
+    const int seg0 = s->rank * (ASP_GRAM_SEGMENTS / s->world), seg1 = (s->rank + 1) * (ASP_GRAM_SEGMENTS / s->world);
     const int nseg = seg1 - seg0;
     const int nslices = nseg * ASP_GRAM_SLICES;
 

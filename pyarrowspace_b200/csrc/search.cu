@@ -408,6 +408,37 @@ int launch_gemv(const asp_space *s, const double *q_dev, int qpitch, int nq, con
 
 }  // namespace
 
+int asp_launch_reciprocal(asp_ctx *ctx, const double *x, int64_t n, double *out)
+{
+    reciprocal_kernel<<<(unsigned)(asp_ceil_div(n, 256) < 1024 ? asp_ceil_div(n, 256) : 1024), 256, 0, ctx->stream>>>(x, n, out);
+    ASP_CUDA(cudaGetLastError());
+    ASP_LAUNCHED(ctx);
+    return ASP_OK;
+}
+
+// exact full scan of the listed queries (completeness test failed / emission buffer full)
+int asp_search_slow_path(const asp_space *s, const double *q_dev, int32_t qpitch, const double *lambda_q_dev,
+                         const double *qnorm_dev, double tau, int64_t topk, const int32_t *slow_list, int nslow,
+                         int64_t *out_idx_dev, double *out_score_dev)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int f = s->f;
+    double *scores = nullptr;
+    ASP_CUDA(cudaMallocAsync(&scores, sizeof(double) * s->n_local, st));
+    for (int i = 0; i < nslow; ++i) {
+        exact_scan_kernel<<<ctx->num_sms * 4, 256, (size_t)f * 8, st>>>(q_dev, qpitch, slow_list, i, s->items, s->n_local, f,
+                                                                        s->fp, s->norms, s->lambdas, qnorm_dev, lambda_q_dev,
+                                                                        tau, scores);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        exact_select_kernel<<<1, 1024, 0, st>>>(scores, s->n_local, s->row0, (int)topk, slow_list, i, out_idx_dev,
+                                                out_score_dev);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    }
+    ASP_CUDA(cudaFreeAsync(scores, st));
+    return ASP_OK;
+}
+
 int asp_search_impl(const asp_space *s, const asp_graph *g, const double *q_dev, int64_t nq, int32_t qpitch,
                     const double *lambda_q_dev, const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev,
                     double *out_score_dev)
@@ -426,9 +457,7 @@ int asp_search_impl(const asp_space *s, const asp_graph *g, const double *q_dev,
     // 1/norm of the queries
     double *inv_nq = nullptr;
     ASP_CUDA(cudaMallocAsync(&inv_nq, sizeof(double) * nq, st));
-    reciprocal_kernel<<<(unsigned)(asp_ceil_div(nq, 256) < 1024 ? asp_ceil_div(nq, 256) : 1024), 256, 0, st>>>(qnorm_dev, nq, inv_nq);
-    ASP_CUDA(cudaGetLastError());
-    ASP_LAUNCHED(ctx);
+    ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, inv_nq));
 
     int32_t *slow_list = nullptr, *slow_count = nullptr;
     ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (nq + 1), st));
@@ -499,20 +528,10 @@ int asp_search_impl(const asp_space *s, const asp_graph *g, const double *q_dev,
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats["search_stage1_ms"] = ms;
     ctx->stats["search_slow_queries"] = nslow;
-    if (nslow > 0) {
-        double *scores = nullptr;
-        ASP_CUDA(cudaMallocAsync(&scores, sizeof(double) * s->n_local, st));
-        for (int i = 0; i < nslow; ++i) {
-            exact_scan_kernel<<<ctx->num_sms * 4, 256, (size_t)f * 8, st>>>(q_dev, qpitch, slow_list, i, s->items, s->n_local, f,
-                                                                            s->fp, s->norms, s->lambdas, qnorm_dev,
-                                                                            lambda_q_dev, tau, scores);
-            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-            exact_select_kernel<<<1, 1024, 0, st>>>(scores, s->n_local, s->row0, (int)topk, slow_list, i, out_idx_dev,
-                                                    out_score_dev);
-            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        }
-        ASP_CUDA(cudaFreeAsync(scores, st));
-    }
+    ctx->stats["search_stage1_is_tc"] = 0.0;
+    if (nslow > 0)
+        ASP_CHECK(asp_search_slow_path(s, q_dev, qpitch, lambda_q_dev, qnorm_dev, tau, topk, slow_list, nslow, out_idx_dev,
+                                       out_score_dev));
     ASP_CUDA(cudaFreeAsync(cand_score, st));
     ASP_CUDA(cudaFreeAsync(cand_idx, st));
     ASP_CUDA(cudaFreeAsync(slow_list, st));

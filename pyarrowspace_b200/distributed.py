@@ -87,6 +87,10 @@ class CudaEngine:
     def from_comm(self, t):
         return t.cpu().numpy()
 
+    def after_collective(self):
+        """NCCL runs on torch's stream, the library on its own: order them before the next library call."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+
 
 def _all_gather_blocks(t_local, world, group):
     """all-gather equal-size blocks; returns a tensor [world, *t_local.shape]."""
@@ -116,6 +120,8 @@ def sharded_build(engine, shard, n_total, cgp, sw, group=None):
         own = segs[rank * per:(rank + 1) * per]
         gathered = _all_gather_blocks(own, world, group)         # [world, per, f, f] == [8, f, f] in order
         segs = gathered.reshape(_lib.GRAM_SEGMENTS, f, f)
+        if hasattr(engine, "after_collective"):
+            engine.after_collective()
     pairs = np.empty((0, 2), dtype=np.int32)
     sums = np.empty((0, 3), dtype=np.float64)
     graph = None

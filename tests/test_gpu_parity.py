@@ -397,6 +397,85 @@ def test_device_resident_inputs(oracle_mod):
     assert np.array_equal(idx_h, idx_d.cpu().numpy()) and np.array_equal(sc_h, sc_d.cpu().numpy())
 
 
+# ----------------------------------------------------------------------------- tcgen05 candidate pass (stage 1 on the 5th-gen tensor cores)
+
+def _force_stage1(mode):
+    if mode is None:
+        os.environ.pop("ASP_SEARCH_STAGE1", None)
+    else:
+        os.environ["ASP_SEARCH_STAGE1"] = mode
+
+
+@pytest.mark.parametrize("n,f,nq", [(700, 64, 130), (3000, 384, 300), (5000, 100, 257), (1100, 768, 128)])
+def test_tc_dot_error_band(n, f, nq):
+    """The bf16-split tcgen05 dot products stay inside the band the completeness proof assumes:
+    |cos~ - cos| <= 2^-13, with the margin (x4) DESIGN.md claims."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import _lib, synth
+    x = synth.make_items(n, f, 71, n_clusters=8) - 22.0                 # mixed signs, cancellation in the dot products
+    q, _ = synth.make_queries(x + 22.0, nq, 71)
+    q -= 0.2
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 1.0, "k": 4, "topk": 5, "p": 2.0, "sigma": 0.5}, x)
+    out = np.zeros((nq, n), dtype=np.float32)
+    _lib.check(_lib.load().asp_debug_tc_dots(aspace._h, q.ctypes.data, nq, out.ctypes.data))
+    exact = q @ x.T
+    scale = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :]
+    err = np.abs(out.astype(np.float64) - exact) / scale
+    assert err.max() < 2.0 ** -13 / 4, err.max()
+    assert err.max() > 0                                                 # it IS the low-precision path
+
+
+@pytest.mark.parametrize("n,f,nq,topk", [(3000, 96, 256, 10), (20000, 384, 1000, 10), (1500, 768, 300, 16), (900, 50, 513, 1)])
+def test_tc_search_equals_fp64_path_and_oracle(oracle_mod, n, f, nq, topk):
+    """Same exact stage 2 behind both candidate passes: the tcgen05 path returns bit-identical (idx, score) to the
+    FP64 DMMA path, and both equal the oracle's lists."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, synth
+    x = synth.make_items(n, f, 400 + f, n_clusters=10)
+    q, _ = synth.make_queries(x, nq, 400 + f)
+    gp = {"eps": 0.6, "k": 6, "topk": topk, "p": 2.0, "sigma": 0.3}
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+    try:
+        for tau in (0.62, 1.0):
+            _force_stage1("tc")
+            idx_tc, sc_tc = aspace.search_batch(q, gl, tau)
+            assert api.stat("search_stage1_is_tc") == 1.0
+            rescored = api.stat("search_rescored_per_query")
+            _force_stage1("fp64")
+            idx_64, sc_64 = aspace.search_batch(q, gl, tau)
+            assert api.stat("search_stage1_is_tc") == 0.0
+            assert np.array_equal(idx_tc, idx_64) and np.array_equal(sc_tc, sc_64)
+            oidx, osc, _ = s.search_batch(q, g, tau)
+            _assert_hits_equal(idx_tc, sc_tc, oidx, osc)
+            assert topk <= rescored < 0.5 * n                            # a real filter, not a full rescan
+    finally:
+        _force_stage1(None)
+
+
+def test_tc_search_with_ties_and_overflow(oracle_mod):
+    """Exact duplicates (ties by index) and more equal-score items than the emission buffer holds (-> exact scan)."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, synth
+    base = synth.make_items(300, 64, 5, n_clusters=4)
+    x = np.concatenate([base, base[:100], np.repeat(base[3:4], 1500, axis=0)])
+    gp = {"eps": 0.6, "k": 6, "topk": 8, "p": 2.0, "sigma": 0.3}
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+    q = np.ascontiguousarray(np.concatenate([base[:255] / 100.0, base[3:4] / 100.0]))
+    oidx, osc, _ = s.search_batch(q, g, 0.7)
+    try:
+        _force_stage1("tc")
+        idx, sc = aspace.search_batch(q, gl, 0.7)                        # 1501 exact ties, all emitted and re-scored
+        assert api.stat("search_slow_queries") == 0
+        _assert_hits_equal(idx, sc, oidx, osc)
+        os.environ["ASP_TC_CAPB"] = "32"                                 # tiny emission buffers: they overflow
+        idx, sc = aspace.search_batch(q, gl, 0.7)
+        assert api.stat("search_slow_queries") >= 1                      # ... and the queries take the exact scan
+        _assert_hits_equal(idx, sc, oidx, osc)
+    finally:
+        _force_stage1(None)
+        os.environ.pop("ASP_TC_CAPB", None)
+
+
 # ----------------------------------------------------------------------------- item graph (K1 item orientation + K2)
 
 @pytest.mark.parametrize("n,f,gp", [

@@ -45,6 +45,7 @@ def test_sass_has_dmma_and_tma():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert sass.count("DMMA.8x8x4") > 500
     assert "UTMALDG" in sass
+    assert "UTCHMMA" in sass and "LDTM" in sass          # tcgen05.mma / tcgen05.ld of the candidate pass
 
 
 def test_module_surface_matches_reference():
