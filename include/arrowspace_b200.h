@@ -162,8 +162,8 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, c
 int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq,
                      double tau, int64_t *out_idx, double *out_score, double *out_lambda_q);
 
-/* Test hook of the tcgen05 candidate pass: raw approximate dot products q.x (bf16 two-term split, f32
- * accumulation in TMEM) of nq queries against every item of the shard, out[nq][n_local] f32 (host or device). */
+/* Test hook of the tcgen05 candidate pass: the approximate cosines (unit-scaled operands, bf16 two-term split,
+ * f32 accumulation in TMEM) of nq queries against every item of the shard, out[nq][n_local] f32 (host or device). */
 int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, float *out);
 
 /* K5: merge `parts` candidate lists per query ([parts][nq][topk], as produced by

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -601,7 +602,7 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
         const char *force = getenv("ASP_SEARCH_STAGE1");
         const bool want_fp64 = force && force[0] == 'f';
         const bool want_tc = force && force[0] == 't';
-        if (!want_fp64 && asp_search_tc_supported(s, nq, topk) && (want_tc || nq >= 256))
+        if (!want_fp64 && asp_search_tc_supported(s, nq, topk, tau) && (want_tc || nq >= 256))
             rc = asp_search_tc_impl(s, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore, nullptr);
         else
             rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
@@ -625,14 +626,23 @@ int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, flo
     asp_ctx *ctx = s->ctx;
     ASP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    // test hook: query norms on the host (left to right), lambdas irrelevant
+    std::vector<double> hq((size_t)nq * s->f), hz(2 * nq, 0.0);
+    ASP_CUDA(cudaMemcpyAsync(hq.data(), queries, sizeof(double) * hq.size(), cudaMemcpyDefault, st));
+    ASP_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nq; ++i) {
+        double n2 = 0.0;
+        for (int j = 0; j < s->f; ++j) n2 += hq[i * s->f + j] * hq[i * s->f + j];
+        hz[nq + i] = sqrt(n2);
+    }
     double *dq = nullptr, *dz = nullptr;
     float *dd = nullptr;
     ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * s->fp, st));
     ASP_CUDA(cudaMallocAsync(&dz, sizeof(double) * 2 * nq, st));
     ASP_CUDA(cudaMallocAsync(&dd, sizeof(float) * (size_t)nq * s->n_local, st));
-    ASP_CUDA(cudaMemsetAsync(dz, 0, sizeof(double) * 2 * nq, st));
+    ASP_CUDA(cudaMemcpyAsync(dz, hz.data(), sizeof(double) * 2 * nq, cudaMemcpyHostToDevice, st));
     ASP_CUDA(cudaMemsetAsync(dd, 0, sizeof(float) * (size_t)nq * s->n_local, st));
-    int rc = upload_pitched(ctx, queries, nq, s->f, s->fp, dq);
+    int rc = upload_pitched(ctx, hq.data(), nq, s->f, s->fp, dq);
     if (rc == ASP_OK) rc = asp_search_tc_impl(s, dq, nq, s->fp, dz, dz + nq, 1.0, 1, nullptr, nullptr, dd);
     if (rc == ASP_OK) rc = asp_copy_out(ctx, out, dd, sizeof(float) * (size_t)nq * s->n_local);
     ASP_CUDA(cudaStreamSynchronize(st));

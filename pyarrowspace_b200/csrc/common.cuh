@@ -132,7 +132,7 @@ int asp_topk_merge_impl(asp_ctx *ctx, const int64_t *idx_dev, const double *scor
                         int64_t nq, int64_t topk, int64_t *out_idx_dev, double *out_score_dev);
 
 // search_tc.cu (tcgen05 stage 1)
-bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk);
+bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau);
 int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
                        const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev, double *out_score_dev,
                        float *dump_dev);

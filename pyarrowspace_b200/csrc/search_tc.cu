@@ -44,14 +44,17 @@ constexpr int TK_LIST = 16;        // running top list per query row (topk <= 16
 constexpr float DELTA_COS = 1.220703125e-4f;   // 2^-13
 
 // ------------------------------------------------------------------ f64 -> (hi, lo) bf16, f64 -> f32
+// rows are scaled to unit length first (row_scale = 1/norm), so the tensor-core dot product IS the cosine and the
+// epilogue compares raw accumulators against one per-row threshold
 __global__ void split_bf16_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int kp,
-                                  __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo)
+                                  const double *__restrict__ row_scale, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo)
 {
     const int64_t total = n * (int64_t)kp;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / kp;
         const int c = (int)(i % kp);
-        double v = (c < f) ? x[r * pitch + c] : 0.0;
+        double v = (c < f) ? x[r * pitch + c] * row_scale[r] : 0.0;
         const __nv_bfloat16 h = __double2bfloat16(v);
         const double rem = v - (double)__bfloat162float(h);
         hi[i] = h;
@@ -59,13 +62,10 @@ __global__ void split_bf16_kernel(const double *__restrict__ x, int64_t n, int f
     }
 }
 
-__global__ void to_f32_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t n, float *__restrict__ fa,
-                              float *__restrict__ fb)
+__global__ void to_f32_kernel(const double *__restrict__ a, int64_t n, float *__restrict__ fa)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         fa[i] = (float)a[i];
-        fb[i] = (float)b[i];
-    }
 }
 
 // ------------------------------------------------------------------ descriptors
@@ -91,8 +91,8 @@ struct TcParams {
     int nchunks;
     int capb;                     // emission capacity per (query, chunk)
     int topk;
-    float tau, beta, delta;       // delta = band of one approximate score
-    const float *inv_nx, *lam_x, *inv_nq, *lam_q;
+    float tau, beta, delta;       // delta = band of one approximate score; tau > 0
+    const float *lam_x, *lam_q;
     float *emit_sc;
     int32_t *emit_ix;
     int32_t *emit_cnt;
@@ -108,7 +108,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on 1024-byte boundaries
     unsigned char *stages = smem_raw + ((1024u - (asp::smem_u32(smem_raw) & 1023u)) & 1023u);   // TC_STAGES * STAGE_BYTES
-    float *s_const = reinterpret_cast<float *>(stages + TC_STAGES * STAGE_BYTES);   // [2][2][TN]: inx, lam per accumulator
+    float *s_const = reinterpret_cast<float *>(stages + TC_STAGES * STAGE_BYTES);   // [2][TN]: item lambdas per accumulator
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
 
@@ -183,23 +183,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const int row = lg * 32 + lane;
         const int64_t gq = (int64_t)qb * TQ + row;
         const bool qvalid = gq < p.nq;
-        const float rq = qvalid ? p.tau * p.inv_nq[gq] : 0.f;
         const float lq = qvalid ? p.lam_q[gq] : 0.f;
         const int et = threadIdx.x - 64;                                         // 0..127
+        const float beta_ub = p.beta > 0.f ? p.beta : 0.f;                       // score <= tau*cos + max(beta, 0)
+        const float inv_tau = 1.0f / p.tau;
         float lst[TK_LIST];
 #pragma unroll
         for (int i = 0; i < TK_LIST; ++i) lst[i] = -INFINITY;
         float theta_k = -INFINITY, theta_emit = -INFINITY;
+        float theta_dot = qvalid ? -INFINITY : INFINITY;                         // raw-accumulator (cosine) filter
         int cnt = 0;
         const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
 
         for (int64_t t = 0; t < ntiles; ++t) {
             const int acc = (int)(t & 1);
             const int64_t item0 = (tile0 + t) * TN;
-            float *c_inx = s_const + acc * 2 * TN, *c_lam = c_inx + TN;
+            float *c_lam = s_const + acc * TN;
             for (int j = et; j < TN; j += 128) {
                 const int64_t n = item0 + j;
-                c_inx[j] = (n < p.n_local) ? p.inv_nx[n] : 0.f;
                 c_lam[j] = (n < p.n_local) ? p.lam_x[n] : 0.f;
             }
             asm volatile("bar.sync 1, 128;\n" ::: "memory");                     // epilogue warps only
@@ -219,30 +220,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                         }
                     }
                 } else {
+                    // fast path: one compare per accumulator (the accumulator is the cosine: unit operands)
+                    bool any = false;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        const float cs = rq * __uint_as_float(r[j]) * c_inx[col];
-                        if (cs + p.beta >= theta_emit) {
-                            const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), cs);
-                            const int64_t n = item0 + col;
-                            if (sc >= theta_emit && qvalid && n < p.n_local) {
-                                if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = (int32_t)n; }
-                                ++cnt;
-                                if (sc > theta_k) {
-                                    float v = sc;
+                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(r[j]) >= theta_dot);
+                    if (any) {
 #pragma unroll
-                                    for (int i = 0; i < TK_LIST; ++i) {
-                                        const float o = lst[i];
-                                        const bool sw = v > o;
-                                        lst[i] = sw ? v : o;
-                                        v = sw ? o : v;
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = __uint_as_float(r[j]);
+                            if (d >= theta_dot) {
+                                const int col = c * 32 + j;
+                                const int64_t n = item0 + col;
+                                const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), p.tau * d);
+                                if (sc >= theta_emit && n < p.n_local) {
+                                    if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = (int32_t)n; }
+                                    ++cnt;
+                                    if (sc > theta_k) {
+                                        float v = sc;
+#pragma unroll
+                                        for (int i = 0; i < TK_LIST; ++i) {
+                                            const float o = lst[i];
+                                            const bool sw = v > o;
+                                            lst[i] = sw ? v : o;
+                                            v = sw ? o : v;
+                                        }
+                                        float th = lst[0];
+#pragma unroll
+                                        for (int i = 1; i < TK_LIST; ++i) th = (i < p.topk) ? lst[i] : th;
+                                        theta_k = th;
+                                        theta_emit = theta_k - 2.0f * p.delta;
+                                        // s <= tau*cos + max(beta,0): below this cosine nothing can reach theta_emit
+                                        theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
                                     }
-                                    float th = lst[0];
-#pragma unroll
-                                    for (int i = 1; i < TK_LIST; ++i) th = (i < p.topk) ? lst[i] : th;
-                                    theta_k = th;
-                                    theta_emit = theta_k - 2.0f * p.delta;
                                 }
                             }
                         }
@@ -377,7 +386,7 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
 // ------------------------------------------------------------------ host side
 struct asp_tc_cache {               // per-space bf16 copies, built on the first tensor-core search
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
-    float *inv32 = nullptr, *lam32 = nullptr;
+    float *lam32 = nullptr;
     int kp = 0;
     CUtensorMap map_hi, map_lo;
 };
@@ -393,11 +402,10 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     const size_t ne = (size_t)s->n_local * c->kp;
     ASP_CUDA(cudaMallocAsync(&c->hi, ne * 2, st));
     ASP_CUDA(cudaMallocAsync(&c->lo, ne * 2, st));
-    ASP_CUDA(cudaMallocAsync(&c->inv32, sizeof(float) * s->n_local, st));
     ASP_CUDA(cudaMallocAsync(&c->lam32, sizeof(float) * s->n_local, st));
-    split_bf16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, s->n_local, s->f, s->fp, c->kp, c->hi, c->lo);
+    split_bf16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, s->n_local, s->f, s->fp, c->kp, s->inv_norms, c->hi, c->lo);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    to_f32_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(s->inv_norms, s->lambdas, s->n_local, c->inv32, c->lam32);
+    to_f32_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(s->lambdas, s->n_local, c->lam32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CHECK(asp_make_bf16_tmap(&c->map_hi, c->hi, s->n_local, c->kp, TN));
     ASP_CHECK(asp_make_bf16_tmap(&c->map_lo, c->lo, s->n_local, c->kp, TN));
@@ -411,14 +419,15 @@ void asp_free_tc_cache(asp_space *s)
     if (!s->tc_cache) return;
     asp_tc_cache *c = static_cast<asp_tc_cache *>(s->tc_cache);
     cudaStream_t st = s->ctx->stream;
-    cudaFreeAsync(c->hi, st); cudaFreeAsync(c->lo, st); cudaFreeAsync(c->inv32, st); cudaFreeAsync(c->lam32, st);
+    cudaFreeAsync(c->hi, st); cudaFreeAsync(c->lo, st); cudaFreeAsync(c->lam32, st);
     delete c;
     s->tc_cache = nullptr;
 }
 
-bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk)
+bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau)
 {
-    return topk >= 1 && topk <= TK_LIST && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL;
+    return topk >= 1 && topk <= TK_LIST && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL && tau > 1e-3 &&
+           tau <= 1e3;
 }
 
 // dump == nullptr: full search.  dump != nullptr: raw approximate dots [nq][n_local] f32 (tests).
@@ -434,17 +443,16 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
 
     // queries: bf16 split + f32 scalars
     __nv_bfloat16 *q_hi = nullptr, *q_lo = nullptr;
-    float *inv_nq32 = nullptr, *lam_q32 = nullptr;
+    float *lam_q32 = nullptr;
     double *inv_nq = nullptr;
     ASP_CUDA(cudaMallocAsync(&q_hi, (size_t)nq * kp * 2, st));
     ASP_CUDA(cudaMallocAsync(&q_lo, (size_t)nq * kp * 2, st));
-    ASP_CUDA(cudaMallocAsync(&inv_nq32, sizeof(float) * nq, st));
     ASP_CUDA(cudaMallocAsync(&lam_q32, sizeof(float) * nq, st));
     ASP_CUDA(cudaMallocAsync(&inv_nq, sizeof(double) * nq, st));
-    split_bf16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, q_hi, q_lo);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, inv_nq));
-    to_f32_kernel<<<64, 256, 0, st>>>(inv_nq, lambda_q_dev, nq, inv_nq32, lam_q32);
+    split_bf16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, q_hi, q_lo);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    to_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, nq, lam_q32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     CUtensorMap map_q_hi, map_q_lo;
     ASP_CHECK(asp_make_bf16_tmap(&map_q_hi, q_hi, nq, kp, TQ));
@@ -475,7 +483,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
     p.delta = (float)(fabs(tau) * DELTA_COS + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
-    p.inv_nx = c->inv32; p.lam_x = c->lam32; p.inv_nq = inv_nq32; p.lam_q = lam_q32;
+    p.lam_x = c->lam32; p.lam_q = lam_q32;
     p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.emit_theta = nullptr; p.dump = dump_dev;
     int32_t *slow_list = nullptr, *slow_count = nullptr;
     unsigned long long *survivors = nullptr;
@@ -491,7 +499,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaMemsetAsync(survivors, 0, sizeof(unsigned long long), st));
     }
 
-    const size_t smem = (size_t)TC_STAGES * STAGE_BYTES + 2 * 2 * TN * sizeof(float) + 1024;
+    const size_t smem = (size_t)TC_STAGES * STAGE_BYTES + 2 * TN * sizeof(float) + 1024;
     dim3 grid((unsigned)qblocks, nchunks);
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));
     if (dump_dev) {
@@ -531,7 +539,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         cudaFreeAsync(p.emit_theta, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
         cudaFreeAsync(survivors, st);
     }
-    cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(inv_nq32, st); cudaFreeAsync(lam_q32, st);
+    cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(lam_q32, st);
     cudaFreeAsync(inv_nq, st);
     return rc;
 }

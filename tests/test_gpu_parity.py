@@ -418,9 +418,8 @@ def test_tc_dot_error_band(n, f, nq):
     aspace, gl = ArrowSpaceBuilder.build({"eps": 1.0, "k": 4, "topk": 5, "p": 2.0, "sigma": 0.5}, x)
     out = np.zeros((nq, n), dtype=np.float32)
     _lib.check(_lib.load().asp_debug_tc_dots(aspace._h, q.ctypes.data, nq, out.ctypes.data))
-    exact = q @ x.T
-    scale = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :]
-    err = np.abs(out.astype(np.float64) - exact) / scale
+    exact = (q @ x.T) / (np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :])
+    err = np.abs(out.astype(np.float64) - exact)
     assert err.max() < 2.0 ** -13 / 4, err.max()
     assert err.max() > 0                                                 # it IS the low-precision path
 
