@@ -98,7 +98,7 @@ class GraphLaplacian:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h and _lib._lib is not None:
+        if h and _lib is not None and getattr(_lib, "_lib", None) is not None:
             _lib._lib.asp_free_graph(h)
             self._h = None
 
@@ -158,7 +158,7 @@ class ArrowSpace:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h and _lib._lib is not None:
+        if h and _lib is not None and getattr(_lib, "_lib", None) is not None:
             _lib._lib.asp_free_space(h)
             self._h = None
 

@@ -40,7 +40,11 @@ constexpr int TC_STAGES = 4;
 constexpr int A_BYTES = TQ * TKB * 2;          // 16 KB
 constexpr int B_BYTES = TN * TKB * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TK_LIST = 16;        // running top list per query row (topk <= 16)
+constexpr int TK_LIST = 16;        // running top list per (query row, column quarter) (topk <= 16)
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane group: each thread owns one query row x 64 of the 256 tile columns
+constexpr int EPI_SPLIT = EPI_WARPS / 4;
+constexpr int EPI_COLS = TN / EPI_SPLIT;
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr float DELTA_COS = 1.220703125e-4f;   // 2^-13
 
 // ------------------------------------------------------------------ f64 -> (hi, lo) bf16, f64 -> f32
@@ -68,6 +72,28 @@ __global__ void to_f32_kernel(const double *__restrict__ a, int64_t n, float *__
         fa[i] = (float)a[i];
 }
 
+__global__ void minmax_kernel(const double *__restrict__ a, int64_t n, double *__restrict__ out /* [grid][2] */)
+{
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = a[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    __shared__ double s_lo[256], s_hi[256];
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            s_lo[threadIdx.x] = fmin(s_lo[threadIdx.x], s_lo[threadIdx.x + off]);
+            s_hi[threadIdx.x] = fmax(s_hi[threadIdx.x], s_hi[threadIdx.x + off]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = s_lo[0]; out[2 * blockIdx.x + 1] = s_hi[0]; }
+}
+
 // ------------------------------------------------------------------ descriptors
 // K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B (what TMA wrote):
 // 8-row groups are 1024 B apart (SBO), LBO unused (1), descriptor version 1 (sm_100).
@@ -93,6 +119,7 @@ struct TcParams {
     int topk;
     float tau, beta, delta;       // delta = band of one approximate score; tau > 0
     const float *lam_x, *lam_q;
+    float lam_min, lam_max;       // range of the item lambdas of the shard (bounds the proximity term per query)
     float *emit_sc;
     int32_t *emit_ix;
     int32_t *emit_cnt;
@@ -100,8 +127,8 @@ struct TcParams {
     float *dump;                  // DUMP mode: raw dots [nq][n_local]
 };
 
-template <bool DUMP>
-__global__ void __launch_bounds__(192, 1)
+template <bool DUMP, int VARIANT>      // VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, const TcParams p)
 {
@@ -111,6 +138,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     float *s_const = reinterpret_cast<float *>(stages + TC_STAGES * STAGE_BYTES);   // [2][TN]: item lambdas per accumulator
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
+    __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score any of its EPI_SPLIT threads has seen (ordered bits)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, chunk = blockIdx.y;
@@ -122,9 +150,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { asp::mbar_init(&full_bar[s], 1); asp::mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], EPI_WARPS); }
         asp::fence_barrier_init();
     }
+    if (threadIdx.x < TQ) s_theta[threadIdx.x] = 0u;                             // ordered bits of -inf... (0 = below every float)
     if (warp == 1) asp::tmem_alloc(&s_tmem_base, 512);
     asp::tc_fence_before();
     __syncthreads();
@@ -169,9 +198,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     const uint32_t a_addr = asp::smem_u32(stages + (size_t)s * STAGE_BYTES);
                     const uint64_t da = make_kmajor_sw128_desc(a_addr);
                     const uint64_t db = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                    if (VARIANT != 3) {
 #pragma unroll
-                    for (int k = 0; k < TKB / 16; ++k)                            // UMMA K = 16 bf16 = 32 B = +2 in the address field
-                        asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_BF16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < TKB / 16; ++k)                        // UMMA K = 16 bf16 = 32 B = +2 in the address field
+                            asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_BF16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                    }
                     asp::umma_commit(&empty_bar[s]);                             // smem stage reusable when these MMAs retire
                 }
                 asp::umma_commit(&tmem_full[acc]);                               // accumulator complete
@@ -180,12 +211,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     } else {
         // ===================== epilogue: warps 2..5, thread <-> query row =====================
         const int lg = warp & 3;                                                 // TMEM lane group this warp may touch
+        const int part = (warp - 2) >> 2;                                        // which EPI_COLS columns of the tile
         const int row = lg * 32 + lane;
         const int64_t gq = (int64_t)qb * TQ + row;
         const bool qvalid = gq < p.nq;
         const float lq = qvalid ? p.lam_q[gq] : 0.f;
-        const int et = threadIdx.x - 64;                                         // 0..127
-        const float beta_ub = p.beta > 0.f ? p.beta : 0.f;                       // score <= tau*cos + max(beta, 0)
+        const int et = threadIdx.x - 64;                                         // 0 .. EPI_WARPS*32-1
+        // score <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the shard's lambda range)
+        // (beta >= 0 on this path; the 0.999 keeps the bound safe against the f32 roundings of the range)
+        const float lam_gap = fmaxf(0.f, fmaxf(lq - p.lam_max, p.lam_min - lq)) * 0.999f;
+        const float beta_ub = p.beta * __fdividef(1.0f, 1.0f + lam_gap) * 1.000001f;
         const float inv_tau = 1.0f / p.tau;
         float lst[TK_LIST];
 #pragma unroll
@@ -193,49 +228,68 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         float theta_k = -INFINITY, theta_emit = -INFINITY;
         float theta_dot = qvalid ? -INFINITY : INFINITY;                         // raw-accumulator (cosine) filter
         int cnt = 0;
-        const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
+        const size_t ebase = (((size_t)gq * p.nchunks + chunk) * EPI_SPLIT + part) * (size_t)p.capb;
+        // order-preserving float <-> uint32 (so the row threshold can be shared with atomicMax)
+        auto f2o = [](float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
+        auto o2f = [](uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); };
 
         for (int64_t t = 0; t < ntiles; ++t) {
             const int acc = (int)(t & 1);
             const int64_t item0 = (tile0 + t) * TN;
             float *c_lam = s_const + acc * TN;
-            for (int j = et; j < TN; j += 128) {
+            for (int j = et; j < TN; j += EPI_WARPS * 32) {
                 const int64_t n = item0 + j;
                 c_lam[j] = (n < p.n_local) ? p.lam_x[n] : 0.f;
             }
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");                     // epilogue warps only
+            asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");    // epilogue warps only
+            if (!DUMP && qvalid) {                                               // adopt the row's shared threshold
+                const uint32_t so = s_theta[row];
+                if (so != 0u) {
+                    const float sh = o2f(so);
+                    if (sh > theta_k) {
+                        theta_k = sh;
+                        theta_emit = theta_k - 2.0f * p.delta;
+                        theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
+                    }
+                }
+            }
             asp::mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
             asp::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < TN / 32; ++c) {
+            for (int c = 0; c < (VARIANT >= 2 ? 0 : EPI_COLS / 32); ++c) {
+                const int col0 = part * EPI_COLS + c * 32;
                 uint32_t r[32];
-                asp::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * TN + c * 32), r);
+                asp::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * TN + col0), r);
                 asp::tmem_ld_wait();
                 if (DUMP) {
                     if (qvalid) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int64_t n = item0 + c * 32 + j;
+                            const int64_t n = item0 + col0 + j;
                             if (n < p.n_local) p.dump[gq * p.n_local + n] = __uint_as_float(r[j]);
                         }
                     }
                 } else {
-                    // fast path: one compare per accumulator (the accumulator is the cosine: unit operands)
-                    bool any = false;
+                    // common path: the accumulator IS the cosine (unit operands); a max tree and one compare
+                    float m[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) any |= (__uint_as_float(r[j]) >= theta_dot);
-                    if (any) {
+                    for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#pragma unroll
+                    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                        for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+                    if (m[0] >= theta_dot) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float d = __uint_as_float(r[j]);
                             if (d >= theta_dot) {
-                                const int col = c * 32 + j;
+                                const int col = col0 + j;
                                 const int64_t n = item0 + col;
                                 const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), p.tau * d);
                                 if (sc >= theta_emit && n < p.n_local) {
                                     if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = (int32_t)n; }
                                     ++cnt;
-                                    if (sc > theta_k) {
+                                    if (sc > lst[TK_LIST - 1]) {
                                         float v = sc;
 #pragma unroll
                                         for (int i = 0; i < TK_LIST; ++i) {
@@ -247,10 +301,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                                         float th = lst[0];
 #pragma unroll
                                         for (int i = 1; i < TK_LIST; ++i) th = (i < p.topk) ? lst[i] : th;
-                                        theta_k = th;
-                                        theta_emit = theta_k - 2.0f * p.delta;
-                                        // s <= tau*cos + max(beta,0): below this cosine nothing can reach theta_emit
-                                        theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
+                                        if (th > theta_k) {
+                                            theta_k = th;
+                                            atomicMax(&s_theta[row], f2o(th));
+                                            theta_emit = theta_k - 2.0f * p.delta;
+                                            // s <= tau*cos + beta*prox_ub: below this cosine nothing can reach theta_emit
+                                            theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
+                                        }
                                     }
                                 }
                             }
@@ -263,8 +320,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             if (lane == 0) asp::mbar_arrive(&tmem_empty[acc]);
         }
         if (!DUMP && qvalid) {
-            p.emit_cnt[gq * p.nchunks + chunk] = cnt;
-            p.emit_theta[gq * p.nchunks + chunk] = theta_k;
+            p.emit_cnt[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = cnt;
+            p.emit_theta[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = theta_k;
         }
     }
     asp::tc_fence_before();
@@ -387,6 +444,7 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
 struct asp_tc_cache {               // per-space bf16 copies, built on the first tensor-core search
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
     float *lam32 = nullptr;
+    float lam_min = 0.f, lam_max = 0.f;
     int kp = 0;
     CUtensorMap map_hi, map_lo;
 };
@@ -407,6 +465,21 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     to_f32_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(s->lambdas, s->n_local, c->lam32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    {
+        double *d_mm = nullptr;
+        std::vector<double> h_mm(2 * 256);
+        ASP_CUDA(cudaMallocAsync(&d_mm, sizeof(double) * 512, st));
+        minmax_kernel<<<256, 256, 0, st>>>(s->lambdas, s->n_local, d_mm);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        ASP_CUDA(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(double) * 512, cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+        ASP_CUDA(cudaFreeAsync(d_mm, st));
+        double lo = INFINITY, hi = -INFINITY;
+        for (int i = 0; i < 256; ++i) { lo = fmin(lo, h_mm[2 * i]); hi = fmax(hi, h_mm[2 * i + 1]); }
+        c->lam_min = (float)lo; c->lam_max = (float)hi;
+        if ((double)c->lam_min > lo) c->lam_min = nextafterf(c->lam_min, -INFINITY);   // round outwards
+        if ((double)c->lam_max < hi) c->lam_max = nextafterf(c->lam_max, INFINITY);
+    }
     ASP_CHECK(asp_make_bf16_tmap(&c->map_hi, c->hi, s->n_local, c->kp, TN));
     ASP_CHECK(asp_make_bf16_tmap(&c->map_lo, c->lo, s->n_local, c->kp, TN));
     ms->tc_cache = c;
@@ -427,7 +500,7 @@ void asp_free_tc_cache(asp_space *s)
 bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau)
 {
     return topk >= 1 && topk <= TK_LIST && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL && tau > 1e-3 &&
-           tau <= 1e3;
+           tau <= 1.0;            // beta = 1 - tau >= 0: the proximity term is bounded from above by prox_ub
 }
 
 // dump == nullptr: full search.  dump != nullptr: raw approximate dots [nq][n_local] f32 (tests).
@@ -473,25 +546,26 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         if (eff >= 0.97 || cc == tiles_total) break;
     }
     const int nchunks = (int)best_chunks;
-    int capb = dump_dev ? 1 : 1024;
+    int capb = dump_dev ? 1 : 1024 / EPI_SPLIT;                      // per (query, chunk, column part)
     if (const char *e = getenv("ASP_TC_CAPB")) {                     // test knob: shrink the emission buffers
         const int v = atoi(e);
-        if (!dump_dev && v >= 32 && v <= 65536) capb = v;
+        if (!dump_dev && v >= 8 && v <= 65536) capb = v;
     }
+    const int nsub = nchunks * EPI_SPLIT;
 
     TcParams p;
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
     p.delta = (float)(fabs(tau) * DELTA_COS + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
-    p.lam_x = c->lam32; p.lam_q = lam_q32;
+    p.lam_x = c->lam32; p.lam_q = lam_q32; p.lam_min = c->lam_min; p.lam_max = c->lam_max;
     p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.emit_theta = nullptr; p.dump = dump_dev;
     int32_t *slow_list = nullptr, *slow_count = nullptr;
     unsigned long long *survivors = nullptr;
     if (!dump_dev) {
-        ASP_CUDA(cudaMallocAsync(&p.emit_sc, sizeof(float) * (size_t)nq * nchunks * capb, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_ix, sizeof(int32_t) * (size_t)nq * nchunks * capb, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_cnt, sizeof(int32_t) * (size_t)nq * nchunks, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_theta, sizeof(float) * (size_t)nq * nchunks, st));
+        ASP_CUDA(cudaMallocAsync(&p.emit_sc, sizeof(float) * (size_t)nq * nsub * capb, st));
+        ASP_CUDA(cudaMallocAsync(&p.emit_ix, sizeof(int32_t) * (size_t)nq * nsub * capb, st));
+        ASP_CUDA(cudaMallocAsync(&p.emit_cnt, sizeof(int32_t) * (size_t)nq * nsub, st));
+        ASP_CUDA(cudaMallocAsync(&p.emit_theta, sizeof(float) * (size_t)nq * nsub, st));
         ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (nq + 1), st));
         ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
         ASP_CUDA(cudaMallocAsync(&survivors, sizeof(unsigned long long), st));
@@ -503,11 +577,14 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     dim3 grid((unsigned)qblocks, nchunks);
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));
     if (dump_dev) {
-        ASP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_kernel<true><<<grid, 192, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
+        ASP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_gemm_kernel<true, 0><<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
     } else {
-        ASP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_kernel<false><<<grid, 192, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
+        const char *var = getenv("ASP_TC_VARIANT");               // profiling only: results are wrong for 2 / 3
+        const int v = var ? atoi(var) : 0;
+        auto k = (v == 2) ? tc_gemm_kernel<false, 2> : (v == 3) ? tc_gemm_kernel<false, 3> : tc_gemm_kernel<false, 0>;
+        ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
     }
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -518,7 +595,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
             q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-            (int)topk, nchunks, capb, p.delta, p.emit_sc, p.emit_ix, p.emit_cnt, p.emit_theta, out_idx_dev, out_score_dev,
+            (int)topk, nsub, capb, p.delta, p.emit_sc, p.emit_ix, p.emit_cnt, p.emit_theta, out_idx_dev, out_score_dev,
             slow_list, slow_count, survivors);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
         int32_t nslow = 0;
