@@ -134,6 +134,7 @@ int asp_ctx_create(int device, asp_ctx **out)
     }
     ASP_CUDA(cudaEventCreate(&ctx->ev0));
     ASP_CUDA(cudaEventCreate(&ctx->ev1));
+    ASP_CUDA(cudaEventCreate(&ctx->ev2));
     const char *no_tma = getenv("ASP_NO_TMA");
     ctx->use_tma = !(no_tma && no_tma[0] == '1');
     *out = ctx;
@@ -147,6 +148,7 @@ void asp_ctx_destroy(asp_ctx *ctx)
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     delete ctx;
 }
 

@@ -45,7 +45,7 @@ struct asp_ctx {
     int64_t launches = 0;
     bool use_tma = true;                 // ASP_NO_TMA=1 switches the operand loaders to cp.async
     std::map<std::string, double> stats;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
 
 struct asp_space {
@@ -61,7 +61,7 @@ struct asp_space {
     CUtensorMap tmap_gram;               // (4, n_local, fp/4), box (4, 32 rows, 32 quads): Gram kernel
     CUtensorMap tmap_rows;               // same tensor, box (4, 128 rows, 4 quads): search / kNN GEMM
     int world = 1, rank = 0;             // shard = Gram segments [rank*8/world, (rank+1)*8/world)
-    void *tc_cache = nullptr;            // bf16 split copies for the tcgen05 search path (search_tc.cu), lazily built
+    void *tc_cache = nullptr;            // fp16 split copies (lambda order) for the tcgen05 search path (search_tc.cu), lazily built
 };
 
 struct asp_graph {
@@ -141,7 +141,7 @@ int asp_launch_reciprocal(asp_ctx *ctx, const double *x, int64_t n, double *out)
 int asp_search_slow_path(const asp_space *s, const double *q_dev, int32_t qpitch, const double *lambda_q_dev,
                          const double *qnorm_dev, double tau, int64_t topk, const int32_t *slow_list_dev, int nslow,
                          int64_t *out_idx_dev, double *out_score_dev);
-int asp_make_bf16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows);
+int asp_make_f16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows);
 
 // knn.cu
 int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists);

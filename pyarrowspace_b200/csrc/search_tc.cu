@@ -4,28 +4,42 @@
 //
 // Why: the f64 score GEMM is bound by the FP64 tensor pipe (35 TFLOP/s measured); 2*Q*N*F = 1.26e13 FLOP per
 // 16k-query step at C4 cannot go below ~360 ms there.  tcgen05 has no f64 kind, but the ANSWER only needs f64 on a
-// few candidates per query: stage 1 computes every dot product from a two-term bf16 split
-//     x = hi + lo + r,  |r| <= 2^-18 |x|        q.x ~ q_lo.x_hi + q_hi.x_lo + q_hi.x_hi      (3 MMAs, f32 accumulate)
-// with a rigorous band  |cos~ - cos| <= DELTA_COS = 2^-13  (split truncation 3*2^-18 + f32 accumulation of 3F/16 MMA
-// steps, 4x margin; checked against f64 in tests/test_gpu_parity.py::test_tc_dot_error_band), and EMITS every item
-// whose approximate score could still be in the top-k:  s~ >= theta_k - 2 DELTA, theta_k = running k-th best.
-// Stage 2 re-scores the emitted items in the reference order in f64 (exactly the oracle's expression) and selects
-// top-k by (score desc, index asc).  Completeness: an item of the true top-k has s >= t_k >= theta* - DELTA, hence
-// s~ >= theta* - 2 DELTA >= theta_run - 2 DELTA: it was emitted.  Only a full emission buffer sends a query to the
-// exact scan.  The result is bit-identical to the FP64 path's (tests assert it).
+// few candidates per query: stage 1 computes every cosine from a two-term fp16 split of the UNIT vectors
+//     128 x^ = hi + lo + r,  |r| <= 2^-22 |128 x^|     q^.x^ ~ (q_lo.x_hi + q_hi.x_lo + q_hi.x_hi) 2^-14   (3 MMAs, f32 accumulate)
+// with the band  |cos~ - cos| <= DELTA_COS(kp)  (split truncation 3*2^-22 + one f32 rounding per K=16 MMA step, x4
+// margin; checked against f64 in tests/test_gpu_parity.py::test_tc_dot_error_band), and EMITS every item whose
+// approximate score could still be in the top-k:  s~ >= theta_k - 2 DELTA, theta_k = running k-th best.
 //
-// Kernel (one CTA per SM, 192 threads):
-//   warp 0     TMA producer: 4-stage ring of {128 queries x 64 k, 256 items x 64 k} bf16 tiles, SWIZZLE_128B
+// Items are visited in LAMBDA ORDER (a bucket sort of the shard by lambda when the cache is built; `perm` maps back).
+// A 256-item tile then spans a tiny lambda interval [lo, hi], so the proximity term of a (query, tile) pair is known
+// up to ~1e-5 BEFORE looking at the accumulators:  s <= tau*cos + beta/(1 + dist(lambda_q, [lo, hi])).  That turns the
+// per-element epilogue into ONE compare of the raw accumulator against a per-(row, tile) threshold (a max tree over
+// 32 TMEM columns + 1 branch); the exact score expression runs only for the few elements that pass.  The running
+// thresholds are shared between the column quarters of a row (shared memory) and between the CTAs that scan
+// different item chunks for the same query (global atomicMax), so late chunks start with a warm threshold.
+//
+// Stage 2 (tc_rescore_kernel), one warp per query: (A) every survivor of the final cut is re-scored in f64 with a
+// warp-cooperative coalesced dot product (error <= EPS ~ 1e-13), the best 32 kept; (B) the candidates within 2 EPS of
+// the k-th best are re-scored in the reference order (sequential, __dmul_rn/__dadd_rn: exactly the oracle's
+// expression) and sorted by (score desc, index asc).  More than 32 candidates inside that band, or a full emission
+// buffer, send the query to the exact scan.  The result is bit-identical to the FP64 path's (tests assert it).
+//
+// Completeness.  Let t_k be the exact k-th best score.  Any running threshold theta is the k-th best APPROXIMATE score
+// of some k distinct items, whose exact scores are >= theta - DELTA, so t_k >= theta - DELTA.  An item of the true top-k
+// has s >= t_k, hence s~ >= s - DELTA >= theta - 2 DELTA: it passes every emission test and the final cut.  The same
+// argument with EPS in place of DELTA covers (A) -> (B).
+//
+// Kernel (one CTA per SM, 64 + 512 threads):
+//   warp 0     TMA producer: 4-stage ring of {128 queries x 64 k, 256 items x 64 k} fp16 tiles, SWIZZLE_128B
 //   warp 1     allocates TMEM (512 columns = 2 accumulators of 128 x 256 f32), issues tcgen05.mma (one lane),
 //              tcgen05.commit -> frees the smem stage / publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> query row, so the running top-k
-//              (16 registers) and the emission cursor are thread local: no atomics, no shuffles
-// Bound: bf16 tensor pipe, 3 * 2*Q*N*Fp FLOP executed for 2*Q*N*F algorithmic.
+//   warps 2-17 epilogue: tcgen05.ld 32 lanes x 32 columns; thread <-> (query row, 64-column quarter of the tile)
+// Bound: fp16 tensor pipe, 3 * 2*Q*N*Fp FLOP executed for 2*Q*N*F algorithmic.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "warp_sort.cuh"
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -35,7 +49,7 @@ using asp::Cand;
 
 constexpr int TQ = 128;            // queries per CTA (UMMA M)
 constexpr int TN = 256;            // items per tile (UMMA N)
-constexpr int TKB = 64;            // bf16 per smem row = 128 B = one swizzle atom
+constexpr int TKB = 64;            // fp16 per smem row = 128 B = one swizzle atom
 constexpr int TC_STAGES = 4;
 constexpr int A_BYTES = TQ * TKB * 2;          // 16 KB
 constexpr int B_BYTES = TN * TKB * 2;          // 32 KB
@@ -45,33 +59,19 @@ constexpr int EPI_WARPS = 16;      // 4 per TMEM lane group: each thread owns on
 constexpr int EPI_SPLIT = EPI_WARPS / 4;
 constexpr int EPI_COLS = TN / EPI_SPLIT;
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
-constexpr float DELTA_COS = 1.220703125e-4f;   // 2^-13
+constexpr double OPERAND_SCALE = 128.0;                                  // unit vectors are stored as fp16(128 x^): lo stays normal
+constexpr float ACC_SCALE = (float)(OPERAND_SCALE * OPERAND_SCALE);      // accumulator = 2^14 cos
+constexpr int LAM_BUCKETS = 1 << 16;
 
-// ------------------------------------------------------------------ f64 -> (hi, lo) bf16, f64 -> f32
-// rows are scaled to unit length first (row_scale = 1/norm), so the tensor-core dot product IS the cosine and the
-// epilogue compares raw accumulators against one per-row threshold
-__global__ void split_bf16_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int kp,
-                                  const double *__restrict__ row_scale, __nv_bfloat16 *__restrict__ hi,
-                                  __nv_bfloat16 *__restrict__ lo)
-{
-    const int64_t total = n * (int64_t)kp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / kp;
-        const int c = (int)(i % kp);
-        double v = (c < f) ? x[r * pitch + c] * row_scale[r] : 0.0;
-        const __nv_bfloat16 h = __double2bfloat16(v);
-        const double rem = v - (double)__bfloat162float(h);
-        hi[i] = h;
-        lo[i] = __double2bfloat16(rem);
-    }
-}
+// band of one approximate cosine: truncation of the two-term split (3 * 2^-22) + one f32 rounding (<= 2^-23 relative,
+// round-toward-zero model) per K=16 MMA step (3 kp / 16 of them), times 4
+inline double delta_cos_of(int kp) { return 4.0 * (3.0 * ldexp(1.0, -22) + (3.0 * kp / 16.0) * ldexp(1.0, -23)); }
 
-__global__ void to_f32_kernel(const double *__restrict__ a, int64_t n, float *__restrict__ fa)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        fa[i] = (float)a[i];
-}
+// order-preserving float <-> uint32 (thresholds are shared with atomicMax); 0 = "none yet", below every float
+__device__ __forceinline__ uint32_t f2o(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
+// ------------------------------------------------------------------ cache construction: lambda order, fp16 split
 __global__ void minmax_kernel(const double *__restrict__ a, int64_t n, double *__restrict__ out /* [grid][2] */)
 {
     double lo = INFINITY, hi = -INFINITY;
@@ -94,6 +94,95 @@ __global__ void minmax_kernel(const double *__restrict__ a, int64_t n, double *_
     if (threadIdx.x == 0) { out[2 * blockIdx.x] = s_lo[0]; out[2 * blockIdx.x + 1] = s_hi[0]; }
 }
 
+__device__ __forceinline__ int lam_bucket(double v, double lo, double inv_width)
+{
+    const double t = (v - lo) * inv_width;
+    int b = (t > 0.0) ? (int)t : 0;                                      // NaN -> 0
+    return b < LAM_BUCKETS ? b : LAM_BUCKETS - 1;
+}
+
+__global__ void bucket_hist_kernel(const double *__restrict__ lam, int64_t n, double lo, double inv_width, uint32_t *__restrict__ hist)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[lam_bucket(lam[i], lo, inv_width)], 1u);
+}
+
+// exclusive scan of LAM_BUCKETS counters by one CTA of 1024 threads (64 counters per thread)
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t *__restrict__ hist /* in: counts, out: cursors */)
+{
+    constexpr int PER = LAM_BUCKETS / 1024;
+    __shared__ uint32_t s_sum[1024];
+    uint32_t loc[PER];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { loc[j] = hist[threadIdx.x * PER + j]; tot += loc[j]; }
+    s_sum[threadIdx.x] = tot;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t v = ((int)threadIdx.x >= off) ? s_sum[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_sum[threadIdx.x] - tot;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { hist[threadIdx.x * PER + j] = run; run += loc[j]; }
+}
+
+__global__ void bucket_scatter_kernel(const double *__restrict__ lam, int64_t n, double lo, double inv_width,
+                                      uint32_t *__restrict__ cursor, int32_t *__restrict__ perm)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        perm[atomicAdd(&cursor[lam_bucket(lam[i], lo, inv_width)], 1u)] = (int32_t)i;
+}
+
+// rows are scaled to unit length first (row_scale = 1/norm), so the tensor-core dot product IS the cosine (x 2^14)
+// and the epilogue compares raw accumulators against one per-(row, tile) threshold.  perm == nullptr: identity.
+__global__ void split_f16_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int kp,
+                                 const double *__restrict__ row_scale, const int32_t *__restrict__ perm,
+                                 __half *__restrict__ hi, __half *__restrict__ lo)
+{
+    const int64_t total = n * (int64_t)kp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / kp;
+        const int c = (int)(i % kp);
+        const int64_t src = perm ? (int64_t)perm[r] : r;
+        const double v = (c < f) ? x[src * pitch + c] * row_scale[src] * OPERAND_SCALE : 0.0;
+        const __half h = __double2half(v);
+        const double rem = v - (double)__half2float(h);
+        hi[i] = h;
+        lo[i] = __double2half(rem);
+    }
+}
+
+// f32 copies of the lambdas in visiting order + per-tile [min, max] rounded outwards
+__global__ void __launch_bounds__(TN) tile_lambda_kernel(const double *__restrict__ lam, const int32_t *__restrict__ perm,
+                                                         int64_t n, float *__restrict__ lam32, float *__restrict__ tile_lo,
+                                                         float *__restrict__ tile_hi)
+{
+    const int64_t i = (int64_t)blockIdx.x * TN + threadIdx.x;
+    double v = NAN;
+    if (i < n) { v = lam[perm[i]]; lam32[i] = (float)v; }
+    __shared__ double s_lo[TN], s_hi[TN];
+    s_lo[threadIdx.x] = (i < n) ? v : INFINITY;
+    s_hi[threadIdx.x] = (i < n) ? v : -INFINITY;
+    __syncthreads();
+    for (int off = TN / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            s_lo[threadIdx.x] = fmin(s_lo[threadIdx.x], s_lo[threadIdx.x + off]);
+            s_hi[threadIdx.x] = fmax(s_hi[threadIdx.x], s_hi[threadIdx.x + off]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { tile_lo[blockIdx.x] = __double2float_rd(s_lo[0]); tile_hi[blockIdx.x] = __double2float_ru(s_hi[0]); }
+}
+
+__global__ void to_f32_kernel(const double *__restrict__ a, int64_t n, float *__restrict__ fa)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        fa[i] = (float)a[i];
+}
+
 // ------------------------------------------------------------------ descriptors
 // K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B (what TMA wrote):
 // 8-row groups are 1024 B apart (SBO), LBO unused (1), descriptor version 1 (sm_100).
@@ -108,23 +197,39 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
-// kind::f16: D f32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC_BF16_128x256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+// kind::f16: D f32 (bit 4), A f16 (bits 7-9 = 0), B f16 (bits 10-12 = 0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC_F16_128x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+
+// r[j] for a run-time j without local memory: a 5-level select tree (31 SEL)
+__device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j)
+{
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? r[i + 16] : r[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[i + 2] : c[i];
+    return __uint_as_float((j & 1) ? d[1] : d[0]);
+}
 
 struct TcParams {
     int64_t nq, n_local;
     int kp;                       // padded feature count (multiple of 64)
     int nchunks;
-    int capb;                     // emission capacity per (query, chunk)
+    int capb;                     // emission capacity per (query, chunk, column quarter)
     int topk;
-    float tau, beta, delta;       // delta = band of one approximate score; tau > 0
-    const float *lam_x, *lam_q;
-    float lam_min, lam_max;       // range of the item lambdas of the shard (bounds the proximity term per query)
+    float tau, beta, delta;       // delta = band of one approximate score; tau > 0, beta = 1 - tau >= 0
+    const float *lam_x, *lam_q;   // lam_x in visiting (lambda) order
+    const float *tile_lo, *tile_hi;
+    const int32_t *perm;          // visiting position -> local item index
+    uint32_t *theta_glob;         // [nq] ordered bits of the best k-th approximate score any CTA has seen
     float *emit_sc;
     int32_t *emit_ix;
     int32_t *emit_cnt;
-    float *emit_theta;
-    float *dump;                  // DUMP mode: raw dots [nq][n_local]
+    float *dump;                  // DUMP mode: approximate cosines [nq][n_local], local item order
 };
 
 template <bool DUMP, int VARIANT>      // VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued
@@ -138,7 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     float *s_const = reinterpret_cast<float *>(stages + TC_STAGES * STAGE_BYTES);   // [2][TN]: item lambdas per accumulator
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score any of its EPI_SPLIT threads has seen (ordered bits)
+    __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score seen by its threads / other CTAs (ordered bits)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, chunk = blockIdx.y;
@@ -153,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], EPI_WARPS); }
         asp::fence_barrier_init();
     }
-    if (threadIdx.x < TQ) s_theta[threadIdx.x] = 0u;                             // ordered bits of -inf... (0 = below every float)
+    if (threadIdx.x < TQ) s_theta[threadIdx.x] = 0u;
     if (warp == 1) asp::tmem_alloc(&s_tmem_base, 512);
     asp::tc_fence_before();
     __syncthreads();
@@ -200,8 +305,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     const uint64_t db = make_kmajor_sw128_desc(a_addr + A_BYTES);
                     if (VARIANT != 3) {
 #pragma unroll
-                        for (int k = 0; k < TKB / 16; ++k)                        // UMMA K = 16 bf16 = 32 B = +2 in the address field
-                            asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_BF16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < TKB / 16; ++k)                        // UMMA K = 16 halves = 32 B = +2 in the address field
+                            asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
                     }
                     asp::umma_commit(&empty_bar[s]);                             // smem stage reusable when these MMAs retire
                 }
@@ -209,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue: warps 2..5, thread <-> query row =====================
+        // ===================== epilogue: warps 2..17, thread <-> (query row, column quarter) =====================
         const int lg = warp & 3;                                                 // TMEM lane group this warp may touch
         const int part = (warp - 2) >> 2;                                        // which EPI_COLS columns of the tile
         const int row = lg * 32 + lane;
@@ -217,21 +322,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const bool qvalid = gq < p.nq;
         const float lq = qvalid ? p.lam_q[gq] : 0.f;
         const int et = threadIdx.x - 64;                                         // 0 .. EPI_WARPS*32-1
-        // score <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the shard's lambda range)
-        // (beta >= 0 on this path; the 0.999 keeps the bound safe against the f32 roundings of the range)
-        const float lam_gap = fmaxf(0.f, fmaxf(lq - p.lam_max, p.lam_min - lq)) * 0.999f;
-        const float beta_ub = p.beta * __fdividef(1.0f, 1.0f + lam_gap) * 1.000001f;
         const float inv_tau = 1.0f / p.tau;
         float lst[TK_LIST];
 #pragma unroll
         for (int i = 0; i < TK_LIST; ++i) lst[i] = -INFINITY;
         float theta_k = -INFINITY, theta_emit = -INFINITY;
-        float theta_dot = qvalid ? -INFINITY : INFINITY;                         // raw-accumulator (cosine) filter
         int cnt = 0;
         const size_t ebase = (((size_t)gq * p.nchunks + chunk) * EPI_SPLIT + part) * (size_t)p.capb;
-        // order-preserving float <-> uint32 (so the row threshold can be shared with atomicMax)
-        auto f2o = [](float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); };
-        auto o2f = [](uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); };
 
         for (int64_t t = 0; t < ntiles; ++t) {
             const int acc = (int)(t & 1);
@@ -241,17 +338,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 const int64_t n = item0 + j;
                 c_lam[j] = (n < p.n_local) ? p.lam_x[n] : 0.f;
             }
+            float tl = 0.f, th = 0.f;
+            if (!DUMP) {
+                tl = p.tile_lo[tile0 + t];
+                th = p.tile_hi[tile0 + t];
+                if (part == 0 && qvalid) {                                       // thresholds found by the CTAs of other chunks
+                    const uint32_t go = p.theta_glob[gq];
+                    if (go > s_theta[row]) atomicMax(&s_theta[row], go);
+                }
+            }
             asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");    // epilogue warps only
-            if (!DUMP && qvalid) {                                               // adopt the row's shared threshold
+            float theta_acc = qvalid ? -INFINITY : INFINITY;                     // raw-accumulator filter of this (row, tile)
+            float beta_ub = p.beta;
+            if (!DUMP && qvalid) {
                 const uint32_t so = s_theta[row];
                 if (so != 0u) {
                     const float sh = o2f(so);
-                    if (sh > theta_k) {
-                        theta_k = sh;
-                        theta_emit = theta_k - 2.0f * p.delta;
-                        theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
-                    }
+                    if (sh > theta_k) { theta_k = sh; theta_emit = theta_k - 2.0f * p.delta; }
                 }
+                // s <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the tile's lambda interval);
+                // the 2.5e-7 / 1.000001 keep the bound safe against the f32 roundings of lambda_q and the interval
+                const float gap = fmaxf(0.f, fmaxf(lq - th, tl - lq) - 2.5e-7f);
+                beta_ub = p.beta * __fdividef(1.0f, 1.0f + gap) * 1.000001f;
+                theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
             }
             asp::mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
             asp::tc_fence_after();
@@ -266,11 +375,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int64_t n = item0 + col0 + j;
-                            if (n < p.n_local) p.dump[gq * p.n_local + n] = __uint_as_float(r[j]);
+                            if (n < p.n_local) p.dump[gq * p.n_local + p.perm[n]] = __uint_as_float(r[j]) * (1.0f / ACC_SCALE);
                         }
                     }
                 } else {
-                    // common path: the accumulator IS the cosine (unit operands); a max tree and one compare
+                    // common path: a max tree and one compare
                     float m[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
@@ -278,36 +387,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     for (int w = 8; w > 0; w >>= 1)
 #pragma unroll
                         for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
-                    if (m[0] >= theta_dot) {
+                    if (m[0] >= theta_acc) {
+                        // rare path: the columns that pass, one at a time (registers cannot be indexed: select tree)
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float d = __uint_as_float(r[j]);
-                            if (d >= theta_dot) {
-                                const int col = col0 + j;
-                                const int64_t n = item0 + col;
-                                const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), p.tau * d);
-                                if (sc >= theta_emit && n < p.n_local) {
-                                    if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = (int32_t)n; }
-                                    ++cnt;
-                                    if (sc > lst[TK_LIST - 1]) {
-                                        float v = sc;
+                        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= theta_acc) ? (1u << j) : 0u;
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float a = pick32(r, j);
+                            if (a < theta_acc) continue;                         // the threshold rose inside this loop
+                            const int col = col0 + j;
+                            const int64_t n = item0 + col;
+                            const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), p.tau * (a * (1.0f / ACC_SCALE)));
+                            if (sc >= theta_emit && n < p.n_local) {
+                                if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = p.perm[n]; }
+                                ++cnt;
+                                if (sc > lst[TK_LIST - 1]) {
+                                    float v = sc;
 #pragma unroll
-                                        for (int i = 0; i < TK_LIST; ++i) {
-                                            const float o = lst[i];
-                                            const bool sw = v > o;
-                                            lst[i] = sw ? v : o;
-                                            v = sw ? o : v;
-                                        }
-                                        float th = lst[0];
+                                    for (int i = 0; i < TK_LIST; ++i) {
+                                        const float o = lst[i];
+                                        const bool sw = v > o;
+                                        lst[i] = sw ? v : o;
+                                        v = sw ? o : v;
+                                    }
+                                    float kth = lst[0];
 #pragma unroll
-                                        for (int i = 1; i < TK_LIST; ++i) th = (i < p.topk) ? lst[i] : th;
-                                        if (th > theta_k) {
-                                            theta_k = th;
-                                            atomicMax(&s_theta[row], f2o(th));
-                                            theta_emit = theta_k - 2.0f * p.delta;
-                                            // s <= tau*cos + beta*prox_ub: below this cosine nothing can reach theta_emit
-                                            theta_dot = (theta_emit - beta_ub) * inv_tau - 1e-6f;
-                                        }
+                                    for (int i = 1; i < TK_LIST; ++i) kth = (i < p.topk) ? lst[i] : kth;
+                                    if (kth > theta_k) {
+                                        theta_k = kth;
+                                        theta_emit = theta_k - 2.0f * p.delta;
+                                        theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
+                                        const uint32_t ko = f2o(kth);
+                                        atomicMax(&s_theta[row], ko);
+                                        atomicMax(&p.theta_glob[gq], ko);
                                     }
                                 }
                             }
@@ -319,10 +433,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             __syncwarp();
             if (lane == 0) asp::mbar_arrive(&tmem_empty[acc]);
         }
-        if (!DUMP && qvalid) {
-            p.emit_cnt[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = cnt;
-            p.emit_theta[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = theta_k;
-        }
+        if (!DUMP && qvalid) p.emit_cnt[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = cnt;
     }
     asp::tc_fence_before();
     __syncthreads();
@@ -354,40 +465,43 @@ __device__ __forceinline__ double seq_dot_row_tc(const double *__restrict__ qv, 
     return d;
 }
 
-constexpr int TR_WARPS = 4;
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
 
-// One warp per query: filter the emitted candidates with the final threshold, re-score the survivors in f64 in the
-// reference order (one lane per candidate), keep the best 32 by (score desc, index asc), emit top-k.
+constexpr int TR_WARPS = 4;
+constexpr int TR_QUEUE = 96;       // survivor queue per warp (flushed in batches of 32)
+
+// One warp per query.  See the header: (A) coalesced f64 re-scoring of every survivor, best 32 kept;
+// (B) reference-order re-scoring of the candidates within 2*eps_fast of the k-th best; sort; emit.
 __global__ void __launch_bounds__(TR_WARPS * 32)
 tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const double *__restrict__ items, int64_t n_local,
                   int f, int pitch, int64_t row0, const double *__restrict__ norm_x, const double *__restrict__ lam_x,
-                  const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nchunks,
-                  int capb, float delta, const float *__restrict__ emit_sc, const int32_t *__restrict__ emit_ix,
-                  const int32_t *__restrict__ emit_cnt, const float *__restrict__ emit_theta,
-                  int64_t *__restrict__ out_idx, double *__restrict__ out_score, int32_t *slow_list, int32_t *slow_count,
-                  unsigned long long *survivor_total)
+                  const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nstreams,
+                  int capb, float delta, double eps_fast, const float *__restrict__ emit_sc,
+                  const int32_t *__restrict__ emit_ix, const int32_t *__restrict__ emit_cnt,
+                  const uint32_t *__restrict__ theta_glob, int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                  int32_t *slow_list, int32_t *slow_count, unsigned long long *survivor_total, unsigned long long *exact_total)
 {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *qs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * f;
-    int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)TR_WARPS * f) + warp * 64;
+    double *qs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * pitch;    // zero padded to the item pitch
+    int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)TR_WARPS * pitch) + warp * TR_QUEUE;
     const int64_t qi = (int64_t)blockIdx.x * TR_WARPS + warp;
     if (qi >= nq) return;
-    for (int j = lane; j < f; j += 32) qs[j] = q[qi * qpitch + j];
+    for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[qi * qpitch + j] : 0.0;
 
-    float theta = -INFINITY;
     bool overflow = false;
-    for (int c = lane; c < nchunks; c += 32) {
-        theta = fmaxf(theta, emit_theta[qi * nchunks + c]);
-        overflow |= emit_cnt[qi * nchunks + c] > capb;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) theta = fmaxf(theta, __shfl_xor_sync(0xffffffffu, theta, off));
+    for (int c = lane; c < nstreams; c += 32) overflow |= emit_cnt[qi * nstreams + c] > capb;
     if (__any_sync(0xffffffffu, overflow)) {
         if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)qi;
         return;
     }
-    const float cutoff = theta - 2.0f * delta;
+    const uint32_t to = theta_glob[qi];
+    const float cutoff = (to != 0u) ? o2f(to) - 2.0f * delta : -INFINITY;
     const double nqv = norm_q[qi], lqv = lam_q[qi];
     __syncwarp();
 
@@ -396,21 +510,33 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     best[1] = asp::cand_empty();
     int qn = 0;                                                                  // queued survivors (warp uniform)
     unsigned long long nsurv = 0;
+    // (A): `count` queued survivors, two rows at a time, every lane a slice of the features (coalesced 16 B loads)
     auto flush = [&](int count) {
-        // lanes < count re-score one survivor each; merged into the running best 32
-        Cand c = asp::cand_empty();
-        if (lane < count) {
-            const int64_t it = queue[lane];
-            const double d = seq_dot_row_tc(qs, items + it * pitch, f);
-            c.s = exact_score_tc(d, nqv, norm_x[it], tau, lqv, lam_x[it]);
-            c.i = (int32_t)it;
+        Cand mine = asp::cand_empty();
+        for (int s0 = 0; s0 < count; s0 += 2) {
+            const int i0 = queue[s0];
+            const int i1 = (s0 + 1 < count) ? queue[s0 + 1] : i0;
+            const double *r0 = items + (int64_t)i0 * pitch, *r1 = items + (int64_t)i1 * pitch;
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll 4
+            for (int j = 2 * lane; j < pitch; j += 64) {
+                const double2 a = *reinterpret_cast<const double2 *>(r0 + j);
+                const double2 b = *reinterpret_cast<const double2 *>(r1 + j);
+                const double2 qq = *reinterpret_cast<const double2 *>(qs + j);
+                d0 = fma(qq.x, a.x, d0); d0 = fma(qq.y, a.y, d0);
+                d1 = fma(qq.x, b.x, d1); d1 = fma(qq.y, b.y, d1);
+            }
+            d0 = warp_sum(d0);
+            d1 = warp_sum(d1);
+            if (lane == s0) { mine.s = exact_score_tc(d0, nqv, norm_x[i0], tau, lqv, lam_x[i0]); mine.i = i0; }
+            if (lane == s0 + 1 && s0 + 1 < count) { mine.s = exact_score_tc(d1, nqv, norm_x[i1], tau, lqv, lam_x[i1]); mine.i = i1; }
         }
-        best[1] = c;
+        best[1] = mine;
         asp::warp_sort_best_first<2>(best, lane);
     };
-    for (int c = 0; c < nchunks; ++c) {
-        const int cnt = emit_cnt[qi * nchunks + c];
-        const size_t base = ((size_t)qi * nchunks + c) * (size_t)capb;
+    for (int c = 0; c < nstreams; ++c) {
+        const int cnt = emit_cnt[qi * nstreams + c];
+        const size_t base = ((size_t)qi * nstreams + c) * (size_t)capb;
         for (int e0 = 0; e0 < cnt; e0 += 32) {
             const int e = e0 + lane;
             const bool keep = (e < cnt) && (emit_sc[base + e] >= cutoff);
@@ -429,22 +555,42 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
         }
     }
     if (qn > 0) { flush(qn); nsurv += qn; }
-    if (lane == 0) atomicAdd(survivor_total, nsurv);
+
+    // (B): candidates whose fast score is within 2 eps of the k-th best fast score
     const int kk = topk < n_local ? topk : (int)n_local;
+    const double kth = __shfl_sync(0xffffffffu, best[0].s, kk - 1);              // -inf when fewer than kk survivors
+    const bool valid = best[0].i != 0x7fffffff;
+    const bool in_band = valid && (best[0].s >= kth - 2.0 * eps_fast);
+    const unsigned band = __ballot_sync(0xffffffffu, in_band);
+    if (band == 0xffffffffu || __popc(band) < kk) {
+        // the band may extend beyond the 32 kept (long runs of ties), or the emission was short: exact scan
+        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)qi;
+        return;
+    }
+    Cand fin[1];
+    fin[0] = asp::cand_empty();
+    if (in_band) {
+        const int64_t it = best[0].i;
+        const double d = seq_dot_row_tc(qs, items + it * pitch, f);
+        fin[0].s = exact_score_tc(d, nqv, norm_x[it], tau, lqv, lam_x[it]);
+        fin[0].i = (int32_t)it;
+    }
+    asp::warp_sort_best_first<1>(fin, lane);
+    if (lane == 0) { atomicAdd(survivor_total, nsurv); atomicAdd(exact_total, (unsigned long long)__popc(band)); }
     if (lane < topk) {
-        const bool ok = (lane < kk) && best[0].i != 0x7fffffff;
-        out_idx[qi * topk + lane] = ok ? row0 + best[0].i : -1;
-        out_score[qi * topk + lane] = ok ? best[0].s : NAN;
+        const bool ok = (lane < kk) && fin[0].i != 0x7fffffff;
+        out_idx[qi * topk + lane] = ok ? row0 + fin[0].i : -1;
+        out_score[qi * topk + lane] = ok ? fin[0].s : NAN;
     }
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------ host side
-struct asp_tc_cache {               // per-space bf16 copies, built on the first tensor-core search
-    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
-    float *lam32 = nullptr;
-    float lam_min = 0.f, lam_max = 0.f;
+struct asp_tc_cache {               // per-space fp16 copies in lambda order, built on the first tensor-core search
+    __half *hi = nullptr, *lo = nullptr;
+    float *lam32 = nullptr, *tile_lo = nullptr, *tile_hi = nullptr;
+    int32_t *perm = nullptr;
     int kp = 0;
     CUtensorMap map_hi, map_lo;
 };
@@ -457,31 +603,48 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     cudaStream_t st = ctx->stream;
     asp_tc_cache *c = new asp_tc_cache();
     c->kp = (s->f + TKB - 1) / TKB * TKB;
-    const size_t ne = (size_t)s->n_local * c->kp;
+    const int64_t n = s->n_local;
+    const size_t ne = (size_t)n * c->kp;
+    const int64_t ntile = asp_ceil_div(n, TN);
     ASP_CUDA(cudaMallocAsync(&c->hi, ne * 2, st));
     ASP_CUDA(cudaMallocAsync(&c->lo, ne * 2, st));
-    ASP_CUDA(cudaMallocAsync(&c->lam32, sizeof(float) * s->n_local, st));
-    split_bf16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, s->n_local, s->f, s->fp, c->kp, s->inv_norms, c->hi, c->lo);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    to_f32_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(s->lambdas, s->n_local, c->lam32);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaMallocAsync(&c->lam32, sizeof(float) * n, st));
+    ASP_CUDA(cudaMallocAsync(&c->perm, sizeof(int32_t) * n, st));
+    ASP_CUDA(cudaMallocAsync(&c->tile_lo, sizeof(float) * ntile, st));
+    ASP_CUDA(cudaMallocAsync(&c->tile_hi, sizeof(float) * ntile, st));
+    // visiting order: bucket sort of the shard by lambda (order inside a bucket is immaterial: the tile intervals are
+    // computed from the lambdas actually placed in the tile)
+    double lam_lo = INFINITY, lam_hi = -INFINITY;
     {
         double *d_mm = nullptr;
         std::vector<double> h_mm(2 * 256);
         ASP_CUDA(cudaMallocAsync(&d_mm, sizeof(double) * 512, st));
-        minmax_kernel<<<256, 256, 0, st>>>(s->lambdas, s->n_local, d_mm);
+        minmax_kernel<<<256, 256, 0, st>>>(s->lambdas, n, d_mm);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
         ASP_CUDA(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(double) * 512, cudaMemcpyDeviceToHost, st));
         ASP_CUDA(cudaStreamSynchronize(st));
         ASP_CUDA(cudaFreeAsync(d_mm, st));
-        double lo = INFINITY, hi = -INFINITY;
-        for (int i = 0; i < 256; ++i) { lo = fmin(lo, h_mm[2 * i]); hi = fmax(hi, h_mm[2 * i + 1]); }
-        c->lam_min = (float)lo; c->lam_max = (float)hi;
-        if ((double)c->lam_min > lo) c->lam_min = nextafterf(c->lam_min, -INFINITY);   // round outwards
-        if ((double)c->lam_max < hi) c->lam_max = nextafterf(c->lam_max, INFINITY);
+        for (int i = 0; i < 256; ++i) { lam_lo = fmin(lam_lo, h_mm[2 * i]); lam_hi = fmax(lam_hi, h_mm[2 * i + 1]); }
     }
-    ASP_CHECK(asp_make_bf16_tmap(&c->map_hi, c->hi, s->n_local, c->kp, TN));
-    ASP_CHECK(asp_make_bf16_tmap(&c->map_lo, c->lo, s->n_local, c->kp, TN));
+    {
+        const double width = (lam_hi > lam_lo) ? (lam_hi - lam_lo) / LAM_BUCKETS : 1.0;
+        uint32_t *cursor = nullptr;
+        ASP_CUDA(cudaMallocAsync(&cursor, sizeof(uint32_t) * LAM_BUCKETS, st));
+        ASP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * LAM_BUCKETS, st));
+        bucket_hist_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(s->lambdas, n, lam_lo, 1.0 / width, cursor);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        bucket_scan_kernel<<<1, 1024, 0, st>>>(cursor);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        bucket_scatter_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(s->lambdas, n, lam_lo, 1.0 / width, cursor, c->perm);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        ASP_CUDA(cudaFreeAsync(cursor, st));
+    }
+    split_f16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, n, s->f, s->fp, c->kp, s->inv_norms, c->perm, c->hi, c->lo);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    tile_lambda_kernel<<<(unsigned)ntile, TN, 0, st>>>(s->lambdas, c->perm, n, c->lam32, c->tile_lo, c->tile_hi);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CHECK(asp_make_f16_tmap(&c->map_hi, c->hi, n, c->kp, TN));
+    ASP_CHECK(asp_make_f16_tmap(&c->map_lo, c->lo, n, c->kp, TN));
     ms->tc_cache = c;
     *out = c;
     return ASP_OK;
@@ -492,7 +655,8 @@ void asp_free_tc_cache(asp_space *s)
     if (!s->tc_cache) return;
     asp_tc_cache *c = static_cast<asp_tc_cache *>(s->tc_cache);
     cudaStream_t st = s->ctx->stream;
-    cudaFreeAsync(c->hi, st); cudaFreeAsync(c->lo, st); cudaFreeAsync(c->lam32, st);
+    cudaFreeAsync(c->hi, st); cudaFreeAsync(c->lo, st); cudaFreeAsync(c->lam32, st); cudaFreeAsync(c->perm, st);
+    cudaFreeAsync(c->tile_lo, st); cudaFreeAsync(c->tile_hi, st);
     delete c;
     s->tc_cache = nullptr;
 }
@@ -500,10 +664,10 @@ void asp_free_tc_cache(asp_space *s)
 bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau)
 {
     return topk >= 1 && topk <= TK_LIST && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL && tau > 1e-3 &&
-           tau <= 1.0;            // beta = 1 - tau >= 0: the proximity term is bounded from above by prox_ub
+           tau <= 1.0 && s->fp <= 6144;   // beta = 1 - tau >= 0: the proximity term is bounded from above by prox_ub
 }
 
-// dump == nullptr: full search.  dump != nullptr: raw approximate dots [nq][n_local] f32 (tests).
+// dump == nullptr: full search.  dump != nullptr: approximate cosines [nq][n_local] f32 (tests).
 int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
                        const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev, double *out_score_dev,
                        float *dump_dev)
@@ -514,8 +678,8 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     ASP_CHECK(ensure_tc_cache(s, &c));
     const int kp = c->kp;
 
-    // queries: bf16 split + f32 scalars
-    __nv_bfloat16 *q_hi = nullptr, *q_lo = nullptr;
+    // queries: fp16 split + f32 scalars
+    __half *q_hi = nullptr, *q_lo = nullptr;
     float *lam_q32 = nullptr;
     double *inv_nq = nullptr;
     ASP_CUDA(cudaMallocAsync(&q_hi, (size_t)nq * kp * 2, st));
@@ -523,13 +687,13 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     ASP_CUDA(cudaMallocAsync(&lam_q32, sizeof(float) * nq, st));
     ASP_CUDA(cudaMallocAsync(&inv_nq, sizeof(double) * nq, st));
     ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, inv_nq));
-    split_bf16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, q_hi, q_lo);
+    split_f16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, nullptr, q_hi, q_lo);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     to_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, nq, lam_q32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     CUtensorMap map_q_hi, map_q_lo;
-    ASP_CHECK(asp_make_bf16_tmap(&map_q_hi, q_hi, nq, kp, TQ));
-    ASP_CHECK(asp_make_bf16_tmap(&map_q_lo, q_lo, nq, kp, TQ));
+    ASP_CHECK(asp_make_f16_tmap(&map_q_hi, q_hi, nq, kp, TQ));
+    ASP_CHECK(asp_make_f16_tmap(&map_q_lo, q_lo, nq, kp, TQ));
 
     // grid: query blocks x item chunks, whole waves of SMs
     const int64_t tiles_total = asp_ceil_div(s->n_local, TN);
@@ -546,7 +710,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         if (eff >= 0.97 || cc == tiles_total) break;
     }
     const int nchunks = (int)best_chunks;
-    int capb = dump_dev ? 1 : 1024 / EPI_SPLIT;                      // per (query, chunk, column part)
+    int capb = dump_dev ? 1 : 1024 / EPI_SPLIT;                      // per (query, chunk, column quarter)
     if (const char *e = getenv("ASP_TC_CAPB")) {                     // test knob: shrink the emission buffers
         const int v = atoi(e);
         if (!dump_dev && v >= 8 && v <= 65536) capb = v;
@@ -556,21 +720,22 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     TcParams p;
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
-    p.delta = (float)(fabs(tau) * DELTA_COS + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
-    p.lam_x = c->lam32; p.lam_q = lam_q32; p.lam_min = c->lam_min; p.lam_max = c->lam_max;
-    p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.emit_theta = nullptr; p.dump = dump_dev;
+    p.delta = (float)(fabs(tau) * delta_cos_of(kp) + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
+    p.lam_x = c->lam32; p.lam_q = lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm;
+    p.theta_glob = nullptr; p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.dump = dump_dev;
     int32_t *slow_list = nullptr, *slow_count = nullptr;
-    unsigned long long *survivors = nullptr;
+    unsigned long long *counters = nullptr;
     if (!dump_dev) {
         ASP_CUDA(cudaMallocAsync(&p.emit_sc, sizeof(float) * (size_t)nq * nsub * capb, st));
         ASP_CUDA(cudaMallocAsync(&p.emit_ix, sizeof(int32_t) * (size_t)nq * nsub * capb, st));
         ASP_CUDA(cudaMallocAsync(&p.emit_cnt, sizeof(int32_t) * (size_t)nq * nsub, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_theta, sizeof(float) * (size_t)nq * nsub, st));
+        ASP_CUDA(cudaMallocAsync(&p.theta_glob, sizeof(uint32_t) * (size_t)nq, st));
         ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (nq + 1), st));
         ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
-        ASP_CUDA(cudaMallocAsync(&survivors, sizeof(unsigned long long), st));
+        ASP_CUDA(cudaMallocAsync(&counters, 2 * sizeof(unsigned long long), st));
+        ASP_CUDA(cudaMemsetAsync(p.theta_glob, 0, sizeof(uint32_t) * (size_t)nq, st));
         ASP_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(int32_t), st));
-        ASP_CUDA(cudaMemsetAsync(survivors, 0, sizeof(unsigned long long), st));
+        ASP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st));
     }
 
     const size_t smem = (size_t)TC_STAGES * STAGE_BYTES + 2 * TN * sizeof(float) + 1024;
@@ -591,30 +756,37 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
 
     int rc = ASP_OK;
     if (!dump_dev) {
-        const size_t rsmem = (size_t)TR_WARPS * s->f * 8 + TR_WARPS * 64 * 4;
+        const double u = 1.1102230246251565e-16;
+        const double eps_fast = (4.0 * s->f + 64.0) * u * (fabs(tau) + fabs(1.0 - tau) + 1.0);
+        const size_t rsmem = (size_t)TR_WARPS * s->fp * 8 + TR_WARPS * TR_QUEUE * 4;
         ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
             q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-            (int)topk, nsub, capb, p.delta, p.emit_sc, p.emit_ix, p.emit_cnt, p.emit_theta, out_idx_dev, out_score_dev,
-            slow_list, slow_count, survivors);
+            (int)topk, nsub, capb, p.delta, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, out_idx_dev,
+            out_score_dev, slow_list, slow_count, counters, counters + 1);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        ASP_CUDA(cudaEventRecord(ctx->ev2, st));
         int32_t nslow = 0;
-        unsigned long long nsurv = 0;
+        unsigned long long cnts[2] = {0, 0};
         ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        ASP_CUDA(cudaMemcpyAsync(&nsurv, survivors, sizeof(nsurv), cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaMemcpyAsync(cnts, counters, sizeof(cnts), cudaMemcpyDeviceToHost, st));
         ASP_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f;
+        float ms = 0.f, ms2 = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        cudaEventElapsedTime(&ms2, ctx->ev1, ctx->ev2);
         ctx->stats["search_stage1_ms"] = ms;
+        ctx->stats["search_stage2_ms"] = ms2;
         ctx->stats["search_slow_queries"] = nslow;
-        ctx->stats["search_rescored_per_query"] = (double)nsurv / (double)nq;
+        ctx->stats["search_rescored_per_query"] = (double)cnts[0] / (double)nq;
+        ctx->stats["search_exact_per_query"] = (double)cnts[1] / (double)nq;
         ctx->stats["search_stage1_is_tc"] = 1.0;
+        ctx->stats["search_delta"] = p.delta;
         if (nslow > 0)
             rc = asp_search_slow_path(s, q_dev, qpitch, lambda_q_dev, qnorm_dev, tau, topk, slow_list, nslow, out_idx_dev,
                                       out_score_dev);
         cudaFreeAsync(p.emit_sc, st); cudaFreeAsync(p.emit_ix, st); cudaFreeAsync(p.emit_cnt, st);
-        cudaFreeAsync(p.emit_theta, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
-        cudaFreeAsync(survivors, st);
+        cudaFreeAsync(p.theta_glob, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
+        cudaFreeAsync(counters, st);
     }
     cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(lam_q32, st);
     cudaFreeAsync(inv_nq, st);

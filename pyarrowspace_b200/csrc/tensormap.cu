@@ -44,21 +44,21 @@ int asp_make_items_tmap(CUtensorMap *out, const double *base, int64_t rows, int3
     return ASP_OK;
 }
 
-// bf16 operand of the tcgen05 path: rows x kp (kp a multiple of 64), K-major.  Box = 64 elements (128 B = one
+// fp16 operand of the tcgen05 path: rows x kp (kp a multiple of 64), K-major.  Box = 64 elements (128 B = one
 // swizzle atom) x box_rows, SWIZZLE_128B: exactly the canonical K-major layout the UMMA shared-memory descriptor
 // (layout type SWIZZLE_128B, SBO = 1024 B) expects.
-int asp_make_bf16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows)
+int asp_make_f16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    if (kp % 64 != 0) ASP_FAIL(ASP_ERR_ARG, "bf16 operand pitch must be a multiple of 64");
+    if (kp % 64 != 0) ASP_FAIL(ASP_ERR_ARG, "fp16 operand pitch must be a multiple of 64");
     cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+    if (r != CUDA_SUCCESS) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
     return ASP_OK;
 }

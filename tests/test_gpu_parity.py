@@ -408,8 +408,8 @@ def _force_stage1(mode):
 
 @pytest.mark.parametrize("n,f,nq", [(700, 64, 130), (3000, 384, 300), (5000, 100, 257), (1100, 768, 128)])
 def test_tc_dot_error_band(n, f, nq):
-    """The bf16-split tcgen05 dot products stay inside the band the completeness proof assumes:
-    |cos~ - cos| <= 2^-13, with the margin (x4) DESIGN.md claims."""
+    """The fp16-split tcgen05 dot products stay inside the band the completeness proof assumes:
+    |cos~ - cos| <= DELTA_COS(kp) = 4 (3 2^-22 + (3 kp / 16) 2^-23), with the margin (x4) DESIGN.md claims."""
     from arrowspace import ArrowSpaceBuilder
     from pyarrowspace_b200 import _lib, synth
     x = synth.make_items(n, f, 71, n_clusters=8) - 22.0                 # mixed signs, cancellation in the dot products
@@ -420,7 +420,10 @@ def test_tc_dot_error_band(n, f, nq):
     _lib.check(_lib.load().asp_debug_tc_dots(aspace._h, q.ctypes.data, nq, out.ctypes.data))
     exact = (q @ x.T) / (np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :])
     err = np.abs(out.astype(np.float64) - exact)
-    assert err.max() < 2.0 ** -13 / 4, err.max()
+    kp = (f + 63) // 64 * 64
+    delta_cos = 4.0 * (3.0 * 2.0 ** -22 + (3.0 * kp / 16.0) * 2.0 ** -23)
+    print("tc dot error: max %.3e, band %.3e, ratio %.1f" % (err.max(), delta_cos, delta_cos / err.max()))
+    assert err.max() < delta_cos / 4, err.max()
     assert err.max() > 0                                                 # it IS the low-precision path
 
 
@@ -452,7 +455,8 @@ def test_tc_search_equals_fp64_path_and_oracle(oracle_mod, n, f, nq, topk):
 
 
 def test_tc_search_with_ties_and_overflow(oracle_mod):
-    """Exact duplicates (ties by index) and more equal-score items than the emission buffer holds (-> exact scan)."""
+    """Exact duplicates (ties by index): short runs are resolved by the reference-order pass of stage 2, runs longer
+    than its 32-candidate band and full emission buffers send the query to the exact scan."""
     from arrowspace import ArrowSpaceBuilder
     from pyarrowspace_b200 import api, synth
     base = synth.make_items(300, 64, 5, n_clusters=4)
@@ -463,8 +467,8 @@ def test_tc_search_with_ties_and_overflow(oracle_mod):
     oidx, osc, _ = s.search_batch(q, g, 0.7)
     try:
         _force_stage1("tc")
-        idx, sc = aspace.search_batch(q, gl, 0.7)                        # 1501 exact ties, all emitted and re-scored
-        assert api.stat("search_slow_queries") == 0
+        idx, sc = aspace.search_batch(q, gl, 0.7)                        # query 255: 1501 exact ties -> exact scan
+        assert 1 <= api.stat("search_slow_queries") < 200                # the duplicated pairs (2 ties) are not slow
         _assert_hits_equal(idx, sc, oidx, osc)
         os.environ["ASP_TC_CAPB"] = "32"                                 # tiny emission buffers: they overflow
         idx, sc = aspace.search_batch(q, gl, 0.7)
