@@ -94,6 +94,18 @@ __global__ void minmax_kernel(const double *__restrict__ a, int64_t n, double *_
     if (threadIdx.x == 0) { out[2 * blockIdx.x] = s_lo[0]; out[2 * blockIdx.x + 1] = s_hi[0]; }
 }
 
+// [lo, 1/bucket width] of the keys from the per-block partials of minmax_kernel
+__global__ void range_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ range)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int i = 0; i < nblocks; ++i) { lo = fmin(lo, partials[2 * i]); hi = fmax(hi, partials[2 * i + 1]); }
+        const double width = (hi > lo) ? (hi - lo) / LAM_BUCKETS : 1.0;
+        range[0] = lo;
+        range[1] = 1.0 / width;
+    }
+}
+
 __device__ __forceinline__ int lam_bucket(double v, double lo, double inv_width)
 {
     const double t = (v - lo) * inv_width;
@@ -101,8 +113,9 @@ __device__ __forceinline__ int lam_bucket(double v, double lo, double inv_width)
     return b < LAM_BUCKETS ? b : LAM_BUCKETS - 1;
 }
 
-__global__ void bucket_hist_kernel(const double *__restrict__ lam, int64_t n, double lo, double inv_width, uint32_t *__restrict__ hist)
+__global__ void bucket_hist_kernel(const double *__restrict__ lam, int64_t n, const double *__restrict__ range, uint32_t *__restrict__ hist)
 {
+    const double lo = range[0], inv_width = range[1];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&hist[lam_bucket(lam[i], lo, inv_width)], 1u);
 }
@@ -112,10 +125,8 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t *__restrict_
 {
     constexpr int PER = LAM_BUCKETS / 1024;
     __shared__ uint32_t s_sum[1024];
-    uint32_t loc[PER];
     uint32_t tot = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) { loc[j] = hist[threadIdx.x * PER + j]; tot += loc[j]; }
+    for (int j = 0; j < PER; ++j) tot += hist[threadIdx.x * PER + j];
     s_sum[threadIdx.x] = tot;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
@@ -125,15 +136,38 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t *__restrict_
         __syncthreads();
     }
     uint32_t run = s_sum[threadIdx.x] - tot;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) { hist[threadIdx.x * PER + j] = run; run += loc[j]; }
+    for (int j = 0; j < PER; ++j) { const uint32_t c = hist[threadIdx.x * PER + j]; hist[threadIdx.x * PER + j] = run; run += c; }
 }
 
-__global__ void bucket_scatter_kernel(const double *__restrict__ lam, int64_t n, double lo, double inv_width,
+__global__ void bucket_scatter_kernel(const double *__restrict__ lam, int64_t n, const double *__restrict__ range,
                                       uint32_t *__restrict__ cursor, int32_t *__restrict__ perm)
 {
+    const double lo = range[0], inv_width = range[1];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         perm[atomicAdd(&cursor[lam_bucket(lam[i], lo, inv_width)], 1u)] = (int32_t)i;
+}
+
+// visiting order: for every query block, the tile whose lambda interval is nearest to the block's median lambda_q
+// (tiles are in ascending lambda order: last tile whose lower end is <= the median)
+__global__ void block_center_kernel(const float *__restrict__ lam_q_sorted, int64_t nq, const float *__restrict__ tile_lo,
+                                    int ntiles, int32_t *__restrict__ center)
+{
+    const int qb = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int64_t)qb * TQ >= nq) return;
+    const int64_t r0 = (int64_t)qb * TQ, r1 = (r0 + TQ < nq) ? r0 + TQ : nq;
+    const float med = lam_q_sorted[(r0 + r1) / 2];
+    int lo = 0, hi = ntiles;                                                // first tile with tile_lo > med
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_lo[mid] > med) hi = mid; else lo = mid + 1;
+    }
+    center[qb] = lo > 0 ? lo - 1 : 0;
+}
+
+__global__ void gather_f32_kernel(const double *__restrict__ a, const int32_t *__restrict__ perm, int64_t n, float *__restrict__ fa)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        fa[i] = (float)a[perm ? perm[i] : i];
 }
 
 // rows are scaled to unit length first (row_scale = 1/norm), so the tensor-core dot product IS the cosine (x 2^14)
@@ -177,12 +211,6 @@ __global__ void __launch_bounds__(TN) tile_lambda_kernel(const double *__restric
     if (threadIdx.x == 0) { tile_lo[blockIdx.x] = __double2float_rd(s_lo[0]); tile_hi[blockIdx.x] = __double2float_ru(s_hi[0]); }
 }
 
-__global__ void to_f32_kernel(const double *__restrict__ a, int64_t n, float *__restrict__ fa)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        fa[i] = (float)a[i];
-}
-
 // ------------------------------------------------------------------ descriptors
 // K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B (what TMA wrote):
 // 8-row groups are 1024 B apart (SBO), LBO unused (1), descriptor version 1 (sm_100).
@@ -219,12 +247,13 @@ struct TcParams {
     int64_t nq, n_local;
     int kp;                       // padded feature count (multiple of 64)
     int nchunks;
-    int capb;                     // emission capacity per (query, chunk, column quarter)
+    int capb;                     // emission capacity per (query, chunk)
     int topk;
     float tau, beta, delta;       // delta = band of one approximate score; tau > 0, beta = 1 - tau >= 0
     const float *lam_x, *lam_q;   // lam_x in visiting (lambda) order
     const float *tile_lo, *tile_hi;
     const int32_t *perm;          // visiting position -> local item index
+    const int32_t *center;        // [query blocks] tile nearest to the block's lambda_q (nullptr: 0)
     uint32_t *theta_glob;         // [nq] ordered bits of the best k-th approximate score any CTA has seen
     float *emit_sc;
     int32_t *emit_ix;
@@ -244,12 +273,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score seen by its threads / other CTAs (ordered bits)
+    __shared__ int s_cnt[TQ];                 // per query row: emission cursor shared by its column-quarter threads
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, chunk = blockIdx.y;
-    const int64_t tiles_total = (p.n_local + TN - 1) / TN;
-    const int64_t tile0 = (tiles_total * chunk) / p.nchunks;
-    const int64_t ntiles = (tiles_total * (chunk + 1)) / p.nchunks - tile0;
+    // visiting order of the query block: centre-out from the tile nearest to its lambda_q (descending proximity
+    // bound, so the thresholds tighten early); the chunk CTAs of a block take interleaved ranks of that order
+    const int tiles_total = (int)((p.n_local + TN - 1) / TN);
+    const int center = p.center ? p.center[qb] : 0;
+    const int side_min = min(center, tiles_total - 1 - center);
+    const bool more_below = center > tiles_total - 1 - center;
+    const int ntiles = (tiles_total - chunk + p.nchunks - 1) / p.nchunks;        // ranks chunk, chunk + nchunks, ...
+    auto tile_of = [&](int t) {
+        const int rank = chunk + t * p.nchunks;
+        if (rank <= 2 * side_min) { const int j = (rank + 1) >> 1; return (rank & 1) ? center + j : center - j; }
+        const int rest = rank - 2 * side_min;
+        return more_below ? center - (side_min + rest) : center + (side_min + rest);
+    };
     const int ksteps = p.kp / TKB;
     const int kiters = 3 * ksteps;                                               // 3 split terms
 
@@ -258,7 +298,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], EPI_WARPS); }
         asp::fence_barrier_init();
     }
-    if (threadIdx.x < TQ) s_theta[threadIdx.x] = 0u;
+    if (threadIdx.x < TQ) { s_theta[threadIdx.x] = 0u; s_cnt[threadIdx.x] = 0; }
     if (warp == 1) asp::tmem_alloc(&s_tmem_base, 512);
     asp::tc_fence_before();
     __syncthreads();
@@ -271,8 +311,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             asp::tma_prefetch_desc(&map_q_hi); asp::tma_prefetch_desc(&map_q_lo);
             asp::tma_prefetch_desc(&map_x_hi); asp::tma_prefetch_desc(&map_x_lo);
             int64_t it = 0;
-            for (int64_t t = 0; t < ntiles; ++t) {
-                const int item0 = (int)((tile0 + t) * TN);
+            for (int t = 0; t < ntiles; ++t) {
+                const int item0 = tile_of(t) * TN;
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const int s = (int)(it % TC_STAGES);
                     asp::mbar_wait(&empty_bar[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
@@ -291,7 +331,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int64_t it = 0;
-            for (int64_t t = 0; t < ntiles; ++t) {
+            for (int t = 0; t < ntiles; ++t) {
                 const int acc = (int)(t & 1);
                 asp::mbar_wait(&tmem_empty[acc], (uint32_t)((((t >> 1) & 1)) ^ 1));
                 asp::tc_fence_after();
@@ -327,12 +367,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
 #pragma unroll
         for (int i = 0; i < TK_LIST; ++i) lst[i] = -INFINITY;
         float theta_k = -INFINITY, theta_emit = -INFINITY;
-        int cnt = 0;
-        const size_t ebase = (((size_t)gq * p.nchunks + chunk) * EPI_SPLIT + part) * (size_t)p.capb;
+        const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
 
-        for (int64_t t = 0; t < ntiles; ++t) {
+        for (int t = 0; t < ntiles; ++t) {
             const int acc = (int)(t & 1);
-            const int64_t item0 = (tile0 + t) * TN;
+            const int tile = tile_of(t);
+            const int64_t item0 = (int64_t)tile * TN;
             float *c_lam = s_const + acc * TN;
             for (int j = et; j < TN; j += EPI_WARPS * 32) {
                 const int64_t n = item0 + j;
@@ -340,8 +380,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             }
             float tl = 0.f, th = 0.f;
             if (!DUMP) {
-                tl = p.tile_lo[tile0 + t];
-                th = p.tile_hi[tile0 + t];
+                tl = p.tile_lo[tile];
+                th = p.tile_hi[tile];
                 if (part == 0 && qvalid) {                                       // thresholds found by the CTAs of other chunks
                     const uint32_t go = p.theta_glob[gq];
                     if (go > s_theta[row]) atomicMax(&s_theta[row], go);
@@ -401,8 +441,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                             const int64_t n = item0 + col;
                             const float sc = fmaf(p.beta, __fdividef(1.0f, 1.0f + fabsf(lq - c_lam[col])), p.tau * (a * (1.0f / ACC_SCALE)));
                             if (sc >= theta_emit && n < p.n_local) {
-                                if (cnt < p.capb) { p.emit_sc[ebase + cnt] = sc; p.emit_ix[ebase + cnt] = p.perm[n]; }
-                                ++cnt;
+                                const int pos = atomicAdd(&s_cnt[row], 1);
+                                if (pos < p.capb) { p.emit_sc[ebase + pos] = sc; p.emit_ix[ebase + pos] = p.perm[n]; }
                                 if (sc > lst[TK_LIST - 1]) {
                                     float v = sc;
 #pragma unroll
@@ -433,7 +473,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             __syncwarp();
             if (lane == 0) asp::mbar_arrive(&tmem_empty[acc]);
         }
-        if (!DUMP && qvalid) p.emit_cnt[(gq * p.nchunks + chunk) * EPI_SPLIT + part] = cnt;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
+        if (!DUMP && qvalid && part == 0) p.emit_cnt[gq * p.nchunks + chunk] = s_cnt[row];
     }
     asp::tc_fence_before();
     __syncthreads();
@@ -483,26 +524,52 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
                   const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nstreams,
                   int capb, float delta, double eps_fast, const float *__restrict__ emit_sc,
                   const int32_t *__restrict__ emit_ix, const int32_t *__restrict__ emit_cnt,
-                  const uint32_t *__restrict__ theta_glob, int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                  const uint32_t *__restrict__ theta_glob, const int32_t *__restrict__ qperm,
+                  int64_t *__restrict__ out_idx, double *__restrict__ out_score,
                   int32_t *slow_list, int32_t *slow_count, unsigned long long *survivor_total, unsigned long long *exact_total)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *qs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * pitch;    // zero padded to the item pitch
     int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)TR_WARPS * pitch) + warp * TR_QUEUE;
-    const int64_t qi = (int64_t)blockIdx.x * TR_WARPS + warp;
+    const int64_t qi = (int64_t)blockIdx.x * TR_WARPS + warp;                    // position in lambda_q order
     if (qi >= nq) return;
-    for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[qi * qpitch + j] : 0.0;
+    const int64_t oq = qperm[qi];                                                // the caller's query index
+    for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[oq * qpitch + j] : 0.0;
 
     bool overflow = false;
     for (int c = lane; c < nstreams; c += 32) overflow |= emit_cnt[qi * nstreams + c] > capb;
     if (__any_sync(0xffffffffu, overflow)) {
-        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)qi;
+        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)oq;
         return;
     }
-    const uint32_t to = theta_glob[qi];
-    const float cutoff = (to != 0u) ? o2f(to) - 2.0f * delta : -INFINITY;
-    const double nqv = norm_q[qi], lqv = lam_q[qi];
+    // final cut: the k-th largest approximate score over ALL emitted candidates of the query (distinct items, so it is
+    // a valid threshold, and the tightest one: the in-kernel thresholds only see one thread's share of the items)
+    const int kk = topk < n_local ? topk : (int)n_local;
+    float cutoff;
+    {
+        Cand top[2];
+        top[0] = asp::cand_empty();
+        top[1] = asp::cand_empty();
+        float floor32 = -INFINITY;                                               // 32nd best so far
+        for (int c = 0; c < nstreams; ++c) {
+            const int cnt = emit_cnt[qi * nstreams + c];
+            const size_t base = ((size_t)qi * nstreams + c) * (size_t)capb;
+            for (int e0 = 0; e0 < cnt; e0 += 32) {
+                const int e = e0 + lane;
+                const float v = (e < cnt) ? emit_sc[base + e] : -INFINITY;
+                if (!__any_sync(0xffffffffu, v > floor32)) continue;
+                top[1].s = (double)v;
+                top[1].i = (e < cnt) ? c * capb + e : 0x7fffffff;
+                asp::warp_sort_best_first<2>(top, lane);
+                floor32 = (float)__shfl_sync(0xffffffffu, top[0].s, 31);
+            }
+        }
+        const float kth = (float)__shfl_sync(0xffffffffu, top[0].s, kk - 1);     // -inf when fewer than kk were emitted
+        cutoff = kth - 2.0f * delta;
+    }
+    (void)theta_glob;
+    const double nqv = norm_q[oq], lqv = lam_q[oq];
     __syncwarp();
 
     Cand best[2];
@@ -557,14 +624,13 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     if (qn > 0) { flush(qn); nsurv += qn; }
 
     // (B): candidates whose fast score is within 2 eps of the k-th best fast score
-    const int kk = topk < n_local ? topk : (int)n_local;
     const double kth = __shfl_sync(0xffffffffu, best[0].s, kk - 1);              // -inf when fewer than kk survivors
     const bool valid = best[0].i != 0x7fffffff;
     const bool in_band = valid && (best[0].s >= kth - 2.0 * eps_fast);
     const unsigned band = __ballot_sync(0xffffffffu, in_band);
     if (band == 0xffffffffu || __popc(band) < kk) {
         // the band may extend beyond the 32 kept (long runs of ties), or the emission was short: exact scan
-        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)qi;
+        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)oq;
         return;
     }
     Cand fin[1];
@@ -579,8 +645,8 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     if (lane == 0) { atomicAdd(survivor_total, nsurv); atomicAdd(exact_total, (unsigned long long)__popc(band)); }
     if (lane < topk) {
         const bool ok = (lane < kk) && fin[0].i != 0x7fffffff;
-        out_idx[qi * topk + lane] = ok ? row0 + fin[0].i : -1;
-        out_score[qi * topk + lane] = ok ? fin[0].s : NAN;
+        out_idx[oq * topk + lane] = ok ? row0 + fin[0].i : -1;
+        out_score[oq * topk + lane] = ok ? fin[0].s : NAN;
     }
 }
 
@@ -594,6 +660,32 @@ struct asp_tc_cache {               // per-space fp16 copies in lambda order, bu
     int kp = 0;
     CUtensorMap map_hi, map_lo;
 };
+
+// ascending bucket order of n f64 keys (65536 buckets over [min, max]); the order inside a bucket is whatever the
+// atomics produce -- callers only rely on the bucket order.  No host synchronisation.
+static int bucket_order(asp_ctx *ctx, const double *keys_dev, int64_t n, int32_t *perm_dev)
+{
+    cudaStream_t st = ctx->stream;
+    double *scratch = nullptr;                                              // [256][2] partials + [2] range
+    uint32_t *cursor = nullptr;
+    ASP_CUDA(cudaMallocAsync(&scratch, sizeof(double) * 514, st));
+    ASP_CUDA(cudaMallocAsync(&cursor, sizeof(uint32_t) * LAM_BUCKETS, st));
+    ASP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * LAM_BUCKETS, st));
+    const int grid = (int)(asp_ceil_div(n, 256) < ctx->num_sms * 4 ? asp_ceil_div(n, 256) : ctx->num_sms * 4);
+    minmax_kernel<<<256, 256, 0, st>>>(keys_dev, n, scratch);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    range_finalize_kernel<<<1, 32, 0, st>>>(scratch, 256, scratch + 512);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    bucket_hist_kernel<<<grid, 256, 0, st>>>(keys_dev, n, scratch + 512, cursor);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(cursor);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    bucket_scatter_kernel<<<grid, 256, 0, st>>>(keys_dev, n, scratch + 512, cursor, perm_dev);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaFreeAsync(scratch, st));
+    ASP_CUDA(cudaFreeAsync(cursor, st));
+    return ASP_OK;
+}
 
 static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
 {
@@ -612,33 +704,8 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     ASP_CUDA(cudaMallocAsync(&c->perm, sizeof(int32_t) * n, st));
     ASP_CUDA(cudaMallocAsync(&c->tile_lo, sizeof(float) * ntile, st));
     ASP_CUDA(cudaMallocAsync(&c->tile_hi, sizeof(float) * ntile, st));
-    // visiting order: bucket sort of the shard by lambda (order inside a bucket is immaterial: the tile intervals are
-    // computed from the lambdas actually placed in the tile)
-    double lam_lo = INFINITY, lam_hi = -INFINITY;
-    {
-        double *d_mm = nullptr;
-        std::vector<double> h_mm(2 * 256);
-        ASP_CUDA(cudaMallocAsync(&d_mm, sizeof(double) * 512, st));
-        minmax_kernel<<<256, 256, 0, st>>>(s->lambdas, n, d_mm);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        ASP_CUDA(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(double) * 512, cudaMemcpyDeviceToHost, st));
-        ASP_CUDA(cudaStreamSynchronize(st));
-        ASP_CUDA(cudaFreeAsync(d_mm, st));
-        for (int i = 0; i < 256; ++i) { lam_lo = fmin(lam_lo, h_mm[2 * i]); lam_hi = fmax(lam_hi, h_mm[2 * i + 1]); }
-    }
-    {
-        const double width = (lam_hi > lam_lo) ? (lam_hi - lam_lo) / LAM_BUCKETS : 1.0;
-        uint32_t *cursor = nullptr;
-        ASP_CUDA(cudaMallocAsync(&cursor, sizeof(uint32_t) * LAM_BUCKETS, st));
-        ASP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * LAM_BUCKETS, st));
-        bucket_hist_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(s->lambdas, n, lam_lo, 1.0 / width, cursor);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        bucket_scan_kernel<<<1, 1024, 0, st>>>(cursor);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        bucket_scatter_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(s->lambdas, n, lam_lo, 1.0 / width, cursor, c->perm);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        ASP_CUDA(cudaFreeAsync(cursor, st));
-    }
+    // visiting order: bucket sort of the shard by lambda
+    ASP_CHECK(bucket_order(ctx, s->lambdas, n, c->perm));
     split_f16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, n, s->f, s->fp, c->kp, s->inv_norms, c->perm, c->hi, c->lo);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     tile_lambda_kernel<<<(unsigned)ntile, TN, 0, st>>>(s->lambdas, c->perm, n, c->lam32, c->tile_lo, c->tile_hi);
@@ -678,26 +745,37 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     ASP_CHECK(ensure_tc_cache(s, &c));
     const int kp = c->kp;
 
-    // queries: fp16 split + f32 scalars
+    // queries: visited in lambda_q order (coherent blocks -> one visiting order per block), fp16 split + f32 scalars
     __half *q_hi = nullptr, *q_lo = nullptr;
     float *lam_q32 = nullptr;
     double *inv_nq = nullptr;
+    int32_t *qperm = nullptr, *center = nullptr;
+    const int64_t qblocks = asp_ceil_div(nq, TQ);
     ASP_CUDA(cudaMallocAsync(&q_hi, (size_t)nq * kp * 2, st));
     ASP_CUDA(cudaMallocAsync(&q_lo, (size_t)nq * kp * 2, st));
     ASP_CUDA(cudaMallocAsync(&lam_q32, sizeof(float) * nq, st));
     ASP_CUDA(cudaMallocAsync(&inv_nq, sizeof(double) * nq, st));
     ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, inv_nq));
-    split_f16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, nullptr, q_hi, q_lo);
+    if (!dump_dev) {
+        ASP_CUDA(cudaMallocAsync(&qperm, sizeof(int32_t) * nq, st));
+        ASP_CUDA(cudaMallocAsync(&center, sizeof(int32_t) * qblocks, st));
+        ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, qperm));
+    }
+    split_f16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, qperm, q_hi, q_lo);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    to_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, nq, lam_q32);
+    gather_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, qperm, nq, lam_q32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    if (!dump_dev) {
+        block_center_kernel<<<(unsigned)asp_ceil_div(qblocks, 128), 128, 0, st>>>(lam_q32, nq, c->tile_lo,
+                                                                               (int)asp_ceil_div(s->n_local, TN), center);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    }
     CUtensorMap map_q_hi, map_q_lo;
     ASP_CHECK(asp_make_f16_tmap(&map_q_hi, q_hi, nq, kp, TQ));
     ASP_CHECK(asp_make_f16_tmap(&map_q_lo, q_lo, nq, kp, TQ));
 
     // grid: query blocks x item chunks, whole waves of SMs
     const int64_t tiles_total = asp_ceil_div(s->n_local, TN);
-    const int64_t qblocks = asp_ceil_div(nq, TQ);
     int64_t best_chunks = 1;
     double best_eff = 0.0;
     for (int w = 1; w <= 16; ++w) {
@@ -710,18 +788,18 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         if (eff >= 0.97 || cc == tiles_total) break;
     }
     const int nchunks = (int)best_chunks;
-    int capb = dump_dev ? 1 : 1024 / EPI_SPLIT;                      // per (query, chunk, column quarter)
+    int capb = dump_dev ? 1 : 1024;                                  // per (query, chunk)
     if (const char *e = getenv("ASP_TC_CAPB")) {                     // test knob: shrink the emission buffers
         const int v = atoi(e);
         if (!dump_dev && v >= 8 && v <= 65536) capb = v;
     }
-    const int nsub = nchunks * EPI_SPLIT;
+    const int nsub = nchunks;
 
     TcParams p;
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
     p.delta = (float)(fabs(tau) * delta_cos_of(kp) + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
-    p.lam_x = c->lam32; p.lam_q = lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm;
+    p.lam_x = c->lam32; p.lam_q = lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm; p.center = center;
     p.theta_glob = nullptr; p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.dump = dump_dev;
     int32_t *slow_list = nullptr, *slow_count = nullptr;
     unsigned long long *counters = nullptr;
@@ -762,7 +840,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
             q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-            (int)topk, nsub, capb, p.delta, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, out_idx_dev,
+            (int)topk, nsub, capb, p.delta, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, qperm, out_idx_dev,
             out_score_dev, slow_list, slow_count, counters, counters + 1);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
         ASP_CUDA(cudaEventRecord(ctx->ev2, st));
@@ -790,5 +868,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     }
     cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(lam_q32, st);
     cudaFreeAsync(inv_nq, st);
+    if (qperm) cudaFreeAsync(qperm, st);
+    if (center) cudaFreeAsync(center, st);
     return rc;
 }
