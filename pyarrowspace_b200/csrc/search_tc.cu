@@ -63,10 +63,6 @@ constexpr double OPERAND_SCALE = 128.0;                                  // unit
 constexpr float ACC_SCALE = (float)(OPERAND_SCALE * OPERAND_SCALE);      // accumulator = 2^14 cos
 constexpr int LAM_BUCKETS = 1 << 16;
 
-// band of one approximate cosine: truncation of the two-term split (3 * 2^-22) + one f32 rounding (<= 2^-23 relative,
-// round-toward-zero model) per K=16 MMA step (3 kp / 16 of them), times 4
-inline double delta_cos_of(int kp) { return 4.0 * (3.0 * ldexp(1.0, -22) + (3.0 * kp / 16.0) * ldexp(1.0, -23)); }
-
 // order-preserving float <-> uint32 (thresholds are shared with atomicMax); 0 = "none yet", below every float
 __device__ __forceinline__ uint32_t f2o(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
@@ -170,23 +166,92 @@ __global__ void gather_f32_kernel(const double *__restrict__ a, const int32_t *_
         fa[i] = (float)a[perm ? perm[i] : i];
 }
 
-// rows are scaled to unit length first (row_scale = 1/norm), so the tensor-core dot product IS the cosine (x 2^14)
-// and the epilogue compares raw accumulators against one per-(row, tile) threshold.  perm == nullptr: identity.
-__global__ void split_f16_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int kp,
-                                 const double *__restrict__ row_scale, const int32_t *__restrict__ perm,
-                                 __half *__restrict__ hi, __half *__restrict__ lo)
+// ---- mean direction of the unit vectors (any unit vector keeps the identity below exact; the mean makes the residuals small)
+constexpr int MD_BLOCKS = 296;
+__global__ void colsum_unit_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const double *__restrict__ row_scale,
+                                   double *__restrict__ partials /* [MD_BLOCKS][f] */)
 {
-    const int64_t total = n * (int64_t)kp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / kp;
-        const int c = (int)(i % kp);
-        const int64_t src = perm ? (int64_t)perm[r] : r;
-        const double v = (c < f) ? x[src * pitch + c] * row_scale[src] * OPERAND_SCALE : 0.0;
-        const __half h = __double2half(v);
-        const double rem = v - (double)__half2float(h);
-        hi[i] = h;
-        lo[i] = __double2half(rem);
+    for (int c = threadIdx.x; c < f; c += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t r = blockIdx.x; r < n; r += gridDim.x) acc += x[r * pitch + c] * row_scale[r];
+        partials[(size_t)blockIdx.x * f + c] = acc;
     }
+}
+
+__global__ void mean_dir_kernel(const double *__restrict__ partials, int nblocks, int f, double *__restrict__ mdir)
+{
+    __shared__ double s_red[256];
+    double n2 = 0.0;
+    for (int c = threadIdx.x; c < f; c += blockDim.x) {
+        double acc = 0.0;
+        for (int b = 0; b < nblocks; ++b) acc += partials[(size_t)b * f + c];
+        mdir[c] = acc;
+        n2 += acc * acc;
+    }
+    s_red[threadIdx.x] = n2;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) s_red[threadIdx.x] += s_red[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double nrm = sqrt(s_red[0]);
+    const double inv = (nrm > 1e-200) ? 1.0 / nrm : 0.0;                 // centred data: m = 0, the residual is the vector itself
+    for (int c = threadIdx.x; c < f; c += blockDim.x) mdir[c] *= inv;
+}
+
+// One warp per row.  With x^ = x / |x| and the unit vector m:
+//     x^ = alpha m + v,  alpha = m.x^,  v orthogonal to m      =>      q^.x^ = beta_q alpha_x + u_q.v_x      (exactly)
+// The operand row holds fp16(128 v) in columns [0, f) (its remainder in `lo`, if wanted) and three rank-1 columns at
+// [f, f+3): items {a_hi, a_hi, a_lo}, queries {b_hi, b_lo, b_hi} (128 alpha = a_hi + a_lo + O(2^-22)), so that ONE K-major
+// contraction over [0, f+3) yields 2^14 (u.v + alpha beta): the rank-1 term to ~2^-21, the residual term to 2^-10 |u||v|
+// from a single fp16 term (or 3 2^-22 |u||v| from the two-term split).  rho = |v| feeds the error band.
+__global__ void __launch_bounds__(256)
+project_split_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int kp, const double *__restrict__ row_scale,
+                     const int32_t *__restrict__ perm, const double *__restrict__ mdir, int is_query,
+                     __half *__restrict__ hi, __half *__restrict__ lo, double *__restrict__ rho)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t src = perm ? (int64_t)perm[r] : r;
+        const double sc = row_scale[src];
+        const double *row = x + src * pitch;
+        double al = 0.0;
+        for (int c = lane; c < f; c += 32) al = fma(mdir[c], row[c] * sc, al);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) al += __shfl_xor_sync(0xffffffffu, al, off);
+        double r2 = 0.0;
+        __half *ph = hi + (size_t)r * kp, *pl = lo ? lo + (size_t)r * kp : nullptr;
+        for (int c = lane; c < kp; c += 32) {
+            double v = 0.0;
+            if (c < f) { v = row[c] * sc - al * mdir[c]; r2 = fma(v, v, r2); }
+            const double vs = v * OPERAND_SCALE;
+            __half h = __double2half(vs);
+            __half l = __double2half(vs - (double)__half2float(h));
+            if (c >= f && c < f + 3) {
+                const double as = al * OPERAND_SCALE;
+                const __half a_hi = __double2half(as);
+                const __half a_lo = __double2half(as - (double)__half2float(a_hi));
+                const int k = c - f;
+                h = is_query ? (k == 1 ? a_lo : a_hi) : (k == 2 ? a_lo : a_hi);
+                l = __double2half(0.0);
+            }
+            ph[c] = h;
+            if (pl) pl[c] = l;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+        if (lane == 0) rho[r] = sqrt(r2) * (1.0 + 1e-12);
+    }
+}
+
+// per-row band of the approximate SCORE (f32, visiting order) from the row's residual norm
+__global__ void row_delta_kernel(const double *__restrict__ rho_q, int64_t nq, double c_main, double c_fixed, double tau_abs,
+                                 double score_slack, float *__restrict__ delta)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
+        delta[i] = __double2float_ru(tau_abs * (rho_q[i] * c_main + c_fixed) + score_slack);
 }
 
 // f32 copies of the lambdas in visiting order + per-tile [min, max] rounded outwards
@@ -249,7 +314,11 @@ struct TcParams {
     int nchunks;
     int capb;                     // emission capacity per (query, chunk)
     int topk;
-    float tau, beta, delta;       // delta = band of one approximate score; tau > 0, beta = 1 - tau >= 0
+    float tau, beta;              // tau > 0, beta = 1 - tau >= 0
+    const float *delta_q;         // [nq] band of one approximate score of the row (visiting order)
+    int nterms;                   // 1: single fp16 term of the residuals; 3: two-term split (lo.hi, hi.lo, hi.hi)
+    int kb_lo, kb_hi;             // 64-wide k blocks of the lo terms (residual columns only) / of hi.hi (all columns)
+    int sub_lo_last, sub_hi_last; // K=16 MMA steps in the last block of each
     const float *lam_x, *lam_q;   // lam_x in visiting (lambda) order
     const float *tile_lo, *tile_hi;
     const int32_t *perm;          // visiting position -> local item index
@@ -290,8 +359,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const int rest = rank - 2 * side_min;
         return more_below ? center - (side_min + rest) : center + (side_min + rest);
     };
-    const int ksteps = p.kp / TKB;
-    const int kiters = 3 * ksteps;                                               // 3 split terms
+    const int klo = (p.nterms == 3) ? p.kb_lo : 0;
+    const int kiters = 2 * klo + p.kb_hi;                                        // small terms first, the rank-1 columns last
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { asp::mbar_init(&full_bar[s], 1); asp::mbar_init(&empty_bar[s], 1); }
@@ -316,7 +385,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
                     const int s = (int)(it % TC_STAGES);
                     asp::mbar_wait(&empty_bar[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
-                    const int seg = ki / ksteps, kc = (ki % ksteps) * TKB;
+                    const int seg = (ki < klo) ? 0 : (ki < 2 * klo) ? 1 : 2;
+                    const int kc = (ki - seg * klo) * TKB;
                     // small terms first: (q_lo, x_hi), (q_hi, x_lo), then (q_hi, x_hi)
                     const CUtensorMap *ma = (seg == 0) ? &map_q_lo : &map_q_hi;
                     const CUtensorMap *mb = (seg == 1) ? &map_x_lo : &map_x_hi;
@@ -343,10 +413,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     const uint32_t a_addr = asp::smem_u32(stages + (size_t)s * STAGE_BYTES);
                     const uint64_t da = make_kmajor_sw128_desc(a_addr);
                     const uint64_t db = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                    // K = 16 halves per MMA = 32 B = +2 in the address field; the last block of a term may be short
+                    const int nsub = (ki == klo - 1 || ki == 2 * klo - 1) ? p.sub_lo_last : (ki == kiters - 1) ? p.sub_hi_last : TKB / 16;
                     if (VARIANT != 3) {
 #pragma unroll
-                        for (int k = 0; k < TKB / 16; ++k)                        // UMMA K = 16 halves = 32 B = +2 in the address field
-                            asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < TKB / 16; ++k)
+                            if (k < nsub) asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
                     }
                     asp::umma_commit(&empty_bar[s]);                             // smem stage reusable when these MMAs retire
                 }
@@ -363,6 +435,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const float lq = qvalid ? p.lam_q[gq] : 0.f;
         const int et = threadIdx.x - 64;                                         // 0 .. EPI_WARPS*32-1
         const float inv_tau = 1.0f / p.tau;
+        const float delta2 = (qvalid && !DUMP) ? 2.0f * p.delta_q[gq] : 0.f;
         float lst[TK_LIST];
 #pragma unroll
         for (int i = 0; i < TK_LIST; ++i) lst[i] = -INFINITY;
@@ -394,7 +467,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 const uint32_t so = s_theta[row];
                 if (so != 0u) {
                     const float sh = o2f(so);
-                    if (sh > theta_k) { theta_k = sh; theta_emit = theta_k - 2.0f * p.delta; }
+                    if (sh > theta_k) { theta_k = sh; theta_emit = theta_k - delta2; }
                 }
                 // s <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the tile's lambda interval);
                 // the 2.5e-7 / 1.000001 keep the bound safe against the f32 roundings of lambda_q and the interval
@@ -457,7 +530,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                                     for (int i = 1; i < TK_LIST; ++i) kth = (i < p.topk) ? lst[i] : kth;
                                     if (kth > theta_k) {
                                         theta_k = kth;
-                                        theta_emit = theta_k - 2.0f * p.delta;
+                                        theta_emit = theta_k - delta2;
                                         theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
                                         const uint32_t ko = f2o(kth);
                                         atomicMax(&s_theta[row], ko);
@@ -522,7 +595,7 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
 tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const double *__restrict__ items, int64_t n_local,
                   int f, int pitch, int64_t row0, const double *__restrict__ norm_x, const double *__restrict__ lam_x,
                   const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nstreams,
-                  int capb, float delta, double eps_fast, const float *__restrict__ emit_sc,
+                  int capb, const float *__restrict__ delta_q, double eps_fast, const float *__restrict__ emit_sc,
                   const int32_t *__restrict__ emit_ix, const int32_t *__restrict__ emit_cnt,
                   const uint32_t *__restrict__ theta_glob, const int32_t *__restrict__ qperm,
                   int64_t *__restrict__ out_idx, double *__restrict__ out_score,
@@ -566,7 +639,7 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
             }
         }
         const float kth = (float)__shfl_sync(0xffffffffu, top[0].s, kk - 1);     // -inf when fewer than kk were emitted
-        cutoff = kth - 2.0f * delta;
+        cutoff = kth - 2.0f * delta_q[qi];
     }
     (void)theta_glob;
     const double nqv = norm_q[oq], lqv = lam_q[oq];
@@ -653,13 +726,32 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
 }  // namespace
 
 // ------------------------------------------------------------------ host side
-struct asp_tc_cache {               // per-space fp16 copies in lambda order, built on the first tensor-core search
-    __half *hi = nullptr, *lo = nullptr;
+struct asp_tc_cache {               // per-space fp16 operands in lambda order, built on the first tensor-core search
+    __half *hi = nullptr, *lo = nullptr;      // lo (remainder of the residual columns) only once a 3-term search needs it
     float *lam32 = nullptr, *tile_lo = nullptr, *tile_hi = nullptr;
     int32_t *perm = nullptr;
-    int kp = 0;
+    double *mdir = nullptr;         // [f] unit mean direction of the shard's unit vectors
+    double rho_max = 1.0;           // largest residual norm |x^ - (m.x^) m| of the shard
+    int kp = 0;                     // operand row: f residual columns + 3 rank-1 columns, padded to a multiple of 64
     CUtensorMap map_hi, map_lo;
 };
+
+static int device_max(asp_ctx *ctx, const double *v_dev, int64_t n, double *out)
+{
+    cudaStream_t st = ctx->stream;
+    double *d_mm = nullptr;
+    std::vector<double> h_mm(512);
+    ASP_CUDA(cudaMallocAsync(&d_mm, sizeof(double) * 512, st));
+    minmax_kernel<<<256, 256, 0, st>>>(v_dev, n, d_mm);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaMemcpyAsync(h_mm.data(), d_mm, sizeof(double) * 512, cudaMemcpyDeviceToHost, st));
+    ASP_CUDA(cudaStreamSynchronize(st));
+    ASP_CUDA(cudaFreeAsync(d_mm, st));
+    double hi = 0.0;
+    for (int i = 0; i < 256; ++i) hi = fmax(hi, h_mm[2 * i + 1]);
+    *out = hi;
+    return ASP_OK;
+}
 
 // ascending bucket order of n f64 keys (65536 buckets over [min, max]); the order inside a bucket is whatever the
 // atomics produce -- callers only rely on the bucket order.  No host synchronisation.
@@ -694,26 +786,55 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     asp_tc_cache *c = new asp_tc_cache();
-    c->kp = (s->f + TKB - 1) / TKB * TKB;
+    c->kp = (s->f + 3 + TKB - 1) / TKB * TKB;
     const int64_t n = s->n_local;
     const size_t ne = (size_t)n * c->kp;
     const int64_t ntile = asp_ceil_div(n, TN);
+    double *partials = nullptr, *rho = nullptr;
     ASP_CUDA(cudaMallocAsync(&c->hi, ne * 2, st));
-    ASP_CUDA(cudaMallocAsync(&c->lo, ne * 2, st));
     ASP_CUDA(cudaMallocAsync(&c->lam32, sizeof(float) * n, st));
     ASP_CUDA(cudaMallocAsync(&c->perm, sizeof(int32_t) * n, st));
     ASP_CUDA(cudaMallocAsync(&c->tile_lo, sizeof(float) * ntile, st));
     ASP_CUDA(cudaMallocAsync(&c->tile_hi, sizeof(float) * ntile, st));
+    ASP_CUDA(cudaMallocAsync(&c->mdir, sizeof(double) * s->f, st));
+    ASP_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)MD_BLOCKS * s->f, st));
+    ASP_CUDA(cudaMallocAsync(&rho, sizeof(double) * n, st));
     // visiting order: bucket sort of the shard by lambda
     ASP_CHECK(bucket_order(ctx, s->lambdas, n, c->perm));
-    split_f16_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, n, s->f, s->fp, c->kp, s->inv_norms, c->perm, c->hi, c->lo);
+    // mean direction, projection, fp16 operands
+    colsum_unit_kernel<<<MD_BLOCKS, 256, 0, st>>>(s->items, n, s->f, s->fp, s->inv_norms, partials);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    mean_dir_kernel<<<1, 256, 0, st>>>(partials, MD_BLOCKS, s->f, c->mdir);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    project_split_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, n, s->f, s->fp, c->kp, s->inv_norms, c->perm, c->mdir, 0,
+                                                          c->hi, nullptr, rho);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CHECK(device_max(ctx, rho, n, &c->rho_max));
     tile_lambda_kernel<<<(unsigned)ntile, TN, 0, st>>>(s->lambdas, c->perm, n, c->lam32, c->tile_lo, c->tile_hi);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaFreeAsync(partials, st));
+    ASP_CUDA(cudaFreeAsync(rho, st));
     ASP_CHECK(asp_make_f16_tmap(&c->map_hi, c->hi, n, c->kp, TN));
-    ASP_CHECK(asp_make_f16_tmap(&c->map_lo, c->lo, n, c->kp, TN));
+    c->map_lo = c->map_hi;
     ms->tc_cache = c;
     *out = c;
+    return ASP_OK;
+}
+
+// the remainders of the residual columns, for the two-term split (3 MMA terms): built when first needed
+static int ensure_tc_lo(const asp_space *s, asp_tc_cache *c)
+{
+    if (c->lo) return ASP_OK;
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    double *rho = nullptr;
+    ASP_CUDA(cudaMallocAsync(&c->lo, (size_t)s->n_local * c->kp * 2, st));
+    ASP_CUDA(cudaMallocAsync(&rho, sizeof(double) * s->n_local, st));
+    project_split_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(s->items, s->n_local, s->f, s->fp, c->kp, s->inv_norms, c->perm, c->mdir, 0,
+                                                          c->hi, c->lo, rho);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaFreeAsync(rho, st));
+    ASP_CHECK(asp_make_f16_tmap(&c->map_lo, c->lo, s->n_local, c->kp, TN));
     return ASP_OK;
 }
 
@@ -722,7 +843,8 @@ void asp_free_tc_cache(asp_space *s)
     if (!s->tc_cache) return;
     asp_tc_cache *c = static_cast<asp_tc_cache *>(s->tc_cache);
     cudaStream_t st = s->ctx->stream;
-    cudaFreeAsync(c->hi, st); cudaFreeAsync(c->lo, st); cudaFreeAsync(c->lam32, st); cudaFreeAsync(c->perm, st);
+    cudaFreeAsync(c->hi, st); if (c->lo) cudaFreeAsync(c->lo, st); cudaFreeAsync(c->lam32, st); cudaFreeAsync(c->perm, st);
+    cudaFreeAsync(c->mdir, st);
     cudaFreeAsync(c->tile_lo, st); cudaFreeAsync(c->tile_hi, st);
     delete c;
     s->tc_cache = nullptr;
@@ -761,8 +883,30 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaMallocAsync(&center, sizeof(int32_t) * qblocks, st));
         ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, qperm));
     }
-    split_f16_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, qperm, q_hi, q_lo);
+    double *rho_q = nullptr;
+    float *delta_q = nullptr;
+    ASP_CUDA(cudaMallocAsync(&rho_q, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&delta_q, sizeof(float) * nq, st));
+    project_split_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, qperm, c->mdir, 1, q_hi, q_lo, rho_q);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    // error band of one approximate cosine, |cos~ - cos| <= rho_q rho_x c_main + c_fixed (margin x2 on a worst-case
+    // model: fp16 roundings of both residuals, round-toward-zero f32 accumulation, truncated rank-1 split)
+    double rho_q_max = 1.0;
+    ASP_CHECK(device_max(ctx, rho_q, nq, &rho_q_max));
+    const double steps = (double)((s->f + 15) / 16);
+    const double c_main1 = 2.0 * c->rho_max * (ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + steps * ldexp(1.0, -23));
+    const double c_main3 = 2.0 * c->rho_max * (3.0 * ldexp(1.0, -22) + 3.0 * steps * ldexp(1.0, -23));
+    const double c_fixed = 2.0 * (3.0 * ldexp(1.0, -22) + 4.0 * ldexp(1.0, -23) + 1e-12);
+    int nterms = (rho_q_max * c_main1 + c_fixed <= 2.5e-4) ? 1 : 3;
+    if (const char *e = getenv("ASP_TC_TERMS")) { const int v = atoi(e); if (v == 1 || v == 3) nterms = v; }
+    if (nterms == 3) ASP_CHECK(ensure_tc_lo(s, c));
+    const double c_main = (nterms == 1) ? c_main1 : c_main3;
+    row_delta_kernel<<<64, 256, 0, st>>>(rho_q, nq, c_main, c_fixed, fabs(tau), (fabs(tau) + fabs(1.0 - tau)) * 2e-6, delta_q);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ctx->stats["search_terms"] = nterms;
+    ctx->stats["search_delta_cos_max"] = rho_q_max * c_main + c_fixed;
+    ctx->stats["search_rho_q_max"] = rho_q_max;
+    ctx->stats["search_rho_x_max"] = c->rho_max;
     gather_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, qperm, nq, lam_q32);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     if (!dump_dev) {
@@ -798,7 +942,10 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     TcParams p;
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
-    p.delta = (float)(fabs(tau) * delta_cos_of(kp) + (fabs(tau) + fabs(1.0 - tau)) * 2e-6);
+    p.delta_q = delta_q; p.nterms = nterms;
+    p.kb_lo = (s->f + TKB - 1) / TKB; p.kb_hi = kp / TKB;
+    p.sub_lo_last = (s->f - (p.kb_lo - 1) * TKB + 15) / 16;
+    p.sub_hi_last = (s->f + 3 - (p.kb_hi - 1) * TKB + 15) / 16;
     p.lam_x = c->lam32; p.lam_q = lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm; p.center = center;
     p.theta_glob = nullptr; p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.dump = dump_dev;
     int32_t *slow_list = nullptr, *slow_count = nullptr;
@@ -840,7 +987,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
             q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-            (int)topk, nsub, capb, p.delta, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, qperm, out_idx_dev,
+            (int)topk, nsub, capb, delta_q, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, qperm, out_idx_dev,
             out_score_dev, slow_list, slow_count, counters, counters + 1);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
         ASP_CUDA(cudaEventRecord(ctx->ev2, st));
@@ -858,7 +1005,6 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ctx->stats["search_rescored_per_query"] = (double)cnts[0] / (double)nq;
         ctx->stats["search_exact_per_query"] = (double)cnts[1] / (double)nq;
         ctx->stats["search_stage1_is_tc"] = 1.0;
-        ctx->stats["search_delta"] = p.delta;
         if (nslow > 0)
             rc = asp_search_slow_path(s, q_dev, qpitch, lambda_q_dev, qnorm_dev, tau, topk, slow_list, nslow, out_idx_dev,
                                       out_score_dev);
@@ -868,6 +1014,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     }
     cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(lam_q32, st);
     cudaFreeAsync(inv_nq, st);
+    cudaFreeAsync(rho_q, st); cudaFreeAsync(delta_q, st);
     if (qperm) cudaFreeAsync(qperm, st);
     if (center) cudaFreeAsync(center, st);
     return rc;

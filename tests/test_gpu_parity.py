@@ -406,24 +406,32 @@ def _force_stage1(mode):
         os.environ["ASP_SEARCH_STAGE1"] = mode
 
 
-@pytest.mark.parametrize("n,f,nq", [(700, 64, 130), (3000, 384, 300), (5000, 100, 257), (1100, 768, 128)])
-def test_tc_dot_error_band(n, f, nq):
-    """The fp16-split tcgen05 dot products stay inside the band the completeness proof assumes:
-    |cos~ - cos| <= DELTA_COS(kp) = 4 (3 2^-22 + (3 kp / 16) 2^-23), with the margin (x4) DESIGN.md claims."""
+@pytest.mark.parametrize("terms", [1, 3])
+@pytest.mark.parametrize("n,f,nq,shift", [(700, 64, 130, 22.0), (3000, 384, 300, 22.0), (5000, 100, 257, 0.0), (1100, 768, 128, 0.0),
+                                          (900, 61, 140, 5.0)])
+def test_tc_dot_error_band(n, f, nq, shift, terms):
+    """The tcgen05 cosines (rank-1 mean-direction term + fp16 residual term(s)) stay inside the band the completeness
+    proof assumes, |cos~ - cos| <= rho_q rho_x c_main + c_fixed, in both modes (1 residual term / two-term split),
+    for data with a large common component (shift 0) and for mixed-sign data (shift 22: cancellation)."""
     from arrowspace import ArrowSpaceBuilder
-    from pyarrowspace_b200 import _lib, synth
-    x = synth.make_items(n, f, 71, n_clusters=8) - 22.0                 # mixed signs, cancellation in the dot products
-    q, _ = synth.make_queries(x + 22.0, nq, 71)
+    from pyarrowspace_b200 import _lib, api, synth
+    x = synth.make_items(n, f, 71, n_clusters=8) - shift
+    q, _ = synth.make_queries(x + shift, nq, 71)
     q -= 0.2
     aspace, gl = ArrowSpaceBuilder.build({"eps": 1.0, "k": 4, "topk": 5, "p": 2.0, "sigma": 0.5}, x)
     out = np.zeros((nq, n), dtype=np.float32)
-    _lib.check(_lib.load().asp_debug_tc_dots(aspace._h, q.ctypes.data, nq, out.ctypes.data))
+    os.environ["ASP_TC_TERMS"] = str(terms)
+    try:
+        _lib.check(_lib.load().asp_debug_tc_dots(aspace._h, q.ctypes.data, nq, out.ctypes.data))
+    finally:
+        os.environ.pop("ASP_TC_TERMS", None)
+    assert api.stat("search_terms") == terms
+    band = api.stat("search_delta_cos_max")
     exact = (q @ x.T) / (np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(x, axis=1)[None, :])
     err = np.abs(out.astype(np.float64) - exact)
-    kp = (f + 63) // 64 * 64
-    delta_cos = 4.0 * (3.0 * 2.0 ** -22 + (3.0 * kp / 16.0) * 2.0 ** -23)
-    print("tc dot error: max %.3e, band %.3e, ratio %.1f" % (err.max(), delta_cos, delta_cos / err.max()))
-    assert err.max() < delta_cos / 4, err.max()
+    print("tc dot error (%d term): max %.3e, band %.3e (rho_q %.3f rho_x %.3f), ratio %.1f"
+          % (terms, err.max(), band, api.stat("search_rho_q_max"), api.stat("search_rho_x_max"), band / err.max()))
+    assert err.max() < band / 2, (err.max(), band)
     assert err.max() > 0                                                 # it IS the low-precision path
 
 
@@ -438,9 +446,12 @@ def test_tc_search_equals_fp64_path_and_oracle(oracle_mod, n, f, nq, topk):
     gp = {"eps": 0.6, "k": 6, "topk": topk, "p": 2.0, "sigma": 0.3}
     aspace, gl, s, g = _build_both(oracle_mod, gp, x)
     try:
-        for tau in (0.62, 1.0):
+        for tau, terms in ((0.62, None), (1.0, None), (0.62, "1"), (0.62, "3")):
             _force_stage1("tc")
+            if terms:
+                os.environ["ASP_TC_TERMS"] = terms
             idx_tc, sc_tc = aspace.search_batch(q, gl, tau)
+            os.environ.pop("ASP_TC_TERMS", None)
             assert api.stat("search_stage1_is_tc") == 1.0
             rescored = api.stat("search_rescored_per_query")
             _force_stage1("fp64")
@@ -452,6 +463,7 @@ def test_tc_search_equals_fp64_path_and_oracle(oracle_mod, n, f, nq, topk):
             assert topk <= rescored < 0.5 * n                            # a real filter, not a full rescan
     finally:
         _force_stage1(None)
+        os.environ.pop("ASP_TC_TERMS", None)
 
 
 def test_tc_search_with_ties_and_overflow(oracle_mod):

@@ -21,15 +21,15 @@ xt = torch.from_numpy(x).cuda()
 qt = torch.from_numpy(qe).cuda()
 exact = (qt @ xt.T) / (qt.norm(dim=1)[:, None] * xt.norm(dim=1)[None, :])
 err = (torch.from_numpy(dots).cuda().double() - exact).abs()
-kp = (f + 63) // 64 * 64
-band = 4.0 * (3.0 * 2.0 ** -22 + (3.0 * kp / 16.0) * 2.0 ** -23)
+band = api.stat("search_delta_cos_max")
+out["terms"] = api.stat("search_terms"); out["rho_q_max"] = api.stat("search_rho_q_max"); out["rho_x_max"] = api.stat("search_rho_x_max")
 out["err_max"] = float(err.max()); out["err_mean"] = float(err.mean()); out["band"] = band
 out["band_over_max"] = band / out["err_max"]; out["dots_checked"] = int(err.numel())
 print(out, flush=True)
 qd = torch.from_numpy(q).cuda()
 for rep in range(4):
     idx, sc = aspace.search_batch(qd, gl, c["tau"])
-    st = {k: api.stat(k) for k in ("search_stage1_ms", "search_stage2_ms", "search_rescored_per_query", "search_exact_per_query", "search_slow_queries", "search_delta")}
+    st = {k: api.stat(k) for k in ("search_stage1_ms", "search_stage2_ms", "search_rescored_per_query", "search_exact_per_query", "search_slow_queries", "search_terms", "search_delta_cos_max")}
     print(rep, st, flush=True)
 out["stats"] = st
 out["top1_is_source"] = float((idx.cpu().numpy()[:, 0] == sel).mean())
