@@ -330,16 +330,22 @@ struct TcParams {
     float *dump;                  // DUMP mode: approximate cosines [nq][n_local], local item order
 };
 
-template <bool DUMP, int VARIANT>      // VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued
+// ARES (1-term mode, <= 7 k blocks): the query operand (128 x kp fp16, <= 112 KB) is loaded ONCE and stays resident in
+// shared memory; only the 32 KB item tiles stream through a 3-stage ring -- a third less L2 -> SM traffic, which is what
+// bounds the kernel once the executed FLOP are down to one term.
+template <bool DUMP, int VARIANT, bool ARES>   // VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on 1024-byte boundaries
-    unsigned char *stages = smem_raw + ((1024u - (asp::smem_u32(smem_raw) & 1023u)) & 1023u);   // TC_STAGES * STAGE_BYTES
-    float *s_const = reinterpret_cast<float *>(stages + TC_STAGES * STAGE_BYTES);   // [2][TN]: item lambdas per accumulator
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2];
+    constexpr int NST = ARES ? 3 : TC_STAGES;                                    // ring depth
+    constexpr int STB = ARES ? B_BYTES : STAGE_BYTES;                            // bytes per ring stage
+    unsigned char *a_res = smem_raw + ((1024u - (asp::smem_u32(smem_raw) & 1023u)) & 1023u);     // ARES: kb_hi * A_BYTES
+    unsigned char *stages = a_res + (ARES ? (size_t)p.kb_hi * A_BYTES : 0);      // NST * STB
+    float *s_const = reinterpret_cast<float *>(stages + NST * STB);              // [2][TN]: item lambdas per accumulator
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2], a_full;
     __shared__ uint32_t s_tmem_base;
     __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score seen by its threads / other CTAs (ordered bits)
     __shared__ int s_cnt[TQ];                 // per query row: emission cursor shared by its column-quarter threads
@@ -364,6 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { asp::mbar_init(&full_bar[s], 1); asp::mbar_init(&empty_bar[s], 1); }
+        asp::mbar_init(&a_full, 1);
         for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], EPI_WARPS); }
         asp::fence_barrier_init();
     }
@@ -379,21 +386,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         if (lane == 0) {
             asp::tma_prefetch_desc(&map_q_hi); asp::tma_prefetch_desc(&map_q_lo);
             asp::tma_prefetch_desc(&map_x_hi); asp::tma_prefetch_desc(&map_x_lo);
+            if (ARES) {
+                asp::mbar_arrive_expect_tx(&a_full, (uint32_t)(p.kb_hi * A_BYTES));
+                for (int kb = 0; kb < p.kb_hi; ++kb) asp::tma_load_2d(a_res + (size_t)kb * A_BYTES, &map_q_hi, &a_full, kb * TKB, qb * TQ);
+            }
             int64_t it = 0;
             for (int t = 0; t < ntiles; ++t) {
                 const int item0 = tile_of(t) * TN;
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = (int)(it % TC_STAGES);
-                    asp::mbar_wait(&empty_bar[s], (uint32_t)(((it / TC_STAGES) & 1) ^ 1));
+                    const int s = (int)(it % NST);
+                    asp::mbar_wait_suspend(&empty_bar[s], (uint32_t)(((it / NST) & 1) ^ 1), 4000);
                     const int seg = (ki < klo) ? 0 : (ki < 2 * klo) ? 1 : 2;
                     const int kc = (ki - seg * klo) * TKB;
                     // small terms first: (q_lo, x_hi), (q_hi, x_lo), then (q_hi, x_hi)
                     const CUtensorMap *ma = (seg == 0) ? &map_q_lo : &map_q_hi;
                     const CUtensorMap *mb = (seg == 1) ? &map_x_lo : &map_x_hi;
-                    unsigned char *dst = stages + (size_t)s * STAGE_BYTES;
-                    asp::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    asp::tma_load_2d(dst, ma, &full_bar[s], kc, qb * TQ);
-                    asp::tma_load_2d(dst + A_BYTES, mb, &full_bar[s], kc, item0);
+                    unsigned char *dst = stages + (size_t)s * STB;
+                    asp::mbar_arrive_expect_tx(&full_bar[s], STB);
+                    if (!ARES) asp::tma_load_2d(dst, ma, &full_bar[s], kc, qb * TQ);
+                    asp::tma_load_2d(dst + (ARES ? 0 : A_BYTES), mb, &full_bar[s], kc, item0);
                 }
             }
         }
@@ -401,18 +412,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int64_t it = 0;
+            if (ARES) { asp::mbar_wait(&a_full, 0); asp::tc_fence_after(); }
             for (int t = 0; t < ntiles; ++t) {
                 const int acc = (int)(t & 1);
                 asp::mbar_wait(&tmem_empty[acc], (uint32_t)((((t >> 1) & 1)) ^ 1));
                 asp::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TN);
                 for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = (int)(it % TC_STAGES);
-                    asp::mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+                    const int s = (int)(it % NST);
+                    asp::mbar_wait(&full_bar[s], (uint32_t)((it / NST) & 1));
                     asp::tc_fence_after();
-                    const uint32_t a_addr = asp::smem_u32(stages + (size_t)s * STAGE_BYTES);
-                    const uint64_t da = make_kmajor_sw128_desc(a_addr);
-                    const uint64_t db = make_kmajor_sw128_desc(a_addr + A_BYTES);
+                    const uint32_t st_addr = asp::smem_u32(stages + (size_t)s * STB);
+                    const uint64_t da = make_kmajor_sw128_desc(ARES ? asp::smem_u32(a_res + (size_t)ki * A_BYTES) : st_addr);
+                    const uint64_t db = make_kmajor_sw128_desc(ARES ? st_addr : st_addr + A_BYTES);
                     // K = 16 halves per MMA = 32 B = +2 in the address field; the last block of a term may be short
                     const int nsub = (ki == klo - 1 || ki == 2 * klo - 1) ? p.sub_lo_last : (ki == kiters - 1) ? p.sub_hi_last : TKB / 16;
                     if (VARIANT != 3) {
@@ -475,7 +487,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 beta_ub = p.beta * __fdividef(1.0f, 1.0f + gap) * 1.000001f;
                 theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
             }
-            asp::mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
+            asp::mbar_wait_suspend(&tmem_full[acc], (uint32_t)((t >> 1) & 1), 8000);
             asp::tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < (VARIANT >= 2 ? 0 : EPI_COLS / 32); ++c) {
@@ -567,13 +579,15 @@ __device__ __forceinline__ double seq_dot_row_tc(const double *__restrict__ qv, 
 {
     double d = 0.0;
     int j = 0;
-    for (; j + 4 <= f; j += 4) {
-        const double2 x0 = *reinterpret_cast<const double2 *>(row + j);
-        const double2 x1 = *reinterpret_cast<const double2 *>(row + j + 2);
-        d = __dadd_rn(d, __dmul_rn(qv[j], x0.x));
-        d = __dadd_rn(d, __dmul_rn(qv[j + 1], x0.y));
-        d = __dadd_rn(d, __dmul_rn(qv[j + 2], x1.x));
-        d = __dadd_rn(d, __dmul_rn(qv[j + 3], x1.y));
+    for (; j + 16 <= f; j += 16) {                                               // 8 loads in flight, then the ordered sum
+        double2 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = *reinterpret_cast<const double2 *>(row + j + 2 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            d = __dadd_rn(d, __dmul_rn(qv[j + 2 * u], x[u].x));
+            d = __dadd_rn(d, __dmul_rn(qv[j + 2 * u + 1], x[u].y));
+        }
     }
     for (; j < f; ++j) d = __dadd_rn(d, __dmul_rn(qv[j], row[j]));
     return d;
@@ -621,9 +635,7 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     const int kk = topk < n_local ? topk : (int)n_local;
     float cutoff;
     {
-        Cand top[2];
-        top[0] = asp::cand_empty();
-        top[1] = asp::cand_empty();
+        float top[2] = {-INFINITY, -INFINITY};                                   // best 32 in top[0], sorted descending by lane
         float floor32 = -INFINITY;                                               // 32nd best so far
         for (int c = 0; c < nstreams; ++c) {
             const int cnt = emit_cnt[qi * nstreams + c];
@@ -632,13 +644,12 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
                 const int e = e0 + lane;
                 const float v = (e < cnt) ? emit_sc[base + e] : -INFINITY;
                 if (!__any_sync(0xffffffffu, v > floor32)) continue;
-                top[1].s = (double)v;
-                top[1].i = (e < cnt) ? c * capb + e : 0x7fffffff;
-                asp::warp_sort_best_first<2>(top, lane);
-                floor32 = (float)__shfl_sync(0xffffffffu, top[0].s, 31);
+                top[1] = v;
+                asp::warp_sort_desc_f32x2(top, lane);
+                floor32 = __shfl_sync(0xffffffffu, top[0], 31);
             }
         }
-        const float kth = (float)__shfl_sync(0xffffffffu, top[0].s, kk - 1);     // -inf when fewer than kk were emitted
+        const float kth = __shfl_sync(0xffffffffu, top[0], kk - 1);              // -inf when fewer than kk were emitted
         cutoff = kth - 2.0f * delta_q[qi];
     }
     (void)theta_glob;
@@ -650,26 +661,33 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     best[1] = asp::cand_empty();
     int qn = 0;                                                                  // queued survivors (warp uniform)
     unsigned long long nsurv = 0;
-    // (A): `count` queued survivors, two rows at a time, every lane a slice of the features (coalesced 16 B loads)
+    // (A): `count` queued survivors, four rows at a time, every lane a slice of the features (coalesced 16 B loads)
     auto flush = [&](int count) {
         Cand mine = asp::cand_empty();
-        for (int s0 = 0; s0 < count; s0 += 2) {
-            const int i0 = queue[s0];
-            const int i1 = (s0 + 1 < count) ? queue[s0 + 1] : i0;
-            const double *r0 = items + (int64_t)i0 * pitch, *r1 = items + (int64_t)i1 * pitch;
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll 4
+        for (int s0 = 0; s0 < count; s0 += 4) {
+            int ii[4];
+            const double *rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ii[u] = queue[(s0 + u < count) ? s0 + u : s0]; rr[u] = items + (int64_t)ii[u] * pitch; }
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
             for (int j = 2 * lane; j < pitch; j += 64) {
-                const double2 a = *reinterpret_cast<const double2 *>(r0 + j);
-                const double2 b = *reinterpret_cast<const double2 *>(r1 + j);
                 const double2 qq = *reinterpret_cast<const double2 *>(qs + j);
-                d0 = fma(qq.x, a.x, d0); d0 = fma(qq.y, a.y, d0);
-                d1 = fma(qq.x, b.x, d1); d1 = fma(qq.y, b.y, d1);
+                double2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const double2 *>(rr[u] + j);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { d[u] = fma(qq.x, a[u].x, d[u]); d[u] = fma(qq.y, a[u].y, d[u]); }
             }
-            d0 = warp_sum(d0);
-            d1 = warp_sum(d1);
-            if (lane == s0) { mine.s = exact_score_tc(d0, nqv, norm_x[i0], tau, lqv, lam_x[i0]); mine.i = i0; }
-            if (lane == s0 + 1 && s0 + 1 < count) { mine.s = exact_score_tc(d1, nqv, norm_x[i1], tau, lqv, lam_x[i1]); mine.i = i1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[u] = warp_sum(d[u]);
+            const int u_mine = lane - s0;                                        // lanes s0 .. s0+3 keep one result each
+            if (u_mine >= 0 && u_mine < 4 && lane < count) {
+                const double dd = (u_mine == 0) ? d[0] : (u_mine == 1) ? d[1] : (u_mine == 2) ? d[2] : d[3];
+                const int it = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
+                mine.s = exact_score_tc(dd, nqv, norm_x[it], tau, lqv, lam_x[it]);
+                mine.i = it;
+            }
         }
         best[1] = mine;
         asp::warp_sort_best_first<2>(best, lane);
@@ -963,24 +981,38 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         ASP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st));
     }
 
-    const size_t smem = (size_t)TC_STAGES * STAGE_BYTES + 2 * TN * sizeof(float) + 1024;
+    // 1-term mode with a query operand of <= 7 k blocks: keep it resident (ARES), stream only the item tiles
+    bool ares = (nterms == 1) && (p.kb_hi <= 7);
+    if (const char *e = getenv("ASP_TC_ARES")) ares = ares && atoi(e) != 0;
+    const size_t smem = (ares ? (size_t)p.kb_hi * A_BYTES + 3 * (size_t)B_BYTES : (size_t)TC_STAGES * STAGE_BYTES) +
+                        2 * TN * sizeof(float) + 1024;
     dim3 grid((unsigned)qblocks, nchunks);
+    const char *var = getenv("ASP_TC_VARIANT");                   // profiling only: results are wrong for 2 / 3
+    const int v = (var && !dump_dev) ? atoi(var) : 0;
+    void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
+        dump_dev ? (ares ? tc_gemm_kernel<true, 0, true> : tc_gemm_kernel<true, 0, false>)
+        : (v == 2) ? (ares ? tc_gemm_kernel<false, 2, true> : tc_gemm_kernel<false, 2, false>)
+        : (v == 3) ? (ares ? tc_gemm_kernel<false, 3, true> : tc_gemm_kernel<false, 3, false>)
+        : (ares ? tc_gemm_kernel<false, 0, true> : tc_gemm_kernel<false, 0, false>);
+    ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));
-    if (dump_dev) {
-        ASP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_kernel<true, 0><<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
-    } else {
-        const char *var = getenv("ASP_TC_VARIANT");               // profiling only: results are wrong for 2 / 3
-        const int v = var ? atoi(var) : 0;
-        auto k = (v == 2) ? tc_gemm_kernel<false, 2> : (v == 3) ? tc_gemm_kernel<false, 3> : tc_gemm_kernel<false, 0>;
-        ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
-    }
+    k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
+    ctx->stats["search_a_resident"] = ares ? 1.0 : 0.0;
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));
 
     int rc = ASP_OK;
-    if (!dump_dev) {
+    if (!dump_dev && v != 0) {                                    // profiling variants: stage 1 only, results are garbage
+        ASP_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->stats["search_stage1_ms"] = ms;
+        ASP_CUDA(cudaMemsetAsync(out_idx_dev, 0xff, sizeof(int64_t) * (size_t)nq * topk, st));
+        ASP_CUDA(cudaMemsetAsync(out_score_dev, 0, sizeof(double) * (size_t)nq * topk, st));
+        cudaFreeAsync(p.emit_sc, st); cudaFreeAsync(p.emit_ix, st); cudaFreeAsync(p.emit_cnt, st);
+        cudaFreeAsync(p.theta_glob, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
+        cudaFreeAsync(counters, st);
+    } else if (!dump_dev) {
         const double u = 1.1102230246251565e-16;
         const double eps_fast = (4.0 * s->f + 64.0) * u * (fabs(tau) + fabs(1.0 - tau) + 1.0);
         const size_t rsmem = (size_t)TR_WARPS * s->fp * 8 + TR_WARPS * TR_QUEUE * 4;

@@ -23,7 +23,8 @@ __device__ __forceinline__ Cand cand_empty()
     return c;
 }
 
-// Sorts 32*NPL elements held as e[t] = element (lane + 32 t), best first in element order.
+// Sorts 32*NPL elements held as e[t] = element (lane + 32 t), best first in element order.  Branch free: every
+// compare-exchange is a predicate and two selects (distinct elements never compare equal; two empties are identical).
 template <int NPL>
 __device__ __forceinline__ void warp_sort_best_first(Cand (&e)[NPL], int lane)
 {
@@ -34,17 +35,18 @@ __device__ __forceinline__ void warp_sort_best_first(Cand (&e)[NPL], int lane)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             if (stride >= 32) {
                 // partner lives in the same lane, slot t ^ (stride/32)
-                constexpr int dummy = 0;
-                (void)dummy;
                 const int ts = stride >> 5;
 #pragma unroll
                 for (int t = 0; t < NPL; ++t) {
                     if ((t & ts) == 0) {
                         const int i = lane + 32 * t;
                         const bool first_block = ((i & size) == 0);      // "ascending" = best first
-                        Cand &lo = e[t], &hi = e[t | ts];
-                        const bool swap = first_block ? cand_better(hi, lo) : cand_better(lo, hi);
-                        if (swap) { Cand tmp = lo; lo = hi; hi = tmp; }
+                        const Cand lo = e[t], hi = e[t | ts];
+                        const bool swap = (cand_better(hi, lo) == first_block);
+                        e[t].s = swap ? hi.s : lo.s;
+                        e[t].i = swap ? hi.i : lo.i;
+                        e[t | ts].s = swap ? lo.s : hi.s;
+                        e[t | ts].i = swap ? lo.i : hi.i;
                     }
                 }
             } else {
@@ -57,9 +59,34 @@ __device__ __forceinline__ void warp_sort_best_first(Cand (&e)[NPL], int lane)
                     const bool first_block = ((i & size) == 0);
                     const bool lower = ((i & stride) == 0);
                     const bool keep_best = (lower == first_block);
-                    const bool o_better = cand_better(o, e[t]);
-                    const bool e_better = cand_better(e[t], o);
-                    if (keep_best ? o_better : e_better) e[t] = o;
+                    const bool take = (cand_better(o, e[t]) == keep_best) && !(o.s == e[t].s && o.i == e[t].i);
+                    e[t].s = take ? o.s : e[t].s;
+                    e[t].i = take ? o.i : e[t].i;
+                }
+            }
+        }
+    }
+}
+
+// Descending sort of 64 floats (2 per lane, element = lane + 32 t): max/min exchanges only.
+__device__ __forceinline__ void warp_sort_desc_f32x2(float (&v)[2], int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32) {
+                const float a = fmaxf(v[0], v[1]), b = fminf(v[0], v[1]);   // size == 64: one descending block
+                v[0] = a;
+                v[1] = b;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int i = lane + 32 * t;
+                    const float o = __shfl_xor_sync(0xffffffffu, v[t], stride);
+                    const bool first_block = ((i & size) == 0);
+                    const bool lower = ((i & stride) == 0);
+                    v[t] = (lower == first_block) ? fmaxf(v[t], o) : fminf(v[t], o);
                 }
             }
         }
