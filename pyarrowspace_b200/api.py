@@ -236,6 +236,14 @@ class ArrowSpace:
         lib = _lib.load()
         f = self.nfeatures
         topk = gl.graph_params["topk"]
+        host_in = not _is_device_tensor(queries)
+        if host_in and self._group is not None:
+            # sharded space, host queries: every rank uploads 1/world of the batch over its own PCIe link and the
+            # shards are all-gathered over NVLink (each rank scores ALL queries against its item shard)
+            q_np = np.ascontiguousarray(queries, dtype=np.float64)
+            if q_np.ndim != 2 or q_np.shape[1] != f:
+                raise ValueError("query length %d must match nfeatures %d" % (q_np.shape[-1], f))
+            queries = _upload_queries_sharded(self, q_np)
         if _is_device_tensor(queries):
             if queries.dim() != 2 or queries.shape[1] != f:
                 raise ValueError("query length %d must match nfeatures %d" % (queries.shape[-1], f))
@@ -268,6 +276,8 @@ class ArrowSpace:
             raise
         if self._group is not None:
             idx, score = _merge_across_ranks(self, idx, score, nq, topk)
+        if host_in and _is_device_tensor(idx):
+            idx, score, lam = idx.cpu().numpy(), score.cpu().numpy(), lam.cpu().numpy()
         return idx, score, lam
 
     # ------------------------------------------------------------------ out of scope
@@ -276,6 +286,25 @@ class ArrowSpace:
 
     def search_energy(self, item, gl, k, w_lambda=None, w_dirichlet=None):
         raise NotImplementedError("search_energy belongs to the energy pipeline (src/lib.rs:232-262)")
+
+
+def _upload_queries_sharded(space, q_np):
+    """Host batch [Q, F] -> device tensor [Q, F] on every rank of the space's group: rank r copies rows
+    [r*per, (r+1)*per) from (pinned) host memory, all_gather_into_tensor over NCCL assembles the batch."""
+    import torch
+    import torch.distributed as dist
+    group = space._group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", _lib.load().asp_ctx_device(space._ctx))
+    nq, f = q_np.shape
+    per = (nq + world - 1) // world
+    r0, r1 = min(rank * per, nq), min((rank + 1) * per, nq)
+    part = torch.zeros((per, f), dtype=torch.float64, device=dev)
+    if r1 > r0:
+        part[: r1 - r0].copy_(torch.from_numpy(q_np[r0:r1]), non_blocking=True)
+    full = torch.empty((world * per, f), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full, part, group=group)
+    return full[:nq]
 
 
 def _merge_across_ranks(space, idx, score, nq, topk):

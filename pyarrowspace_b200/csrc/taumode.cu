@@ -27,8 +27,7 @@
 namespace {
 
 constexpr int TM_THREADS = 256;
-constexpr int TM_PARTS = 16;
-constexpr int CH_NNZ = 1536;     // upper-adjacency entries staged per chunk (>= longest row, f <= 1500)
+constexpr int CH_NNZ_MAX = 1536; // upper-adjacency entries staged per chunk (>= longest row); per-variant value CHN below
 constexpr int CH_ROWS = 256;
 constexpr double TAU_FLOOR = 1e-9;
 
@@ -141,8 +140,8 @@ median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use
     }
 }
 
-template <int FPL, int R>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+template <int FPL, int R, int CHN, int THR>
+__global__ void __launch_bounds__(THR, 1)
 taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
                const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ deg,
                const TmChunk *__restrict__ chunks, int nchunks, int tau_mode, double tau_fixed,
@@ -153,9 +152,9 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     constexpr int XS = T + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *xs = reinterpret_cast<double *>(smem_raw);                 // f * XS
-    double *s_val = xs + (size_t)f * XS;                               // CH_NNZ   (aliased by red[TM_PARTS][T])
-    int32_t *s_col = reinterpret_cast<int32_t *>(s_val + CH_NNZ);      // CH_NNZ
-    int32_t *s_rptr = s_col + CH_NNZ;                                  // CH_ROWS + 1
+    double *s_val = xs + (size_t)f * XS;                               // CHN   (aliased by red[(THR / 16)][T])
+    int32_t *s_col = reinterpret_cast<int32_t *>(s_val + CHN);         // CHN
+    int32_t *s_rptr = s_col + CHN;                                     // CH_ROWS + 1
     double *s_deg = reinterpret_cast<double *>(s_rptr + CH_ROWS + 2);  // CH_ROWS
     double *s_tau = s_deg + CH_ROWS;                                   // T
     double *s_n2 = s_tau + T;                                          // T
@@ -170,7 +169,7 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
         __syncthreads();                                               // previous tile fully consumed
 
         // ---- A: load, transpose into shared memory
-        for (int t = warp; t < T; t += TM_THREADS / 32) {
+        for (int t = warp; t < T; t += THR / 32) {
             const int64_t item = item0 + t;
             double v[FPL];
             if (item < n) {
@@ -217,11 +216,11 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
             const int ra0 = chunks[c].row_begin, ra1 = chunks[c].row_end;
             const int e0 = uptr[ra0], e1 = uptr[ra1];
             __syncthreads();
-            for (int i = threadIdx.x; i < e1 - e0; i += TM_THREADS) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
-            for (int i = threadIdx.x; i <= ra1 - ra0; i += TM_THREADS) s_rptr[i] = uptr[ra0 + i] - e0;
-            for (int i = threadIdx.x; i < ra1 - ra0; i += TM_THREADS) s_deg[i] = deg[ra0 + i];
+            for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
+            for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
+            for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
             __syncthreads();
-            for (int a = ra0 + p; a < ra1; a += TM_PARTS) {
+            for (int a = ra0 + p; a < ra1; a += (THR / 16)) {
                 double xa[R], s[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) { xa[r] = xs[a * XS + g + 16 * r]; s[r] = 0.0; }
@@ -248,7 +247,7 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
             const int64_t item = item0 + t;
             if (item < n) {
                 double num = 0.0;
-                for (int q = 0; q < TM_PARTS; ++q) num += red[q * T + t];
+                for (int q = 0; q < (THR / 16); ++q) num += red[q * T + t];
                 const double n2 = s_n2[t];
                 const double tau = s_tau[t];
                 double e = NAN, lam = NAN;
@@ -265,7 +264,7 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     }
 }
 
-template <int FPL, int R>
+template <int FPL, int R, int CHN, int THR>
 int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const double *x, int64_t n, int f, int pitch,
               const TmChunk *d_chunks, int nchunks, double *oe, double *ot, double *ol, double *on, double *oi,
               int *zero_flag)
@@ -280,14 +279,19 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
         ASP_CUDA(cudaGetLastError());
         ASP_LAUNCHED(ctx);
     }
-    const size_t smem = (size_t)f * (T + 1) * 8 + (size_t)CH_NNZ * 12 + (CH_ROWS + 2) * 4 + (size_t)CH_ROWS * 8 +
+    static_assert((size_t)CHN * 12 >= (size_t)(THR / 16) * T * 8, "the part reduction aliases the staged weights and columns");
+    const size_t smem = (size_t)f * (T + 1) * 8 + (size_t)CHN * 12 + (CH_ROWS + 2) * 4 + (size_t)CH_ROWS * 8 +
                         (size_t)T * 16 + 64;
     if (smem > 227 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "taumode kernel: %d features do not fit in shared memory", f);
-    auto kern = taumode_kernel<FPL, R>;
+    auto kern = taumode_kernel<FPL, R, CHN, THR>;
     ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;                                                       // resident CTAs per SM: their load / gather phases overlap
+    ASP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THR, smem));
+    if (occ < 1) occ = 1;
     const int64_t ntiles = (n + T - 1) / T;
-    const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
-    kern<<<grid, TM_THREADS, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
+    const int64_t slots = (int64_t)ctx->num_sms * occ;
+    const int grid = (int)(ntiles < slots ? ntiles : slots);
+    kern<<<grid, THR, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
                                                   nchunks, sw->tau_mode, sw->tau_fixed, medians, oe, ot, ol, on, oi, zero_flag);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
@@ -304,7 +308,8 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
     if (n == 0) return ASP_OK;
     if (f != g->nnodes) ASP_FAIL(ASP_ERR_ARG, "vector length %d must equal the graph's node count %lld", f, (long long)g->nnodes);
     if (!g->d_uptr) ASP_FAIL(ASP_ERR_ARG, "graph has no upper adjacency (not a feature graph)");
-    // chunk the upper adjacency by rows: <= CH_NNZ entries and <= CH_ROWS rows per chunk
+    // chunk the upper adjacency by rows: <= chn entries and <= CH_ROWS rows per chunk
+    const int chn = CH_NNZ_MAX;
     std::vector<TmChunk> chunks;
     {
         std::vector<int32_t> uptr(g->nnodes + 1);
@@ -319,8 +324,8 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
         int a0 = 0;
         while (a0 < g->nnodes) {
             int a1 = a0;
-            while (a1 < g->nnodes && (a1 - a0) < CH_ROWS && (uptr[a1 + 1] - uptr[a0]) <= CH_NNZ) ++a1;
-            if (a1 == a0) ASP_FAIL(ASP_ERR_UNSUPPORTED, "graph row %d has more than %d upper neighbours", a0, CH_NNZ);
+            while (a1 < g->nnodes && (a1 - a0) < CH_ROWS && (uptr[a1 + 1] - uptr[a0]) <= chn) ++a1;
+            if (a1 == a0) ASP_FAIL(ASP_ERR_UNSUPPORTED, "graph row %d has more than %d upper neighbours", a0, chn);
             chunks.push_back(TmChunk{a0, a1});
             a0 = a1;
         }
@@ -331,10 +336,10 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
     ASP_CUDA(cudaStreamSynchronize(ctx->stream));     // chunks vector goes out of scope
     int rc;
     const int nch = (int)chunks.size();
-    if (f <= 128)       rc = launch_tm<4, 4>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 384)  rc = launch_tm<12, 4>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 768)  rc = launch_tm<24, 2>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 1500) rc = launch_tm<48, 1>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f <= 128)       rc = launch_tm<4, 4, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    else if (f <= 384)  rc = launch_tm<12, 4, CH_NNZ_MAX, 512>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    else if (f <= 768)  rc = launch_tm<24, 2, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    else if (f <= 1500) rc = launch_tm<48, 1, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
     else { rc = ASP_ERR_UNSUPPORTED; asp_set_error("taumode kernel supports at most 1500 features (got %d)", f); }
     cudaFreeAsync(d_chunks, ctx->stream);
     return rc;
