@@ -132,6 +132,21 @@ int asp_topk_merge_impl(asp_ctx *ctx, const int64_t *idx_dev, const double *scor
                         int64_t nq, int64_t topk, int64_t *out_idx_dev, double *out_score_dev);
 
 // search_tc.cu (tcgen05 stage 1)
+struct asp_tc_batch {                     // device buffers of one batch of query vectors between stage 1 and stage 2
+    int64_t nq = 0;
+    int nsub = 0, capb = 0, nterms = 0, variant = 0;
+    double delta_cos_max = 0.0;
+    void *q_hi = nullptr, *q_lo = nullptr;
+    float *lam_q32 = nullptr, *delta_q = nullptr;    // visiting order
+    double *inv_nq = nullptr, *rho_q = nullptr;
+    int32_t *qperm = nullptr, *center = nullptr;     // visiting position -> caller's query index (nullptr: identity)
+    float *emit_sc = nullptr;                        // [nq][nsub][capb] approximate scores
+    int32_t *emit_ix = nullptr, *emit_cnt = nullptr; // local item indices; [nq][nsub] counts (> capb: overflow)
+    uint32_t *theta_glob = nullptr;
+};
+int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
+                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, float *dump_dev, asp_tc_batch *b);
+void asp_tc_batch_free(asp_ctx *ctx, asp_tc_batch *b);
 bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau);
 int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
                        const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev, double *out_score_dev,

@@ -54,7 +54,7 @@ constexpr int TC_STAGES = 4;
 constexpr int A_BYTES = TQ * TKB * 2;          // 16 KB
 constexpr int B_BYTES = TN * TKB * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TK_LIST = 16;        // running top list per (query row, column quarter) (topk <= 16)
+constexpr int TK_LIST_MAX = 32;    // running top list per (query row, column quarter): 16 or 32 registers (topk <= 32)
 constexpr int EPI_WARPS = 16;      // 4 per TMEM lane group: each thread owns one query row x 64 of the 256 tile columns
 constexpr int EPI_SPLIT = EPI_WARPS / 4;
 constexpr int EPI_COLS = TN / EPI_SPLIT;
@@ -292,6 +292,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
 
 // kind::f16: D f32 (bit 4), A f16 (bits 7-9 = 0), B f16 (bits 10-12 = 0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t IDESC_F16_128x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+constexpr uint32_t IDESC_F16_256x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TQ) >> 4) << 24);   // cta_group::2
 
 // r[j] for a run-time j without local memory: a 5-level select tree (31 SEL)
 __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j)
@@ -315,6 +316,7 @@ struct TcParams {
     int capb;                     // emission capacity per (query, chunk)
     int topk;
     float tau, beta;              // tau > 0, beta = 1 - tau >= 0
+    float score_floor;            // candidates below it are never emitted (kNN: 1 - eps - band; search: -inf)
     const float *delta_q;         // [nq] band of one approximate score of the row (visiting order)
     int nterms;                   // 1: single fp16 term of the residuals; 3: two-term split (lo.hi, hi.lo, hi.hi)
     int kb_lo, kb_hi;             // 64-wide k blocks of the lo terms (residual columns only) / of hi.hi (all columns)
@@ -333,19 +335,28 @@ struct TcParams {
 // ARES (1-term mode, <= 7 k blocks): the query operand (128 x kp fp16, <= 112 KB) is loaded ONCE and stays resident in
 // shared memory; only the 32 KB item tiles stream through a 3-stage ring -- a third less L2 -> SM traffic, which is what
 // bounds the kernel once the executed FLOP are down to one term.
-template <bool DUMP, int VARIANT, bool ARES>   // VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued
+// PAIR (with ARES): clusters of two CTAs (two query blocks of the same chunk) on the two SMs of a TPC run ONE
+// tcgen05.mma.cta_group::2 of M = 256: each CTA keeps its own 128 query rows resident and loads only HALF of every item
+// tile (128 of the 256 rows, 16 KB per stage, 6 stages); the leader CTA issues the MMAs, which read both halves and write
+// each CTA's rows into its own TMEM.  Half the L2 -> SM item traffic and shared-memory operand reads per SM, twice the
+// pipeline depth.  Barriers: TMA loads of both CTAs complete on the LEADER's full barrier; tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely on the leader's
+// "accumulator drained" barrier.
+template <bool DUMP, int VARIANT, bool ARES, bool PAIR, int LISTN>   // LISTN: running list per thread (>= topk); VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued, 4 epilogue loads TMEM only
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, const TcParams p)
 {
+    static_assert(!PAIR || ARES, "the CTA-pair kernel keeps the query operand resident");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on 1024-byte boundaries
-    constexpr int NST = ARES ? 3 : TC_STAGES;                                    // ring depth
-    constexpr int STB = ARES ? B_BYTES : STAGE_BYTES;                            // bytes per ring stage
+    constexpr int NST = PAIR ? 6 : ARES ? 3 : TC_STAGES;                         // ring depth
+    constexpr int STB = PAIR ? B_BYTES / 2 : ARES ? B_BYTES : STAGE_BYTES;       // bytes per ring stage
+    constexpr int MAXST = 6;
     unsigned char *a_res = smem_raw + ((1024u - (asp::smem_u32(smem_raw) & 1023u)) & 1023u);     // ARES: kb_hi * A_BYTES
     unsigned char *stages = a_res + (ARES ? (size_t)p.kb_hi * A_BYTES : 0);      // NST * STB
     float *s_const = reinterpret_cast<float *>(stages + NST * STB);              // [2][TN]: item lambdas per accumulator
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tmem_full[2], tmem_empty[2], a_full;
+    __shared__ __align__(8) uint64_t full_bar[MAXST], empty_bar[MAXST], tmem_full[2], tmem_empty[2], a_full;
     __shared__ uint32_t s_tmem_base;
     __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score seen by its threads / other CTAs (ordered bits)
     __shared__ int s_cnt[TQ];                 // per query row: emission cursor shared by its column-quarter threads
@@ -355,7 +366,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     // visiting order of the query block: centre-out from the tile nearest to its lambda_q (descending proximity
     // bound, so the thresholds tighten early); the chunk CTAs of a block take interleaved ranks of that order
     const int tiles_total = (int)((p.n_local + TN - 1) / TN);
-    const int center = p.center ? p.center[qb] : 0;
+    const uint32_t cta_rank = PAIR ? asp::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int center = p.center ? p.center[PAIR ? (qb & ~1) : qb] : 0;           // a pair walks ONE tile sequence
     const int side_min = min(center, tiles_total - 1 - center);
     const bool more_below = center > tiles_total - 1 - center;
     const int ntiles = (tiles_total - chunk + p.nchunks - 1) / p.nchunks;        // ranks chunk, chunk + nchunks, ...
@@ -369,15 +382,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     const int kiters = 2 * klo + p.kb_hi;                                        // small terms first, the rank-1 columns last
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { asp::mbar_init(&full_bar[s], 1); asp::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < MAXST; ++s) { asp::mbar_init(&full_bar[s], 1); asp::mbar_init(&empty_bar[s], 1); }
         asp::mbar_init(&a_full, 1);
-        for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { asp::mbar_init(&tmem_full[a], 1); asp::mbar_init(&tmem_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         asp::fence_barrier_init();
     }
     if (threadIdx.x < TQ) { s_theta[threadIdx.x] = 0u; s_cnt[threadIdx.x] = 0; }
-    if (warp == 1) asp::tmem_alloc(&s_tmem_base, 512);
+    if (warp == 1) { if (PAIR) asp::tmem_alloc_pair(&s_tmem_base, 512); else asp::tmem_alloc(&s_tmem_base, 512); }
     asp::tc_fence_before();
     __syncthreads();
+    if (PAIR) asp::cluster_sync_all();                                           // both CTAs' barriers initialised
     asp::tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
@@ -386,7 +400,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         if (lane == 0) {
             asp::tma_prefetch_desc(&map_q_hi); asp::tma_prefetch_desc(&map_q_lo);
             asp::tma_prefetch_desc(&map_x_hi); asp::tma_prefetch_desc(&map_x_lo);
-            if (ARES) {
+            if (PAIR) {
+                // completions of BOTH CTAs' loads are credited to the leader's barriers (only its MMA thread waits)
+                const uint32_t a_bar = asp::mapa_shared(asp::smem_u32(&a_full), 0);
+                if (leader) asp::mbar_arrive_expect_tx(&a_full, (uint32_t)(2 * p.kb_hi * A_BYTES));
+                for (int kb = 0; kb < p.kb_hi; ++kb) asp::tma_load_2d_pair(a_res + (size_t)kb * A_BYTES, &map_q_hi, a_bar, kb * TKB, qb * TQ);
+            } else if (ARES) {
                 asp::mbar_arrive_expect_tx(&a_full, (uint32_t)(p.kb_hi * A_BYTES));
                 for (int kb = 0; kb < p.kb_hi; ++kb) asp::tma_load_2d(a_res + (size_t)kb * A_BYTES, &map_q_hi, &a_full, kb * TKB, qb * TQ);
             }
@@ -402,15 +421,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     const CUtensorMap *ma = (seg == 0) ? &map_q_lo : &map_q_hi;
                     const CUtensorMap *mb = (seg == 1) ? &map_x_lo : &map_x_hi;
                     unsigned char *dst = stages + (size_t)s * STB;
-                    asp::mbar_arrive_expect_tx(&full_bar[s], STB);
-                    if (!ARES) asp::tma_load_2d(dst, ma, &full_bar[s], kc, qb * TQ);
-                    asp::tma_load_2d(dst + (ARES ? 0 : A_BYTES), mb, &full_bar[s], kc, item0);
+                    if (PAIR) {                                                  // this CTA's half of the item tile (map_x_lo = half-box map)
+                        if (leader) asp::mbar_arrive_expect_tx(&full_bar[s], 2 * STB);
+                        asp::tma_load_2d_pair(dst, &map_x_lo, asp::mapa_shared(asp::smem_u32(&full_bar[s]), 0), kc, item0 + (int)cta_rank * (TN / 2));
+                    } else {
+                        asp::mbar_arrive_expect_tx(&full_bar[s], STB);
+                        if (!ARES) asp::tma_load_2d(dst, ma, &full_bar[s], kc, qb * TQ);
+                        asp::tma_load_2d(dst + (ARES ? 0 : A_BYTES), mb, &full_bar[s], kc, item0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (PAIR: the leader CTA only) =====================
+        if (lane == 0 && leader) {
             int64_t it = 0;
             if (ARES) { asp::mbar_wait(&a_full, 0); asp::tc_fence_after(); }
             for (int t = 0; t < ntiles; ++t) {
@@ -430,11 +454,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     if (VARIANT != 3) {
 #pragma unroll
                         for (int k = 0; k < TKB / 16; ++k)
-                            if (k < nsub) asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                            if (k < nsub) {
+                                if (PAIR) asp::umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_256x256, (ki > 0 || k > 0) ? 1u : 0u);
+                                else asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                            }
                     }
-                    asp::umma_commit(&empty_bar[s]);                             // smem stage reusable when these MMAs retire
+                    if (PAIR) asp::umma_commit_pair(&empty_bar[s]); else asp::umma_commit(&empty_bar[s]);   // stage reusable when these MMAs retire
                 }
-                asp::umma_commit(&tmem_full[acc]);                               // accumulator complete
+                if (PAIR) asp::umma_commit_pair(&tmem_full[acc]); else asp::umma_commit(&tmem_full[acc]);   // accumulator complete
             }
         }
     } else {
@@ -448,38 +475,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const int et = threadIdx.x - 64;                                         // 0 .. EPI_WARPS*32-1
         const float inv_tau = 1.0f / p.tau;
         const float delta2 = (qvalid && !DUMP) ? 2.0f * p.delta_q[gq] : 0.f;
-        float lst[TK_LIST];
+        float lst[LISTN];
 #pragma unroll
-        for (int i = 0; i < TK_LIST; ++i) lst[i] = -INFINITY;
-        float theta_k = -INFINITY, theta_emit = -INFINITY;
+        for (int i = 0; i < LISTN; ++i) lst[i] = -INFINITY;
+        float theta_k = -INFINITY, theta_emit = p.score_floor;   // never emit below the floor (-inf: none)
         const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
 
+        // per-tile inputs are fetched one tile AHEAD (registers), so their global-memory latency hides behind the previous
+        // tile's accumulator wait and processing instead of delaying the release of the accumulator
+        float nx_lam = 0.f, nx_tl = 0.f, nx_th = 0.f;
+        uint32_t nx_go = 0u;
+        auto prefetch = [&](int t) {
+            if (t >= ntiles) return;
+            const int tile = tile_of(t);
+            if (et < TN) { const int64_t n = (int64_t)tile * TN + et; nx_lam = (n < p.n_local) ? p.lam_x[n] : 0.f; }
+            if (!DUMP) {
+                nx_tl = p.tile_lo[tile];
+                nx_th = p.tile_hi[tile];
+                if (part == 0 && qvalid) nx_go = p.theta_glob[gq];
+            }
+        };
+        prefetch(0);
         for (int t = 0; t < ntiles; ++t) {
             const int acc = (int)(t & 1);
             const int tile = tile_of(t);
             const int64_t item0 = (int64_t)tile * TN;
             float *c_lam = s_const + acc * TN;
-            for (int j = et; j < TN; j += EPI_WARPS * 32) {
-                const int64_t n = item0 + j;
-                c_lam[j] = (n < p.n_local) ? p.lam_x[n] : 0.f;
-            }
-            float tl = 0.f, th = 0.f;
-            if (!DUMP) {
-                tl = p.tile_lo[tile];
-                th = p.tile_hi[tile];
-                if (part == 0 && qvalid) {                                       // thresholds found by the CTAs of other chunks
-                    const uint32_t go = p.theta_glob[gq];
-                    if (go > s_theta[row]) atomicMax(&s_theta[row], go);
-                }
-            }
+            if (et < TN) c_lam[et] = nx_lam;
+            const float tl = nx_tl, th = nx_th;
+            if (!DUMP && part == 0 && qvalid && nx_go > s_theta[row]) atomicMax(&s_theta[row], nx_go);   // other chunks' thresholds
             asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");    // epilogue warps only
+            prefetch(t + 1);
             float theta_acc = qvalid ? -INFINITY : INFINITY;                     // raw-accumulator filter of this (row, tile)
             float beta_ub = p.beta;
             if (!DUMP && qvalid) {
                 const uint32_t so = s_theta[row];
                 if (so != 0u) {
                     const float sh = o2f(so);
-                    if (sh > theta_k) { theta_k = sh; theta_emit = theta_k - delta2; }
+                    if (sh > theta_k) { theta_k = sh; theta_emit = fmaxf(theta_k - delta2, p.score_floor); }
                 }
                 // s <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the tile's lambda interval);
                 // the 2.5e-7 / 1.000001 keep the bound safe against the f32 roundings of lambda_q and the interval
@@ -490,11 +523,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             asp::mbar_wait_suspend(&tmem_full[acc], (uint32_t)((t >> 1) & 1), 8000);
             asp::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < (VARIANT >= 2 ? 0 : EPI_COLS / 32); ++c) {
+            for (int c = 0; c < ((VARIANT == 2 || VARIANT == 3) ? 0 : EPI_COLS / 32); ++c) {
                 const int col0 = part * EPI_COLS + c * 32;
                 uint32_t r[32];
                 asp::tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * TN + col0), r);
                 asp::tmem_ld_wait();
+                if (VARIANT == 4) continue;
                 if (DUMP) {
                     if (qvalid) {
 #pragma unroll
@@ -528,10 +562,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                             if (sc >= theta_emit && n < p.n_local) {
                                 const int pos = atomicAdd(&s_cnt[row], 1);
                                 if (pos < p.capb) { p.emit_sc[ebase + pos] = sc; p.emit_ix[ebase + pos] = p.perm[n]; }
-                                if (sc > lst[TK_LIST - 1]) {
+                                if (sc > lst[LISTN - 1]) {
                                     float v = sc;
 #pragma unroll
-                                    for (int i = 0; i < TK_LIST; ++i) {
+                                    for (int i = 0; i < LISTN; ++i) {
                                         const float o = lst[i];
                                         const bool sw = v > o;
                                         lst[i] = sw ? v : o;
@@ -539,10 +573,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                                     }
                                     float kth = lst[0];
 #pragma unroll
-                                    for (int i = 1; i < TK_LIST; ++i) kth = (i < p.topk) ? lst[i] : kth;
+                                    for (int i = 1; i < LISTN; ++i) kth = (i < p.topk) ? lst[i] : kth;
                                     if (kth > theta_k) {
                                         theta_k = kth;
-                                        theta_emit = theta_k - delta2;
+                                        theta_emit = fmaxf(theta_k - delta2, p.score_floor);
                                         theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
                                         const uint32_t ko = f2o(kth);
                                         atomicMax(&s_theta[row], ko);
@@ -556,14 +590,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
             }
             asp::tc_fence_before();
             __syncwarp();
-            if (lane == 0) asp::mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (PAIR) asp::mbar_arrive_cluster(asp::mapa_shared(asp::smem_u32(&tmem_empty[acc]), 0));   // the leader's MMA thread waits
+                else asp::mbar_arrive(&tmem_empty[acc]);
+            }
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
         if (!DUMP && qvalid && part == 0) p.emit_cnt[gq * p.nchunks + chunk] = s_cnt[row];
     }
     asp::tc_fence_before();
     __syncthreads();
-    if (warp == 1) asp::tmem_dealloc(tmem_base, 512);
+    if (PAIR) asp::cluster_sync_all();                                           // the leader's MMAs read the peer's shared memory
+    if (warp == 1) { if (PAIR) asp::tmem_dealloc_pair(tmem_base, 512); else asp::tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------ stage 2
@@ -621,7 +659,7 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)TR_WARPS * pitch) + warp * TR_QUEUE;
     const int64_t qi = (int64_t)blockIdx.x * TR_WARPS + warp;                    // position in lambda_q order
     if (qi >= nq) return;
-    const int64_t oq = qperm[qi];                                                // the caller's query index
+    const int64_t oq = qperm ? (int64_t)qperm[qi] : qi;                          // the caller's query index
     for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[oq * qpitch + j] : 0.0;
 
     bool overflow = false;
@@ -748,10 +786,11 @@ struct asp_tc_cache {               // per-space fp16 operands in lambda order, 
     __half *hi = nullptr, *lo = nullptr;      // lo (remainder of the residual columns) only once a 3-term search needs it
     float *lam32 = nullptr, *tile_lo = nullptr, *tile_hi = nullptr;
     int32_t *perm = nullptr;
+    bool lambda_ordered = false;    // items in lambda order (needs the lambdas); else identity order (item graph before the lambdas)
     double *mdir = nullptr;         // [f] unit mean direction of the shard's unit vectors
     double rho_max = 1.0;           // largest residual norm |x^ - (m.x^) m| of the shard
     int kp = 0;                     // operand row: f residual columns + 3 rank-1 columns, padded to a multiple of 64
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi, map_lo, map_hi_half;      // boxes of 256 item rows; 128 for the CTA-pair kernel
 };
 
 static int device_max(asp_ctx *ctx, const double *v_dev, int64_t n, double *out)
@@ -797,10 +836,19 @@ static int bucket_order(asp_ctx *ctx, const double *keys_dev, int64_t n, int32_t
     return ASP_OK;
 }
 
+__global__ void iota_kernel(int32_t *__restrict__ p, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+
 static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
 {
     asp_space *ms = const_cast<asp_space *>(s);
-    if (ms->tc_cache) { *out = static_cast<asp_tc_cache *>(ms->tc_cache); return ASP_OK; }
+    if (ms->tc_cache) {
+        asp_tc_cache *have = static_cast<asp_tc_cache *>(ms->tc_cache);
+        if (have->lambda_ordered || !s->have_lambdas) { *out = have; return ASP_OK; }
+        asp_free_tc_cache(ms);                                          // built before the lambdas existed: rebuild in lambda order
+    }
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     asp_tc_cache *c = new asp_tc_cache();
@@ -817,8 +865,10 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     ASP_CUDA(cudaMallocAsync(&c->mdir, sizeof(double) * s->f, st));
     ASP_CUDA(cudaMallocAsync(&partials, sizeof(double) * (size_t)MD_BLOCKS * s->f, st));
     ASP_CUDA(cudaMallocAsync(&rho, sizeof(double) * n, st));
-    // visiting order: bucket sort of the shard by lambda
-    ASP_CHECK(bucket_order(ctx, s->lambdas, n, c->perm));
+    // visiting order: bucket sort of the shard by lambda (identity while the space has no lambdas: item graph)
+    c->lambda_ordered = s->have_lambdas;
+    if (s->have_lambdas) ASP_CHECK(bucket_order(ctx, s->lambdas, n, c->perm));
+    else { iota_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(c->perm, n); ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx); }
     // mean direction, projection, fp16 operands
     colsum_unit_kernel<<<MD_BLOCKS, 256, 0, st>>>(s->items, n, s->f, s->fp, s->inv_norms, partials);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
@@ -828,11 +878,18 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
                                                           c->hi, nullptr, rho);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CHECK(device_max(ctx, rho, n, &c->rho_max));
-    tile_lambda_kernel<<<(unsigned)ntile, TN, 0, st>>>(s->lambdas, c->perm, n, c->lam32, c->tile_lo, c->tile_hi);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    if (s->have_lambdas) {
+        tile_lambda_kernel<<<(unsigned)ntile, TN, 0, st>>>(s->lambdas, c->perm, n, c->lam32, c->tile_lo, c->tile_hi);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    } else {
+        ASP_CUDA(cudaMemsetAsync(c->lam32, 0, sizeof(float) * n, st));
+        ASP_CUDA(cudaMemsetAsync(c->tile_lo, 0, sizeof(float) * ntile, st));
+        ASP_CUDA(cudaMemsetAsync(c->tile_hi, 0, sizeof(float) * ntile, st));
+    }
     ASP_CUDA(cudaFreeAsync(partials, st));
     ASP_CUDA(cudaFreeAsync(rho, st));
     ASP_CHECK(asp_make_f16_tmap(&c->map_hi, c->hi, n, c->kp, TN));
+    ASP_CHECK(asp_make_f16_tmap(&c->map_hi_half, c->hi, n, c->kp, TN / 2));
     c->map_lo = c->map_hi;
     ms->tc_cache = c;
     *out = c;
@@ -870,47 +927,49 @@ void asp_free_tc_cache(asp_space *s)
 
 bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau)
 {
-    return topk >= 1 && topk <= TK_LIST && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL && tau > 1e-3 &&
+    return topk >= 1 && topk <= TK_LIST_MAX && nq >= 1 && s->n_local >= 1 && s->n_local < 2147483647LL && tau > 1e-3 &&
            tau <= 1.0 && s->fp <= 6144;   // beta = 1 - tau >= 0: the proximity term is bounded from above by prox_ub
 }
 
-// dump == nullptr: full search.  dump != nullptr: approximate cosines [nq][n_local] f32 (tests).
-int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
-                       const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev, double *out_score_dev,
-                       float *dump_dev)
+// ------------------------------------------------------------------ stage 1 for one batch of query vectors
+// Prepares the query operands (lambda_q order when lambdas are given, projection, per-row bands), runs tc_gemm_kernel and
+// leaves the emission lists in `b` for the caller's stage 2 (search: tc_rescore_kernel; item graph: knn.cu).
+// lambda_q_dev == nullptr: no lambda term (kNN): identity query order.  dump_dev != nullptr: approximate cosines
+// [nq][n_local] f32 (tests), no emission.
+int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
+                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, float *dump_dev, asp_tc_batch *b)
 {
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     asp_tc_cache *c = nullptr;
     ASP_CHECK(ensure_tc_cache(s, &c));
     const int kp = c->kp;
+    *b = asp_tc_batch();
+    b->nq = nq;
 
-    // queries: visited in lambda_q order (coherent blocks -> one visiting order per block), fp16 split + f32 scalars
     __half *q_hi = nullptr, *q_lo = nullptr;
-    float *lam_q32 = nullptr;
-    double *inv_nq = nullptr;
-    int32_t *qperm = nullptr, *center = nullptr;
     const int64_t qblocks = asp_ceil_div(nq, TQ);
     ASP_CUDA(cudaMallocAsync(&q_hi, (size_t)nq * kp * 2, st));
     ASP_CUDA(cudaMallocAsync(&q_lo, (size_t)nq * kp * 2, st));
-    ASP_CUDA(cudaMallocAsync(&lam_q32, sizeof(float) * nq, st));
-    ASP_CUDA(cudaMallocAsync(&inv_nq, sizeof(double) * nq, st));
-    ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, inv_nq));
-    if (!dump_dev) {
-        ASP_CUDA(cudaMallocAsync(&qperm, sizeof(int32_t) * nq, st));
-        ASP_CUDA(cudaMallocAsync(&center, sizeof(int32_t) * qblocks, st));
-        ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, qperm));
+    b->q_hi = q_hi; b->q_lo = q_lo;
+    ASP_CUDA(cudaMallocAsync(&b->lam_q32, sizeof(float) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&b->inv_nq, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&b->rho_q, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&b->delta_q, sizeof(float) * nq, st));
+    ASP_CHECK(asp_launch_reciprocal(ctx, qnorm_dev, nq, b->inv_nq));
+    const bool by_lambda = !dump_dev && lambda_q_dev && c->lambda_ordered;
+    if (by_lambda) {
+        // queries visited in lambda_q order: coherent blocks -> one visiting order per block
+        ASP_CUDA(cudaMallocAsync(&b->qperm, sizeof(int32_t) * nq, st));
+        ASP_CUDA(cudaMallocAsync(&b->center, sizeof(int32_t) * qblocks, st));
+        ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, b->qperm));
     }
-    double *rho_q = nullptr;
-    float *delta_q = nullptr;
-    ASP_CUDA(cudaMallocAsync(&rho_q, sizeof(double) * nq, st));
-    ASP_CUDA(cudaMallocAsync(&delta_q, sizeof(float) * nq, st));
-    project_split_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, inv_nq, qperm, c->mdir, 1, q_hi, q_lo, rho_q);
+    project_split_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, b->inv_nq, b->qperm, c->mdir, 1, q_hi, q_lo, b->rho_q);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     // error band of one approximate cosine, |cos~ - cos| <= rho_q rho_x c_main + c_fixed (margin x2 on a worst-case
     // model: fp16 roundings of both residuals, round-toward-zero f32 accumulation, truncated rank-1 split)
     double rho_q_max = 1.0;
-    ASP_CHECK(device_max(ctx, rho_q, nq, &rho_q_max));
+    ASP_CHECK(device_max(ctx, b->rho_q, nq, &rho_q_max));
     const double steps = (double)((s->f + 15) / 16);
     const double c_main1 = 2.0 * c->rho_max * (ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + steps * ldexp(1.0, -23));
     const double c_main3 = 2.0 * c->rho_max * (3.0 * ldexp(1.0, -22) + 3.0 * steps * ldexp(1.0, -23));
@@ -919,17 +978,23 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     if (const char *e = getenv("ASP_TC_TERMS")) { const int v = atoi(e); if (v == 1 || v == 3) nterms = v; }
     if (nterms == 3) ASP_CHECK(ensure_tc_lo(s, c));
     const double c_main = (nterms == 1) ? c_main1 : c_main3;
-    row_delta_kernel<<<64, 256, 0, st>>>(rho_q, nq, c_main, c_fixed, fabs(tau), (fabs(tau) + fabs(1.0 - tau)) * 2e-6, delta_q);
+    row_delta_kernel<<<64, 256, 0, st>>>(b->rho_q, nq, c_main, c_fixed, fabs(tau), (fabs(tau) + fabs(1.0 - tau)) * 2e-6, b->delta_q);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    b->nterms = nterms;
+    b->delta_cos_max = rho_q_max * c_main + c_fixed;
     ctx->stats["search_terms"] = nterms;
-    ctx->stats["search_delta_cos_max"] = rho_q_max * c_main + c_fixed;
+    ctx->stats["search_delta_cos_max"] = b->delta_cos_max;
     ctx->stats["search_rho_q_max"] = rho_q_max;
     ctx->stats["search_rho_x_max"] = c->rho_max;
-    gather_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, qperm, nq, lam_q32);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    if (!dump_dev) {
-        block_center_kernel<<<(unsigned)asp_ceil_div(qblocks, 128), 128, 0, st>>>(lam_q32, nq, c->tile_lo,
-                                                                               (int)asp_ceil_div(s->n_local, TN), center);
+    if (lambda_q_dev) {
+        gather_f32_kernel<<<64, 256, 0, st>>>(lambda_q_dev, b->qperm, nq, b->lam_q32);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    } else {
+        ASP_CUDA(cudaMemsetAsync(b->lam_q32, 0, sizeof(float) * nq, st));
+    }
+    if (by_lambda) {
+        block_center_kernel<<<(unsigned)asp_ceil_div(qblocks, 128), 128, 0, st>>>(b->lam_q32, nq, c->tile_lo,
+                                                                               (int)asp_ceil_div(s->n_local, TN), b->center);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     }
     CUtensorMap map_q_hi, map_q_lo;
@@ -955,99 +1020,133 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
         const int v = atoi(e);
         if (!dump_dev && v >= 8 && v <= 65536) capb = v;
     }
-    const int nsub = nchunks;
+    b->nsub = nchunks; b->capb = capb;
 
     TcParams p;
     p.nq = nq; p.n_local = s->n_local; p.kp = kp; p.nchunks = nchunks; p.capb = capb; p.topk = (int)topk;
     p.tau = (float)tau; p.beta = (float)(1.0 - tau);
-    p.delta_q = delta_q; p.nterms = nterms;
+    p.score_floor = (score_floor > -1e300) ? nextafterf((float)score_floor, -INFINITY) : -INFINITY;
+    p.delta_q = b->delta_q; p.nterms = nterms;
     p.kb_lo = (s->f + TKB - 1) / TKB; p.kb_hi = kp / TKB;
     p.sub_lo_last = (s->f - (p.kb_lo - 1) * TKB + 15) / 16;
     p.sub_hi_last = (s->f + 3 - (p.kb_hi - 1) * TKB + 15) / 16;
-    p.lam_x = c->lam32; p.lam_q = lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm; p.center = center;
+    p.lam_x = c->lam32; p.lam_q = b->lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm; p.center = b->center;
     p.theta_glob = nullptr; p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.dump = dump_dev;
-    int32_t *slow_list = nullptr, *slow_count = nullptr;
-    unsigned long long *counters = nullptr;
     if (!dump_dev) {
-        ASP_CUDA(cudaMallocAsync(&p.emit_sc, sizeof(float) * (size_t)nq * nsub * capb, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_ix, sizeof(int32_t) * (size_t)nq * nsub * capb, st));
-        ASP_CUDA(cudaMallocAsync(&p.emit_cnt, sizeof(int32_t) * (size_t)nq * nsub, st));
-        ASP_CUDA(cudaMallocAsync(&p.theta_glob, sizeof(uint32_t) * (size_t)nq, st));
-        ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (nq + 1), st));
-        ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
-        ASP_CUDA(cudaMallocAsync(&counters, 2 * sizeof(unsigned long long), st));
-        ASP_CUDA(cudaMemsetAsync(p.theta_glob, 0, sizeof(uint32_t) * (size_t)nq, st));
-        ASP_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(int32_t), st));
-        ASP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st));
+        ASP_CUDA(cudaMallocAsync(&b->emit_sc, sizeof(float) * (size_t)nq * nchunks * capb, st));
+        ASP_CUDA(cudaMallocAsync(&b->emit_ix, sizeof(int32_t) * (size_t)nq * nchunks * capb, st));
+        ASP_CUDA(cudaMallocAsync(&b->emit_cnt, sizeof(int32_t) * (size_t)nq * nchunks, st));
+        ASP_CUDA(cudaMallocAsync(&b->theta_glob, sizeof(uint32_t) * (size_t)nq, st));
+        ASP_CUDA(cudaMemsetAsync(b->theta_glob, 0, sizeof(uint32_t) * (size_t)nq, st));
+        p.emit_sc = b->emit_sc; p.emit_ix = b->emit_ix; p.emit_cnt = b->emit_cnt; p.theta_glob = b->theta_glob;
     }
 
     // 1-term mode with a query operand of <= 7 k blocks: keep it resident (ARES), stream only the item tiles
     bool ares = (nterms == 1) && (p.kb_hi <= 7);
     if (const char *e = getenv("ASP_TC_ARES")) ares = ares && atoi(e) != 0;
+    const bool wide = topk > 16;                                  // 32-entry running lists
+    const bool pair = ares && !dump_dev && !wide && getenv("ASP_TC_PAIR") && atoi(getenv("ASP_TC_PAIR")) != 0;
     const size_t smem = (ares ? (size_t)p.kb_hi * A_BYTES + 3 * (size_t)B_BYTES : (size_t)TC_STAGES * STAGE_BYTES) +
                         2 * TN * sizeof(float) + 1024;
-    dim3 grid((unsigned)qblocks, nchunks);
-    const char *var = getenv("ASP_TC_VARIANT");                   // profiling only: results are wrong for 2 / 3
-    const int v = (var && !dump_dev) ? atoi(var) : 0;
+    const int64_t grid_x = pair ? (qblocks + 1) / 2 * 2 : qblocks;
+    dim3 grid((unsigned)grid_x, nchunks);
+    const char *var = getenv("ASP_TC_VARIANT");                   // profiling only: results are wrong for 2 / 3 / 4
+    const int v = (var && !dump_dev && !wide) ? atoi(var) : 0;
     void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
-        dump_dev ? (ares ? tc_gemm_kernel<true, 0, true> : tc_gemm_kernel<true, 0, false>)
-        : (v == 2) ? (ares ? tc_gemm_kernel<false, 2, true> : tc_gemm_kernel<false, 2, false>)
-        : (v == 3) ? (ares ? tc_gemm_kernel<false, 3, true> : tc_gemm_kernel<false, 3, false>)
-        : (ares ? tc_gemm_kernel<false, 0, true> : tc_gemm_kernel<false, 0, false>);
+        dump_dev ? (ares ? tc_gemm_kernel<true, 0, true, false, 16> : tc_gemm_kernel<true, 0, false, false, 16>)
+        : wide ? (ares ? tc_gemm_kernel<false, 0, true, false, 32> : tc_gemm_kernel<false, 0, false, false, 32>)
+        : pair ? ((v == 2) ? tc_gemm_kernel<false, 2, true, true, 16> : (v == 3) ? tc_gemm_kernel<false, 3, true, true, 16>
+                  : (v == 4) ? tc_gemm_kernel<false, 4, true, true, 16> : tc_gemm_kernel<false, 0, true, true, 16>)
+        : (v == 4 && ares) ? tc_gemm_kernel<false, 4, true, false, 16>
+        : (v == 2) ? (ares ? tc_gemm_kernel<false, 2, true, false, 16> : tc_gemm_kernel<false, 2, false, false, 16>)
+        : (v == 3) ? (ares ? tc_gemm_kernel<false, 3, true, false, 16> : tc_gemm_kernel<false, 3, false, false, 16>)
+        : (ares ? tc_gemm_kernel<false, 0, true, false, 16> : tc_gemm_kernel<false, 0, false, false, 16>);
     ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));
-    k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
-    ctx->stats["search_a_resident"] = ares ? 1.0 : 0.0;
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ASP_CUDA(cudaLaunchKernelEx(&cfg, k, map_q_hi, map_q_lo, c->map_hi, c->map_hi_half, p));
+    } else {
+        k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
+    }
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));
+    b->variant = v;
+    ctx->stats["search_cta_pair"] = pair ? 1.0 : 0.0;
+    ctx->stats["search_a_resident"] = ares ? 1.0 : 0.0;
+    return ASP_OK;
+}
 
-    int rc = ASP_OK;
-    if (!dump_dev && v != 0) {                                    // profiling variants: stage 1 only, results are garbage
+void asp_tc_batch_free(asp_ctx *ctx, asp_tc_batch *b)
+{
+    cudaStream_t st = ctx->stream;
+    void *ptrs[] = {b->q_hi, b->q_lo, b->lam_q32, b->inv_nq, b->rho_q, b->delta_q, b->qperm, b->center,
+                    b->emit_sc, b->emit_ix, b->emit_cnt, b->theta_glob};
+    for (void *ptr : ptrs)
+        if (ptr) cudaFreeAsync(ptr, st);
+    *b = asp_tc_batch();
+}
+
+// dump == nullptr: full search.  dump != nullptr: approximate cosines [nq][n_local] f32 (tests).
+int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
+                       const double *qnorm_dev, double tau, int64_t topk, int64_t *out_idx_dev, double *out_score_dev,
+                       float *dump_dev)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    asp_tc_batch b;
+    int rc = asp_tc_stage1(s, q_dev, nq, qpitch, lambda_q_dev, qnorm_dev, tau, topk, -INFINITY, dump_dev, &b);
+    if (rc != ASP_OK || dump_dev) { asp_tc_batch_free(ctx, &b); return rc; }
+
+    if (b.variant != 0) {                                         // profiling variants: stage 1 only, results are garbage
         ASP_CUDA(cudaStreamSynchronize(st));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         ctx->stats["search_stage1_ms"] = ms;
         ASP_CUDA(cudaMemsetAsync(out_idx_dev, 0xff, sizeof(int64_t) * (size_t)nq * topk, st));
         ASP_CUDA(cudaMemsetAsync(out_score_dev, 0, sizeof(double) * (size_t)nq * topk, st));
-        cudaFreeAsync(p.emit_sc, st); cudaFreeAsync(p.emit_ix, st); cudaFreeAsync(p.emit_cnt, st);
-        cudaFreeAsync(p.theta_glob, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
-        cudaFreeAsync(counters, st);
-    } else if (!dump_dev) {
-        const double u = 1.1102230246251565e-16;
-        const double eps_fast = (4.0 * s->f + 64.0) * u * (fabs(tau) + fabs(1.0 - tau) + 1.0);
-        const size_t rsmem = (size_t)TR_WARPS * s->fp * 8 + TR_WARPS * TR_QUEUE * 4;
-        ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
-            q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-            (int)topk, nsub, capb, delta_q, eps_fast, p.emit_sc, p.emit_ix, p.emit_cnt, p.theta_glob, qperm, out_idx_dev,
-            out_score_dev, slow_list, slow_count, counters, counters + 1);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        ASP_CUDA(cudaEventRecord(ctx->ev2, st));
-        int32_t nslow = 0;
-        unsigned long long cnts[2] = {0, 0};
-        ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        ASP_CUDA(cudaMemcpyAsync(cnts, counters, sizeof(cnts), cudaMemcpyDeviceToHost, st));
-        ASP_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f, ms2 = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        cudaEventElapsedTime(&ms2, ctx->ev1, ctx->ev2);
-        ctx->stats["search_stage1_ms"] = ms;
-        ctx->stats["search_stage2_ms"] = ms2;
-        ctx->stats["search_slow_queries"] = nslow;
-        ctx->stats["search_rescored_per_query"] = (double)cnts[0] / (double)nq;
-        ctx->stats["search_exact_per_query"] = (double)cnts[1] / (double)nq;
-        ctx->stats["search_stage1_is_tc"] = 1.0;
-        if (nslow > 0)
-            rc = asp_search_slow_path(s, q_dev, qpitch, lambda_q_dev, qnorm_dev, tau, topk, slow_list, nslow, out_idx_dev,
-                                      out_score_dev);
-        cudaFreeAsync(p.emit_sc, st); cudaFreeAsync(p.emit_ix, st); cudaFreeAsync(p.emit_cnt, st);
-        cudaFreeAsync(p.theta_glob, st); cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st);
-        cudaFreeAsync(counters, st);
+        asp_tc_batch_free(ctx, &b);
+        return ASP_OK;
     }
-    cudaFreeAsync(q_hi, st); cudaFreeAsync(q_lo, st); cudaFreeAsync(lam_q32, st);
-    cudaFreeAsync(inv_nq, st);
-    cudaFreeAsync(rho_q, st); cudaFreeAsync(delta_q, st);
-    if (qperm) cudaFreeAsync(qperm, st);
-    if (center) cudaFreeAsync(center, st);
+    int32_t *slow_list = nullptr, *slow_count = nullptr;
+    unsigned long long *counters = nullptr;
+    ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (nq + 1), st));
+    ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
+    ASP_CUDA(cudaMallocAsync(&counters, 2 * sizeof(unsigned long long), st));
+    ASP_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(int32_t), st));
+    ASP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st));
+    const double u = 1.1102230246251565e-16;
+    const double eps_fast = (4.0 * s->f + 64.0) * u * (fabs(tau) + fabs(1.0 - tau) + 1.0);
+    const size_t rsmem = (size_t)TR_WARPS * s->fp * 8 + TR_WARPS * TR_QUEUE * 4;
+    ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
+        q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
+        (int)topk, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix, b.emit_cnt, b.theta_glob, b.qperm, out_idx_dev,
+        out_score_dev, slow_list, slow_count, counters, counters + 1);
+    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    ASP_CUDA(cudaEventRecord(ctx->ev2, st));
+    int32_t nslow = 0;
+    unsigned long long cnts[2] = {0, 0};
+    ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ASP_CUDA(cudaMemcpyAsync(cnts, counters, sizeof(cnts), cudaMemcpyDeviceToHost, st));
+    ASP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f, ms2 = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms2, ctx->ev1, ctx->ev2);
+    ctx->stats["search_stage1_ms"] = ms;
+    ctx->stats["search_stage2_ms"] = ms2;
+    ctx->stats["search_slow_queries"] = nslow;
+    ctx->stats["search_rescored_per_query"] = (double)cnts[0] / (double)nq;
+    ctx->stats["search_exact_per_query"] = (double)cnts[1] / (double)nq;
+    ctx->stats["search_stage1_is_tc"] = 1.0;
+    if (nslow > 0)
+        rc = asp_search_slow_path(s, q_dev, qpitch, lambda_q_dev, qnorm_dev, tau, topk, slow_list, nslow, out_idx_dev, out_score_dev);
+    cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st); cudaFreeAsync(counters, st);
+    asp_tc_batch_free(ctx, &b);
     return rc;
 }

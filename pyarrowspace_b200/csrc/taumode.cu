@@ -26,7 +26,6 @@
 
 namespace {
 
-constexpr int TM_THREADS = 256;
 constexpr int CH_NNZ_MAX = 1536; // upper-adjacency entries staged per chunk (>= longest row); per-variant value CHN below
 constexpr int CH_ROWS = 256;
 constexpr double TAU_FLOOR = 1e-9;

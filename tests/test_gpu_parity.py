@@ -546,3 +546,41 @@ def test_c2_shape_parity(oracle_mod):
     idx1, sc1 = aspace.search_batch(q, gl, 1.0)                         # tau = 1: pure cosine order
     cos = (x[idx1[:50, 0]] * q[:50]).sum(1) / (np.linalg.norm(x[idx1[:50, 0]], axis=1) * np.linalg.norm(q[:50], axis=1))
     np.testing.assert_allclose(sc1[:50, 0], cos, rtol=1e-12)
+
+
+def test_c3_shape_parity(oracle_mod):
+    """BASELINE.json configs[2] (CVE-shaped 768 features, k = 25, x12, tau sweep 1.0 / 0.8 / 0.62) at 40k items:
+    the streaming (non-resident) tensor-core kernel with 13 k-blocks, parity on graph, lambdas and every tau."""
+    from pyarrowspace_b200 import api, synth
+    c = synth.config("C3")
+    n = 40_000
+    x = synth.make_items(n, c["f"], c["seed"], c["scale"])
+    q, sel = synth.make_queries(x, 384, c["seed"], c["scale"])
+    aspace, gl, s, g = _build_both(oracle_mod, c["graph_params"], x)
+    _assert_graph_equal(gl, g)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+    for tau in (1.0, 0.8, 0.62):
+        idx, sc = aspace.search_batch(q, gl, tau)
+        assert api.stat("search_stage1_is_tc") == 1.0 and api.stat("search_a_resident") == 0.0
+        oidx, osc, _ = s.search_batch(q, g, tau)
+        _assert_hits_equal(idx, sc, oidx, osc)
+        assert (idx[:, 0] == sel).mean() > 0.99
+
+
+def test_cta_pair_kernel_matches(oracle_mod):
+    """The experimental cta_group::2 candidate kernel (ASP_TC_PAIR=1: two CTAs share one M = 256 MMA) returns the same
+    bits as the default 1-SM kernel."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, synth
+    x = synth.make_items(30_000, 384, 9, n_clusters=12)
+    q, _ = synth.make_queries(x, 700, 9)                                 # odd number of query blocks: a padded pair
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 0.6, "k": 6, "topk": 10, "p": 2.0, "sigma": 0.3}, x)
+    idx0, sc0 = aspace.search_batch(q, gl, 0.62)
+    assert api.stat("search_cta_pair") == 0.0
+    os.environ["ASP_TC_PAIR"] = "1"
+    try:
+        idx1, sc1 = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_cta_pair") == 1.0
+    finally:
+        os.environ.pop("ASP_TC_PAIR", None)
+    assert np.array_equal(idx0, idx1) and np.array_equal(sc0, sc1)

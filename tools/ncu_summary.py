@@ -22,11 +22,13 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
         "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__inst_executed_pipe_tensor.sum",
         "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__cycles_elapsed.avg.per_second", "launch__shared_mem_per_block_static"]
 
 
 def short(name):
-    for key in ("search_gemm_kernel", "gram_slice_kernel", "taumode_kernel", "rescore_kernel", "search_gemv_kernel",
+    for key in ("tc_gemm_kernel", "tc_rescore_kernel", "project_split_kernel", "median_kernel", "search_gemm_kernel", "gram_slice_kernel", "taumode_kernel", "rescore_kernel", "search_gemv_kernel",
                 "feature_select_kernel", "gram_segment_reduce", "gram_final_reduce", "sort_rows", "fill_kernel",
                 "count_mirror", "scan_", "weights_compact", "exact_", "topk_merge", "reciprocal", "zero_lambda",
                 "knn_"):
@@ -64,10 +66,10 @@ def launches(tag):
     print("wrote launches_%s.md: %d launches, %.1f ms total" % (tag, len(order), total / 1e3))
 
 
-def full(tag):
+def full(tag, reports=None):
     summary = {}
     for fn in sorted(os.listdir(OUT)):
-        if not fn.endswith(".ncu-rep"):
+        if not fn.endswith(".ncu-rep") or (reports and fn not in reports):
             continue
         p = subprocess.run(["ncu", "-i", os.path.join(OUT, fn), "--page", "raw", "--csv"], capture_output=True, text=True)
         rows = list(csv.reader(io.StringIO(p.stdout)))
@@ -96,4 +98,4 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    full(tag)
+    full(tag, set(sys.argv[2:]) or None)
