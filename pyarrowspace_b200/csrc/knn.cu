@@ -185,9 +185,173 @@ __global__ void knn_exact_select_kernel(const double *__restrict__ scores, int64
     if (threadIdx.x == 0) out_cnt[row] = s_keep;
 }
 
+// ---------------------------------------------------------------- tcgen05 candidate pass (search_tc.cu) + exact stage 2
+// Stage 1 is the search's tensor-core kernel with tau = 1 (score = cosine), the items themselves as queries, lists of
+// k + 1 (the item finds itself) and an emission floor at 1 - eps; this kernel is the item-graph stage 2, one warp per row:
+//   cut    (k+1)-th largest approximate cosine over all emitted candidates, minus 2 x the row's band
+//   (A)    survivors re-scored in f64 with a coalesced warp-cooperative dot product, best 32 kept
+//   (B)    the candidates within 2 eps_fast of the (k+1)-th best get the oracle's distance (left-to-right dot,
+//          d = 1 - max(0, dot/(|a||b|))); self dropped, d <= eps decided on those values, k smallest by (d, index).
+// A band that may extend beyond the 32 kept, a k-th neighbour whose cosine is not clearly positive (rectification ties
+// at d = 1 are ordered by index over ALL such items) or a full emission buffer send the row to the exact scan.
+constexpr int KT_QUEUE = 96;
+
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(KR_WARPS * 32)
+knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pitch, const double *__restrict__ norms,
+                      double eps, int kk, int64_t b0, int64_t nq, int nsub, int capb, const float *__restrict__ delta_q,
+                      double eps_fast, const float *__restrict__ emit_sc, const int32_t *__restrict__ emit_ix,
+                      const int32_t *__restrict__ emit_cnt, const int32_t *__restrict__ qperm, int64_t out_row0,
+                      int32_t *__restrict__ out_idx, double *__restrict__ out_dist, int32_t *__restrict__ out_cnt,
+                      int32_t *slow_list, int32_t *slow_count, unsigned long long *survivor_total)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *xs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * pitch;
+    int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)KR_WARPS * pitch) + warp * KT_QUEUE;
+    const int64_t qi = (int64_t)blockIdx.x * KR_WARPS + warp;                    // visiting position inside the batch
+    if (qi >= nq) return;
+    const int64_t i = b0 + (qperm ? (int64_t)qperm[qi] : qi);                    // the row (item) this warp resolves
+    for (int j = lane; j < pitch; j += 32) xs[j] = items[i * pitch + j];         // rows are zero padded to the pitch
+    const int kq = kk + 1;                                                       // the item finds itself
+
+    bool overflow = false;
+    for (int c = lane; c < nsub; c += 32) overflow |= emit_cnt[qi * nsub + c] > capb;
+    if (__any_sync(0xffffffffu, overflow)) {
+        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)i;
+        return;
+    }
+    float cutoff;
+    {
+        float top[2] = {-INFINITY, -INFINITY};
+        float floor32 = -INFINITY;
+        for (int c = 0; c < nsub; ++c) {
+            const int cnt = emit_cnt[qi * nsub + c];
+            const size_t base = ((size_t)qi * nsub + c) * (size_t)capb;
+            for (int e0 = 0; e0 < cnt; e0 += 32) {
+                const int e = e0 + lane;
+                const float v = (e < cnt) ? emit_sc[base + e] : -INFINITY;
+                if (!__any_sync(0xffffffffu, v > floor32)) continue;
+                top[1] = v;
+                asp::warp_sort_desc_f32x2(top, lane);
+                floor32 = __shfl_sync(0xffffffffu, top[0], 31);
+            }
+        }
+        const float kth = __shfl_sync(0xffffffffu, top[0], kq - 1);              // -inf when fewer than k+1 were emitted
+        cutoff = kth - 2.0f * delta_q[qi];
+    }
+    const double ni = norms[i];
+    __syncwarp();
+
+    Cand best[2];
+    best[0] = asp::cand_empty();
+    best[1] = asp::cand_empty();
+    int qn = 0;
+    unsigned long long nsurv = 0;
+    auto flush = [&](int count) {
+        Cand mine = asp::cand_empty();
+        for (int s0 = 0; s0 < count; s0 += 4) {
+            int ii[4];
+            const double *rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ii[u] = queue[(s0 + u < count) ? s0 + u : s0]; rr[u] = items + (int64_t)ii[u] * pitch; }
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+            for (int j = 2 * lane; j < pitch; j += 64) {
+                const double2 qq = *reinterpret_cast<const double2 *>(xs + j);
+                double2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const double2 *>(rr[u] + j);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { d[u] = fma(qq.x, a[u].x, d[u]); d[u] = fma(qq.y, a[u].y, d[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) d[u] = warp_sum_f64(d[u]);
+            const int u_mine = lane - s0;
+            if (u_mine >= 0 && u_mine < 4 && lane < count) {
+                const double dd = (u_mine == 0) ? d[0] : (u_mine == 1) ? d[1] : (u_mine == 2) ? d[2] : d[3];
+                const int it = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
+                const double den = ni * norms[it];
+                mine.s = (den != 0.0) ? dd / den : 0.0;                          // fast cosine
+                mine.i = it;
+            }
+        }
+        best[1] = mine;
+        asp::warp_sort_best_first<2>(best, lane);
+    };
+    for (int c = 0; c < nsub; ++c) {
+        const int cnt = emit_cnt[qi * nsub + c];
+        const size_t base = ((size_t)qi * nsub + c) * (size_t)capb;
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            const bool keep = (e < cnt) && (emit_sc[base + e] >= cutoff);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) queue[qn + __popc(m & ((1u << lane) - 1))] = emit_ix[base + e];
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                flush(32);
+                nsurv += 32;
+                __syncwarp();
+                if (lane < qn - 32) queue[lane] = queue[32 + lane];
+                qn -= 32;
+                __syncwarp();
+            }
+        }
+    }
+    if (qn > 0) { flush(qn); nsurv += qn; }
+
+    const double kth = __shfl_sync(0xffffffffu, best[0].s, kq - 1);              // -inf when fewer than k+1 survivors
+    const bool valid = best[0].i != 0x7fffffff;
+    const bool in_band = valid && (best[0].s >= kth - 2.0 * eps_fast);
+    const unsigned band = __ballot_sync(0xffffffffu, in_band);
+    if (band == 0xffffffffu || (kth != -INFINITY && kth <= 4.0 * eps_fast)) {
+        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)i;
+        return;
+    }
+    Cand fin[1];
+    fin[0] = asp::cand_empty();
+    if (in_band && best[0].i != (int32_t)i) {
+        const int64_t j = best[0].i;
+        const double d = exact_dist(seq_dot_row(xs, items + j * pitch, f), ni, norms[j]);
+        if (d <= eps) { fin[0].s = -d; fin[0].i = (int32_t)j; }                   // GRAPH_VARIABLES.md:7
+    }
+    asp::warp_sort_best_first<1>(fin, lane);                                     // (-d desc, index asc) == (d asc, index asc)
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, fin[0].i != 0x7fffffff));
+    const int keep = nvalid < kk ? nvalid : kk;
+    const int64_t orow = i - out_row0;
+    if (lane < keep) { out_idx[orow * kk + lane] = fin[0].i; out_dist[orow * kk + lane] = -fin[0].s; }
+    if (lane == 0) { out_cnt[orow] = keep; atomicAdd(survivor_total, nsurv); }
+}
+
 }  // namespace
 
-int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists)
+// exact scan of the rows listed in slow_list (device), one row at a time
+static int knn_slow_rows(asp_space *s, const asp_graph_params *gp, int64_t kk, const int32_t *slow_list, int nslow, asp_knn_lists *lists)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = s->n_local;
+    const int f = s->f;
+    double *scores = nullptr;
+    ASP_CUDA(cudaMallocAsync(&scores, sizeof(double) * n, st));
+    for (int i = 0; i < nslow; ++i) {
+        knn_exact_scan_kernel<<<ctx->num_sms * 4, 256, (size_t)f * 8, st>>>(s->items, n, f, s->fp, s->norms, gp->eps, slow_list, i, scores);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        knn_exact_select_kernel<<<1, 1024, 0, st>>>(scores, n, (int)kk, slow_list, i, lists->idx, lists->dist, lists->cnt);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    }
+    ASP_CUDA(cudaFreeAsync(scores, st));
+    return ASP_OK;
+}
+
+static int item_knn_fp64(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists)
 {
     constexpr int LIST = 32;
     constexpr int STAGES = 3;
@@ -276,21 +440,96 @@ int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists)
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats["knn_stage1_ms"] = ms;
     ctx->stats["knn_slow_rows"] = nslow;
-    if (nslow > 0) {
-        double *scores = nullptr;
-        ASP_CUDA(cudaMallocAsync(&scores, sizeof(double) * n, st));
-        for (int i = 0; i < nslow; ++i) {
-            knn_exact_scan_kernel<<<ctx->num_sms * 4, 256, (size_t)f * 8, st>>>(s->items, n, f, s->fp, s->norms, gp->eps,
-                                                                                slow_list, i, scores);
-            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-            knn_exact_select_kernel<<<1, 1024, 0, st>>>(scores, n, (int)kk, slow_list, i, lists->idx, lists->dist, lists->cnt);
-            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        }
-        ASP_CUDA(cudaFreeAsync(scores, st));
-    }
+    ctx->stats["knn_stage1_is_tc"] = 0.0;
+    if (nslow > 0) ASP_CHECK(knn_slow_rows(s, gp, kk, slow_list, nslow, lists));
     ASP_CUDA(cudaFreeAsync(cand_score, st));
     ASP_CUDA(cudaFreeAsync(cand_idx, st));
     ASP_CUDA(cudaFreeAsync(slow_list, st));
     ASP_CUDA(cudaFreeAsync(slow_count, st));
     return ASP_OK;
+}
+
+// Item-graph neighbour lists on the tensor cores: batches of 64k rows through asp_tc_stage1, exact stage 2 above.
+static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, asp_knn_lists *lists)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = s->n_local;
+    const int f = s->f;
+    const double u = 1.1102230246251565e-16;
+    const double eps_fast = (4.0 * f + 64.0) * u * 2.0;
+    const double floor = (gp->eps < 2.0) ? 1.0 - gp->eps - eps_fast : -INFINITY;   // cos < 1 - eps can never be a neighbour
+    int32_t *slow_list = nullptr, *slow_count = nullptr;
+    unsigned long long *counter = nullptr;
+    ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (n + 1), st));
+    ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
+    ASP_CUDA(cudaMallocAsync(&counter, sizeof(unsigned long long), st));
+    ASP_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(int32_t), st));
+    ASP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    const size_t rsmem = (size_t)KR_WARPS * s->fp * 8 + KR_WARPS * KT_QUEUE * 4;
+    ASP_CUDA(cudaFuncSetAttribute(knn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    int64_t batch = 65536;
+    if (const char *e = getenv("ASP_KNN_BATCH")) { const long v = atol(e); if (v >= 128) batch = v; }
+    double stage1_ms = 0.0, stage2_ms = 0.0;
+    int rc = ASP_OK;
+    for (int64_t b0 = 0; b0 < n && rc == ASP_OK; b0 += batch) {
+        const int64_t nq = (n - b0 < batch) ? n - b0 : batch;
+        asp_tc_batch b;
+        rc = asp_tc_stage1(s, s->items + b0 * s->fp, nq, s->fp, nullptr, s->norms + b0, 1.0, kk + 1, floor, nullptr, &b);
+        if (rc == ASP_OK) {
+            knn_tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, KR_WARPS), KR_WARPS * 32, rsmem, st>>>(
+                s->items, n, f, s->fp, s->norms, gp->eps, (int)kk, b0, nq, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix,
+                b.emit_cnt, b.qperm, 0, lists->idx, lists->dist, lists->cnt, slow_list, slow_count, counter);
+            if (cudaGetLastError() != cudaSuccess) { asp_set_error("knn_tc_rescore_kernel launch failed"); rc = ASP_ERR_CUDA; }
+            ASP_LAUNCHED(ctx);
+            cudaEventRecord(ctx->ev2, st);
+            cudaEventSynchronize(ctx->ev2);
+            float m1 = 0.f, m2 = 0.f;
+            cudaEventElapsedTime(&m1, ctx->ev0, ctx->ev1);
+            cudaEventElapsedTime(&m2, ctx->ev1, ctx->ev2);
+            stage1_ms += m1; stage2_ms += m2;
+        }
+        asp_tc_batch_free(ctx, &b);
+    }
+    int32_t nslow = 0;
+    unsigned long long nsurv = 0;
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaMemcpyAsync(&nsurv, counter, sizeof(nsurv), cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+        ctx->stats["knn_stage1_ms"] = stage1_ms;
+        ctx->stats["knn_stage2_ms"] = stage2_ms;
+        ctx->stats["knn_slow_rows"] = nslow;
+        ctx->stats["knn_stage1_is_tc"] = 1.0;
+        ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)n;
+        if (nslow > 0) rc = knn_slow_rows(s, gp, kk, slow_list, nslow, lists);
+    }
+    cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st); cudaFreeAsync(counter, st);
+    return rc;
+}
+
+int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = s->n_local;
+    int64_t kk = gp->k;
+    if (kk > n - 1) kk = n - 1;
+    if (kk < 0) kk = 0;
+    const char *force = getenv("ASP_KNN_STAGE1");
+    const bool want_fp64 = force && force[0] == 'f', want_tc = force && force[0] == 't';
+    const bool tc_ok = kk >= 1 && kk + 1 <= 31 && n < 2147483647LL && s->fp <= 6144;
+    if (!tc_ok || want_fp64 || (!want_tc && n < 8192)) return item_knn_fp64(s, gp, lists);
+
+    lists->m = n;
+    lists->kk = (int32_t)kk;
+    ASP_CUDA(cudaMallocAsync(&lists->idx, sizeof(int32_t) * (size_t)n * lists->kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists->dist, sizeof(double) * (size_t)n * lists->kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists->cnt, sizeof(int32_t) * (size_t)n, st));
+    ASP_CUDA(cudaMemsetAsync(lists->cnt, 0, sizeof(int32_t) * (size_t)n, st));
+    row_norms_kernel<<<(unsigned)(asp_ceil_div(n, 128) < 65535 ? asp_ceil_div(n, 128) : 65535), 128, 0, st>>>(
+        s->items, n, s->f, s->fp, s->norms, s->inv_norms);
+    ASP_CUDA(cudaGetLastError());
+    ASP_LAUNCHED(ctx);
+    return item_knn_tc(s, gp, kk, lists);
 }

@@ -478,7 +478,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         float lst[LISTN];
 #pragma unroll
         for (int i = 0; i < LISTN; ++i) lst[i] = -INFINITY;
-        float theta_k = -INFINITY, theta_emit = p.score_floor;   // never emit below the floor (-inf: none)
+        const float floor_row = p.score_floor - 0.5f * delta2;                    // exact-score floor minus the row's band (-inf: none)
+        float theta_k = -INFINITY, theta_emit = floor_row;
         const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
 
         // per-tile inputs are fetched one tile AHEAD (registers), so their global-memory latency hides behind the previous
@@ -512,7 +513,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 const uint32_t so = s_theta[row];
                 if (so != 0u) {
                     const float sh = o2f(so);
-                    if (sh > theta_k) { theta_k = sh; theta_emit = fmaxf(theta_k - delta2, p.score_floor); }
+                    if (sh > theta_k) { theta_k = sh; theta_emit = fmaxf(theta_k - delta2, floor_row); }
                 }
                 // s <= tau*cos + beta*prox_ub, prox_ub = 1/(1 + distance of lambda_q to the tile's lambda interval);
                 // the 2.5e-7 / 1.000001 keep the bound safe against the f32 roundings of lambda_q and the interval
@@ -576,7 +577,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                                     for (int i = 1; i < LISTN; ++i) kth = (i < p.topk) ? lst[i] : kth;
                                     if (kth > theta_k) {
                                         theta_k = kth;
-                                        theta_emit = fmaxf(theta_k - delta2, p.score_floor);
+                                        theta_emit = fmaxf(theta_k - delta2, floor_row);
                                         theta_acc = ((theta_emit - beta_ub) * inv_tau - 1e-6f) * ACC_SCALE;
                                         const uint32_t ko = f2o(kth);
                                         atomicMax(&s_theta[row], ko);
