@@ -175,8 +175,21 @@ int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int pa
 
 /* K1 (item orientation) + K2 for the shard's rows against `all_items` (n_total x f, host or
  * device; NULL = the shard itself, single GPU): eps / k-NN graph on rectified-cosine distance,
- * weights, symmetrised Laplacian CSR over n_total nodes.  Single-GPU in this round. */
+ * weights, symmetrised Laplacian CSR over n_total nodes.  Single GPU; candidates on the tensor cores (tcgen05) for
+ * n >= 8192 and k <= 30, FP64 DMMA otherwise; same exact stage 2 and answers. */
 int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
+
+/* Multi-GPU item graph (BASELINE.json configs C4/C5: "items sharded over 8 GPUs, NCCL halo exchange"): every rank
+ * holds ALL items (the halo rows arrive by all-gather) in a world-1 space and resolves the eps / k-NN lists of ITS rows
+ * [row_begin, row_end) on the tensor cores; the lists are all-gathered and the Laplacian is assembled from them.
+ *   asp_item_knn_rows: out_idx / out_dist [rows][*out_kk] (only the first out_cnt[r] entries of a row are valid,
+ *                      ascending (distance, index)), out_cnt [rows]; host or device pointers.  Replaces the per-row scan
+ *                      of the crate's graph construction (src/lib.rs:289; GRAPH_VARIABLES.md:7-8).
+ *   asp_graph_from_knn: K2 from complete lists of m nodes (host or device pointers). */
+int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, int32_t *out_idx,
+                      double *out_dist, int32_t *out_cnt, int32_t *out_kk);
+int asp_graph_from_knn(asp_ctx *ctx, int64_t m, int32_t kk, const int32_t *idx, const double *dist, const int32_t *cnt,
+                       const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
 
 /* ---- teardown / stats ---------------------------------------------------------------------- */
 void asp_free_space(asp_space *s);

@@ -421,6 +421,13 @@ class ArrowSpaceBuilder:
         return aspace, GraphLaplacian._wrap(hg)
 
     @staticmethod
+    def build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=None, **extras):
+        """Extension: the item graph across the GPUs of one box (one process per GPU): all-gather of the item shards
+        (halo rows), every rank resolves its rows on the tensor cores, all-gather of the neighbour lists."""
+        from .distributed import build_item_graph_sharded
+        return build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=group, **extras)
+
+    @staticmethod
     def build_energy(items, energy_params=None, graph_params=None):
         raise NotImplementedError("build_energy belongs to the energy pipeline (src/lib.rs:333-376)")
 

@@ -704,4 +704,58 @@ int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches 
     return ASP_OK;
 }
 
+int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, int32_t *out_idx,
+                      double *out_dist, int32_t *out_cnt, int32_t *out_kk)
+{
+    if (!s || !gp || !out_cnt || !out_kk) ASP_FAIL(ASP_ERR_ARG, "asp_item_knn_rows: NULL argument");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_knn_lists lists;
+    int rc = asp_item_knn_rows_impl(s, gp, row_begin, row_end, &lists);
+    if (rc == ASP_OK) {
+        const size_t rows = (size_t)lists.m;
+        *out_kk = lists.kk;
+        if (rows > 0 && out_idx) rc = asp_copy_out(ctx, out_idx, lists.idx, sizeof(int32_t) * rows * lists.kk);
+        if (rc == ASP_OK && rows > 0 && out_dist) rc = asp_copy_out(ctx, out_dist, lists.dist, sizeof(double) * rows * lists.kk);
+        if (rc == ASP_OK && rows > 0) rc = asp_copy_out(ctx, out_cnt, lists.cnt, sizeof(int32_t) * rows);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (lists.idx) cudaFreeAsync(lists.idx, ctx->stream);
+    if (lists.dist) cudaFreeAsync(lists.dist, ctx->stream);
+    if (lists.cnt) cudaFreeAsync(lists.cnt, ctx->stream);
+    return rc;
+}
+
+int asp_graph_from_knn(asp_ctx *ctx, int64_t m, int32_t kk, const int32_t *idx, const double *dist, const int32_t *cnt,
+                       const asp_graph_params *gp, const asp_switches *sw_in, asp_graph **out_graph)
+{
+    if (!ctx || !idx || !dist || !cnt || !gp || !out_graph || m <= 0 || kk <= 0) ASP_FAIL(ASP_ERR_ARG, "asp_graph_from_knn: bad argument");
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    asp_switches sw;
+    if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    asp_knn_lists lists;
+    lists.m = m; lists.kk = kk;
+    ASP_CUDA(cudaMallocAsync(&lists.idx, sizeof(int32_t) * (size_t)m * kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists.dist, sizeof(double) * (size_t)m * kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists.cnt, sizeof(int32_t) * (size_t)m, st));
+    int rc = asp_copy_in(ctx, lists.idx, idx, sizeof(int32_t) * (size_t)m * kk);
+    if (rc == ASP_OK) rc = asp_copy_in(ctx, lists.dist, dist, sizeof(double) * (size_t)m * kk);
+    if (rc == ASP_OK) rc = asp_copy_in(ctx, lists.cnt, cnt, sizeof(int32_t) * (size_t)m);
+    asp_graph *g = nullptr;
+    if (rc == ASP_OK) {
+        g = new asp_graph();
+        g->ctx = ctx;
+        g->gp = *gp;
+        if (!g->gp.has_sigma) { g->gp.sigma = gp->eps * 0.5; g->gp.has_sigma = 1; }
+        g->sw = sw;
+        rc = asp_assemble_laplacian(ctx, &lists, gp, &sw, g);
+    }
+    cudaFreeAsync(lists.idx, st); cudaFreeAsync(lists.dist, st); cudaFreeAsync(lists.cnt, st);
+    if (rc != ASP_OK) { if (g) asp_free_graph(g); return rc; }
+    ASP_CUDA(cudaStreamSynchronize(st));
+    *out_graph = g;
+    return ASP_OK;
+}
+
 }  // extern "C"

@@ -160,3 +160,4 @@ int asp_make_f16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t 
 
 // knn.cu
 int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists);
+int asp_item_knn_rows_impl(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, asp_knn_lists *lists);

@@ -450,7 +450,8 @@ static int item_knn_fp64(asp_space *s, const asp_graph_params *gp, asp_knn_lists
 }
 
 // Item-graph neighbour lists on the tensor cores: batches of 64k rows through asp_tc_stage1, exact stage 2 above.
-static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, asp_knn_lists *lists)
+// rows [row_begin, row_end) against all items of the space; lists->idx/dist/cnt hold (row_end - row_begin) rows
+static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int64_t row_begin, int64_t row_end, asp_knn_lists *lists)
 {
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -472,14 +473,14 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, asp
     if (const char *e = getenv("ASP_KNN_BATCH")) { const long v = atol(e); if (v >= 128) batch = v; }
     double stage1_ms = 0.0, stage2_ms = 0.0;
     int rc = ASP_OK;
-    for (int64_t b0 = 0; b0 < n && rc == ASP_OK; b0 += batch) {
-        const int64_t nq = (n - b0 < batch) ? n - b0 : batch;
+    for (int64_t b0 = row_begin; b0 < row_end && rc == ASP_OK; b0 += batch) {
+        const int64_t nq = (row_end - b0 < batch) ? row_end - b0 : batch;
         asp_tc_batch b;
         rc = asp_tc_stage1(s, s->items + b0 * s->fp, nq, s->fp, nullptr, s->norms + b0, 1.0, kk + 1, floor, nullptr, &b);
         if (rc == ASP_OK) {
             knn_tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, KR_WARPS), KR_WARPS * 32, rsmem, st>>>(
                 s->items, n, f, s->fp, s->norms, gp->eps, (int)kk, b0, nq, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix,
-                b.emit_cnt, b.qperm, 0, lists->idx, lists->dist, lists->cnt, slow_list, slow_count, counter);
+                b.emit_cnt, b.qperm, row_begin, lists->idx, lists->dist, lists->cnt, slow_list, slow_count, counter);
             if (cudaGetLastError() != cudaSuccess) { asp_set_error("knn_tc_rescore_kernel launch failed"); rc = ASP_ERR_CUDA; }
             ASP_LAUNCHED(ctx);
             cudaEventRecord(ctx->ev2, st);
@@ -501,8 +502,12 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, asp
         ctx->stats["knn_stage2_ms"] = stage2_ms;
         ctx->stats["knn_slow_rows"] = nslow;
         ctx->stats["knn_stage1_is_tc"] = 1.0;
-        ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)n;
-        if (nslow > 0) rc = knn_slow_rows(s, gp, kk, slow_list, nslow, lists);
+        ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)(row_end > row_begin ? row_end - row_begin : 1);
+        if (nslow > 0) {                                              // the exact kernels index the lists by GLOBAL row
+            asp_knn_lists shifted = *lists;
+            shifted.idx = lists->idx - row_begin * kk; shifted.dist = lists->dist - row_begin * kk; shifted.cnt = lists->cnt - row_begin;
+            rc = knn_slow_rows(s, gp, kk, slow_list, nslow, &shifted);
+        }
     }
     cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st); cudaFreeAsync(counter, st);
     return rc;
@@ -531,5 +536,31 @@ int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists)
         s->items, n, s->f, s->fp, s->norms, s->inv_norms);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
-    return item_knn_tc(s, gp, kk, lists);
+    return item_knn_tc(s, gp, kk, 0, n, lists);
+}
+
+// neighbour lists of rows [row_begin, row_end) only (multi-GPU item graph: every rank holds all items and resolves
+// its own rows); tensor-core pass only
+int asp_item_knn_rows_impl(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, asp_knn_lists *lists)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = s->n_local, rows = row_end - row_begin;
+    int64_t kk = gp->k;
+    if (kk > n - 1) kk = n - 1;
+    if (row_begin < 0 || row_end > n || rows < 0) ASP_FAIL(ASP_ERR_ARG, "row range [%lld, %lld) outside [0, %lld)", (long long)row_begin, (long long)row_end, (long long)n);
+    if (kk < 1 || kk + 1 > 31 || n >= 2147483647LL || s->fp > 6144)
+        ASP_FAIL(ASP_ERR_UNSUPPORTED, "the row-range item graph needs 1 <= k <= 30 (got %lld) and <= 6144 features", (long long)gp->k);
+    lists->m = rows;
+    lists->kk = (int32_t)kk;
+    ASP_CUDA(cudaMallocAsync(&lists->idx, sizeof(int32_t) * (size_t)(rows > 0 ? rows : 1) * lists->kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists->dist, sizeof(double) * (size_t)(rows > 0 ? rows : 1) * lists->kk, st));
+    ASP_CUDA(cudaMallocAsync(&lists->cnt, sizeof(int32_t) * (size_t)(rows > 0 ? rows : 1), st));
+    ASP_CUDA(cudaMemsetAsync(lists->cnt, 0, sizeof(int32_t) * (size_t)(rows > 0 ? rows : 1), st));
+    row_norms_kernel<<<(unsigned)(asp_ceil_div(n, 128) < 65535 ? asp_ceil_div(n, 128) : 65535), 128, 0, st>>>(
+        s->items, n, s->f, s->fp, s->norms, s->inv_norms);
+    ASP_CUDA(cudaGetLastError());
+    ASP_LAUNCHED(ctx);
+    if (rows == 0) return ASP_OK;
+    return item_knn_tc(s, gp, kk, row_begin, row_end, lists);
 }

@@ -7,6 +7,9 @@ The path shards by rows: rank r owns the rows of Gram s
           2. (rare) rank-ordered continuation of left-to-right column sums for the pairs whose
              distance falls inside the rounding band: rank r continues rank r-1's sums
   search  3. all-gather of the per-shard top-k lists (16 * Q * topk bytes per rank) + merge kernel
+  item graph (nodes = items)
+          4. all-gather of the item shards (the "halo rows": every rank scores ITS rows against ALL items)
+          5. all-gather of the per-rank neighbour lists (12 * N * k bytes), Laplacian assembled on every rank
 
 The summation tree of the Gram is fixed (segments -> slices), so every world size produces
 bit-identical graphs, lambdas and result lists.
@@ -81,6 +84,39 @@ class CudaEngine:
     def compute_lambdas(self, space, graph):
         _lib.check(self.lib.asp_space_compute_lambdas(space, graph))
 
+    # ---- item graph
+    def full_space(self, x_full):
+        """world-1 space over all items (device tensor)."""
+        n, f = x_full.shape
+        h = C.c_void_p()
+        self.torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_space_create(self.ctx, x_full.data_ptr(), n, f, n, 1, 0, C.byref(h)))
+        return h
+
+    def knn_rows(self, space, cgp, r0, r1):
+        """-> (idx int32[rows, kk], dist f64[rows, kk], cnt int32[rows]) device tensors."""
+        t = self.torch
+        rows = r1 - r0
+        kmax = max(1, min(int(cgp.k), 30))
+        idx = t.full((max(rows, 1), kmax), -1, dtype=t.int32, device=self.device)
+        dist = t.zeros((max(rows, 1), kmax), dtype=t.float64, device=self.device)
+        cnt = t.zeros((max(rows, 1),), dtype=t.int32, device=self.device)
+        kk = C.c_int32(0)
+        t.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_item_knn_rows(space, C.byref(cgp), r0, r1, idx.data_ptr(), dist.data_ptr(), cnt.data_ptr(), C.byref(kk)))
+        if kk.value != kmax:                       # k was capped at n - 1: the library wrote rows of kk entries
+            idx = idx.reshape(-1)[: rows * kk.value].reshape(rows, kk.value)
+            dist = dist.reshape(-1)[: rows * kk.value].reshape(rows, kk.value)
+        return idx[:rows], dist[:rows], cnt[:rows]
+
+    def graph_from_knn(self, n, idx, dist, cnt, cgp, sw):
+        hg = C.c_void_p()
+        idx, dist, cnt = idx.contiguous(), dist.contiguous(), cnt.contiguous()
+        self.torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_graph_from_knn(self.ctx, n, idx.shape[1], idx.data_ptr(), dist.data_ptr(), cnt.data_ptr(),
+                                               C.byref(cgp), C.byref(sw), C.byref(hg)))
+        return hg
+
     def to_comm(self, arr):
         return self.torch.from_numpy(arr).to(self.device)
 
@@ -145,6 +181,63 @@ def sharded_build(engine, shard, n_total, cgp, sw, group=None):
         raise RuntimeError("exact-pair resolution did not converge")
     engine.compute_lambdas(space, graph)
     return space, graph
+
+
+def _all_gather_ragged(t_local, counts, group):
+    """all-gather row blocks of different lengths (counts[r] rows on rank r) -> [sum(counts), ...]."""
+    import torch
+    world = len(counts)
+    per = max(counts)
+    pad = torch.zeros((per,) + tuple(t_local.shape[1:]), dtype=t_local.dtype, device=t_local.device)
+    if t_local.shape[0]:
+        pad[: t_local.shape[0]] = t_local
+    g = _all_gather_blocks(pad, world, group)
+    return torch.cat([g[r, : counts[r]] for r in range(world)], dim=0)
+
+
+def sharded_item_graph(engine, shard, n_total, row0, cgp, sw, group=None):
+    """Steps 4-5 above.  `shard` = rows [row0, row0 + len(shard)) of the item matrix as a tensor on the engine's
+    device.  Returns (world-1 space handle over ALL items, graph handle over n_total nodes) -- identical on every rank."""
+    dist = _dist()
+    import torch
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.tensor([shard.shape[0], row0], dtype=torch.int64, device=shard.device)
+    meta = _all_gather_blocks(mine, world, group).cpu().tolist()
+    counts = [int(m[0]) for m in meta]
+    starts = [int(m[1]) for m in meta]
+    if sum(counts) != n_total or starts != [sum(counts[:r]) for r in range(world)]:
+        raise ValueError("item shards must be contiguous row blocks in rank order (got starts %s, counts %s)" % (starts, counts))
+    x_full = _all_gather_ragged(shard, counts, group) if world > 1 else shard
+    if hasattr(engine, "after_collective"):
+        engine.after_collective()
+    space = engine.full_space(x_full)
+    idx, dst, cnt = engine.knn_rows(space, cgp, row0, row0 + counts[rank])
+    if world > 1:
+        idx = _all_gather_ragged(idx, counts, group)
+        dst = _all_gather_ragged(dst, counts, group)
+        cnt = _all_gather_ragged(cnt, counts, group)
+        if hasattr(engine, "after_collective"):
+            engine.after_collective()
+    graph = engine.graph_from_knn(n_total, idx, dst, cnt, cgp, sw)
+    return space, graph
+
+
+def build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=None, **extras):
+    """Multi-GPU item graph: every rank passes its contiguous row block; returns (ArrowSpace over all items, GraphLaplacian
+    over n_total nodes), the same on every rank."""
+    from . import api
+    import torch
+    gp = api.parse_graph_params(graph_params) or dict(api.DEFAULT_GRAPH_PARAMS)
+    cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+    sw = _lib.make_switches(extras.get("kernel", "inv_power"))
+    engine = CudaEngine(extras.get("device"))
+    if not (hasattr(items_shard, "data_ptr") and items_shard.is_cuda):
+        items_shard = torch.from_numpy(np.ascontiguousarray(items_shard, dtype=np.float64)).to(engine.device)
+    dist = _dist()
+    if group is None:
+        group = dist.group.WORLD
+    space, graph = sharded_item_graph(engine, items_shard.contiguous(), int(n_total), int(row0), cgp, sw, group)
+    return api.ArrowSpace._wrap(space, engine.ctx), api.GraphLaplacian._wrap(graph)
 
 
 def build_sharded(graph_params, items_shard, n_total, group=None, **extras):

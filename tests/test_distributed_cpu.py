@@ -138,3 +138,96 @@ def test_synthetic_shards_are_consistent():
         for r in (0, world - 1):
             r0, r1 = shard_rows(n, world, r)
             assert np.array_equal(synth.make_items(n, f, 44, rows=(r0, r1)), full[r0:r1])
+
+
+# ----------------------------------------------------------------------------- item graph across ranks (steps 4-5)
+
+class NumpyKnnEngine:
+    """Stands in for CudaEngine in `sharded_item_graph`: brute-force neighbour lists in numpy (the oracle's distance and
+    selection rule) and a numpy symmetrise + Laplacian."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def full_space(self, x_full):
+        return {"x": x_full.numpy().copy()}
+
+    def knn_rows(self, space, cgp, r0, r1):
+        x = space["x"]
+        n = x.shape[0]
+        kk = min(int(cgp.k), n - 1)
+        nrm = np.sqrt((x * x).sum(1))
+        idx = np.full((r1 - r0, kk), -1, dtype=np.int32)
+        dst = np.zeros((r1 - r0, kk))
+        cnt = np.zeros(r1 - r0, dtype=np.int32)
+        for i in range(r0, r1):
+            c = (x @ x[i]) / (nrm * nrm[i])
+            d = 1.0 - np.maximum(c, 0.0)
+            cand = [(d[j], j) for j in range(n) if j != i and d[j] <= cgp.eps]
+            cand.sort()
+            for e, (dj, j) in enumerate(cand[:kk]):
+                idx[i - r0, e], dst[i - r0, e] = j, dj
+            cnt[i - r0] = min(len(cand), kk)
+        t = self.torch
+        return t.from_numpy(idx), t.from_numpy(dst), t.from_numpy(cnt)
+
+    def graph_from_knn(self, n, idx, dist, cnt, cgp, sw):
+        idx, dist, cnt = idx.numpy(), dist.numpy(), cnt.numpy()
+        sigma = cgp.sigma if cgp.has_sigma else cgp.eps * 0.5
+        w = np.zeros((n, n))
+        for i in range(n):
+            for e in range(cnt[i]):
+                j = idx[i, e]
+                wij = 1.0 / (1.0 + (dist[i, e] / sigma) ** cgp.p)
+                w[i, j] = max(w[i, j], wij)
+                w[j, i] = max(w[j, i], wij)
+        return {"edges": sorted((i, j) for i in range(n) for j in range(i + 1, n) if w[i, j] > 0)}
+
+
+def _item_graph_worker(rank, world, port, n, f, q):
+    import torch
+    import torch.distributed as dist
+    try:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        from pyarrowspace_b200 import _lib, synth
+        from pyarrowspace_b200.distributed import sharded_item_graph
+        # deliberately ragged contiguous blocks
+        cuts = [0] + [int(n * (r + 1) / world) + (3 if r % 2 == 0 and r + 1 < world else 0) for r in range(world)]
+        cuts[-1] = n
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        shard = torch.from_numpy(synth.make_items(n, f, 5, n_clusters=4)[r0:r1].copy())
+        cgp = _lib.make_params(0.4, 4, 3, 2.0, None)
+        space, graph = sharded_item_graph(NumpyKnnEngine(), shard, n, r0, cgp, _lib.make_switches(), None)
+        q.put((rank, graph["edges"], space["x"].shape))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:                                              # pragma: no cover
+        q.put((rank, "error", repr(e)))
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_item_graph_over_gloo(world, oracle_mod):
+    """Halo all-gather of ragged item shards + all-gather of the per-rank neighbour lists reproduce the single-process
+    oracle's item graph on every rank."""
+    import torch.multiprocessing as mp
+    from pyarrowspace_b200 import synth
+    n, f = 240, 10
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_item_graph_worker, args=(r, world, port, n, f, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] != "error" for r in res), res
+    x = synth.make_items(n, f, 5, n_clusters=4)
+    s, g = oracle_mod.build({"eps": 0.4, "k": 4, "topk": 3, "p": 2.0, "sigma": None}, x, nodes="items")
+    want = [tuple(int(v) for v in e) for e in g.edges()]
+    for r in res:
+        assert r[2] == (n, f)
+        assert [tuple(e) for e in r[1]] == want

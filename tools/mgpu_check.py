@@ -42,6 +42,37 @@ def main():
             print("world", world, "n", n, "f", f, "edges/idx/score/lambda vs oracle:", e[:4], " vs single GPU (bitwise):", e[4:])
             ok = ok and all(e)
         dist.barrier()
+    # item graph across the ranks: halo all-gather of the item shards, rows resolved per rank on the tensor cores,
+    # all-gather of the neighbour lists; every rank must end with the single-GPU graph (bitwise) == the oracle's edges
+    import time
+    for n, f, gp in [(24000, 96, {"eps": 0.3, "k": 12, "topk": 3, "p": 2.0, "sigma": None}),
+                     (int(os.environ.get("IG_N", 60000)), 384, {"eps": 10.0, "k": 25, "topk": 3, "p": 2.0, "sigma": None})]:
+        per = (n + world - 1) // world
+        r0, r1 = min(rank * per, n), min((rank + 1) * per, n)
+        full = synth.make_items(n, f, 11, n_clusters=16)
+        shard = torch.from_numpy(full[r0:r1].copy()).cuda()
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.time()
+        aspace, gl = ArrowSpaceBuilder.build_item_graph_sharded(gp, shard, n, r0, device=local)
+        torch.cuda.synchronize(); dist.barrier(); dt = time.time() - t0
+        os.environ["ASP_KNN_STAGE1"] = "tc"
+        torch.cuda.synchronize(); t1 = time.time()
+        a1, g1 = ArrowSpaceBuilder.build_item_graph(gp, torch.from_numpy(full).cuda(), device=local)
+        torch.cuda.synchronize(); d1 = time.time() - t1
+        os.environ.pop("ASP_KNN_STAGE1", None)
+        same = all(np.array_equal(a, b) for a, b in zip(gl.csr(), g1.csr()))
+        flags = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            e = [bool(flags.item())]
+            if n <= 30000:
+                import oracle
+                s, g = oracle.build(gp, full, nodes="items")
+                e.append(np.array_equal(gl.edges(), g.edges()))
+            print("world", world, "item graph n", n, "f", f, "sharded %.3f s, single GPU %.3f s" % (dt, d1),
+                  "all ranks == single GPU (bitwise):", e[0], "" if len(e) < 2 else "== oracle edges: %s" % e[1])
+            ok = ok and all(e)
+        del aspace, gl, a1, g1
+        dist.barrier()
     if rank == 0:
         print("MGPU_CHECK", "OK" if ok else "FAILED")
     dist.destroy_process_group()
