@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-queries", type=int, default=64)
     ap.add_argument("--ref-queries", type=int, default=256, help="--impl reference: queries per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-item-graph", action="store_true", help="skip the item-graph (nodes = items) build of the C4 matrix")
     return ap.parse_args()
 
 
@@ -281,6 +282,8 @@ def main():
         slow = api.stat("search_slow_queries", local)
         stage1_is_tc = api.stat("search_stage1_is_tc", local) == 1.0
         rescored = api.stat("search_rescored_per_query", local) if stage1_is_tc else None
+        sstat = {k: api.stat(k, local) for k in ("search_terms", "search_stage2_ms", "search_a_resident", "search_delta_cos_max",
+                                                  "search_rho_q_max", "search_rho_x_max", "search_exact_per_query")}
         # end to end: pinned host queries in, host results out, every step
         for w in range(2):
             aspace.search_batch(q_host[w % nbatch].numpy(), gl, tau)
@@ -292,6 +295,35 @@ def main():
         barrier_sync()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- item graph (nodes = items) of the same matrix: the graph-build workload of C4 (eps / k-NN lists of all 1M items
+    # against all 1M items on the tensor cores, exact stage 2, Laplacian CSR); sharded over the ranks when N > 1
+    item_graph = None
+    if not args.no_item_graph:
+        del aspace, gl
+        ig_ms = []
+        with torch.cuda.stream(stream):
+            for rep in range(2):
+                barrier_sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if world == 1:
+                    a_ig, g_ig = ArrowSpaceBuilder.build_item_graph(gp, x_dev, device=local)
+                else:
+                    a_ig, g_ig = ArrowSpaceBuilder.build_item_graph_sharded(gp, x_dev, n, r0, device=local)
+                e1.record(stream)
+                barrier_sync()
+                ig_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+                ig_nnz = g_ig.nnz
+                ig_stats = {k: api.stat(k, local) for k in ("knn_stage1_ms", "knn_stage2_ms", "knn_slow_rows", "knn_rescored_per_row")}
+                del a_ig, g_ig
+        ig_exec = 2.0 * n * (r1 - r0) * 16.0 * ((f + 3 + 15) // 16)
+        item_graph = {"ms": min(ig_ms), "items_per_s": n / (min(ig_ms) * 1e-3), "nnz": int(ig_nnz),
+                      "rows_per_rank": r1 - r0, "stage1_ms": ig_stats["knn_stage1_ms"], "stage2_ms": ig_stats["knn_stage2_ms"],
+                      "exact_scan_rows": ig_stats["knn_slow_rows"], "rescored_per_row": ig_stats["knn_rescored_per_row"],
+                      "algorithmic_flop": 2.0 * n * (r1 - r0) * f, "executed_fp16_flop": ig_exec,
+                      "stage1_tflops": ig_exec / (ig_stats["knn_stage1_ms"] * 1e-3) / 1e12 if ig_stats["knn_stage1_ms"] > 0 else None,
+                      "note": "rows of this rank against all %d items; N > 1: + all-gather of the item shards and of the lists" % n}
 
     # sanity: a perturbed copy must find its source item (size-independent property)
     stage1_ms = max_over_ranks(float(np.mean(stage1)))
@@ -317,7 +349,7 @@ def main():
     except Exception:
         pass
     if stage1_is_tc:
-        terms = int(api.stat("search_terms", local))
+        terms = int(sstat["search_terms"])
         ksteps = (f + 3 + 15) // 16 + (2 * ((f + 15) // 16) if terms == 3 else 0)   # K=16 MMA steps per (query, item) tile pair
         executed = 2.0 * Q * n_local * 16.0 * ksteps
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
@@ -336,12 +368,12 @@ def main():
                     "algorithmic_tflops": gemm_flop / (stage1_ms * 1e-3) / 1e12,
                     "fp64_tensor_peak_tflops": fp64_peak_tflops,
                     "kernel_ms": stage1_ms, "share_of_step": stage1_ms / step_ms,
-                    "stage2_ms": api.stat("search_stage2_ms", local),
-                    "mma_terms": terms, "query_operand_resident": api.stat("search_a_resident", local) == 1.0,
-                    "band_cos_max": api.stat("search_delta_cos_max", local),
-                    "residual_norms": {"rho_q_max": api.stat("search_rho_q_max", local), "rho_x_max": api.stat("search_rho_x_max", local)},
+                    "stage2_ms": sstat["search_stage2_ms"],
+                    "mma_terms": terms, "query_operand_resident": sstat["search_a_resident"] == 1.0,
+                    "band_cos_max": sstat["search_delta_cos_max"],
+                    "residual_norms": {"rho_q_max": sstat["search_rho_q_max"], "rho_x_max": sstat["search_rho_x_max"]},
                     "rescored_candidates_per_query": rescored,
-                    "reference_order_rescored_per_query": api.stat("search_exact_per_query", local),
+                    "reference_order_rescored_per_query": sstat["search_exact_per_query"],
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peak == sustained
                                     else "MEASURED_PEAKS.json bf16_tflops (burst): the kernel ran above the sustained figure %.1f" % sustained)
                                    if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
@@ -375,6 +407,7 @@ def main():
                   "graph_ms": float(np.mean(stages["graph_ms"])),
                   "lambda": {"ms": lam_ms, "bound": "hbm", "achieved_gbs": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9,
                              "frac": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak}},
+        "item_graph": item_graph,
         "clocks": clk,
     }
     if not args.no_cpu_baseline:

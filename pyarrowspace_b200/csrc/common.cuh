@@ -145,7 +145,8 @@ struct asp_tc_batch {                     // device buffers of one batch of quer
     uint32_t *theta_glob = nullptr;
 };
 int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
-                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, float *dump_dev, asp_tc_batch *b);
+                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, int force_terms, int capb_override,
+                  float *dump_dev, asp_tc_batch *b);
 void asp_tc_batch_free(asp_ctx *ctx, asp_tc_batch *b);
 bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, double tau);
 int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,

@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(KR_WARPS * 32)
 knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pitch, const double *__restrict__ norms,
                       double eps, int kk, int64_t b0, int64_t nq, int nsub, int capb, const float *__restrict__ delta_q,
                       double eps_fast, const float *__restrict__ emit_sc, const int32_t *__restrict__ emit_ix,
-                      const int32_t *__restrict__ emit_cnt, const int32_t *__restrict__ qperm, int64_t out_row0,
+                      const int32_t *__restrict__ emit_cnt, const int32_t *__restrict__ qperm, const int32_t *__restrict__ row_map,
+                      int64_t out_row0,
                       int32_t *__restrict__ out_idx, double *__restrict__ out_dist, int32_t *__restrict__ out_cnt,
                       int32_t *slow_list, int32_t *slow_count, unsigned long long *survivor_total)
 {
@@ -217,7 +218,8 @@ knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pi
     int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)KR_WARPS * pitch) + warp * KT_QUEUE;
     const int64_t qi = (int64_t)blockIdx.x * KR_WARPS + warp;                    // visiting position inside the batch
     if (qi >= nq) return;
-    const int64_t i = b0 + (qperm ? (int64_t)qperm[qi] : qi);                    // the row (item) this warp resolves
+    const int64_t qp = qperm ? (int64_t)qperm[qi] : qi;                          // position in the batch as passed
+    const int64_t i = row_map ? (int64_t)row_map[qp] : b0 + qp;                  // the row (item) this warp resolves
     for (int j = lane; j < pitch; j += 32) xs[j] = items[i * pitch + j];         // rows are zero padded to the pitch
     const int kq = kk + 1;                                                       // the item finds itself
 
@@ -450,7 +452,23 @@ static int item_knn_fp64(asp_space *s, const asp_graph_params *gp, asp_knn_lists
 }
 
 // Item-graph neighbour lists on the tensor cores: batches of 64k rows through asp_tc_stage1, exact stage 2 above.
-// rows [row_begin, row_end) against all items of the space; lists->idx/dist/cnt hold (row_end - row_begin) rows
+__global__ void gather_rows_kernel(const double *__restrict__ items, int pitch, const double *__restrict__ norms,
+                                   const int32_t *__restrict__ rows, int64_t nrows, double *__restrict__ out, double *__restrict__ out_norms)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        const int64_t src = rows[r];
+        for (int j = lane; j < pitch; j += 32) out[r * pitch + j] = items[src * pitch + j];
+        if (lane == 0) out_norms[r] = norms[src];
+    }
+}
+
+// rows [row_begin, row_end) against all items of the space; lists->idx/dist/cnt hold (row_end - row_begin) rows.
+//   pass 1  every row, candidate pass with as few MMA terms as the residual norms allow (usually ONE fp16 term)
+//   pass 2  the rows whose emission lists or bands overflowed (dense neighbourhoods: the 1-term band of ~1e-4 in cosine
+//           can hold hundreds of neighbours) are gathered and redone with the two-term split (band ~1e-6)
+//   pass 3  what is still unresolved (long runs of exact ties around the k-th neighbour) takes the exact scan
 static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int64_t row_begin, int64_t row_end, asp_knn_lists *lists)
 {
     asp_ctx *ctx = s->ctx;
@@ -460,28 +478,32 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
     const double u = 1.1102230246251565e-16;
     const double eps_fast = (4.0 * f + 64.0) * u * 2.0;
     const double floor = (gp->eps < 2.0) ? 1.0 - gp->eps - eps_fast : -INFINITY;   // cos < 1 - eps can never be a neighbour
-    int32_t *slow_list = nullptr, *slow_count = nullptr;
+    const int64_t rows = row_end - row_begin;
+    int32_t *slow1 = nullptr, *slow2 = nullptr, *counts = nullptr;                  // counts[0], counts[1]
     unsigned long long *counter = nullptr;
-    ASP_CUDA(cudaMallocAsync(&slow_list, sizeof(int32_t) * (n + 1), st));
-    ASP_CUDA(cudaMallocAsync(&slow_count, sizeof(int32_t), st));
+    ASP_CUDA(cudaMallocAsync(&slow1, sizeof(int32_t) * (rows + 1), st));
+    ASP_CUDA(cudaMallocAsync(&slow2, sizeof(int32_t) * (rows + 1), st));
+    ASP_CUDA(cudaMallocAsync(&counts, sizeof(int32_t) * 2, st));
     ASP_CUDA(cudaMallocAsync(&counter, sizeof(unsigned long long), st));
-    ASP_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(int32_t), st));
+    ASP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 2, st));
     ASP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     const size_t rsmem = (size_t)KR_WARPS * s->fp * 8 + KR_WARPS * KT_QUEUE * 4;
     ASP_CUDA(cudaFuncSetAttribute(knn_tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     int64_t batch = 65536;
     if (const char *e = getenv("ASP_KNN_BATCH")) { const long v = atol(e); if (v >= 128) batch = v; }
     double stage1_ms = 0.0, stage2_ms = 0.0;
-    int rc = ASP_OK;
-    for (int64_t b0 = row_begin; b0 < row_end && rc == ASP_OK; b0 += batch) {
-        const int64_t nq = (row_end - b0 < batch) ? row_end - b0 : batch;
+    int rc = ASP_OK, terms_pass1 = 0;
+
+    // one batch of query rows: q = their vectors (contiguous), row_map = their item indices (nullptr: b0 + position)
+    auto run_batch = [&](const double *q, const double *qn, int64_t nq, int64_t b0, const int32_t *row_map, int terms,
+                         int32_t *slow_list, int32_t *slow_count, int *terms_used) -> int {
         asp_tc_batch b;
-        rc = asp_tc_stage1(s, s->items + b0 * s->fp, nq, s->fp, nullptr, s->norms + b0, 1.0, kk + 1, floor, nullptr, &b);
-        if (rc == ASP_OK) {
+        int r = asp_tc_stage1(s, q, nq, s->fp, nullptr, qn, 1.0, kk + 1, floor, terms, 2048, nullptr, &b);
+        if (r == ASP_OK) {
             knn_tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, KR_WARPS), KR_WARPS * 32, rsmem, st>>>(
                 s->items, n, f, s->fp, s->norms, gp->eps, (int)kk, b0, nq, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix,
-                b.emit_cnt, b.qperm, row_begin, lists->idx, lists->dist, lists->cnt, slow_list, slow_count, counter);
-            if (cudaGetLastError() != cudaSuccess) { asp_set_error("knn_tc_rescore_kernel launch failed"); rc = ASP_ERR_CUDA; }
+                b.emit_cnt, b.qperm, row_map, row_begin, lists->idx, lists->dist, lists->cnt, slow_list, slow_count, counter);
+            if (cudaGetLastError() != cudaSuccess) { asp_set_error("knn_tc_rescore_kernel launch failed"); r = ASP_ERR_CUDA; }
             ASP_LAUNCHED(ctx);
             cudaEventRecord(ctx->ev2, st);
             cudaEventSynchronize(ctx->ev2);
@@ -489,27 +511,65 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
             cudaEventElapsedTime(&m1, ctx->ev0, ctx->ev1);
             cudaEventElapsedTime(&m2, ctx->ev1, ctx->ev2);
             stage1_ms += m1; stage2_ms += m2;
+            *terms_used = b.nterms;
         }
         asp_tc_batch_free(ctx, &b);
+        return r;
+    };
+
+    for (int64_t b0 = row_begin; b0 < row_end && rc == ASP_OK; b0 += batch) {
+        const int64_t nq = (row_end - b0 < batch) ? row_end - b0 : batch;
+        rc = run_batch(s->items + b0 * s->fp, s->norms + b0, nq, b0, nullptr, 0, slow1, counts, &terms_pass1);
     }
-    int32_t nslow = 0;
+    int32_t h_counts[2] = {0, 0};
+    if (rc == ASP_OK) {
+        ASP_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    const int32_t n_pass2 = (terms_pass1 == 1) ? h_counts[0] : 0;
+    const int32_t *final_list = slow1;
+    int32_t n_final = h_counts[0];
+    if (rc == ASP_OK && n_pass2 > 0) {
+        double *qbuf = nullptr, *qnorm = nullptr;
+        const int64_t chunk = n_pass2 < batch ? n_pass2 : batch;
+        ASP_CUDA(cudaMallocAsync(&qbuf, sizeof(double) * (size_t)chunk * s->fp, st));
+        ASP_CUDA(cudaMallocAsync(&qnorm, sizeof(double) * (size_t)chunk, st));
+        for (int64_t c0 = 0; c0 < n_pass2 && rc == ASP_OK; c0 += chunk) {
+            const int64_t nq = (n_pass2 - c0 < chunk) ? n_pass2 - c0 : chunk;
+            gather_rows_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(s->items, s->fp, s->norms, slow1 + c0, nq, qbuf, qnorm);
+            ASP_LAUNCHED(ctx);
+            int used = 0;
+            rc = run_batch(qbuf, qnorm, nq, 0, slow1 + c0, 3, slow2, counts + 1, &used);
+        }
+        cudaFreeAsync(qbuf, st); cudaFreeAsync(qnorm, st);
+        if (rc == ASP_OK) {
+            ASP_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+            ASP_CUDA(cudaStreamSynchronize(st));
+        }
+        final_list = slow2;
+        n_final = h_counts[1];
+    }
     unsigned long long nsurv = 0;
     if (rc == ASP_OK) {
-        ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         ASP_CUDA(cudaMemcpyAsync(&nsurv, counter, sizeof(nsurv), cudaMemcpyDeviceToHost, st));
         ASP_CUDA(cudaStreamSynchronize(st));
         ctx->stats["knn_stage1_ms"] = stage1_ms;
         ctx->stats["knn_stage2_ms"] = stage2_ms;
-        ctx->stats["knn_slow_rows"] = nslow;
+        ctx->stats["knn_rows_two_term"] = n_pass2;
+        ctx->stats["knn_slow_rows"] = n_final;
         ctx->stats["knn_stage1_is_tc"] = 1.0;
-        ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)(row_end > row_begin ? row_end - row_begin : 1);
-        if (nslow > 0) {                                              // the exact kernels index the lists by GLOBAL row
+        ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)(rows > 0 ? rows : 1);
+        if (n_final > 8192) {
+            asp_set_error("item graph: %d rows need the exact scan even after the two-term pass (long runs of ties around the "
+                          "k-th neighbour?); use ASP_KNN_STAGE1=fp64", n_final);
+            rc = ASP_ERR_UNSUPPORTED;
+        } else if (n_final > 0) {                                     // the exact kernels index the lists by GLOBAL row
             asp_knn_lists shifted = *lists;
             shifted.idx = lists->idx - row_begin * kk; shifted.dist = lists->dist - row_begin * kk; shifted.cnt = lists->cnt - row_begin;
-            rc = knn_slow_rows(s, gp, kk, slow_list, nslow, &shifted);
+            rc = knn_slow_rows(s, gp, kk, final_list, n_final, &shifted);
         }
     }
-    cudaFreeAsync(slow_list, st); cudaFreeAsync(slow_count, st); cudaFreeAsync(counter, st);
+    cudaFreeAsync(slow1, st); cudaFreeAsync(slow2, st); cudaFreeAsync(counts, st); cudaFreeAsync(counter, st);
     return rc;
 }
 

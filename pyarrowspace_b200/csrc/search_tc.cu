@@ -938,7 +938,8 @@ bool asp_search_tc_supported(const asp_space *s, int64_t nq, int64_t topk, doubl
 // lambda_q_dev == nullptr: no lambda term (kNN): identity query order.  dump_dev != nullptr: approximate cosines
 // [nq][n_local] f32 (tests), no emission.
 int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t qpitch, const double *lambda_q_dev,
-                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, float *dump_dev, asp_tc_batch *b)
+                  const double *qnorm_dev, double tau, int64_t topk, double score_floor, int force_terms, int capb_override,
+                  float *dump_dev, asp_tc_batch *b)
 {
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -977,6 +978,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     const double c_fixed = 2.0 * (3.0 * ldexp(1.0, -22) + 4.0 * ldexp(1.0, -23) + 1e-12);
     int nterms = (rho_q_max * c_main1 + c_fixed <= 2.5e-4) ? 1 : 3;
     if (const char *e = getenv("ASP_TC_TERMS")) { const int v = atoi(e); if (v == 1 || v == 3) nterms = v; }
+    if (force_terms == 1 || force_terms == 3) nterms = force_terms;
     if (nterms == 3) ASP_CHECK(ensure_tc_lo(s, c));
     const double c_main = (nterms == 1) ? c_main1 : c_main3;
     row_delta_kernel<<<64, 256, 0, st>>>(b->rho_q, nq, c_main, c_fixed, fabs(tau), (fabs(tau) + fabs(1.0 - tau)) * 2e-6, b->delta_q);
@@ -1016,7 +1018,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
         if (eff >= 0.97 || cc == tiles_total) break;
     }
     const int nchunks = (int)best_chunks;
-    int capb = dump_dev ? 1 : 1024;                                  // per (query, chunk)
+    int capb = dump_dev ? 1 : (capb_override > 0 ? capb_override : 1024);   // per (query, chunk)
     if (const char *e = getenv("ASP_TC_CAPB")) {                     // test knob: shrink the emission buffers
         const int v = atoi(e);
         if (!dump_dev && v >= 8 && v <= 65536) capb = v;
@@ -1101,7 +1103,7 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     asp_tc_batch b;
-    int rc = asp_tc_stage1(s, q_dev, nq, qpitch, lambda_q_dev, qnorm_dev, tau, topk, -INFINITY, dump_dev, &b);
+    int rc = asp_tc_stage1(s, q_dev, nq, qpitch, lambda_q_dev, qnorm_dev, tau, topk, -INFINITY, 0, 0, dump_dev, &b);
     if (rc != ASP_OK || dump_dev) { asp_tc_batch_free(ctx, &b); return rc; }
 
     if (b.variant != 0) {                                         // profiling variants: stage 1 only, results are garbage

@@ -14,6 +14,11 @@ lab = torch.randint(0, 256, (n,), generator=g, device="cuda")
 x = centres[lab] + 0.3 * torch.randn(n, f, generator=g, device="cuda", dtype=torch.float64)
 x = x / x.norm(dim=1, keepdim=True) * 100.0 + 25.0
 gp = {"eps": 10.0, "k": 25, "topk": 10, "p": 2.0, "sigma": None}
+if os.environ.get("SYNTH"):                      # the bench's C4 matrix
+    from pyarrowspace_b200 import synth
+    c = synth.config("C4")
+    x = torch.from_numpy(synth.make_items(n, f, c["seed"], c["scale"])).cuda()
+    gp = c["graph_params"]
 out = {"n": n, "f": f}
 for mode in modes:
     os.environ["ASP_KNN_STAGE1"] = mode
@@ -21,7 +26,7 @@ for mode in modes:
         torch.cuda.synchronize(); t0 = time.time()
         aspace, gl = ArrowSpaceBuilder.build_item_graph(gp, x)
         torch.cuda.synchronize(); dt = time.time() - t0
-        st = {k: api.stat(k) for k in ("knn_stage1_ms", "knn_stage2_ms", "knn_slow_rows", "knn_rescored_per_row", "knn_stage1_is_tc")}
+        st = {k: api.stat(k) for k in ("knn_stage1_ms", "knn_stage2_ms", "knn_slow_rows", "knn_rows_two_term", "knn_rescored_per_row", "knn_stage1_is_tc")}
         print(mode, rep, "wall %.3f s" % dt, st, "nnz", gl.nnz if hasattr(gl, "nnz") else None, flush=True)
         del aspace, gl
     out[mode] = dict(st, wall_s=dt)
