@@ -30,6 +30,9 @@ _DEBUG = False
 DEFAULT_GRAPH_PARAMS = {"eps": 1e-3, "k": 6, "topk": 3, "p": 2.0, "sigma": 1e-3}
 
 
+LAST_CALL_TRACE = {}       # host-side wall times of the last search call (diagnostics: tools/latency.py)
+
+
 class PanicException(BaseException):
     """Stand-in for pyo3_runtime.PanicException: the reference `.unwrap()`s / `assert_ne!`s inside
     build and search (src/lib.rs:156-159,277,279), which surfaces as a BaseException subclass."""
@@ -233,6 +236,8 @@ class ArrowSpace:
         return idx, score
 
     def _search_batch(self, queries, gl, tau, want_lambda):
+        import time
+        t_a = time.perf_counter()
         lib = _lib.load()
         f = self.nfeatures
         topk = gl.graph_params["topk"]
@@ -266,8 +271,11 @@ class ArrowSpace:
             score = np.empty((nq, topk), dtype=np.float64)
             lam = np.empty(nq, dtype=np.float64)
             qp, ip, sp, lp = q.ctypes.data, idx.ctypes.data, score.ctypes.data, lam.ctypes.data
+        t_b = time.perf_counter()
         try:
             _lib.check(lib.asp_search_batch(self._h, gl._h, qp, nq, tau, ip, sp, lp))
+            LAST_CALL_TRACE["prepare_ms"] = (t_b - t_a) * 1e3
+            LAST_CALL_TRACE["library_ms"] = (time.perf_counter() - t_b) * 1e3
         except LibraryError as e:
             if e.code == _lib.ASP_ERR_LAMBDA_ZERO:                          # src/lib.rs:156-159
                 raise PanicException("assertion `left != right` failed: %s\n  left: 0.0\n right: 0.0" % e.message)

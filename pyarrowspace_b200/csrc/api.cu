@@ -81,15 +81,15 @@ __global__ void zero_lambda_check_kernel(const double *lam, int64_t n, int *flag
 }
 
 // upload an n x f row-major matrix (host or device) into a pitched, zero padded device buffer
-int upload_pitched(asp_ctx *ctx, const double *src, int64_t n, int32_t f, int32_t pitch, double *dst)
+int upload_pitched(cudaStream_t st, const double *src, int64_t n, int32_t f, int32_t pitch, double *dst)
 {
     if (pitch == f) {       // one contiguous copy (a 2-D copy from pageable memory is staged row by row: ~1 GB/s)
-        ASP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n * f, cudaMemcpyDefault, ctx->stream));
+        ASP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n * f, cudaMemcpyDefault, st));
         return ASP_OK;
     }
-    ASP_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)n * pitch, ctx->stream));
+    ASP_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)n * pitch, st));
     ASP_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * pitch, src, sizeof(double) * f, sizeof(double) * f, (size_t)n,
-                               cudaMemcpyDefault, ctx->stream));
+                               cudaMemcpyDefault, st));
     return ASP_OK;
 }
 
@@ -149,6 +149,8 @@ void asp_ctx_destroy(asp_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     delete ctx;
 }
 
@@ -225,7 +227,7 @@ int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, i
     ASP_CUDA(cudaMallocAsync(&s->norms, sizeof(double) * n_local, ctx->stream));
     ASP_CUDA(cudaMallocAsync(&s->inv_norms, sizeof(double) * n_local, ctx->stream));
     ASP_CUDA(cudaMallocAsync(&s->lambdas, sizeof(double) * n_local, ctx->stream));
-    int rc = upload_pitched(ctx, items_shard, n_local, f, s->fp, s->items);
+    int rc = upload_pitched(ctx->stream, items_shard, n_local, f, s->fp, s->items);
     if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_gram, s->items, n_local, s->fp, ASP_ROW_UNIT, 32);
     if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n_local, s->fp, 128, 4);
     if (rc == ASP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -255,7 +257,7 @@ void asp_free_graph(asp_graph *g)
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     cudaStream_t st = g->ctx->stream;
-    void *bufs[] = {g->d_indptr, g->d_indices, g->d_data, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg};
+    void *bufs[] = {g->d_indptr, g->d_indices, g->d_data, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, g->d_tm_chunks};
     for (void *b : bufs)
         if (b) cudaFreeAsync(b, st);
     delete g;
@@ -562,6 +564,48 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw_in
     return ASP_OK;
 }
 
+// One device-resident batch: lambda_q (src/lib.rs:154), the lambda_q != 0 guard (src/lib.rs:156-159), candidate pass +
+// exact stage 2.  `flags` is a 2-int device scratch.  Synchronises ctx->stream before returning.
+static int search_device_batch(const asp_space *s, const asp_graph *g, const double *dq, int64_t nq, double tau, int64_t topk,
+                               double *dlam, double *dnorm, int *flags, int64_t *didx, double *dscore)
+{
+    asp_ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int32_t f = s->f, fp = s->fp;
+    ASP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, st));
+    ASP_CHECK(asp_launch_taumode(ctx, g, &g->sw, dq, nq, f, fp, nullptr, nullptr, dlam, dnorm, nullptr, flags));
+    zero_lambda_check_kernel<<<64, 256, 0, st>>>(dlam, nq, flags + 1);
+    ASP_LAUNCHED(ctx);
+    int h[2] = {0, 0};
+    ASP_CUDA(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    ASP_CUDA(cudaStreamSynchronize(st));
+    if (h[0]) ASP_FAIL(ASP_ERR_ZERO_VECTOR, "a query vector is all zeros: its Rayleigh quotient is undefined");
+    if (h[1]) ASP_FAIL(ASP_ERR_LAMBDA_ZERO, "The lambdas are zero, check the magnitude of items and eps.");   // src/lib.rs:156-159
+    if (topk <= 0) return ASP_OK;
+    // stage 1 on tcgen05 (fp16 split) for batches, FP64 DMMA / GEMV otherwise; same exact stage 2, same answers
+    const char *force = getenv("ASP_SEARCH_STAGE1");
+    const bool want_fp64 = force && force[0] == 'f';
+    const bool want_tc = force && force[0] == 't';
+    int rc;
+    // small batches against a large shard stream the fp16 operands (2 * kp bytes per item) instead of the f64 rows
+    if (!want_fp64 && asp_search_tc_supported(s, nq, topk, tau) && (want_tc || nq >= 256 || s->n_local >= 131072))
+        rc = asp_search_tc_impl(s, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore, nullptr);
+    else
+        rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
+    if (rc == ASP_OK) ASP_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+// Large host batches are pipelined in TWO pieces: a short head (1/32 of the batch) and the rest.  The head's kernels run
+// under the H2D copy of the rest (copy stream `up`), the head's D2H copy (copy stream `down`) under the kernels of the
+// rest.  The head is sized so that its kernels last about as long as the rest's upload: more or larger pieces were
+// measured and lose, because every piece pays its own host synchronisations, GEMM tail and threshold warm-up (an 8k-query
+// head costs 7.9 ms against 6.7 ms pro rata at C4; tools/latency.py, profiles/latency_r01.json).
+// Result arrays handed in by the caller are usually freshly allocated pageable memory whose first touch page-faults at
+// ~3 GB/s inside the D2H copy (10.5 MB per 64k queries: 3 ms after the last kernel); they are touched on this thread
+// while the kernels run instead (ctx->on_wait).
+constexpr int64_t ASP_PIPE_MIN_BATCH = 32768;
+
 int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq, double tau,
                      int64_t *out_idx, double *out_score, double *out_lambda_q)
 {
@@ -583,34 +627,96 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     ASP_CUDA(cudaMallocAsync(&dlam, sizeof(double) * nq, st));
     ASP_CUDA(cudaMallocAsync(&dnorm, sizeof(double) * nq, st));
     ASP_CUDA(cudaMallocAsync(&flags, sizeof(int) * 2, st));
-    ASP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, st));
-    int rc = upload_pitched(ctx, queries, nq, f, fp, dq);
-    if (rc == ASP_OK)
-        rc = asp_launch_taumode(ctx, g, &g->sw, dq, nq, f, fp, nullptr, nullptr, dlam, dnorm, nullptr, flags);   // src/lib.rs:154
-    if (rc == ASP_OK) {
-        zero_lambda_check_kernel<<<64, 256, 0, st>>>(dlam, nq, flags + 1);
-        ASP_LAUNCHED(ctx);
-        int h[2] = {0, 0};
-        ASP_CUDA(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-        ASP_CUDA(cudaStreamSynchronize(st));
-        if (h[0]) { asp_set_error("a query vector is all zeros: its Rayleigh quotient is undefined"); rc = ASP_ERR_ZERO_VECTOR; }
-        else if (h[1]) { asp_set_error("The lambdas are zero, check the magnitude of items and eps."); rc = ASP_ERR_LAMBDA_ZERO; }   // src/lib.rs:156-159
-    }
-    if (rc == ASP_OK && out_lambda_q) rc = asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq);
-    if (rc == ASP_OK && topk > 0) {
+    if (topk > 0) {
         ASP_CUDA(cudaMallocAsync(&didx, sizeof(int64_t) * (size_t)nq * topk, st));
         ASP_CUDA(cudaMallocAsync(&dscore, sizeof(double) * (size_t)nq * topk, st));
-        // stage 1 on tcgen05 (bf16 split) for batches, FP64 DMMA / GEMV otherwise; same exact stage 2, same answers
-        const char *force = getenv("ASP_SEARCH_STAGE1");
-        const bool want_fp64 = force && force[0] == 'f';
-        const bool want_tc = force && force[0] == 't';
-        if (!want_fp64 && asp_search_tc_supported(s, nq, topk, tau) && (want_tc || nq >= 256))
-            rc = asp_search_tc_impl(s, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore, nullptr);
-        else
-            rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
-        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
-        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
-        ASP_CUDA(cudaStreamSynchronize(st));
+    }
+    const char *nopipe = getenv("ASP_NO_PIPELINE");
+    const bool host_io = !asp_is_device_ptr(queries) && !asp_is_device_ptr(out_idx) && !asp_is_device_ptr(out_score) &&
+                         (!out_lambda_q || !asp_is_device_ptr(out_lambda_q));
+    int64_t head = std::max<int64_t>(1024, (nq / 32 + 127) / 128 * 128);
+    if (const char *e = getenv("ASP_PIPE_HEAD")) { const long v = atol(e); if (v >= 128 && v < nq) head = v; }   // tuning knob
+    int rc = ASP_OK;
+    auto prefault = [=](int64_t q0, int64_t qn) {                 // first touch of the caller's result pages
+        if (out_lambda_q) memset(out_lambda_q + q0, 0, sizeof(double) * qn);
+        if (topk > 0) {
+            memset(out_idx + q0 * topk, 0, sizeof(int64_t) * (size_t)qn * topk);
+            memset(out_score + q0 * topk, 0, sizeof(double) * (size_t)qn * topk);
+        }
+    };
+    const bool touch = host_io && (size_t)nq * (topk + 1) * 16 >= (1u << 18);
+    if (host_io && nq >= ASP_PIPE_MIN_BATCH && !(nopipe && nopipe[0] == '1')) {
+        if (!ctx->up_stream) {
+            ASP_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+            ASP_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+        }
+        const int nch = 2;
+        const int64_t bounds[3] = {0, head, nq};
+        cudaEvent_t up[nch], done[nch], alloc_ready;
+        for (auto &e : up) cudaEventCreate(&e);
+        for (auto &e : done) cudaEventCreate(&e);
+        cudaEventCreate(&alloc_ready);
+        cudaEvent_t start_c[nch];                                  // timeline diagnostics (search_pipe_* stats)
+        for (auto &e : start_c) cudaEventCreate(&e);
+        // the copy stream may touch dq only once the allocation is ordered on st
+        cudaEventRecord(alloc_ready, st);
+        cudaStreamWaitEvent(ctx->up_stream, alloc_ready, 0);
+        for (int c = 0; c < nch && rc == ASP_OK; ++c) {
+            const int64_t q0 = bounds[c], qn = bounds[c + 1] - q0;
+            rc = upload_pitched(ctx->up_stream, queries + q0 * f, qn, f, fp, dq + q0 * fp);
+            if (rc == ASP_OK && cudaEventRecord(up[c], ctx->up_stream) != cudaSuccess) rc = ASP_ERR_CUDA;
+        }
+        prefault(0, head);                                         // under the head's upload
+        for (int c = 0; c < nch && rc == ASP_OK; ++c) {
+            const int64_t q0 = bounds[c], qn = bounds[c + 1] - q0;
+            cudaStreamWaitEvent(st, up[c], 0);
+            cudaEventRecord(start_c[c], st);
+            if (c == 1) ctx->on_wait = [=]() { prefault(head, nq - head); };   // under the kernels of the rest (the head's are too short)
+            rc = search_device_batch(s, g, dq + q0 * fp, qn, tau, topk, dlam + q0, dnorm + q0, flags,
+                                     didx ? didx + q0 * topk : nullptr, dscore ? dscore + q0 * topk : nullptr);
+            if (ctx->on_wait) { auto fn = std::move(ctx->on_wait); ctx->on_wait = nullptr; if (rc == ASP_OK) fn(); }
+            if (rc != ASP_OK) break;
+            // results of this piece: D2H on the second copy stream (for pageable destinations the runtime stages the copy
+            // and returns when it has landed; the piece is small next to the kernels that follow)
+            cudaEventRecord(done[c], st);
+            cudaStreamWaitEvent(ctx->down_stream, done[c], 0);
+            if (out_lambda_q)
+                cudaMemcpyAsync(out_lambda_q + q0, dlam + q0, sizeof(double) * qn, cudaMemcpyDeviceToHost, ctx->down_stream);
+            if (topk > 0) {
+                cudaMemcpyAsync(out_idx + q0 * topk, didx + q0 * topk, sizeof(int64_t) * (size_t)qn * topk, cudaMemcpyDeviceToHost, ctx->down_stream);
+                cudaMemcpyAsync(out_score + q0 * topk, dscore + q0 * topk, sizeof(double) * (size_t)qn * topk, cudaMemcpyDeviceToHost, ctx->down_stream);
+            }
+        }
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->up_stream), e2 = cudaStreamSynchronize(ctx->down_stream);
+        if (rc == ASP_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+            asp_set_error("pipelined search: copy stream failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            rc = ASP_ERR_CUDA;
+        }
+        if (rc == ASP_OK) {                                        // device timeline relative to the start of the uploads
+            float ms = 0.f;
+            const char *names[6] = {"search_pipe_up0_ms", "search_pipe_up1_ms", "search_pipe_start0_ms", "search_pipe_done0_ms",
+                                    "search_pipe_start1_ms", "search_pipe_done1_ms"};
+            cudaEvent_t evs[6] = {up[0], up[1], start_c[0], done[0], start_c[1], done[1]};
+            for (int i = 0; i < 6; ++i)
+                if (cudaEventElapsedTime(&ms, alloc_ready, evs[i]) == cudaSuccess) ctx->stats[names[i]] = ms; else cudaGetLastError();
+        }
+        for (auto &e : up) cudaEventDestroy(e);
+        for (auto &e : done) cudaEventDestroy(e);
+        for (auto &e : start_c) cudaEventDestroy(e);
+        cudaEventDestroy(alloc_ready);
+        ctx->stats["search_pipeline_chunks"] = nch;
+    } else {
+        rc = upload_pitched(st, queries, nq, f, fp, dq);
+        if (touch) ctx->on_wait = [=]() { prefault(0, nq); };
+        if (rc == ASP_OK) rc = search_device_batch(s, g, dq, nq, tau, topk, dlam, dnorm, flags, didx, dscore);
+        if (ctx->on_wait) { auto fn = std::move(ctx->on_wait); ctx->on_wait = nullptr; if (rc == ASP_OK) fn(); }
+        if (rc == ASP_OK && out_lambda_q) rc = asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq);
+        if (rc == ASP_OK && topk > 0) {
+            rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
+            if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
+            ASP_CUDA(cudaStreamSynchronize(st));
+        }
+        ctx->stats["search_pipeline_chunks"] = 1;
     }
     cudaFreeAsync(dq, st);
     cudaFreeAsync(dlam, st);
@@ -644,7 +750,7 @@ int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, flo
     ASP_CUDA(cudaMallocAsync(&dd, sizeof(float) * (size_t)nq * s->n_local, st));
     ASP_CUDA(cudaMemcpyAsync(dz, hz.data(), sizeof(double) * 2 * nq, cudaMemcpyHostToDevice, st));
     ASP_CUDA(cudaMemsetAsync(dd, 0, sizeof(float) * (size_t)nq * s->n_local, st));
-    int rc = upload_pitched(ctx, hq.data(), nq, s->f, s->fp, dq);
+    int rc = upload_pitched(ctx->stream, hq.data(), nq, s->f, s->fp, dq);
     if (rc == ASP_OK) rc = asp_search_tc_impl(s, dq, nq, s->fp, dz, dz + nq, 1.0, 1, nullptr, nullptr, dd);
     if (rc == ASP_OK) rc = asp_copy_out(ctx, out, dd, sizeof(float) * (size_t)nq * s->n_local);
     ASP_CUDA(cudaStreamSynchronize(st));

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <functional>
 #include <map>
 #include <vector>
 
@@ -46,6 +47,8 @@ struct asp_ctx {
     bool use_tma = true;                 // ASP_NO_TMA=1 switches the operand loaders to cp.async
     std::map<std::string, double> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;   // copy streams of the pipelined host search (lazily created)
+    std::function<void()> on_wait;       // host work the search runs once, right before its long wait for the kernels
 };
 
 struct asp_space {
@@ -82,6 +85,9 @@ struct asp_graph {
     double  *d_uval = nullptr;
     double  *d_deg = nullptr;            // nnodes
     int64_t  unnz = 0;
+    // row chunks of the upper adjacency the lambda kernel stages through shared memory (taumode.cu), built on first use
+    mutable void *d_tm_chunks = nullptr;
+    mutable int   n_tm_chunks = 0;
 };
 
 // ------------------------------------------------------------------ launch bookkeeping

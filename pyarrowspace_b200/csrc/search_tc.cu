@@ -90,12 +90,17 @@ __global__ void minmax_kernel(const double *__restrict__ a, int64_t n, double *_
     if (threadIdx.x == 0) { out[2 * blockIdx.x] = s_lo[0]; out[2 * blockIdx.x + 1] = s_hi[0]; }
 }
 
-// [lo, 1/bucket width] of the keys from the per-block partials of minmax_kernel
+// [lo, 1/bucket width] of the keys from the per-block partials of minmax_kernel (one warp)
 __global__ void range_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ range)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double lo = INFINITY, hi = -INFINITY;
-        for (int i = 0; i < nblocks; ++i) { lo = fmin(lo, partials[2 * i]); hi = fmax(hi, partials[2 * i + 1]); }
+    double lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < nblocks; i += 32) { lo = fmin(lo, partials[2 * i]); hi = fmax(hi, partials[2 * i + 1]); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (threadIdx.x == 0) {
         const double width = (hi > lo) ? (hi - lo) / LAM_BUCKETS : 1.0;
         range[0] = lo;
         range[1] = 1.0 / width;
@@ -116,23 +121,49 @@ __global__ void bucket_hist_kernel(const double *__restrict__ lam, int64_t n, co
         atomicAdd(&hist[lam_bucket(lam[i], lo, inv_width)], 1u);
 }
 
-// exclusive scan of LAM_BUCKETS counters by one CTA of 1024 threads (64 counters per thread)
+// exclusive scan of LAM_BUCKETS counters by one CTA of 1024 threads (64 counters per thread, held in registers: all 16
+// 16-byte loads of a thread are in flight together)
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t *__restrict__ hist /* in: counts, out: cursors */)
 {
     constexpr int PER = LAM_BUCKETS / 1024;
-    __shared__ uint32_t s_sum[1024];
+    static_assert(PER % 4 == 0, "vector loads");
+    __shared__ uint32_t s_warp[32];
+    uint4 *mine = reinterpret_cast<uint4 *>(hist + threadIdx.x * PER);
+    uint4 v[PER / 4];
+#pragma unroll
+    for (int j = 0; j < PER / 4; ++j) v[j] = mine[j];
     uint32_t tot = 0;
-    for (int j = 0; j < PER; ++j) tot += hist[threadIdx.x * PER + j];
-    s_sum[threadIdx.x] = tot;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = ((int)threadIdx.x >= off) ? s_sum[threadIdx.x - off] : 0u;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER / 4; ++j) tot += v[j].x + v[j].y + v[j].z + v[j].w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = tot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
     }
-    uint32_t run = s_sum[threadIdx.x] - tot;
-    for (int j = 0; j < PER; ++j) { const uint32_t c = hist[threadIdx.x * PER + j]; hist[threadIdx.x * PER + j] = run; run += c; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off) wi += t;
+        }
+        s_warp[lane] = wi - w;                                           // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - tot;
+#pragma unroll
+    for (int j = 0; j < PER / 4; ++j) {
+        uint4 o;
+        o.x = run; run += v[j].x;
+        o.y = run; run += v[j].y;
+        o.z = run; run += v[j].z;
+        o.w = run; run += v[j].w;
+        mine[j] = o;
+    }
 }
 
 __global__ void bucket_scatter_kernel(const double *__restrict__ lam, int64_t n, const double *__restrict__ range,
@@ -642,9 +673,14 @@ __device__ __forceinline__ double warp_sum(double v)
 constexpr int TR_WARPS = 4;
 constexpr int TR_QUEUE = 96;       // survivor queue per warp (flushed in batches of 32)
 
-// One warp per query.  See the header: (A) coalesced f64 re-scoring of every survivor, best 32 kept;
+// WPQ warps per query.  See the header: (A) coalesced f64 re-scoring of every survivor, best 32 kept;
 // (B) reference-order re-scoring of the candidates within 2*eps_fast of the k-th best; sort; emit.
-__global__ void __launch_bounds__(TR_WARPS * 32)
+// WPQ == 1 (throughput shape): TR_WARPS independent queries per CTA.  WPQ > 1 (latency shape, small batches such as the
+// reference's one-query-per-call `search`): one CTA per query, warp w takes the emission streams w, w + WPQ, ...; the
+// per-warp top lists are merged pairwise through shared memory.  Every quantity that decides the result (cut-off, fast
+// scores, the 32 kept, the band) is a function of the SET of emitted candidates, so all WPQ give bit-identical output.
+template <int WPQ>
+__global__ void __launch_bounds__((WPQ == 1 ? TR_WARPS : WPQ) * 32)
 tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const double *__restrict__ items, int64_t n_local,
                   int f, int pitch, int64_t row0, const double *__restrict__ norm_x, const double *__restrict__ lam_x,
                   const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nstreams,
@@ -655,18 +691,38 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
                   int32_t *slow_list, int32_t *slow_count, unsigned long long *survivor_total, unsigned long long *exact_total)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int NWARPS = (WPQ == 1) ? TR_WARPS : WPQ;
+    constexpr int QCOPIES = (WPQ == 1) ? TR_WARPS : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *qs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * pitch;    // zero padded to the item pitch
-    int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)TR_WARPS * pitch) + warp * TR_QUEUE;
-    const int64_t qi = (int64_t)blockIdx.x * TR_WARPS + warp;                    // position in lambda_q order
+    const int wq = (WPQ == 1) ? 0 : warp;                                        // this warp's rank within its query
+    double *qs = reinterpret_cast<double *>(smem_raw) + (size_t)((WPQ == 1) ? warp : 0) * pitch;   // zero padded to the item pitch
+    int32_t *queue = reinterpret_cast<int32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)QCOPIES * pitch) + warp * TR_QUEUE;
+    // merge areas of the latency shape (unused when WPQ == 1)
+    double *x_s = reinterpret_cast<double *>(smem_raw) + (size_t)QCOPIES * pitch + (size_t)(NWARPS * TR_QUEUE) / 2;
+    int32_t *x_i = reinterpret_cast<int32_t *>(x_s + NWARPS * 32);
+    float *x_f = reinterpret_cast<float *>(x_i + NWARPS * 32);
+    __shared__ float s_cutoff;
+    __shared__ unsigned long long s_nsurv;
+    const int64_t qi = (WPQ == 1) ? (int64_t)blockIdx.x * TR_WARPS + warp : (int64_t)blockIdx.x;   // position in lambda_q order
     if (qi >= nq) return;
     const int64_t oq = qperm ? (int64_t)qperm[qi] : qi;                          // the caller's query index
-    for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[oq * qpitch + j] : 0.0;
+    if (WPQ == 1) {
+        for (int j = lane; j < pitch; j += 32) qs[j] = (j < f) ? q[oq * qpitch + j] : 0.0;
+    } else {
+        for (int j = threadIdx.x; j < pitch; j += NWARPS * 32) qs[j] = (j < f) ? q[oq * qpitch + j] : 0.0;
+        if (threadIdx.x == 0) s_nsurv = 0ull;
+    }
 
     bool overflow = false;
-    for (int c = lane; c < nstreams; c += 32) overflow |= emit_cnt[qi * nstreams + c] > capb;
-    if (__any_sync(0xffffffffu, overflow)) {
-        if (lane == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)oq;
+    if (WPQ == 1) {
+        for (int c = lane; c < nstreams; c += 32) overflow |= emit_cnt[qi * nstreams + c] > capb;
+        overflow = __any_sync(0xffffffffu, overflow);
+    } else {
+        for (int c = threadIdx.x; c < nstreams; c += NWARPS * 32) overflow |= emit_cnt[qi * nstreams + c] > capb;
+        overflow = __syncthreads_or(overflow ? 1 : 0) != 0;                      // also publishes qs / s_nsurv
+    }
+    if (overflow) {                                                              // uniform over the query's warps
+        if (lane == 0 && wq == 0) slow_list[atomicAdd(slow_count, 1)] = (int32_t)oq;
         return;
     }
     // final cut: the k-th largest approximate score over ALL emitted candidates of the query (distinct items, so it is
@@ -676,20 +732,44 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     {
         float top[2] = {-INFINITY, -INFINITY};                                   // best 32 in top[0], sorted descending by lane
         float floor32 = -INFINITY;                                               // 32nd best so far
-        for (int c = 0; c < nstreams; ++c) {
+        for (int c = wq; c < nstreams; c += WPQ) {
             const int cnt = emit_cnt[qi * nstreams + c];
             const size_t base = ((size_t)qi * nstreams + c) * (size_t)capb;
-            for (int e0 = 0; e0 < cnt; e0 += 32) {
-                const int e = e0 + lane;
-                const float v = (e < cnt) ? emit_sc[base + e] : -INFINITY;
-                if (!__any_sync(0xffffffffu, v > floor32)) continue;
-                top[1] = v;
-                asp::warp_sort_desc_f32x2(top, lane);
-                floor32 = __shfl_sync(0xffffffffu, top[0], 31);
+            for (int e0 = 0; e0 < cnt; e0 += 128) {                              // four loads in flight per lane
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u + lane; v[u] = (e < cnt) ? emit_sc[base + e] : -INFINITY; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!__any_sync(0xffffffffu, v[u] > floor32)) continue;
+                    top[1] = v[u];
+                    asp::warp_sort_desc_f32x2(top, lane);
+                    floor32 = __shfl_sync(0xffffffffu, top[0], 31);
+                }
             }
         }
-        const float kth = __shfl_sync(0xffffffffu, top[0], kk - 1);              // -inf when fewer than kk were emitted
-        cutoff = kth - 2.0f * delta_q[qi];
+        if (WPQ > 1) {                                                           // pairwise merge of the warps' sorted lists
+            x_f[warp * 32 + lane] = top[0];
+            __syncthreads();
+#pragma unroll 1
+            for (int step = 1; step < WPQ; step <<= 1) {
+                if ((warp & (2 * step - 1)) == 0 && warp + step < WPQ) {
+                    top[1] = x_f[(warp + step) * 32 + lane];
+                    asp::warp_sort_desc_f32x2(top, lane);
+                    x_f[warp * 32 + lane] = top[0];
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
+                const float kth = __shfl_sync(0xffffffffu, top[0], kk - 1);
+                if (lane == 0) s_cutoff = kth - 2.0f * delta_q[qi];
+            }
+            __syncthreads();
+            cutoff = s_cutoff;
+        } else {
+            const float kth = __shfl_sync(0xffffffffu, top[0], kk - 1);          // -inf when fewer than kk were emitted
+            cutoff = kth - 2.0f * delta_q[qi];
+        }
     }
     (void)theta_glob;
     const double nqv = norm_q[oq], lqv = lam_q[oq];
@@ -731,27 +811,59 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
         best[1] = mine;
         asp::warp_sort_best_first<2>(best, lane);
     };
-    for (int c = 0; c < nstreams; ++c) {
+    for (int c = wq; c < nstreams; c += WPQ) {
         const int cnt = emit_cnt[qi * nstreams + c];
         const size_t base = ((size_t)qi * nstreams + c) * (size_t)capb;
-        for (int e0 = 0; e0 < cnt; e0 += 32) {
-            const int e = e0 + lane;
-            const bool keep = (e < cnt) && (emit_sc[base + e] >= cutoff);
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) queue[qn + __popc(m & ((1u << lane) - 1))] = emit_ix[base + e];
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                flush(32);
-                nsurv += 32;
+        for (int e0 = 0; e0 < cnt; e0 += 128) {                                  // four loads in flight per lane
+            float sc4[4];
+            int32_t ix4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 32 * u + lane;
+                sc4[u] = (e < cnt) ? emit_sc[base + e] : -INFINITY;
+                ix4[u] = (e < cnt) ? emit_ix[base + e] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 32 * u + lane;
+                const bool keep = (e < cnt) && (sc4[u] >= cutoff);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m == 0u) continue;
+                if (keep) queue[qn + __popc(m & ((1u << lane) - 1))] = ix4[u];
+                qn += __popc(m);
                 __syncwarp();
-                if (lane < qn - 32) queue[lane] = queue[32 + lane];
-                qn -= 32;
-                __syncwarp();
+                if (qn >= 32) {
+                    flush(32);
+                    nsurv += 32;
+                    __syncwarp();
+                    if (lane < qn - 32) queue[lane] = queue[32 + lane];
+                    qn -= 32;
+                    __syncwarp();
+                }
             }
         }
     }
     if (qn > 0) { flush(qn); nsurv += qn; }
+
+    if (WPQ > 1) {                                                               // pairwise merge of the warps' best-32 lists
+        x_s[warp * 32 + lane] = best[0].s;
+        x_i[warp * 32 + lane] = best[0].i;
+        if (lane == 0) atomicAdd(&s_nsurv, nsurv);
+        __syncthreads();
+#pragma unroll 1
+        for (int step = 1; step < WPQ; step <<= 1) {
+            if ((warp & (2 * step - 1)) == 0 && warp + step < WPQ) {
+                best[1].s = x_s[(warp + step) * 32 + lane];
+                best[1].i = x_i[(warp + step) * 32 + lane];
+                asp::warp_sort_best_first<2>(best, lane);
+                x_s[warp * 32 + lane] = best[0].s;
+                x_i[warp * 32 + lane] = best[0].i;
+            }
+            __syncthreads();
+        }
+        if (warp != 0) return;
+        nsurv = s_nsurv;
+    }
 
     // (B): candidates whose fast score is within 2 eps of the k-th best fast score
     const double kth = __shfl_sync(0xffffffffu, best[0].s, kk - 1);              // -inf when fewer than kk survivors
@@ -964,7 +1076,11 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
         // queries visited in lambda_q order: coherent blocks -> one visiting order per block
         ASP_CUDA(cudaMallocAsync(&b->qperm, sizeof(int32_t) * nq, st));
         ASP_CUDA(cudaMallocAsync(&b->center, sizeof(int32_t) * qblocks, st));
-        ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, b->qperm));
+        if (nq > TQ) ASP_CHECK(bucket_order(ctx, lambda_q_dev, nq, b->qperm));
+        else {              // one query block: its visiting order starts at one of its own lambdas whatever the query order
+            iota_kernel<<<1, 128, 0, st>>>(b->qperm, nq);
+            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        }
     }
     project_split_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(q_dev, nq, s->f, qpitch, kp, b->inv_nq, b->qperm, c->mdir, 1, q_hi, q_lo, b->rho_q);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
@@ -1125,18 +1241,27 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     ASP_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), st));
     const double u = 1.1102230246251565e-16;
     const double eps_fast = (4.0 * s->f + 64.0) * u * (fabs(tau) + fabs(1.0 - tau) + 1.0);
-    const size_t rsmem = (size_t)TR_WARPS * s->fp * 8 + TR_WARPS * TR_QUEUE * 4;
-    ASP_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    tc_rescore_kernel<<<(unsigned)asp_ceil_div(nq, TR_WARPS), TR_WARPS * 32, rsmem, st>>>(
-        q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-        (int)topk, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix, b.emit_cnt, b.theta_glob, b.qperm, out_idx_dev,
-        out_score_dev, slow_list, slow_count, counters, counters + 1);
+    // small batches (the reference's one query per call, latency bound): a whole CTA per query
+    const int wpq = (nq <= 64) ? 32 : (nq <= 1024) ? 8 : 1;
+    auto launch_rescore = [&](auto kern, int nwarps, int qcopies, unsigned grid) -> int {
+        const size_t rsmem = (size_t)qcopies * s->fp * 8 + (size_t)nwarps * TR_QUEUE * 4 + (size_t)nwarps * 32 * 16;
+        ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        kern<<<grid, nwarps * 32, rsmem, st>>>(
+            q_dev, qpitch, nq, s->items, s->n_local, s->f, s->fp, s->row0, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
+            (int)topk, b.nsub, b.capb, b.delta_q, eps_fast, b.emit_sc, b.emit_ix, b.emit_cnt, b.theta_glob, b.qperm, out_idx_dev,
+            out_score_dev, slow_list, slow_count, counters, counters + 1);
+        return ASP_OK;
+    };
+    if (wpq == 32) ASP_CHECK(launch_rescore(tc_rescore_kernel<32>, 32, 1, (unsigned)nq));
+    else if (wpq == 8) ASP_CHECK(launch_rescore(tc_rescore_kernel<8>, 8, 1, (unsigned)nq));
+    else ASP_CHECK(launch_rescore(tc_rescore_kernel<1>, TR_WARPS, TR_WARPS, (unsigned)asp_ceil_div(nq, TR_WARPS)));
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev2, st));
     int32_t nslow = 0;
     unsigned long long cnts[2] = {0, 0};
     ASP_CUDA(cudaMemcpyAsync(&nslow, slow_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     ASP_CUDA(cudaMemcpyAsync(cnts, counters, sizeof(cnts), cudaMemcpyDeviceToHost, st));
+    if (ctx->on_wait) { auto fn = std::move(ctx->on_wait); ctx->on_wait = nullptr; fn(); }   // host work hidden behind both stages
     ASP_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f, ms2 = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

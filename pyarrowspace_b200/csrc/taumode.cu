@@ -307,10 +307,11 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
     if (n == 0) return ASP_OK;
     if (f != g->nnodes) ASP_FAIL(ASP_ERR_ARG, "vector length %d must equal the graph's node count %lld", f, (long long)g->nnodes);
     if (!g->d_uptr) ASP_FAIL(ASP_ERR_ARG, "graph has no upper adjacency (not a feature graph)");
-    // chunk the upper adjacency by rows: <= chn entries and <= CH_ROWS rows per chunk
-    const int chn = CH_NNZ_MAX;
-    std::vector<TmChunk> chunks;
-    {
+    // chunk the upper adjacency by rows: <= chn entries and <= CH_ROWS rows per chunk.  The table depends on the graph
+    // only: it is built and uploaded once (a per-call H2D copy would queue behind the query uploads of a pipelined search)
+    if (!g->d_tm_chunks) {
+        const int chn = CH_NNZ_MAX;
+        std::vector<TmChunk> chunks;
         std::vector<int32_t> uptr(g->nnodes + 1);
         // host mirror of uptr: rebuild from the host CSR (cheap, f rows)
         int32_t acc = 0;
@@ -328,18 +329,20 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
             chunks.push_back(TmChunk{a0, a1});
             a0 = a1;
         }
+        void *d = nullptr;
+        ASP_CUDA(cudaMallocAsync(&d, sizeof(TmChunk) * chunks.size(), ctx->stream));
+        ASP_CUDA(cudaMemcpyAsync(d, chunks.data(), sizeof(TmChunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
+        ASP_CUDA(cudaStreamSynchronize(ctx->stream));     // chunks vector goes out of scope
+        g->d_tm_chunks = d;
+        g->n_tm_chunks = (int)chunks.size();
     }
-    TmChunk *d_chunks = nullptr;
-    ASP_CUDA(cudaMallocAsync(&d_chunks, sizeof(TmChunk) * chunks.size(), ctx->stream));
-    ASP_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(TmChunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
-    ASP_CUDA(cudaStreamSynchronize(ctx->stream));     // chunks vector goes out of scope
+    const TmChunk *d_chunks = static_cast<const TmChunk *>(g->d_tm_chunks);
     int rc;
-    const int nch = (int)chunks.size();
+    const int nch = g->n_tm_chunks;
     if (f <= 128)       rc = launch_tm<4, 4, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
     else if (f <= 384)  rc = launch_tm<12, 4, CH_NNZ_MAX, 512>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
     else if (f <= 768)  rc = launch_tm<24, 2, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
     else if (f <= 1500) rc = launch_tm<48, 1, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
     else { rc = ASP_ERR_UNSUPPORTED; asp_set_error("taumode kernel supports at most 1500 features (got %d)", f); }
-    cudaFreeAsync(d_chunks, ctx->stream);
     return rc;
 }

@@ -597,3 +597,42 @@ def test_cta_pair_kernel_matches(oracle_mod):
     finally:
         os.environ.pop("ASP_TC_PAIR", None)
     assert np.array_equal(idx0, idx1) and np.array_equal(sc0, sc1)
+
+
+def test_pipelined_host_batches_equal_single_shot(oracle_mod):
+    """Host batches of >= 32768 queries are cut into a short head and the rest; the rest's H2D copy and the head's D2H
+    copy overlap the kernels of the other piece (asp_search_batch).  Each piece is an independent exact search, so the result is bit-identical
+    to the single-shot path (ASP_NO_PIPELINE=1), to a device-resident batch, and equal to the oracle on a sample.
+    The lambda_q == 0 guard (src/lib.rs:156-159) still fires when the offending query sits in a later chunk."""
+    import torch
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, synth
+    from pyarrowspace_b200.api import PanicException
+    n, f, nq = 6000, 64, 2 * 16384 + 777                 # ragged last chunk
+    x = synth.make_items(n, f, 901, n_clusters=12)
+    q, _ = synth.make_queries(x, nq, 902)
+    gp = {"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+    qp = torch.from_numpy(q).pin_memory().numpy()
+    idx_p, sc_p = aspace.search_batch(qp, gl, 0.62)
+    assert api.stat("search_pipeline_chunks") == 2.0
+    idx_pg, sc_pg = aspace.search_batch(q, gl, 0.62)     # pageable host memory takes the same route
+    os.environ["ASP_NO_PIPELINE"] = "1"
+    try:
+        idx_1, sc_1 = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_pipeline_chunks") == 1.0
+    finally:
+        os.environ.pop("ASP_NO_PIPELINE", None)
+    idx_d, sc_d = aspace.search_batch(torch.from_numpy(q).cuda(), gl, 0.62)
+    for a, b in ((idx_p, idx_1), (sc_p, sc_1), (idx_pg, idx_1), (sc_pg, sc_1), (idx_d.cpu().numpy(), idx_1), (sc_d.cpu().numpy(), sc_1)):
+        assert np.array_equal(a, b)
+    head = max(1024, (nq // 32 + 127) // 128 * 128)
+    sel = np.r_[0:50, head - 25:head + 25, nq - 50:nq]
+    oidx, osc, _ = s.search_batch(q[sel], g, 0.62)
+    _assert_hits_equal(idx_p[sel], sc_p[sel], oidx, osc)
+    bad = q.copy()
+    bad[head + 5] = 0.0
+    with pytest.raises(PanicException):
+        aspace.search_batch(bad, gl, 0.62)
+    idx_again, _ = aspace.search_batch(qp, gl, 0.62)     # the library is usable after the failed call
+    assert np.array_equal(idx_again, idx_1)
