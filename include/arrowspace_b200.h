@@ -103,6 +103,12 @@ int asp_shard_rows(int64_t n_total, int world, int rank, int64_t *row0, int64_t 
 int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, int32_t f,
                      int64_t n_total, int world, int rank, asp_space **out);
 
+/* World-1 space over a device buffer the caller keeps alive until asp_free_space (n x f f64 row-major, f % 4 == 0,
+ * 16-byte aligned): no copy.  Used by the multi-GPU item graph so that the all-gathered item matrix (the halo rows
+ * of BASELINE.json config C5: 54 GB per rank) exists once.  No reference counterpart (the reference always copies,
+ * src/helpers.rs:24-46). */
+int asp_space_adopt(asp_ctx *ctx, double *items_dev, int64_t n, int32_t f, asp_space **out);
+
 /* K1 (API orientation): per-segment partial Gram X_s^T X_s of the owned segments, FP64 DMMA fed
  * by TMA.  out_dev: DEVICE buffer [ASP_GRAM_SEGMENTS][f][f] f64; only the owned segments'
  * blocks are written (the others are left untouched).  [exchange]: all-gather the blocks. */

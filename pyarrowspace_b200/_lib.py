@@ -62,6 +62,7 @@ SYMBOLS = {
                          C.POINTER(_vp), C.POINTER(_vp)]),
     "asp_shard_rows": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "asp_space_create": (_int, [_vp, _vp, _i64, _i32, _i64, _int, _int, C.POINTER(_vp)]),
+    "asp_space_adopt": (_int, [_vp, _vp, _i64, _i32, C.POINTER(_vp)]),
     "asp_space_gram_partials": (_int, [_vp, _vp]),
     "asp_graph_from_gram": (_int, [_vp, _vp, _i32, _i64, C.POINTER(GraphParams), C.POINTER(Switches),
                                    _vp, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_vp)]),

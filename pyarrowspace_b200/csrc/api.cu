@@ -239,13 +239,39 @@ int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, i
     return ASP_OK;
 }
 
+// World-1 space over a device buffer the CALLER keeps alive (n x f f64 row-major, f a multiple of 4, 16-byte aligned): no
+// copy.  For the multi-GPU item graph, where the all-gathered item matrix (C5: 54 GB per rank) must not exist twice.
+int asp_space_adopt(asp_ctx *ctx, double *items_dev, int64_t n, int32_t f, asp_space **out)
+{
+    if (!ctx || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_adopt: NULL argument");
+    if (!items_dev || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    if (!asp_is_device_ptr(items_dev) || (f & 3) != 0 || (reinterpret_cast<uintptr_t>(items_dev) & 15) != 0)
+        ASP_FAIL(ASP_ERR_ARG, "asp_space_adopt: needs 16-byte aligned device memory and a feature count that is a multiple of 4 (got %d)", f);
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_space *s = new asp_space();
+    s->ctx = ctx;
+    s->n_local = n; s->row0 = 0; s->n_total = n;
+    s->f = f; s->fp = f;
+    s->world = 1; s->rank = 0;
+    s->items = items_dev;
+    s->owns_items = false;
+    ASP_CUDA(cudaMallocAsync(&s->norms, sizeof(double) * n, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->inv_norms, sizeof(double) * n, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->lambdas, sizeof(double) * n, ctx->stream));
+    int rc = asp_make_items_tmap(&s->tmap_gram, s->items, n, s->fp, ASP_ROW_UNIT, 32);
+    if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n, s->fp, 128, 4);
+    if (rc != ASP_OK) { asp_free_space(s); return rc; }
+    *out = s;
+    return ASP_OK;
+}
+
 void asp_free_space(asp_space *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStream_t st = s->ctx->stream;
     asp_free_tc_cache(s);
-    if (s->items) cudaFreeAsync(s->items, st);
+    if (s->items && s->owns_items) cudaFreeAsync(s->items, st);
     if (s->norms) cudaFreeAsync(s->norms, st);
     if (s->inv_norms) cudaFreeAsync(s->inv_norms, st);
     if (s->lambdas) cudaFreeAsync(s->lambdas, st);

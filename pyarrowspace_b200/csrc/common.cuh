@@ -57,6 +57,7 @@ struct asp_space {
     int32_t f = 0;
     int32_t fp = 0;                      // row pitch in doubles: f rounded up to a multiple of 4, zero padded
     double *items = nullptr;             // device, n_local x fp
+    bool owns_items = true;              // false: adopted from the caller (asp_space_adopt)
     double *norms = nullptr;             // device, n_local: sqrt(sum x^2), left-to-right
     double *inv_norms = nullptr;         // device, n_local: 1/norm (0 for zero rows)
     double *lambdas = nullptr;           // device, n_local

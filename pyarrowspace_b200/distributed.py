@@ -90,7 +90,14 @@ class CudaEngine:
         n, f = x_full.shape
         h = C.c_void_p()
         self.torch.cuda.current_stream(self.device).synchronize()
-        _lib.check(self.lib.asp_space_create(self.ctx, x_full.data_ptr(), n, f, n, 1, 0, C.byref(h)))
+        if f % 4 == 0 and x_full.is_contiguous() and x_full.data_ptr() % 16 == 0:
+            # no second copy of the gathered matrix (C5: 54 GB per rank): the library works on the tensor itself,
+            # which the ArrowSpace keeps alive (build_item_graph_sharded)
+            _lib.check(self.lib.asp_space_adopt(self.ctx, x_full.data_ptr(), n, f, C.byref(h)))
+            self.adopted = x_full
+        else:
+            _lib.check(self.lib.asp_space_create(self.ctx, x_full.data_ptr(), n, f, n, 1, 0, C.byref(h)))
+            self.adopted = None
         return h
 
     def knn_rows(self, space, cgp, r0, r1):
@@ -195,6 +202,20 @@ def _all_gather_ragged(t_local, counts, group):
     return torch.cat([g[r, : counts[r]] for r in range(world)], dim=0)
 
 
+def _all_gather_rows(t_local, counts, group):
+    """Row blocks of rank order -> [sum(counts), ...].  Equal blocks are gathered straight into the result (no padded
+    staging, no concatenation: the gathered item matrix of C5 is 54 GB); ragged blocks take the padded route."""
+    import torch
+    if len(set(counts)) == 1 and t_local.is_contiguous():
+        out = torch.empty((sum(counts),) + tuple(t_local.shape[1:]), dtype=t_local.dtype, device=t_local.device)
+        try:
+            _dist().all_gather_into_tensor(out, t_local, group=group)
+            return out
+        except (RuntimeError, NotImplementedError):
+            del out
+    return _all_gather_ragged(t_local, counts, group)
+
+
 def sharded_item_graph(engine, shard, n_total, row0, cgp, sw, group=None):
     """Steps 4-5 above.  `shard` = rows [row0, row0 + len(shard)) of the item matrix as a tensor on the engine's
     device.  Returns (world-1 space handle over ALL items, graph handle over n_total nodes) -- identical on every rank."""
@@ -207,15 +228,15 @@ def sharded_item_graph(engine, shard, n_total, row0, cgp, sw, group=None):
     starts = [int(m[1]) for m in meta]
     if sum(counts) != n_total or starts != [sum(counts[:r]) for r in range(world)]:
         raise ValueError("item shards must be contiguous row blocks in rank order (got starts %s, counts %s)" % (starts, counts))
-    x_full = _all_gather_ragged(shard, counts, group) if world > 1 else shard
+    x_full = _all_gather_rows(shard, counts, group) if world > 1 else shard
     if hasattr(engine, "after_collective"):
         engine.after_collective()
     space = engine.full_space(x_full)
     idx, dst, cnt = engine.knn_rows(space, cgp, row0, row0 + counts[rank])
     if world > 1:
-        idx = _all_gather_ragged(idx, counts, group)
-        dst = _all_gather_ragged(dst, counts, group)
-        cnt = _all_gather_ragged(cnt, counts, group)
+        idx = _all_gather_rows(idx.contiguous(), counts, group)
+        dst = _all_gather_rows(dst.contiguous(), counts, group)
+        cnt = _all_gather_rows(cnt.contiguous(), counts, group)
         if hasattr(engine, "after_collective"):
             engine.after_collective()
     graph = engine.graph_from_knn(n_total, idx, dst, cnt, cgp, sw)
@@ -237,7 +258,9 @@ def build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=Non
     if group is None:
         group = dist.group.WORLD
     space, graph = sharded_item_graph(engine, items_shard.contiguous(), int(n_total), int(row0), cgp, sw, group)
-    return api.ArrowSpace._wrap(space, engine.ctx), api.GraphLaplacian._wrap(graph)
+    aspace = api.ArrowSpace._wrap(space, engine.ctx)
+    aspace._keepalive = getattr(engine, "adopted", None)       # the adopted item matrix outlives the space handle
+    return aspace, api.GraphLaplacian._wrap(graph)
 
 
 def build_sharded(graph_params, items_shard, n_total, group=None, **extras):
