@@ -517,18 +517,34 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
         return r;
     };
 
+    // Dense neighbourhoods (C5: 34k items per cluster in 768 dimensions, where the distances inside a cluster concentrate)
+    // overflow the 1-term band on EVERY row: when more than half of the first batch does, the remaining batches go
+    // straight to the two-term split instead of paying for a pass that decides nothing.
+    bool direct3 = false;
+    int64_t rows_direct3 = 0;
+    int32_t h_counts[2] = {0, 0};
     for (int64_t b0 = row_begin; b0 < row_end && rc == ASP_OK; b0 += batch) {
         const int64_t nq = (row_end - b0 < batch) ? row_end - b0 : batch;
+        if (direct3) {
+            int used = 0;
+            rc = run_batch(s->items + b0 * s->fp, s->norms + b0, nq, b0, nullptr, 3, slow2, counts + 1, &used);
+            rows_direct3 += nq;
+            continue;
+        }
         rc = run_batch(s->items + b0 * s->fp, s->norms + b0, nq, b0, nullptr, 0, slow1, counts, &terms_pass1);
+        if (rc == ASP_OK && b0 == row_begin && terms_pass1 == 1 && b0 + batch < row_end) {
+            ASP_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+            ASP_CUDA(cudaStreamSynchronize(st));
+            direct3 = (int64_t)h_counts[0] * 2 > nq;
+        }
     }
-    int32_t h_counts[2] = {0, 0};
     if (rc == ASP_OK) {
         ASP_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
         ASP_CUDA(cudaStreamSynchronize(st));
     }
     const int32_t n_pass2 = (terms_pass1 == 1) ? h_counts[0] : 0;
-    const int32_t *final_list = slow1;
-    int32_t n_final = h_counts[0];
+    const int32_t *final_list = direct3 ? slow2 : slow1;
+    int32_t n_final = direct3 ? h_counts[1] : h_counts[0];
     if (rc == ASP_OK && n_pass2 > 0) {
         double *qbuf = nullptr, *qnorm = nullptr;
         const int64_t chunk = n_pass2 < batch ? n_pass2 : batch;
@@ -555,7 +571,8 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
         ASP_CUDA(cudaStreamSynchronize(st));
         ctx->stats["knn_stage1_ms"] = stage1_ms;
         ctx->stats["knn_stage2_ms"] = stage2_ms;
-        ctx->stats["knn_rows_two_term"] = n_pass2;
+        ctx->stats["knn_rows_two_term"] = (double)n_pass2 + (double)rows_direct3;
+        ctx->stats["knn_rows_one_term_wasted"] = n_pass2;
         ctx->stats["knn_slow_rows"] = n_final;
         ctx->stats["knn_stage1_is_tc"] = 1.0;
         ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)(rows > 0 ? rows : 1);

@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -194,7 +195,8 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
         if (threadIdx.x < T) {
             const int t = threadIdx.x;
             double n2 = 0.0, sm = 0.0;
-            for (int ff = 0; ff < f; ++ff) {
+#pragma unroll 8
+            for (int ff = 0; ff < f; ++ff) {                           // loads and products run ahead; only the adds are a chain
                 const double xv = xs[ff * XS + t];
                 n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
                 sm = __dadd_rn(sm, xv);

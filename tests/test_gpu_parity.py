@@ -537,6 +537,37 @@ def test_item_graph_duplicates_and_hubs(oracle_mod, stage1):
     assert np.diff(gl.csr()[0]).max() > 64
 
 
+def test_item_graph_dense_clusters_switch_to_two_term(oracle_mod):
+    """Dense neighbourhoods (2 clusters of 4500, relative noise 6e-2): the one-term band (~5e-5 in cosine) holds ~2800
+    members of a row's cluster, so with emission lists of 512 entries most rows of the first batch overflow and the
+    remaining batch goes straight to the two-term split (band ~3e-6: a dozen candidates).  This is the C5 regime in
+    miniature (34k items per cluster against lists of 2048, profiles/c5_item_graph_8gpu_r01.json).  The graph is still
+    the oracle's."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api
+    rng = np.random.default_rng(77)
+    ncl, per, f = 2, 4500, 64
+    centres = rng.standard_normal((ncl, f))
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    x = np.repeat(centres, per, axis=0) * (1.0 + 6e-2 * rng.standard_normal((ncl * per, f)))
+    x = x * 100.0 + 60.0                  # dominant mean direction (as in the bench data): the one-term mode is chosen first
+    x = np.ascontiguousarray(x[rng.permutation(ncl * per)])
+    gp = {"eps": 0.5, "k": 5, "topk": 3, "p": 2.0, "sigma": 0.1}
+    os.environ.update({"ASP_KNN_STAGE1": "tc", "ASP_KNN_BATCH": "4500", "ASP_TC_CAPB": "512"})
+    try:
+        aspace, gl = ArrowSpaceBuilder.build_item_graph(gp, x)
+    finally:
+        for k in ("ASP_KNN_STAGE1", "ASP_KNN_BATCH", "ASP_TC_CAPB"):
+            os.environ.pop(k, None)
+    n = ncl * per
+    stats = {k: api.stat(k) for k in ("knn_rows_two_term", "knn_rows_one_term_wasted", "knn_slow_rows", "knn_rescored_per_row")}
+    assert stats["knn_rows_two_term"] >= 4500 + 2250, stats           # the second batch + the overflowed half of the first
+    assert stats["knn_rows_one_term_wasted"] <= 4500, stats           # only the first batch paid for the undecided pass
+    assert stats["knn_slow_rows"] < 0.05 * n, stats
+    s, g = oracle_mod.build(gp, x, nodes="items")
+    _assert_graph_equal(gl, g)
+
+
 # ----------------------------------------------------------------------------- BASELINE-size cases
 
 def test_c2_shape_parity(oracle_mod):
