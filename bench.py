@@ -33,6 +33,27 @@ if ROOT not in sys.path:
 FLAGSHIP = "C4"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the
+    first communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,7 +164,7 @@ def run_reference(args, cfg):
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def gram_roofline(n_local, f, ms, peak):
@@ -162,6 +183,7 @@ def gram_roofline(n_local, f, ms, peak):
 # --------------------------------------------------------------------------- GPU arm
 def main():
     args = parse_args()
+    quiet_stdout()
     from pyarrowspace_b200 import synth
     cfg = synth.config(FLAGSHIP)
     if args.features:
@@ -438,7 +460,7 @@ def main():
                       "to %d items (linear scan); oracle build of the sample %.2f s = %.0f items/s"
                       % (ns, r["nq"], n / ns, n, r["build_s"], ns / r["build_s"]),
             "build_items_per_s": ns / r["build_s"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
