@@ -281,6 +281,7 @@ def main():
             if rep == 0:
                 del aspace, gl
     build_launches = (lib.asp_ctx_launch_count(ctx) - launches0) // (3 + args.build_reps)
+    feature_graph_nnz = int(gl.nnz)
 
     # ---- search: W warm-up steps, then exactly K timed steps
     clocks = ClockSampler(local)
@@ -445,7 +446,14 @@ def main():
                   "gram": gram_roofline(n_local, f, gram_ms, fp64_peak_tflops),
                   "graph_ms": float(np.mean(stages["graph_ms"])),
                   "lambda": {"ms": lam_ms, "bound": "hbm", "achieved_gbs": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9,
-                             "frac": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak}},
+                             "frac": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
+                             # the bound that actually binds at this graph density: one 8-byte shared-memory gather per
+                             # strictly-upper non-zero of L per item, against 128 B/clk/SM
+                             "gather": {"upper_nnz": (feature_graph_nnz - f) // 2,
+                                        "smem_bytes": 8.0 * n_local * ((feature_graph_nnz - f) // 2),
+                                        "smem_floor_ms": 8.0 * n_local * ((feature_graph_nnz - f) // 2) /
+                                                         (148 * 128.0 * (clk or {}).get("sm_mhz", 1900.0) * 1e6) * 1e3,
+                                        "note": "lambda_ms = median_kernel (radix selection, HBM pass 1) + taumode_kernel (HBM pass 2 + gathers)"}}},
         "item_graph": item_graph,
         "single_query": single,
         "clocks": clk,

@@ -9,8 +9,8 @@
 // shared-memory X tile dominate (8 bytes per nonzero per item) -- see DESIGN.md.
 //
 // Two kernels:
-//  median_kernel   one warp per vector, values in registers, warp-cooperative quickselect (counts through
-//                  __reduce_add_sync); streaming, high occupancy
+//  median_kernel   one warp per vector, order-preserving 64-bit keys in registers, MSB-first radix selection through a
+//                  256-bin shared-memory histogram per warp (2-3 passes for F = 384); streaming, high occupancy
 //  taumode_kernel  CTA = 256 threads, one tile of T = 16*R items at a time, grid-stride (persistent):
 //   A. warp w loads item rows (coalesced) and stores them transposed into shared memory
 //      xs[feature][item] (row stride T+1: conflict free both ways)
@@ -33,115 +33,169 @@ constexpr double TAU_FLOOR = 1e-9;
 
 struct TmChunk { int row_begin; int row_end; };
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x)
+// ---- radix selection on order-preserving 64-bit keys (the streaming median kernel below)
+// key(x) is monotone in x for every non-NaN double (-0.0 is folded into +0.0 first); absent elements carry the largest key.
+__device__ __forceinline__ unsigned long long f64_key(double x)
 {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x + 0.0);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k)
+{
+    const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
 }
 
-// rank-th smallest (0-based) of the n finite values spread over the warp's registers
-// (v[j] of lane l is element l + 32 j; absent elements are +inf).  Also returns the number of
-// elements <= result in *count_le.
+// rank-th smallest key (0-based) of the n present keys held as k[j] of lane l = element l + 32 j.  MSB-first radix
+// selection, 8 bits per pass through a 256-bin histogram in shared memory (one per warp); the bytes all present keys
+// share are skipped (embeddings of one scale share sign, exponent and often the first mantissa bits), and the walk
+// stops as soon as the selected bin holds one key -- two or three passes for F = 384.  *count_le = number of keys <= result.
 template <int FPL>
-__device__ double warp_select(const double (&v)[FPL], int rank, int lane, uint32_t seed, int *count_le)
+__device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FPL], int n, int rank, int lane,
+                                                uint32_t *hist /* [256] of this warp */, int *count_le)
 {
-    double lo = -INFINITY, hi = INFINITY;
-    int nbelow = 0;                       // elements <= lo
-    int ca = 0;                           // this lane's elements inside (lo, hi)
+    // common leading bytes
+    uint32_t dhi = 0, dlo = 0;
+    const unsigned long long k0 = __shfl_sync(0xffffffffu, k[0], 0);            // element 0 is always present
 #pragma unroll
-    for (int j = 0; j < FPL; ++j) ca += (v[j] < hi) ? 1 : 0;
-    for (int iter = 0;; ++iter) {
-        // inclusive scan of the per-lane active counts
-        int incl = ca;
+    for (int j = 0; j < FPL; ++j) {
+        const bool present = (lane + 32 * j) < n;
+        const unsigned long long d = present ? (k[j] ^ k0) : 0ull;
+        dhi |= (uint32_t)(d >> 32);
+        dlo |= (uint32_t)d;
+    }
+    dhi = __reduce_or_sync(0xffffffffu, dhi);
+    dlo = __reduce_or_sync(0xffffffffu, dlo);
+    if ((dhi | dlo) == 0u) { *count_le = n; return k0; }                         // all keys equal
+    const int lead = dhi ? __clz(dhi) : 32 + __clz(dlo);                         // identical leading bits
+    // the first digit is the 8 most significant bits that VARY (not a byte boundary): the keys spread over all 256 bins,
+    // so the shared-memory atomics of the first -- and only populous -- pass hardly collide
+    const int top = 64 - lead;                                                   // low bits that may differ, >= 1
+    int shift = top > 8 ? top - 8 : 0;
+    int width = top - shift;
+    unsigned long long prefix = (top == 64) ? 0ull : (k0 >> top) << top;
+    unsigned long long mask = (top == 64) ? 0ull : ~0ull << top;
+    int below = 0;                                                               // keys smaller than every key under the prefix
+    int r = rank;
+    for (;;) {
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total <= 0) { *count_le = nbelow; return NAN; }       // only with NaN / inf data
-        const int pick = (int)(hash32(seed + iter) % (uint32_t)total);
-        const unsigned ballot = __ballot_sync(0xffffffffu, incl > pick);
-        const int owner = __ffs(ballot) - 1;
-        double pv = 0.0;
-        if (lane == owner) {
-            const int want = pick - (incl - ca);
-            int seen = 0;
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) {
-                const bool act = (v[j] > lo) && (v[j] < hi);
-                if (act && seen == want) pv = v[j];
-                seen += act ? 1 : 0;
-            }
-        }
-        pv = __shfl_sync(0xffffffffu, pv, owner);
-        int clt = 0, ceq = 0;
+        for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0u;
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < FPL; ++j) {
-            clt += ((v[j] > lo) && (v[j] < pv)) ? 1 : 0;
-            ceq += (v[j] == pv) ? 1 : 0;
+            const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
+            if (act) atomicAdd(&hist[(uint32_t)(k[j] >> shift) & ((1u << width) - 1u)], 1u);
         }
-        const int tlt = __reduce_add_sync(0xffffffffu, clt);
-        const int teq = __reduce_add_sync(0xffffffffu, ceq);
-        if (rank < nbelow + tlt) {
-            hi = pv;
-            ca = clt;
-        } else if (rank < nbelow + tlt + teq) {
-            *count_le = nbelow + tlt + teq;
-            return pv;
-        } else {
-            lo = pv;
-            nbelow += tlt + teq;
-            ca = ca - clt - ceq;
+        __syncwarp();
+        // lane l owns bins 8l .. 8l+7
+        uint32_t c[8];
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 8 * lane), h1 = *reinterpret_cast<const uint4 *>(hist + 8 * lane + 4);
+        c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
+        uint32_t tot = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) tot += c[b];
+        uint32_t incl = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
         }
+        const unsigned owners = __ballot_sync(0xffffffffu, incl > (uint32_t)r);
+        const int owner = __ffs(owners) - 1;                                     // first lane whose inclusive count exceeds r
+        uint32_t run = incl - tot, digit = 0, cnt = 0, before = 0;
+        if (lane == owner) {
+            bool found = false;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool here = !found && (run + c[b] > (uint32_t)r);
+                if (here) { digit = 8 * lane + b; cnt = c[b]; before = run; found = true; }
+                run += c[b];
+            }
+        }
+        digit = __shfl_sync(0xffffffffu, digit, owner);
+        cnt = __shfl_sync(0xffffffffu, cnt, owner);
+        before = __shfl_sync(0xffffffffu, before, owner);
+        below += (int)before;
+        r -= (int)before;
+        prefix |= (unsigned long long)digit << shift;
+        mask |= (unsigned long long)((1u << width) - 1u) << shift;
+        __syncwarp();                                                            // the histogram is reused by the next pass
+        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }         // cnt equal keys
+        if (cnt == 1u) {                                                         // one key left under the prefix: fetch it
+            unsigned long long mine = 0ull;
+            bool have = false;
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) {
+                const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
+                if (act) { mine = k[j]; have = true; }
+            }
+            const int src = __ffs(__ballot_sync(0xffffffffu, have)) - 1;
+            *count_le = below + 1;
+            return __shfl_sync(0xffffffffu, mine, src);
+        }
+        const int next = shift > 8 ? shift - 8 : 0;
+        width = shift - next;
+        shift = next;
     }
 }
 
 template <int FPL>
-__device__ double warp_median(const double (&v)[FPL], int n, int lane, uint32_t seed)
+__device__ double warp_median_radix(const unsigned long long (&k)[FPL], int n, int lane, uint32_t *hist)
 {
     int cle = 0;
-    if (n & 1) return warp_select<FPL>(v, n / 2, lane, seed, &cle);
-    const double vlo = warp_select<FPL>(v, n / 2 - 1, lane, seed, &cle);
-    double vhi = vlo;
-    if (cle < n / 2 + 1) {               // the next order statistic is the smallest element > vlo
-        double m = INFINITY;
+    if (n & 1) return key_f64(warp_radix_select<FPL>(k, n, n / 2, lane, hist, &cle));
+    const unsigned long long klo = warp_radix_select<FPL>(k, n, n / 2 - 1, lane, hist, &cle);
+    unsigned long long khi = klo;
+    if (cle < n / 2 + 1) {                   // the next order statistic is the smallest key > klo
+        unsigned long long m = ~0ull;
 #pragma unroll
         for (int j = 0; j < FPL; ++j)
-            if (v[j] > vlo && v[j] < m) m = v[j];
+            if ((lane + 32 * j) < n && k[j] > klo && k[j] < m) m = k[j];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
-        vhi = m;
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
+            m = (o < m) ? o : m;
+        }
+        khi = m;
     }
-    return 0.5 * (vlo + vhi);            // oracle.c median_of: 0.5 * (s[n/2-1] + s[n/2])
+    return 0.5 * (key_f64(klo) + key_f64(khi));   // oracle.c median_of: 0.5 * (s[n/2-1] + s[n/2])
 }
 
-// K3a: per-vector median (tau before flooring), one warp per vector, grid-stride.  A pure streaming pass with
-// small footprint (no shared memory, FPL f64 registers per lane): many resident warps hide the shuffle latency
-// of the selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
+// K3a: per-vector median (tau before flooring), one warp per vector, grid-stride.  A pure streaming pass with a small
+// footprint (1 KB of shared memory per warp, FPL 64-bit keys per lane): many resident warps hide the latency of the
+// selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
 template <int FPL>
 __global__ void __launch_bounds__(256)
 median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use_abs, double *__restrict__ out_median)
 {
+    __shared__ __align__(16) uint32_t s_hist[8][256];
     const int lane = threadIdx.x & 31;
+    uint32_t *hist = s_hist[threadIdx.x >> 5];
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t item = warp; item < n; item += nwarps) {
         const double *row = x + item * pitch;
-        double v[FPL];
+        unsigned long long k[FPL];
 #pragma unroll
         for (int j = 0; j < FPL; ++j) {
             const int ff = lane + 32 * j;
-            v[j] = (ff < f) ? row[ff] : INFINITY;
-            if (use_abs && ff < f) v[j] = fabs(v[j]);
+            double v = (ff < f) ? row[ff] : 0.0;
+            if (use_abs) v = fabs(v);
+            k[j] = (ff < f) ? f64_key(v) : ~0ull;
         }
-        const double med = warp_median<FPL>(v, f, lane, (uint32_t)(item * 2654435761ULL));
+        const double med = warp_median_radix<FPL>(k, f, lane, hist);
         if (lane == 0) out_median[item] = med;
     }
 }
 
+// THR compute threads + AUXW auxiliary warps.  The left-to-right sums of phase A' are one dependent chain per item (the
+// oracle's order), i.e. T busy threads for ~10 us per tile; they run on the auxiliary warps WHILE the compute warps walk
+// the graph (phase B only needs the transposed tile), and meet them again at the reduction (phase C).
+template <int R>
+struct TmAux { static constexpr int T = 16 * R; static constexpr int WARPS = (T + 31) / 32; };
+
 template <int FPL, int R, int CHN, int THR>
-__global__ void __launch_bounds__(THR, 1)
+__global__ void __launch_bounds__(THR + 32 * TmAux<R>::WARPS, 1)
 taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
                const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ deg,
                const TmChunk *__restrict__ chunks, int nchunks, int tau_mode, double tau_fixed,
@@ -160,89 +214,94 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     double *s_n2 = s_tau + T;                                          // T
     double *red = s_val;
 
+    const bool is_aux = threadIdx.x >= THR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = threadIdx.x & 15, p = threadIdx.x >> 4;
     const int64_t ntiles = (n + T - 1) / T;
+    auto compute_sync = []() { asm volatile("bar.sync 1, %0;\n" ::"n"(THR) : "memory"); };   // the compute warps only
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t item0 = tile * T;
         __syncthreads();                                               // previous tile fully consumed
 
-        // ---- A: load, transpose into shared memory
-        for (int t = warp; t < T; t += THR / 32) {
-            const int64_t item = item0 + t;
-            double v[FPL];
-            if (item < n) {
-                const double *row = x + item * pitch;
+        // ---- A: load, transpose into shared memory (compute warps)
+        if (!is_aux) {
+            for (int t = warp; t < T; t += THR / 32) {
+                const int64_t item = item0 + t;
+                double v[FPL];
+                if (item < n) {
+                    const double *row = x + item * pitch;
+#pragma unroll
+                    for (int j = 0; j < FPL; ++j) {
+                        const int ff = lane + 32 * j;
+                        v[j] = (ff < f) ? row[ff] : INFINITY;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < FPL; ++j) v[j] = (lane + 32 * j < f) ? 0.0 : INFINITY;
+                }
 #pragma unroll
                 for (int j = 0; j < FPL; ++j) {
                     const int ff = lane + 32 * j;
-                    v[j] = (ff < f) ? row[ff] : INFINITY;
+                    if (ff < f) xs[ff * XS + t] = v[j];
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < FPL; ++j) v[j] = (lane + 32 * j < f) ? 0.0 : INFINITY;
-            }
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) {
-                const int ff = lane + 32 * j;
-                if (ff < f) xs[ff * XS + t] = v[j];
             }
         }
         __syncthreads();
 
-        // ---- A': left-to-right sums (norm^2; mean)
-        if (threadIdx.x < T) {
-            const int t = threadIdx.x;
-            double n2 = 0.0, sm = 0.0;
-#pragma unroll 8
-            for (int ff = 0; ff < f; ++ff) {                           // loads and products run ahead; only the adds are a chain
-                const double xv = xs[ff * XS + t];
-                n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
-                sm = __dadd_rn(sm, xv);
-            }
-            s_n2[t] = n2;
-            double tau;
-            if (tau_mode == ASP_TAU_MEAN) tau = sm / (double)f;
-            else if (tau_mode == ASP_TAU_FIXED) tau = tau_fixed;
-            else tau = (item0 + t < n) ? medians[item0 + t] : 1.0;
-            s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
-        }
-
-        // ---- B: x^T L x through the strictly-upper adjacency
         double en[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) en[r] = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            const int ra0 = chunks[c].row_begin, ra1 = chunks[c].row_end;
-            const int e0 = uptr[ra0], e1 = uptr[ra1];
-            __syncthreads();
-            for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
-            for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
-            for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
-            __syncthreads();
-            for (int a = ra0 + p; a < ra1; a += (THR / 16)) {
-                double xa[R], s[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) { xa[r] = xs[a * XS + g + 16 * r]; s[r] = 0.0; }
-                const int jb = s_rptr[a - ra0], je = s_rptr[a - ra0 + 1];
-                for (int j = jb; j < je; ++j) {
-                    const int b = s_col[j];
-                    const double w = s_val[j];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) s[r] = fma(w, xs[b * XS + g + 16 * r], s[r]);
+        if (is_aux) {
+            // ---- A': left-to-right sums (norm^2; mean), one thread per item
+            const int t = threadIdx.x - THR;
+            if (t < T) {
+                double n2 = 0.0, sm = 0.0;
+#pragma unroll 8
+                for (int ff = 0; ff < f; ++ff) {                       // loads and products run ahead; only the adds are a chain
+                    const double xv = xs[ff * XS + t];
+                    n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
+                    sm = __dadd_rn(sm, xv);
                 }
-                const double dg = s_deg[a - ra0];
-#pragma unroll
-                for (int r = 0; r < R; ++r) en[r] = fma(xa[r], fma(dg, xa[r], -2.0 * s[r]), en[r]);
+                s_n2[t] = n2;
+                double tau;
+                if (tau_mode == ASP_TAU_MEAN) tau = sm / (double)f;
+                else if (tau_mode == ASP_TAU_FIXED) tau = tau_fixed;
+                else tau = (item0 + t < n) ? medians[item0 + t] : 1.0;
+                s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
             }
-        }
-        __syncthreads();
-
-        // ---- C: reduce the parts in order, finish
+        } else {
+            // ---- B: x^T L x through the strictly-upper adjacency
+            for (int c = 0; c < nchunks; ++c) {
+                const int ra0 = chunks[c].row_begin, ra1 = chunks[c].row_end;
+                const int e0 = uptr[ra0], e1 = uptr[ra1];
+                compute_sync();
+                for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
+                for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
+                for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
+                compute_sync();
+                for (int a = ra0 + p; a < ra1; a += (THR / 16)) {
+                    double xa[R], s[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) red[p * T + g + 16 * r] = en[r];
-        __syncthreads();
+                    for (int r = 0; r < R; ++r) { xa[r] = xs[a * XS + g + 16 * r]; s[r] = 0.0; }
+                    const int jb = s_rptr[a - ra0], je = s_rptr[a - ra0 + 1];
+                    for (int j = jb; j < je; ++j) {
+                        const int b = s_col[j];
+                        const double w = s_val[j];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) s[r] = fma(w, xs[b * XS + g + 16 * r], s[r]);
+                    }
+                    const double dg = s_deg[a - ra0];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) en[r] = fma(xa[r], fma(dg, xa[r], -2.0 * s[r]), en[r]);
+                }
+            }
+            compute_sync();                                            // the staged weights are dead: red[] aliases them
+            // ---- C: the parts' partial energies
+#pragma unroll
+            for (int r = 0; r < R; ++r) red[p * T + g + 16 * r] = en[r];
+        }
+        __syncthreads();                                               // partial energies, norms and taus are in shared memory
         if (threadIdx.x < T) {
             const int t = threadIdx.x;
             const int64_t item = item0 + t;
@@ -287,12 +346,13 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
     auto kern = taumode_kernel<FPL, R, CHN, THR>;
     ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;                                                       // resident CTAs per SM: their load / gather phases overlap
-    ASP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THR, smem));
+    constexpr int NTHREADS = THR + 32 * TmAux<R>::WARPS;
+    ASP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
     if (occ < 1) occ = 1;
     const int64_t ntiles = (n + T - 1) / T;
     const int64_t slots = (int64_t)ctx->num_sms * occ;
     const int grid = (int)(ntiles < slots ? ntiles : slots);
-    kern<<<grid, THR, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
+    kern<<<grid, NTHREADS, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
                                                   nchunks, sw->tau_mode, sw->tau_fixed, medians, oe, ot, ol, on, oi, zero_flag);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
