@@ -165,7 +165,7 @@ __device__ double warp_median_radix(const unsigned long long (&k)[FPL], int n, i
 // footprint (1 KB of shared memory per warp, FPL 64-bit keys per lane): many resident warps hide the latency of the
 // selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
 template <int FPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FPL <= 12 ? 4 : 1)     // 64 registers: 32 warps per SM hide the selection's latency
 median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use_abs, double *__restrict__ out_median)
 {
     __shared__ __align__(16) uint32_t s_hist[8][256];

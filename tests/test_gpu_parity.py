@@ -667,3 +667,33 @@ def test_pipelined_host_batches_equal_single_shot(oracle_mod):
         aspace.search_batch(bad, gl, 0.62)
     idx_again, _ = aspace.search_batch(qp, gl, 0.62)     # the library is usable after the failed call
     assert np.array_equal(idx_again, idx_1)
+
+
+def test_adopted_device_buffer(oracle_mod):
+    """asp_space_adopt: the library works on the caller's device buffer in place (no copy; how the all-gathered item
+    matrix of the multi-GPU item graph stays single).  Same graph as the copying route and as the oracle; feature counts
+    that are not a multiple of 4 are refused (the Python layer then copies)."""
+    import torch
+    from pyarrowspace_b200 import _lib, api, synth
+    lib = _lib.load()
+    ctx = _lib.context(None)
+    x = synth.make_items(9000, 64, 31, n_clusters=40)
+    gp = {"eps": 0.5, "k": 6, "topk": 3, "p": 2.0, "sigma": 0.1}
+    cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+    sw = _lib.make_switches()
+    xd = torch.from_numpy(x).cuda()
+    torch.cuda.synchronize()
+    hs, hg = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.asp_space_adopt(ctx, xd.data_ptr(), x.shape[0], x.shape[1], C.byref(hs)))
+    _lib.check(lib.asp_item_graph(hs, C.byref(cgp), C.byref(sw), C.byref(hg)))
+    aspace, gl = api.ArrowSpace._wrap(hs, ctx), api.GraphLaplacian._wrap(hg)
+    aspace._keepalive = xd
+    assert (aspace.nitems, aspace.nfeatures) == x.shape
+    s, g = oracle_mod.build(gp, x, nodes="items")
+    _assert_graph_equal(gl, g)
+    del aspace, gl
+    xd[:] = 0.0                                            # the buffer is the caller's again
+    bad = torch.zeros((16, 6), dtype=torch.float64, device="cuda")
+    h2 = C.c_void_p()
+    assert lib.asp_space_adopt(ctx, bad.data_ptr(), 16, 6, C.byref(h2)) == _lib.ASP_ERR_ARG
+    assert lib.asp_space_adopt(ctx, x.ctypes.data, x.shape[0], x.shape[1], C.byref(h2)) == _lib.ASP_ERR_ARG   # host memory
