@@ -401,6 +401,7 @@ def main():
                               "shared across CTAs); exact f64 stage 2 follows"
                               % ("ONE fp16 term" if terms == 1 else "the two-term fp16 split (3 MMA terms)"),
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_nominal": 2250.0, "frac_of_nominal": achieved / 2250.0,     # dense 16-bit datasheet figure (report both)
                     "traffic": prof.get("tc_gemm_dram_bytes_per_launch"),
                     "algorithmic": "2*Q*N_local*F = %.3e FLOP per launch; EXECUTED 2*Q*N_local*16*%d = %.3e fp16 tensor FLOP "
                                    "(achieved/frac count the executed FLOP against the measured 16-bit dense tensor peak)"
