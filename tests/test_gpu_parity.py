@@ -697,3 +697,69 @@ def test_adopted_device_buffer(oracle_mod):
     h2 = C.c_void_p()
     assert lib.asp_space_adopt(ctx, bad.data_ptr(), 16, 6, C.byref(h2)) == _lib.ASP_ERR_ARG
     assert lib.asp_space_adopt(ctx, x.ctypes.data, x.shape[0], x.shape[1], C.byref(h2)) == _lib.ASP_ERR_ARG   # host memory
+
+
+@pytest.mark.parametrize("f", [47, 48, 130, 384])
+def test_median_selection_edge_cases(oracle_mod, f):
+    """The radix-selection median (taumode.cu) against the oracle's sort on rows built to hit its corners: all entries equal,
+    two distinct values, long runs of duplicates around the middle, mixed signs and zeros of both signs, values that differ
+    only in the last mantissa bits, values spanning many binades; odd and even lengths.  tau = max(median, 1e-9) must be
+    EXACT (a selection, not an approximation)."""
+    from pyarrowspace_b200 import _lib, synth
+    rng = np.random.default_rng(500 + f)
+    x = synth.make_items(600, f, 9, n_clusters=5)
+    aspace, gl, s, g = _build_both(oracle_mod, {"eps": 0.6, "k": 4, "topk": 3, "p": 2.0, "sigma": 0.3}, x)
+    rows = []
+    rows.append(np.full(f, 3.25))                                               # all equal
+    rows.append(np.where(np.arange(f) % 2 == 0, 1.5, 2.5))                      # two values, the middle straddles them
+    r = rng.standard_normal(f) + 4.0
+    r[: f // 2 + 3] = r[0]                                                      # a run of duplicates covering the median
+    rows.append(rng.permutation(r))
+    r = rng.standard_normal(f)
+    r[::5] = 0.0
+    r[1::7] = -0.0
+    rows.append(r)                                                              # mixed signs, +-0: median near / below 0 -> floor
+    rows.append(1.0 + np.arange(f) * 2.0 ** -52)                                # neighbours in the last bits
+    rows.append(rng.permutation(2.0 ** rng.integers(-300, 300, f) * rng.uniform(1, 2, f)))   # many binades
+    rows.append(-np.abs(rng.standard_normal(f)) - 1.0)                          # all negative
+    rows.append(np.abs(rng.standard_normal(f)) * 1e-12)                         # around the floor
+    q = np.ascontiguousarray(np.stack(rows) + 0.0 * x[0])
+    q[3] = rows[3]                                                              # keep the signed zeros
+    nq = q.shape[0]
+    for tau_mode in ("median", "median_abs"):
+        sw = _lib.make_switches("inv_power", tau_mode)
+        e, t, lam = (np.empty(nq) for _ in range(3))
+        _lib.check(_lib.load().asp_query_lambda(_lib.context(), gl._h, C.byref(sw), q.ctypes.data, nq, e.ctypes.data,
+                                                t.ctypes.data, lam.ctypes.data))
+        oe, ot, ol = g.taumode(q, switches=oracle_mod.make_switches(tau_mode=tau_mode))
+        np.testing.assert_array_equal(t, ot)
+        np.testing.assert_allclose(e[1:3], oe[1:3], rtol=RTOL)                  # (the constant row's energy is pure cancellation)
+        np.testing.assert_allclose(lam[1:3], ol[1:3], rtol=RTOL)
+
+
+def test_small_batches_on_the_tensor_core_route(oracle_mod):
+    """One query per call and batches of 7 / 33 / 64 through the tcgen05 candidate pass with a whole CTA per query in
+    stage 2 (`tc_rescore_kernel<32>`; the default route for shards of >= 131072 items, forced here on a small space):
+    bit-identical to the f64 route and equal to the oracle."""
+    from pyarrowspace_b200 import api, synth
+    n, f = 20000, 64
+    x = synth.make_items(n, f, 61, n_clusters=20)
+    q, _ = synth.make_queries(x, 64, 62)
+    gp = {"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}
+    aspace, gl, s, g = _build_both(oracle_mod, gp, x)
+    oidx, osc, _ = s.search_batch(q, g, 0.62)
+    try:
+        for nq in (1, 7, 33, 64):
+            _force_stage1("tc")
+            idx_tc, sc_tc = aspace.search_batch(q[:nq], gl, 0.62)
+            assert api.stat("search_stage1_is_tc") == 1.0
+            _force_stage1("fp64")
+            idx_64, sc_64 = aspace.search_batch(q[:nq], gl, 0.62)
+            assert np.array_equal(idx_tc, idx_64) and np.array_equal(sc_tc, sc_64)
+            _assert_hits_equal(idx_tc, sc_tc, oidx[:nq], osc[:nq])
+        _force_stage1("tc")
+        one = aspace.search(q[5], gl, 0.62)                                      # the reference's call shape
+        assert [i for i, _ in one] == list(oidx[5])
+        np.testing.assert_allclose([v for _, v in one], osc[5], rtol=RTOL, atol=0)
+    finally:
+        _force_stage1(None)
