@@ -1,4 +1,4 @@
-// search_tc.cu -- K4, throughput path: stage 1 of the batched lambda-aware search on the 5th-generation tensor
+// search_tc.cu -- K4 (batches) and K4' (small batches on large shards): stage 1 of the lambda-aware search on the 5th-generation tensor
 // cores (tcgen05.mma, accumulators in TMEM, operands by TMA), stage 2 exact.
 // (replaces ArrowSpace::search_lambda_aware, /root/reference/src/lib.rs:173; score TAUMODE.md:33.)
 //
@@ -18,7 +18,9 @@
 // thresholds are shared between the column quarters of a row (shared memory) and between the CTAs that scan
 // different item chunks for the same query (global atomicMax), so late chunks start with a warm threshold.
 //
-// Stage 2 (tc_rescore_kernel), one warp per query: (A) every survivor of the final cut is re-scored in f64 with a
+// Stage 2 (tc_rescore_kernel<WPQ>), one warp per query for batches, a whole CTA per query for small batches (the
+// reference's one query per call: the per-query work is a chain of dependent global loads, so it is spread over
+// 8 or 32 warps and the per-warp lists are merged pairwise): (A) every survivor of the final cut is re-scored in f64 with a
 // warp-cooperative coalesced dot product (error <= EPS ~ 1e-13), the best 32 kept; (B) the candidates within 2 EPS of
 // the k-th best are re-scored in the reference order (sequential, __dmul_rn/__dadd_rn: exactly the oracle's
 // expression) and sorted by (score desc, index asc).  More than 32 candidates inside that band, or a full emission
