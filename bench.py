@@ -125,6 +125,13 @@ def cpu_oracle_run(cfg, n_items, nq, reps, label):
     """Oracle build on n_items rows of the workload + `reps` search batches of nq queries, all host threads."""
     import oracle
     from pyarrowspace_b200 import synth
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would turn the
+    # CPU arm into a single-thread run at N > 1 (rank 0 is the only rank that works here; the others exit)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
     x = synth.make_items(cfg["n"], cfg["f"], cfg["seed"], cfg["scale"], rows=(0, n_items))
     q, _ = synth.make_queries(x, nq, cfg["seed"], cfg["scale"])
     t0 = time.perf_counter()
