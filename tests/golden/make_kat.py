@@ -1,5 +1,5 @@
 """Regenerates tests/golden/oracle_vectors.npz: oracle outputs on the reference's two KAT inputs and on
-two small seeded synthetic cases.  kat.json itself is transcribed from the reference's README.md:37-69
+two small seeded synthetic cases (+ the item graph of a third).  kat.json itself is transcribed from the reference's README.md:37-69
 and tests/test_0.py:4-61 (the reference engine -- crate arrowspace 0.18.0 -- is not vendored and cannot
 be imported here, so there is no reference run to record).
 
@@ -42,6 +42,11 @@ def main():
         qs, _ = synth.make_queries(x, nq, seed)
         for k, v in run_case(x, gp, qs, 0.62).items():
             out["%s_%s" % (name, k)] = v
+    # item graph (nodes = items): Laplacian CSR only
+    x = synth.make_items(2500, 48, 7, scale=100.0, n_clusters=12)
+    s, g = oracle.build({"eps": 0.5, "k": 8, "topk": 3, "p": 2.0, "sigma": 0.2}, x, nodes="items")
+    indptr, indices, data = g.csr()
+    out.update(itemsC_indptr=indptr, itemsC_indices=indices.astype(np.int32), itemsC_data=data)
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -93,6 +93,22 @@ def test_golden_fixture(golden):
     _assert_hits_equal(idx, sc, golden["synthB_idx"], golden["synthB_score"])
 
 
+@pytest.mark.parametrize("stage1", ["fp64", "tc"])
+def test_golden_item_graph(golden, stage1):
+    """Item graph (nodes = items) against the committed fixture, both candidate passes."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(2500, 48, 7, scale=100.0, n_clusters=12)
+    os.environ["ASP_KNN_STAGE1"] = stage1
+    try:
+        aspace, gl = ArrowSpaceBuilder.build_item_graph({"eps": 0.5, "k": 8, "topk": 3, "p": 2.0, "sigma": 0.2}, x)
+    finally:
+        os.environ.pop("ASP_KNN_STAGE1", None)
+    ip, ix, dt = gl.csr()
+    assert np.array_equal(ip, golden["itemsC_indptr"]) and np.array_equal(ix, golden["itemsC_indices"])
+    np.testing.assert_allclose(dt, golden["itemsC_data"], rtol=RTOL)
+
+
 # ----------------------------------------------------------------------------- stage by stage
 
 @pytest.mark.parametrize("n,f", [(5, 3), (33, 24), (1000, 50), (4097, 130), (20000, 384)])

@@ -84,6 +84,10 @@ def test_golden_vectors(oracle_mod, kat, golden):
     idx, sc, lq = s.search_batch(q, g, 0.62)
     assert (idx == golden["synthA_idx"]).all() and (sc == golden["synthA_score"]).all()
     assert (s.lambdas() == golden["synthA_lambdas"]).all() and (lq == golden["synthA_lambda_q"]).all()
+    x = synth.make_items(2500, 48, 7, scale=100.0, n_clusters=12)                 # item graph (nodes = items)
+    s, g = oracle_mod.build({"eps": 0.5, "k": 8, "topk": 3, "p": 2.0, "sigma": 0.2}, x, nodes="items")
+    ip, ix, dt = g.csr()
+    assert (ip == golden["itemsC_indptr"]).all() and (ix == golden["itemsC_indices"]).all() and (dt == golden["itemsC_data"]).all()
 
 
 @pytest.mark.parametrize("nodes", ["feature_columns", "items"])
