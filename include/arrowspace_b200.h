@@ -20,6 +20,7 @@
 #ifndef ARROWSPACE_B200_H
 #define ARROWSPACE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -181,6 +182,20 @@ int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, flo
  * asp_search_batch on each shard) into the global top-k by (score desc, index asc). */
 int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int parts, int64_t nq,
                    int64_t topk, int64_t *out_idx, double *out_score);
+
+/* K5 over NVLink peer memory (no NCCL call in the exchange): every rank stores its [nq][topk] lists into slot [rank] of
+ * EVERY rank's exchange buffer (P2P stores), raises a flag there, and merges when all flags show `epoch`.
+ * peer_bases[r] = device address, valid in THIS process, of rank r's exchange buffer (asp_peer_exchange_bytes(world,
+ * cap, topk) bytes, zero-filled before the first call; mapping it is the caller's plumbing -- api.py uses
+ * torch.distributed._symmetric_memory).  `epoch` = 1, 2, 3 ... per call on that buffer, the same on every rank;
+ * nq <= cap.  idx / score / outputs are device memory.  A rank that never shows up is reported (ASP_ERR_CUDA) after
+ * a bounded wait.  No reference counterpart.  Written at the end of round 1, not yet run on a multi-GPU box:
+ * opt-in through ASP_PEER_MERGE=1 in the Python layer. */
+#define ASP_PEER_MAX_WORLD 8
+size_t asp_peer_exchange_bytes(int world, int64_t cap, int64_t topk);
+int asp_peer_merge(asp_ctx *ctx, int world, int rank, const uint64_t *peer_bases, int64_t cap, int64_t epoch,
+                   const int64_t *idx_dev, const double *score_dev, int64_t nq, int64_t topk, int64_t *out_idx_dev,
+                   double *out_score_dev);
 
 /* ---- item graph (nodes = items; the graph-build workload of configs C4/C5) ------------------ */
 

@@ -78,6 +78,8 @@ SYMBOLS = {
     "asp_search_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "asp_debug_tc_dots": (_int, [_vp, _vp, _i64, _vp]),
     "asp_topk_merge": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp]),
+    "asp_peer_exchange_bytes": (C.c_size_t, [_int, _i64, _i64]),
+    "asp_peer_merge": (_int, [_vp, _int, _int, C.POINTER(C.c_uint64), _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp]),
     "asp_item_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
     "asp_item_knn_rows": (_int, [_vp, C.POINTER(GraphParams), _i64, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
     "asp_graph_from_knn": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),

@@ -16,6 +16,7 @@ Every numeric step runs in libarrowspace_b200.so (hand-written sm_100a CUDA).  T
 path: without the library or without a GPU the calls raise.
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -337,8 +338,35 @@ def _upload_queries_sharded(space, q_np):
     return full[:nq]
 
 
+def _peer_exchange(space, world, nq, topk, dev):
+    """Exchange buffer of the peer-memory merge (csrc/peer.cu): one symmetric allocation per space, mapped by every rank
+    of the group (torch.distributed._symmetric_memory is the plumbing; the kernels that use the peer pointers are ours)."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    st = getattr(space, "_peer", None)
+    if st is None or st["cap"] < nq or st["topk"] != topk:
+        lib = _lib.load()
+        cap = max(int(nq), 65536)
+        nbytes = lib.asp_peer_exchange_bytes(world, cap, topk)
+        if nbytes == 0:
+            raise ValueError("peer merge supports at most %d ranks" % 8)
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        group = space._group if space._group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, group)
+        buf.zero_()
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier(group)                                   # every rank's flags are zero before anyone publishes
+        ptrs = (C.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+        st = dict(buf=buf, hdl=hdl, ptrs=ptrs, cap=cap, topk=topk, epoch=0)
+        space._peer = st
+    return st
+
+
 def _merge_across_ranks(space, idx, score, nq, topk):
-    """K5 host side: all-gather the per-shard (idx, score) lists, merge on the device."""
+    """K5 host side: all-gather the per-shard (idx, score) lists, merge on the device.  ASP_PEER_MERGE=1: the lists travel
+    as P2P stores into every rank's exchange buffer and the merge kernel waits on flags instead (csrc/peer.cu; opt-in
+    until it has been run on a multi-GPU box)."""
     import torch
     import torch.distributed as dist
     lib = _lib.load()
@@ -348,6 +376,18 @@ def _merge_across_ranks(space, idx, score, nq, topk):
     was_numpy = isinstance(idx, np.ndarray)
     t_idx = torch.from_numpy(idx).to(dev) if was_numpy else idx
     t_sc = torch.from_numpy(score).to(dev) if was_numpy else score
+    if os.environ.get("ASP_PEER_MERGE", "0") == "1" and topk > 0 and nq > 0:
+        st = _peer_exchange(space, world, nq, topk, dev)
+        st["epoch"] += 1
+        out_idx = torch.empty((nq, topk), dtype=torch.int64, device=dev)
+        out_sc = torch.empty((nq, topk), dtype=torch.float64, device=dev)
+        t_idx, t_sc = t_idx.contiguous(), t_sc.contiguous()
+        torch.cuda.current_stream(dev).synchronize()
+        _lib.check(lib.asp_peer_merge(space._ctx, world, dist.get_rank(group), st["ptrs"], st["cap"], st["epoch"],
+                                      t_idx.data_ptr(), t_sc.data_ptr(), nq, topk, out_idx.data_ptr(), out_sc.data_ptr()))
+        if was_numpy:
+            return out_idx.cpu().numpy(), out_sc.cpu().numpy()
+        return out_idx, out_sc
     all_idx = torch.empty((world, nq, topk), dtype=torch.int64, device=dev)
     all_sc = torch.empty((world, nq, topk), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(all_idx, t_idx.contiguous(), group=group)

@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node N tools/mgpu_check.py : sharded build + search over NCCL against the CPU oracle
-and against the single-GPU result (bit identical)."""
+and against the single-GPU result (bit identical).  CHECK_PEER=1 also runs the peer-memory merge (csrc/peer.cu)."""
 import os
 import sys
 
@@ -28,6 +28,18 @@ def main():
         aspace, gl = ArrowSpaceBuilder.build_sharded(gp, shard, n, device=local)
         idx, sc = aspace.search_batch(q, gl, 0.62)
         lam = aspace.lambdas()
+        if os.environ.get("CHECK_PEER"):                      # csrc/peer.cu: P2P exchange + flag-driven merge vs the NCCL route
+            os.environ["ASP_PEER_MERGE"] = "1"
+            same = True
+            for rep in range(3):                              # three calls: both parities and a reused slot
+                idx_p, sc_p = aspace.search_batch(q, gl, 0.62)
+                same = same and np.array_equal(idx_p, idx) and np.array_equal(sc_p, sc)
+            os.environ.pop("ASP_PEER_MERGE")
+            flag = torch.tensor([1 if same else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print("world", world, "n", n, "peer-memory merge == NCCL merge on every rank (bitwise):", bool(flag.item()))
+            ok = ok and bool(flag.item())
         if rank == 0:
             import oracle
             s, g = oracle.build(gp, full)
