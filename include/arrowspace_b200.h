@@ -189,8 +189,8 @@ int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int pa
  * cap, topk) bytes, zero-filled before the first call; mapping it is the caller's plumbing -- api.py uses
  * torch.distributed._symmetric_memory).  `epoch` = 1, 2, 3 ... per call on that buffer, the same on every rank;
  * nq <= cap.  idx / score / outputs are device memory.  A rank that never shows up is reported (ASP_ERR_CUDA) after
- * a bounded wait.  No reference counterpart.  Written at the end of round 1, not yet run on a multi-GPU box:
- * opt-in through ASP_PEER_MERGE=1 in the Python layer. */
+ * a bounded wait.  No reference counterpart.  Checked on 2 GPUs (bitwise equal to the NCCL route); not yet run on 4 / 8
+ * GPUs nor timed: opt-in through ASP_PEER_MERGE=1 in the Python layer. */
 #define ASP_PEER_MAX_WORLD 8
 size_t asp_peer_exchange_bytes(int world, int64_t cap, int64_t topk);
 int asp_peer_merge(asp_ctx *ctx, int world, int rank, const uint64_t *peer_bases, int64_t cap, int64_t epoch,

@@ -365,8 +365,8 @@ def _peer_exchange(space, world, nq, topk, dev):
 
 def _merge_across_ranks(space, idx, score, nq, topk):
     """K5 host side: all-gather the per-shard (idx, score) lists, merge on the device.  ASP_PEER_MERGE=1: the lists travel
-    as P2P stores into every rank's exchange buffer and the merge kernel waits on flags instead (csrc/peer.cu; opt-in
-    until it has been run on a multi-GPU box)."""
+    as P2P stores into every rank's exchange buffer and the merge kernel waits on flags instead (csrc/peer.cu; bitwise
+    equal to this route on 2 GPUs, opt-in until it has been run on 8 and timed)."""
     import torch
     import torch.distributed as dist
     lib = _lib.load()

@@ -18,8 +18,10 @@
 // merge of e, and nobody finishes e+1 before all flags e+1 are up, so when A overwrites the parity of e (call e+2) every
 // rank is done reading it.
 //
-// STATUS: written at the end of round 1 without multi-GPU time to run it; OFF unless ASP_PEER_MERGE=1 (api.py).  First
-// thing to validate next round: ASP_PEER_MERGE=1 torchrun ... tools/mgpu_check.py (bitwise equal to the NCCL route).
+// STATUS (end of round 1): correct on 2 GPUs -- `CHECK_PEER=1 QUICK=1 torchrun --nproc-per-node 2 tools/mgpu_check.py` gives
+// results bitwise equal to the NCCL route over three consecutive calls (both parities, slot reuse;
+// profiles/mgpu_check_peer_merge_2gpu_r01.log).  Not yet run on 4 / 8 GPUs and not yet timed, so it stays OFF unless
+// ASP_PEER_MERGE=1 (api.py).
 #include "common.cuh"
 
 #include <algorithm>

@@ -54,6 +54,11 @@ def main():
             print("world", world, "n", n, "f", f, "edges/idx/score/lambda vs oracle:", e[:4], " vs single GPU (bitwise):", e[4:])
             ok = ok and all(e)
         dist.barrier()
+    if os.environ.get("QUICK"):                               # build / search / merge checks only
+        if rank == 0:
+            print("MGPU_CHECK", "OK" if ok else "FAILED")
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     # item graph across the ranks: halo all-gather of the item shards, rows resolved per rank on the tensor cores,
     # all-gather of the neighbour lists; every rank must end with the single-GPU graph (bitwise) == the oracle's edges
     import time
