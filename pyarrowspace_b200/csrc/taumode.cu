@@ -164,8 +164,11 @@ __device__ double warp_median_radix(const unsigned long long (&k)[FPL], int n, i
 // K3a: per-vector median (tau before flooring), one warp per vector, grid-stride.  A pure streaming pass with a small
 // footprint (1 KB of shared memory per warp, FPL 64-bit keys per lane): many resident warps hide the latency of the
 // selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
-template <int FPL>
-__global__ void __launch_bounds__(256, FPL <= 12 ? 4 : 1)     // 64 registers: 32 warps per SM hide the selection's latency
+// PF (ASP_MEDIAN_PREFETCH=1, not yet the default: written after the GPU budget of round 1 was spent): the row of the warp's
+// NEXT item is requested before the selection on the current one, so the loads -- 59 % of this kernel's stall samples -- overlap
+// the selection instead of preceding it.  Costs FPL more 64-bit registers (3 instead of 4 CTAs per SM at F <= 384).
+template <int FPL, bool PF>
+__global__ void __launch_bounds__(256, FPL <= 12 ? (PF ? 3 : 4) : 1)     // 64 registers: 32 warps per SM hide the selection's latency
 median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use_abs, double *__restrict__ out_median)
 {
     __shared__ __align__(16) uint32_t s_hist[8][256];
@@ -173,15 +176,26 @@ median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use
     uint32_t *hist = s_hist[threadIdx.x >> 5];
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double nv[FPL];                                                      // PF: the next item's values, in flight
+    if (PF && warp < n) {
+        const double *row = x + warp * pitch;
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; nv[j] = (ff < f) ? row[ff] : 0.0; }
+    }
     for (int64_t item = warp; item < n; item += nwarps) {
         const double *row = x + item * pitch;
         unsigned long long k[FPL];
 #pragma unroll
         for (int j = 0; j < FPL; ++j) {
             const int ff = lane + 32 * j;
-            double v = (ff < f) ? row[ff] : 0.0;
+            double v = PF ? nv[j] : ((ff < f) ? row[ff] : 0.0);
             if (use_abs) v = fabs(v);
             k[j] = (ff < f) ? f64_key(v) : ~0ull;
+        }
+        if (PF && item + nwarps < n) {
+            const double *nrow = x + (item + nwarps) * pitch;
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; nv[j] = (ff < f) ? nrow[ff] : 0.0; }
         }
         const double med = warp_median_radix<FPL>(k, f, lane, hist);
         if (lane == 0) out_median[item] = med;
@@ -194,7 +208,7 @@ median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use
 template <int R>
 struct TmAux { static constexpr int T = 16 * R; static constexpr int WARPS = (T + 31) / 32; };
 
-template <int FPL, int R, int CHN, int THR>
+template <int FPL, int R, int CHN, int THR, bool PF>
 __global__ void __launch_bounds__(THR + 32 * TmAux<R>::WARPS, 1)
 taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
                const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ deg,
@@ -272,13 +286,47 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
             }
         } else {
             // ---- B: x^T L x through the strictly-upper adjacency
+            // PF (ASP_TM_PREFETCH=1, not yet the default: written after the GPU budget of round 1 was spent): the adjacency of
+            // chunk c+1 is fetched into registers while chunk c is walked, so the L2 round trip of the staging -- 24 % of this
+            // kernel's stall samples -- is no longer exposed between two barriers.
+            constexpr int NPF = (CHN + THR - 1) / THR;
+            int32_t pf_col[NPF], pf_rptr = 0;
+            double pf_val[NPF], pf_deg = 0.0;
+            int pf_ra0 = 0, pf_ra1 = 0, pf_e0 = 0, pf_e1 = 0;
+            auto fetch = [&](int c) {
+                pf_ra0 = chunks[c].row_begin; pf_ra1 = chunks[c].row_end;
+                pf_e0 = uptr[pf_ra0]; pf_e1 = uptr[pf_ra1];
+#pragma unroll
+                for (int u = 0; u < NPF; ++u) {
+                    const int i = (int)threadIdx.x + u * THR;
+                    if (i < pf_e1 - pf_e0) { pf_col[u] = ucol[pf_e0 + i]; pf_val[u] = uval[pf_e0 + i]; }
+                }
+                if ((int)threadIdx.x <= pf_ra1 - pf_ra0) pf_rptr = uptr[pf_ra0 + threadIdx.x] - pf_e0;
+                if ((int)threadIdx.x < pf_ra1 - pf_ra0) pf_deg = deg[pf_ra0 + threadIdx.x];
+            };
+            if (PF) fetch(0);
             for (int c = 0; c < nchunks; ++c) {
-                const int ra0 = chunks[c].row_begin, ra1 = chunks[c].row_end;
-                const int e0 = uptr[ra0], e1 = uptr[ra1];
-                compute_sync();
-                for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
-                for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
-                for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
+                int ra0, ra1;
+                if (PF) {
+                    ra0 = pf_ra0; ra1 = pf_ra1;
+                    const int ne = pf_e1 - pf_e0;
+                    compute_sync();                                    // the previous chunk is consumed
+#pragma unroll
+                    for (int u = 0; u < NPF; ++u) {
+                        const int i = (int)threadIdx.x + u * THR;
+                        if (i < ne) { s_col[i] = pf_col[u]; s_val[i] = pf_val[u]; }
+                    }
+                    if ((int)threadIdx.x <= ra1 - ra0) s_rptr[threadIdx.x] = pf_rptr;
+                    if ((int)threadIdx.x < ra1 - ra0) s_deg[threadIdx.x] = pf_deg;
+                    if (c + 1 < nchunks) fetch(c + 1);                 // in flight during the walk below
+                } else {
+                    ra0 = chunks[c].row_begin; ra1 = chunks[c].row_end;
+                    const int e0 = uptr[ra0], e1 = uptr[ra1];
+                    compute_sync();
+                    for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
+                    for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
+                    for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
+                }
                 compute_sync();
                 for (int a = ra0 + p; a < ra1; a += (THR / 16)) {
                     double xa[R], s[R];
@@ -335,7 +383,9 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
         ASP_CUDA(cudaMallocAsync(&medians, sizeof(double) * n, ctx->stream));
         const int64_t want = asp_ceil_div(n, 8);
         const int mgrid = (int)(want < (int64_t)ctx->num_sms * 8 ? want : (int64_t)ctx->num_sms * 8);
-        median_kernel<FPL><<<mgrid, 256, 0, ctx->stream>>>(x, n, f, pitch, sw->tau_mode == ASP_TAU_MEDIAN_ABS ? 1 : 0, medians);
+        const char *mpf = getenv("ASP_MEDIAN_PREFETCH");
+        auto mk = (mpf && mpf[0] == '1') ? median_kernel<FPL, true> : median_kernel<FPL, false>;
+        mk<<<mgrid, 256, 0, ctx->stream>>>(x, n, f, pitch, sw->tau_mode == ASP_TAU_MEDIAN_ABS ? 1 : 0, medians);
         ASP_CUDA(cudaGetLastError());
         ASP_LAUNCHED(ctx);
     }
@@ -343,7 +393,10 @@ int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const do
     const size_t smem = (size_t)f * (T + 1) * 8 + (size_t)CHN * 12 + (CH_ROWS + 2) * 4 + (size_t)CH_ROWS * 8 +
                         (size_t)T * 16 + 64;
     if (smem > 227 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "taumode kernel: %d features do not fit in shared memory", f);
-    auto kern = taumode_kernel<FPL, R, CHN, THR>;
+    // the register-prefetch variant needs one thread per staged row pointer (CH_ROWS + 1 <= THR)
+    const char *pf_env = getenv("ASP_TM_PREFETCH");
+    const bool pf = (THR > CH_ROWS) && pf_env && pf_env[0] == '1';
+    auto kern = pf ? taumode_kernel<FPL, R, CHN, THR, (THR > CH_ROWS)> : taumode_kernel<FPL, R, CHN, THR, false>;
     ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;                                                       // resident CTAs per SM: their load / gather phases overlap
     constexpr int NTHREADS = THR + 32 * TmAux<R>::WARPS;
