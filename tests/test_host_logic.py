@@ -170,3 +170,14 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_peer_exchange_buffer_size():
+    """asp_peer_exchange_bytes (pure host arithmetic, no GPU): 4 KB of flags + two parities of `world` slots of
+    cap x topk (int64 index, f64 score) pairs; unsupported shapes give 0."""
+    from pyarrowspace_b200 import _lib
+    lib = _lib.load()
+    assert lib.asp_peer_exchange_bytes(8, 65536, 10) == 4096 + 2 * 8 * 65536 * 10 * 16
+    assert lib.asp_peer_exchange_bytes(2, 1000, 3) == 4096 + 2 * 2 * 1000 * 3 * 16
+    assert lib.asp_peer_exchange_bytes(9, 10, 10) == 0 and lib.asp_peer_exchange_bytes(0, 10, 10) == 0
+    assert lib.asp_peer_exchange_bytes(2, 0, 10) == 0 and lib.asp_peer_exchange_bytes(2, 10, 0) == 0
