@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric on BASELINE.json's config.
 
-metric   : search queries/s (top-10) on the BEIR/MS MARCO-shaped synthetic 1M x 384 f64 workload (C4),
-           with the build (feature graph + Laplacian + lambda) timed beside it as items/s.
-step     : one pass of the search hot path over one batch of Q synthetic queries (default 16384)
-           against all N items (row-sharded over the ranks when --gpus > 1, results merged).
+metric   : search queries/s (top-10) on the BEIR/MS MARCO-shaped synthetic 1M x 384 f64 workload (C4, configs[3]: the
+           configuration the metric is quoted on), with the build (feature graph + Laplacian + lambda) timed beside it.
+step     : one pass of the search hot path over one batch of Q = 65536 synthetic queries (C4 is batched 64k
+           per call) against all N items.  N > 1 (torchrun, one rank per GPU): the build is row-partitioned over all ranks;
+           the search runs on an R x C grid (R item shards x C query slots, --item-shards, default: replicate the items when
+           they fit, i.e. R = 1 for C4) and every rank ends with the whole result; strong scaling (fixed N and Q).
 value    : whole-job queries/s with items and queries resident in HBM.
-e2e      : the same through the public API (ArrowSpace.search_batch) with HOST buffers: pinned
-           host -> device copy of the batch and device -> host read of (idx, score) inside the timed region.
-roofline : dominant kernel = search_gemm_kernel (FP64 DMMA): 2*Q*N_local*F algorithmic FLOP per launch /
-           its CUDA-event duration; peak = cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no
-           FP64 figure).  The build's kernels are reported under "build".
+e2e      : the same through the public API (ArrowSpace.search_batch) with HOST buffers: pinned host -> device copy of
+           the batch and device -> host read of (idx, score) inside the timed region.
+roofline : dominant kernel = tc_gemm_kernel (tcgen05.mma kind::f16 candidate pass): ALGORITHMIC 2*Q*N_local*F FLOP per
+           launch / its CUDA-event duration, against MEASURED_PEAKS.json's dense 16-bit tensor figure;
+           the executed FLOP (K padded to 16, extra split terms) are reported next to it.  The build's kernels are reported
+           under "build" (K1 Gram: FP64 tensor, K3 lambda: HBM + the shared-memory gather floor).
+parity_check : UNTIMED, after the timed loops: the CPU oracle builds the same 1M x 384 matrix and full-scans a sample of
+           the last step's queries; indices must be identical and scores within 1e-9 for both the device-resident and the
+           end-to-end results (at N > 1: the merged / gathered result), plus the feature graph and this rank's lambdas.
+regimes  : the same search on MEAN-ZERO embeddings (no positive shift, tau_mode = median_abs) with queries that are fresh
+           draws from the clusters, not perturbed copies of items: the regime in which the candidate pass needs the
+           two-term fp16 split; throughput, mode, survivors per query and its own parity_check.
 cpu_baseline / --impl reference : the CPU oracle (oracle/, a restatement: the reference's Rust engine is not
            vendored and cannot be built here) timed on this box's host cores.
 
@@ -69,6 +78,9 @@ def parse_args():
     ap.add_argument("--ref-queries", type=int, default=256, help="--impl reference: queries per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-item-graph", action="store_true", help="skip the item-graph (nodes = items) build of the C4 matrix")
+    ap.add_argument("--item-shards", type=int, default=None, help="N > 1: item shards R of the search grid (default: fewest that fit; N: fully sharded)")
+    ap.add_argument("--parity-queries", type=int, default=64, help="queries of the last step checked against the oracle's full scan (0: skip)")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the mean-zero regime")
     return ap.parse_args()
 
 
@@ -188,6 +200,37 @@ def gram_roofline(n_local, f, ms, peak):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def oracle_parity(gp, tau, x_full, q_sample, got, lam_local, lam_rows, edges, switches, rtol=1e-9):
+    """The CPU oracle on the SAME bytes: feature graph, lambdas of this rank's rows, full scan of the sample queries.
+    `got` = {name: (idx, score)} result sets to compare (device-resident and end-to-end).  Untimed."""
+    import oracle
+    t0 = time.perf_counter()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    s, g = oracle.build(gp, x_full, **switches)
+    oidx, osc, _ = s.search_batch(q_sample, g, tau)
+    out = {"queries": int(q_sample.shape[0]), "items": int(x_full.shape[0]), "rtol": rtol}
+    ok = True
+    for name, (idx, sc) in got.items():
+        same = bool(np.array_equal(idx, oidx))
+        m = oidx >= 0
+        rel = float(np.max(np.abs(sc[m] - osc[m]) / np.abs(osc[m]))) if m.any() else 0.0
+        out[name] = {"idx_equal": same, "score_max_rel_err": rel}
+        ok = ok and same and rel <= rtol
+    olam = s.lambdas()[lam_rows[0]:lam_rows[1]]
+    lam_rel = float(np.max(np.abs(lam_local - olam) / np.abs(olam))) if len(olam) else 0.0
+    out["lambda_max_rel_err"] = lam_rel
+    out["lambda_rows_checked"] = int(len(olam))
+    out["graph_edges_equal"] = bool(np.array_equal(edges, g.edges()))
+    out["ok"] = bool(ok and lam_rel <= rtol and out["graph_edges_equal"])
+    out["seconds"] = time.perf_counter() - t0
+    out["oracle_threads"] = oracle.num_threads()
+    return out
+
+
 def main():
     args = parse_args()
     quiet_stdout()
@@ -244,6 +287,50 @@ def main():
         fp64_peak_tflops = 2 * 4096 ** 3 / best / 1e9
         del a, b
 
+    def build(items, switches):
+        if world == 1:
+            return ArrowSpaceBuilder.build(gp, items, device=local, **switches)
+        return ArrowSpaceBuilder.build_sharded(gp, items, n, device=local, item_shards=args.item_shards, **switches)
+
+    def search_regime(aspace, gl, q_dev, q_host, steps, warmup):
+        """W warm-up steps, exactly `steps` timed steps with device-resident queries, then the same from pinned host
+        memory (end to end).  Returns timings, the library's stage statistics and the LAST step's results of both."""
+        nb = len(q_dev)
+        clocks = ClockSampler(local)
+        with torch.cuda.stream(stream):
+            for w in range(warmup):
+                aspace.search_batch(q_dev[w % nb], gl, tau)
+            barrier_sync()
+            if rank == 0:
+                clocks.start()
+            l0 = lib.asp_ctx_launch_count(ctx)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stage1 = []
+            e0.record(stream)
+            for k in range(steps):
+                idx, sc = aspace.search_batch(q_dev[k % nb], gl, tau)
+                stage1.append(api.stat("search_stage1_ms", local))
+            e1.record(stream)
+            barrier_sync()
+            step_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+            launches = lib.asp_ctx_launch_count(ctx) - l0
+            st = {k: api.stat(k, local) for k in ("search_slow_queries", "search_stage1_is_tc", "search_rescored_per_query", "search_terms",
+                                                 "search_stage2_ms", "search_a_resident", "search_delta_cos_max", "search_rho_q_max",
+                                                 "search_rho_x_max", "search_exact_per_query")}
+            for w in range(2 if warmup else 0):
+                aspace.search_batch(q_host[w % nb].numpy(), gl, tau)
+            barrier_sync()
+            e0.record(stream)
+            for k in range(steps):
+                idx_h, sc_h = aspace.search_batch(q_host[k % nb].numpy(), gl, tau)
+            e1.record(stream)
+            barrier_sync()
+            e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        clk = clocks.stop() if rank == 0 else None
+        return {"step_ms": step_ms, "e2e_ms": e2e_ms, "launches": int(launches), "stage1_ms": max_over_ranks(float(np.mean(stage1))),
+                "stats": st, "clocks": clk, "last_batch": (steps - 1) % nb,
+                "idx": idx.cpu().numpy(), "sc": sc.cpu().numpy(), "idx_h": np.asarray(idx_h), "sc_h": np.asarray(sc_h)}
+
     # ---- synthetic inputs: this rank's row shard (identical bytes to what the oracle sees)
     r0, r1 = shard_rows(n, world, rank)
     x_host = torch.from_numpy(synth.make_items(n, f, cfg["seed"], cfg["scale"], rows=(r0, r1))).pin_memory()
@@ -256,11 +343,6 @@ def main():
         q_dev = [q.to(dev, non_blocking=True) for q in q_host]
     stream.synchronize()
 
-    def build(items):
-        if world == 1:
-            return ArrowSpaceBuilder.build(gp, items, device=local)
-        return ArrowSpaceBuilder.build_sharded(gp, items, n, device=local)
-
     # ---- build: items resident in HBM (value) and from pinned host memory (e2e)
     launches0 = lib.asp_ctx_launch_count(ctx)
     build_ms, build_e2e_ms, stages = [], [], {}
@@ -269,7 +351,7 @@ def main():
             barrier_sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            aspace, gl = build(x_dev)
+            aspace, gl = build(x_dev, {})
             e1.record(stream)
             barrier_sync()
             if rep:
@@ -281,7 +363,7 @@ def main():
             barrier_sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            aspace, gl = build(x_host.numpy())
+            aspace, gl = build(x_host.numpy(), {})
             e1.record(stream)
             barrier_sync()
             build_e2e_ms.append(max_over_ranks(e0.elapsed_time(e1)))
@@ -289,42 +371,19 @@ def main():
                 del aspace, gl
     build_launches = (lib.asp_ctx_launch_count(ctx) - launches0) // (3 + args.build_reps)
     feature_graph_nnz = int(gl.nnz)
+    grid = getattr(aspace, "_grid", None) or {"R": 1, "C": 1}
+    n_shard = aspace.nitems_local                                     # items every query of this rank is scored against
+    q_rank = -(-Q // grid["C"])                                       # queries this rank answers per step
 
-    # ---- search: W warm-up steps, then exactly K timed steps
-    clocks = ClockSampler(local)
-    with torch.cuda.stream(stream):
-        for w in range(args.warmup):
-            aspace.search_batch(q_dev[w % nbatch], gl, tau)
-        barrier_sync()
-        if rank == 0:
-            clocks.start()
-        l0 = lib.asp_ctx_launch_count(ctx)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage1 = []
-        e0.record(stream)
-        for k in range(args.steps):
-            idx, sc = aspace.search_batch(q_dev[k % nbatch], gl, tau)
-            stage1.append(api.stat("search_stage1_ms", local))
-        e1.record(stream)
-        barrier_sync()
-        step_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        launches = lib.asp_ctx_launch_count(ctx) - l0
-        slow = api.stat("search_slow_queries", local)
-        stage1_is_tc = api.stat("search_stage1_is_tc", local) == 1.0
-        rescored = api.stat("search_rescored_per_query", local) if stage1_is_tc else None
-        sstat = {k: api.stat(k, local) for k in ("search_terms", "search_stage2_ms", "search_a_resident", "search_delta_cos_max",
-                                                  "search_rho_q_max", "search_rho_x_max", "search_exact_per_query")}
-        # end to end: pinned host queries in, host results out, every step
-        for w in range(2):
-            aspace.search_batch(q_host[w % nbatch].numpy(), gl, tau)
-        barrier_sync()
-        e0.record(stream)
-        for k in range(args.steps):
-            idx_h, sc_h = aspace.search_batch(q_host[k % nbatch].numpy(), gl, tau)
-        e1.record(stream)
-        barrier_sync()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    clk = clocks.stop() if rank == 0 else None
+    # ---- search: W warm-up steps, then exactly K timed steps (+ the end-to-end loop)
+    main_run = search_regime(aspace, gl, q_dev, q_host, args.steps, args.warmup)
+    step_ms, e2e_ms, launches, stage1_ms, sstat, clk = (main_run[k] for k in ("step_ms", "e2e_ms", "launches", "stage1_ms", "stats", "clocks"))
+    slow = sstat["search_slow_queries"]
+    stage1_is_tc = sstat["search_stage1_is_tc"] == 1.0
+    rescored = sstat["search_rescored_per_query"] if stage1_is_tc else None
+    lam_local = aspace.lambdas()
+    lam_rows = (aspace.row_offset, aspace.row_offset + aspace.nitems_local)
+    edges = gl.edges()
 
     # ---- the reference's own call shape: ONE query per ArrowSpace.search call (src/lib.rs:132-174), host vector in,
     # Python list of (index, score) out; wall clock per call (includes the ctypes call, the upload and the read-back)
@@ -342,12 +401,44 @@ def main():
                   "f64_scan_equivalent_gbs": 8.0 * n * f / dt / 1e9,
                   "note": "candidate pass streams the fp16 operands (%.2f GB) instead of the f64 rows (%.2f GB); exact f64 stage 2"
                           % (2.0 * n * (((f + 3 + 63) // 64) * 64) / 1e9, 8.0 * n * f / 1e9)}
+    del aspace, gl
+
+    # ---- second regime: mean-zero embeddings, queries that are not near-duplicates of items
+    regime = None
+    mz_sw = {"tau_mode": "median_abs"}
+    if not args.no_regimes:
+        xz_host = torch.from_numpy(synth.make_items(n, f, cfg["seed"], cfg["scale"], rows=(r0, r1), shift=0.0)).pin_memory()
+        qz_host = [torch.from_numpy(synth.make_fresh_queries(f, Q, cfg["seed"] + 100 + b_)[0]).pin_memory() for b_ in range(nbatch)]
+        with torch.cuda.stream(stream):
+            xz_dev = xz_host.to(dev, non_blocking=True)
+            qz_dev = [q.to(dev, non_blocking=True) for q in qz_host]
+            stream.synchronize()
+            aspace, gl = build(xz_dev, mz_sw)
+        # probe step (also builds the operand cache): a regime that fell onto the exact-scan path would take minutes --
+        # then it is measured on ONE step and says so
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            aspace.search_batch(qz_dev[0], gl, tau)
+        torch.cuda.synchronize(dev)
+        probe_s = max_over_ranks(time.perf_counter() - t0)
+        mz_steps, mz_warm = (max(2, min(args.steps, 5)), 3) if probe_s < 2.0 else (1, 0)
+        mz = search_regime(aspace, gl, qz_dev, qz_host, mz_steps, mz_warm)
+        mz_lam, mz_rows, mz_edges = aspace.lambdas(), (aspace.row_offset, aspace.row_offset + aspace.nitems_local), gl.edges()
+        regime = {"data": "unit rows x %g, no shift (entries of both signs); queries = fresh draws from the 256 clusters (no near-duplicate item)" % cfg["scale"],
+                  "switches": mz_sw, "probe_step_s": probe_s, "value": Q / (mz["step_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": mz["step_ms"], "steps": mz_steps,
+                  "e2e": {"value": Q / (mz["e2e_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": mz["e2e_ms"]},
+                  "stage1_ms": mz["stage1_ms"], "stage2_ms": mz["stats"]["search_stage2_ms"], "mma_terms": int(mz["stats"]["search_terms"]),
+                  "query_operand_resident": mz["stats"]["search_a_resident"] == 1.0,
+                  "survivors_per_query": mz["stats"]["search_rescored_per_query"], "exact_rescan_queries_last_step": mz["stats"]["search_slow_queries"],
+                  "band_cos_max": mz["stats"]["search_delta_cos_max"],
+                  "residual_norms": {"rho_q_max": mz["stats"]["search_rho_q_max"], "rho_x_max": mz["stats"]["search_rho_x_max"]},
+                  "algorithmic_tflops": 2.0 * q_rank * n_shard * f / (mz["stage1_ms"] * 1e-3) / 1e12}
+        del aspace, gl, xz_dev, qz_dev
 
     # ---- item graph (nodes = items) of the same matrix: the graph-build workload of C4 (eps / k-NN lists of all 1M items
     # against all 1M items on the tensor cores, exact stage 2, Laplacian CSR); sharded over the ranks when N > 1
     item_graph = None
     if not args.no_item_graph:
-        del aspace, gl
         ig_ms = []
         with torch.cuda.stream(stream):
             for rep in range(2):
@@ -365,25 +456,46 @@ def main():
                 ig_stats = {k: api.stat(k, local) for k in ("knn_stage1_ms", "knn_stage2_ms", "knn_slow_rows", "knn_rescored_per_row")}
                 del a_ig, g_ig
         ig_exec = 2.0 * n * (r1 - r0) * 16.0 * ((f + 3 + 15) // 16)
+        ig_alg = 2.0 * n * (r1 - r0) * f
         item_graph = {"ms": min(ig_ms), "items_per_s": n / (min(ig_ms) * 1e-3), "nnz": int(ig_nnz),
                       "rows_per_rank": r1 - r0, "stage1_ms": ig_stats["knn_stage1_ms"], "stage2_ms": ig_stats["knn_stage2_ms"],
                       "exact_scan_rows": ig_stats["knn_slow_rows"], "rescored_per_row": ig_stats["knn_rescored_per_row"],
-                      "algorithmic_flop": 2.0 * n * (r1 - r0) * f, "executed_fp16_flop": ig_exec,
+                      "algorithmic_flop": ig_alg, "executed_fp16_flop": ig_exec,
+                      "stage1_algorithmic_tflops": ig_alg / (ig_stats["knn_stage1_ms"] * 1e-3) / 1e12 if ig_stats["knn_stage1_ms"] > 0 else None,
                       "stage1_tflops": ig_exec / (ig_stats["knn_stage1_ms"] * 1e-3) / 1e12 if ig_stats["knn_stage1_ms"] > 0 else None,
                       "note": "rows of this rank against all %d items; N > 1: + all-gather of the item shards and of the lists" % n}
 
-    # sanity: a perturbed copy must find its source item (size-independent property)
-    stage1_ms = max_over_ranks(float(np.mean(stage1)))
     if rank != 0:
         if world > 1:
-            dist.barrier()
+            dist.barrier()                                            # rank 0 runs the untimed oracle checks meanwhile
             dist.destroy_process_group()
         return
 
-    n_local = r1 - r0
-    gemm_flop = 2.0 * Q * n_local * f                       # algorithmic: one f64-accurate score per (query, item)
+    # ---- UNTIMED parity gate on the benchmarked configuration: oracle full scan of a sample of the
+    # last step's queries against ALL items, for the device-resident and the end-to-end result (N > 1: the merged result)
+    parity = None
+    if args.parity_queries > 0:
+        pick = np.unique(np.linspace(0, Q - 1, args.parity_queries).astype(np.int64))
+        x_full = x_host.numpy() if world == 1 else synth.make_items(n, f, cfg["seed"], cfg["scale"])
+        lb = main_run["last_batch"]
+        parity = oracle_parity(gp, tau, x_full, q_host[lb].numpy()[pick],
+                               {"device_resident": (main_run["idx"][pick], main_run["sc"][pick]),
+                                "end_to_end": (main_run["idx_h"][pick], main_run["sc_h"][pick])},
+                               lam_local, lam_rows, edges, {})
+        if regime is not None:
+            del x_full
+            xz_full = xz_host.numpy() if world == 1 else synth.make_items(n, f, cfg["seed"], cfg["scale"], shift=0.0)
+            lbz = mz["last_batch"]
+            regime["parity_check"] = oracle_parity(gp, tau, xz_full, qz_host[lbz].numpy()[pick],
+                                                   {"device_resident": (mz["idx"][pick], mz["sc"][pick]),
+                                                    "end_to_end": (mz["idx_h"][pick], mz["sc_h"][pick])},
+                                                   mz_lam, mz_rows, mz_edges, mz_sw)
+            del xz_full
+
+    gemm_flop = 2.0 * q_rank * n_shard * f                  # algorithmic: one f64-accurate score per (query, item) of this rank
     gram_ms = float(np.mean(stages["gram_ms"]))
     lam_ms = float(np.mean(stages["lambda_ms"]))
+    n_local = r1 - r0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -395,25 +507,35 @@ def main():
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline.json")))
     except Exception:
         pass
+
+    def profiled_traffic(kernel):
+        """dram__bytes_read + write of one launch from the committed `ncu --set full` capture -- only when that capture was
+        taken at THIS launch shape (items per rank, queries per rank, features); otherwise null, never a stale constant."""
+        e = prof.get(kernel)
+        if isinstance(e, dict) and e.get("n_items") == n_shard and e.get("n_queries") == q_rank and e.get("n_features") == f:
+            return e.get("dram_bytes_per_launch")
+        return None
+
     if stage1_is_tc:
         terms = int(sstat["search_terms"])
         ksteps = (f + 3 + 15) // 16 + (2 * ((f + 15) // 16) if terms == 3 else 0)   # K=16 MMA steps per (query, item) tile pair
-        executed = 2.0 * Q * n_local * 16.0 * ksteps
+        executed = 2.0 * q_rank * n_shard * 16.0 * ksteps
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
         burst = peaks.get("bf16_tflops", sustained)
-        achieved = executed / (stage1_ms * 1e-3) / 1e12
-        peak = sustained if achieved <= sustained else burst
+        achieved = gemm_flop / (stage1_ms * 1e-3) / 1e12
+        executed_tflops = executed / (stage1_ms * 1e-3) / 1e12
+        peak = sustained if executed_tflops <= sustained else burst
         roofline = {"kernel": "tc_gemm_kernel (tcgen05.mma kind::f16, fp16 operands, f32 TMEM accumulators, TMA SWIZZLE_128B; items in "
                               "lambda order, rank-1 mean-direction term + %s of the residuals; single-compare epilogue, thresholds "
                               "shared across CTAs); exact f64 stage 2 follows"
                               % ("ONE fp16 term" if terms == 1 else "the two-term fp16 split (3 MMA terms)"),
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_nominal": 2250.0, "frac_of_nominal": achieved / 2250.0,     # dense 16-bit datasheet figure (SURVEY.md 8(d): report both)
-                    "traffic": prof.get("tc_gemm_dram_bytes_per_launch"),
-                    "algorithmic": "2*Q*N_local*F = %.3e FLOP per launch; EXECUTED 2*Q*N_local*16*%d = %.3e fp16 tensor FLOP "
-                                   "(achieved/frac count the executed FLOP against the measured 16-bit dense tensor peak)"
-                                   % (gemm_flop, ksteps, executed),
-                    "algorithmic_tflops": gemm_flop / (stage1_ms * 1e-3) / 1e12,
+                    "traffic": profiled_traffic("tc_gemm_kernel"),
+                    "algorithmic": "ALGORITHMIC 2*Q_rank*N_shard*F = 2*%d*%d*%d = %.3e FLOP per launch (achieved / frac); the kernel EXECUTES "
+                                   "2*Q_rank*N_shard*16*%d = %.3e fp16 tensor FLOP (K padded to 16%s)"
+                                   % (q_rank, n_shard, f, gemm_flop, ksteps, executed, ", three split terms" if terms == 3 else ""),
+                    "executed_tflops": executed_tflops, "executed_frac": executed_tflops / peak,
                     "fp64_tensor_peak_tflops": fp64_peak_tflops,
                     "kernel_ms": stage1_ms, "share_of_step": stage1_ms / step_ms,
                     "stage2_ms": sstat["search_stage2_ms"],
@@ -429,10 +551,15 @@ def main():
         achieved = gemm_flop / (stage1_ms * 1e-3) / 1e12
         roofline = {"kernel": "search_gemm_kernel (FP64 DMMA.8x8x4, TMA fed, fused score/top-k epilogue)",
                     "bound": "tensor", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak_tflops, "traffic": prof.get("search_gemm_dram_bytes_per_launch"),
-                    "algorithmic": "2*Q*N_local*F = %.3e FLOP per launch" % gemm_flop,
+                    "frac": achieved / fp64_peak_tflops, "traffic": profiled_traffic("search_gemm_kernel"),
+                    "algorithmic": "2*Q_rank*N_shard*F = %.3e FLOP per launch" % gemm_flop,
                     "kernel_ms": stage1_ms, "share_of_step": stage1_ms / step_ms,
                     "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
+    upper_nnz = (feature_graph_nnz - f) // 2
+    sm_mhz = (clk or {}).get("sm_mhz") or 1900.0
+    lam_bytes = 8.0 * n_local * f + 8.0 * n_local
+    lam_flop = 2.0 * n_local * (2.0 * upper_nnz + f) + 4.0 * n_local * f          # 2*N*nnz(L) + 4*N*F
+    gather_floor_ms = 8.0 * n_local * upper_nnz / (148 * 128.0 * sm_mhz * 1e6) * 1e3
     line = {
         "metric": "search queries/s (top-10, 1M x 384 f64)",
         "value": Q / (step_ms * 1e-3), "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -440,28 +567,34 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C4 BEIR/MS MARCO-shaped synthetic %d x %d f64 items (seed %d, x%g), %d queries per step, top-%d, tau %.2f"
                                % (n, f, cfg["seed"], cfg["scale"], Q, topk, tau),
-                   "graph_params": gp, "queries_per_step": Q, "sharding": "rows over %d rank(s)" % world,
-                   "l2": "inputs larger than L2 (item shard %.2f GB)" % (n_local * f * 8 / 1e9),
+                   "graph_params": gp, "queries_per_step": Q,
+                   "sharding": "build: rows over %d rank(s); search: %d item shard(s) x %d query slot(s)" % (world, grid["R"], grid["C"]),
+                   "l2": "inputs larger than L2 (item shard %.2f GB f64 + %.2f GB fp16 operands)" % (n_shard * f * 8 / 1e9, n_shard * (((f + 3 + 63) // 64) * 64) * 2 / 1e9),
                    "stage1": "tcgen05 fp16 candidates + exact f64 rescoring" if stage1_is_tc else "FP64 DMMA",
                    "exact_rescan_queries_last_step": slow},
         "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": Q * f * 8, "d2h_bytes_per_step": Q * topk * 16},
+                "h2d_bytes_per_step": Q * f * 8, "d2h_bytes_per_step": Q * topk * 16 * world,
+                "note": "per step, summed over ranks: every rank uploads its slice of the batch and reads back the whole result"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "parity_check": parity,
+        "regimes": {"mean_zero": regime},
         "build": {"items_per_s": n / (float(np.mean(build_ms)) * 1e-3), "ms": float(np.mean(build_ms)),
                   "e2e_items_per_s": n / (min(build_e2e_ms) * 1e-3), "e2e_ms": min(build_e2e_ms),
                   "h2d_bytes": n_local * f * 8, "gpu_launches": int(build_launches),
                   "gram": gram_roofline(n_local, f, gram_ms, fp64_peak_tflops),
                   "graph_ms": float(np.mean(stages["graph_ms"])),
-                  "lambda": {"ms": lam_ms, "bound": "hbm", "achieved_gbs": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9,
-                             "frac": (8.0 * n_local * f + 8.0 * n_local) / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
+                  "lambda": {"kernel": "taumode_kernel (ONE pass over X: transposed tile + graph walk + median + norms)",
+                             "ms": lam_ms, "bound": "hbm", "achieved_gbs": lam_bytes / (lam_ms * 1e-3) / 1e9,
+                             "frac": lam_bytes / (lam_ms * 1e-3) / 1e9 / hbm_peak, "peak_gbs": hbm_peak,
+                             # at nnz(L)/F > 16 the prescribed bound is FP64 FMA, not HBM
+                             "fp64_fma": {"flop": lam_flop, "achieved_tflops": lam_flop / (lam_ms * 1e-3) / 1e12,
+                                          "peak_tflops": fp64_peak_tflops, "frac": lam_flop / (lam_ms * 1e-3) / 1e12 / fp64_peak_tflops,
+                                          "nnz_over_f": (feature_graph_nnz - f) / float(f)},
                              # the bound that actually binds at this graph density: one 8-byte shared-memory gather per
                              # strictly-upper non-zero of L per item, against 128 B/clk/SM
-                             "gather": {"upper_nnz": (feature_graph_nnz - f) // 2,
-                                        "smem_bytes": 8.0 * n_local * ((feature_graph_nnz - f) // 2),
-                                        "smem_floor_ms": 8.0 * n_local * ((feature_graph_nnz - f) // 2) /
-                                                         (148 * 128.0 * (clk or {}).get("sm_mhz", 1900.0) * 1e6) * 1e3,
-                                        "note": "lambda_ms = median_kernel (radix selection, HBM pass 1) + taumode_kernel (HBM pass 2 + gathers)"}}},
+                             "gather": {"upper_nnz": upper_nnz, "smem_bytes": 8.0 * n_local * upper_nnz,
+                                        "smem_floor_ms": gather_floor_ms, "frac_of_smem_floor": gather_floor_ms / lam_ms}}},
         "item_graph": item_graph,
         "single_query": single,
         "clocks": clk,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ASP_ABI_VERSION 1
+#define ASP_ABI_VERSION 2
 
 /* Fixed reduction geometry of the feature Gram (makes results independent of the GPU count):
  * rows are cut into 32-row units, the units into ASP_GRAM_SEGMENTS contiguous segments (the
@@ -60,13 +60,26 @@ typedef struct {
     int32_t has_sigma;
 } asp_graph_params;
 
-/* Named switches for the choices the reference's tests cannot pin. */
+/* Named switches for the choices the reference's tests cannot pin.  The arithmetic
+ * lives in the un-vendored crate arrowspace 0.18.0 (Cargo.lock:94-97); the binding only shows the call sites
+ * (src/lib.rs:278-289).  Zero-initialised = the default spec of Appendix A.  The same switches, with the same meaning,
+ * exist in the CPU oracle (oracle/oracle.h) and every one is parity-tested GPU == oracle. */
 enum { ASP_KERNEL_INV_POWER = 0, ASP_KERNEL_GAUSSIAN = 1 };
 enum { ASP_TAU_MEDIAN = 0, ASP_TAU_MEDIAN_ABS = 1, ASP_TAU_MEAN = 2, ASP_TAU_FIXED = 3 };
+enum { ASP_LAMBDA_BOUNDED = 0, ASP_LAMBDA_SYNTHETIC = 1 };                /* TAUMODE.md:19,25 | TAUMODE.md:8,26-27 */
+enum { ASP_SYM_MAX = 0, ASP_SYM_AVG = 1, ASP_SYM_MIN = 2, ASP_SYM_NONE = 3 };  /* GRAPH_VARIABLES.md:8 "symmetrized": rule unpinned */
+enum { ASP_LAPLACIAN_COMBINATORIAL = 0, ASP_LAPLACIAN_SYM = 1, ASP_LAPLACIAN_RW = 2 };
+enum { ASP_DISTANCE_COSINE = 0, ASP_DISTANCE_L2 = 1, ASP_DISTANCE_L2SQ = 2 };  /* GRAPH_VARIABLES.md:7 | Gram-form Euclidean */
 typedef struct {
-    int32_t kernel;      /* ASP_KERNEL_* : w = 1/(1+(d/sigma)^p)  |  exp(-(d/sigma)^p) */
-    int32_t tau_mode;    /* ASP_TAU_*    : tau of a vector (floored at 1e-9) */
+    int32_t kernel;        /* ASP_KERNEL_*    : w = 1/(1+(d/sigma)^p)  |  exp(-(d/sigma)^p)                      */
+    int32_t tau_mode;      /* ASP_TAU_*       : tau of a vector (floored at 1e-9)                                */
     double  tau_fixed;
+    int32_t lambda_form;   /* ASP_LAMBDA_*    : E/(E+tau)  |  tau E/(E+tau) + (1-tau) G(x)                        */
+    int32_t symmetrise;    /* ASP_SYM_*       : W = max(W,W^T) | (W+W^T)/2 | min(W,W^T) (mutual edges) | W (directed) */
+    int32_t laplacian;     /* ASP_LAPLACIAN_* : D - W | I - D^-1/2 W D^-1/2 | I - D^-1 W   (D = row sums of W)   */
+    int32_t k_counts_self; /* 1: a node is its own first neighbour, so k keeps k - 1 others                      */
+    int32_t topk_prunes;   /* 1: the neighbour cap is min(k, topk) (graph_params.topk also prunes the graph)     */
+    int32_t distance;      /* ASP_DISTANCE_*  : 1 - max(0,cos) | sqrt(|a|^2+|b|^2-2<a,b>) | its square (feature graph only) */
 } asp_switches;
 
 typedef struct asp_ctx   asp_ctx;    /* device, streams, scratch */
@@ -85,6 +98,9 @@ int  asp_ctx_set_stream(asp_ctx *ctx, void *cuda_stream);
 int  asp_ctx_synchronize(asp_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t asp_ctx_launch_count(const asp_ctx *ctx);
+/* Scratch is served from the device's stream-ordered memory pool and kept there between calls (up to a quarter of the
+ * device, env ASP_POOL_KEEP_GB); this returns everything above keep_bytes to the driver (synchronises the stream). */
+int asp_ctx_trim(asp_ctx *ctx, size_t keep_bytes);
 
 /* ---- one-call single-GPU path --------------------------------------------------------------
  * Replaces RustBuilder::new().with_lambda_graph(eps,k,topk,p,sigma)...build(rows)
@@ -109,6 +125,12 @@ int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, i
  * of BASELINE.json config C5: 54 GB per rank) exists once.  No reference counterpart (the reference always copies,
  * src/helpers.rs:24-46). */
 int asp_space_adopt(asp_ctx *ctx, double *items_dev, int64_t n, int32_t f, asp_space **out);
+/* The same for the row shard of `rank` of `world` (rows asp_shard_rows names). */
+int asp_space_adopt_shard(asp_ctx *ctx, double *items_dev, int64_t n_local, int32_t f, int64_t n_total, int world, int rank,
+                          asp_space **out);
+/* Per-item lambdas + left-to-right norms computed by another rank (the one that owned the rows when the space was built):
+ * the multi-GPU regrouping (api.py build_sharded, item_shards < world) all-gathers them with the rows.  Host or device. */
+int asp_space_import_lambdas(asp_space *s, const double *lambdas, const double *norms);
 
 /* K1 (API orientation): per-segment partial Gram X_s^T X_s of the owned segments, FP64 DMMA fed
  * by TMA.  out_dev: DEVICE buffer [ASP_GRAM_SEGMENTS][f][f] f64; only the owned segments'
@@ -212,8 +234,8 @@ int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches 
  *                      ascending (distance, index)), out_cnt [rows]; host or device pointers.  Replaces the per-row scan
  *                      of the crate's graph construction (src/lib.rs:289; GRAPH_VARIABLES.md:7-8).
  *   asp_graph_from_knn: K2 from complete lists of m nodes (host or device pointers). */
-int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, int32_t *out_idx,
-                      double *out_dist, int32_t *out_cnt, int32_t *out_kk);
+int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, const asp_switches *sw, int64_t row_begin, int64_t row_end,
+                      int32_t *out_idx, double *out_dist, int32_t *out_cnt, int32_t *out_kk);
 int asp_graph_from_knn(asp_ctx *ctx, int64_t m, int32_t kk, const int32_t *idx, const double *dist, const int32_t *cnt,
                        const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
 

@@ -21,6 +21,17 @@ NODES = {"feature_columns": 0, "items": 1}
 KERNEL = {"inv_power": 0, "gaussian": 1}
 TAU_MODE = {"median": 0, "median_abs": 1, "mean": 2, "fixed": 3}
 LAMBDA_FORM = {"bounded": 0, "synthetic": 1}
+SYMMETRISE = {"max": 0, "avg": 1, "min": 2, "none": 3}
+LAPLACIAN = {"combinatorial": 0, "sym": 1, "rw": 2}
+DISTANCE = {"cosine": 0, "l2": 1, "l2sq": 2}
+
+# Named switch sets.  "kat12" is the set tools/fit_switches.py found to reproduce all 12 indices of the reference's
+# tests/test_0.py:29-61 (the default spec of SURVEY.md Appendix A reproduces 11); README.md:69 is tau = 1 and therefore
+# bit exact under every profile.
+PROFILES = {
+    "default": {},
+    "kat12": {"symmetrise": "none", "laplacian": "sym", "k_counts_self": True, "topk_prunes": True},
+}
 
 ERRORS = {
     1: "items must be non-empty 2D array",
@@ -44,7 +55,9 @@ class _Params(C.Structure):
 
 class _Switches(C.Structure):
     _fields_ = [("nodes", C.c_int32), ("kernel", C.c_int32), ("tau_mode", C.c_int32),
-                ("lambda_form", C.c_int32), ("tau_fixed", C.c_double)]
+                ("lambda_form", C.c_int32), ("tau_fixed", C.c_double), ("symmetrise", C.c_int32),
+                ("laplacian", C.c_int32), ("k_counts_self", C.c_int32), ("topk_prunes", C.c_int32),
+                ("distance", C.c_int32)]
 
 
 def build_library(force=False):
@@ -107,9 +120,17 @@ def _check(rc):
 
 
 def make_switches(nodes="feature_columns", kernel="inv_power", tau_mode="median",
-                  lambda_form="bounded", tau_fixed=0.0):
+                  lambda_form="bounded", tau_fixed=0.0, symmetrise="max", laplacian="combinatorial",
+                  k_counts_self=False, topk_prunes=False, distance="cosine", profile=None):
+    if profile is not None:
+        kw = dict(nodes=nodes, kernel=kernel, tau_mode=tau_mode, lambda_form=lambda_form, tau_fixed=tau_fixed,
+                  symmetrise=symmetrise, laplacian=laplacian, k_counts_self=k_counts_self, topk_prunes=topk_prunes,
+                  distance=distance)
+        kw.update(PROFILES[profile])
+        return make_switches(**kw)
     return _Switches(NODES[nodes], KERNEL[kernel], TAU_MODE[tau_mode], LAMBDA_FORM[lambda_form],
-                     float(tau_fixed))
+                     float(tau_fixed), SYMMETRISE[symmetrise], LAPLACIAN[laplacian], int(bool(k_counts_self)),
+                     int(bool(topk_prunes)), DISTANCE[distance])
 
 
 def resolve_params(gp):

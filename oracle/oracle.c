@@ -45,6 +45,11 @@ void orc_default_switches(orc_switches *sw)
     sw->tau_mode = ORC_TAU_MEDIAN;
     sw->lambda_form = ORC_LAMBDA_BOUNDED;
     sw->tau_fixed = 0.0;
+    sw->symmetrise = ORC_SYM_MAX;
+    sw->laplacian = ORC_LAPLACIAN_COMBINATORIAL;
+    sw->k_counts_self = 0;
+    sw->topk_prunes = 0;
+    sw->distance = ORC_DISTANCE_COSINE;
 }
 
 int orc_num_threads(void)
@@ -166,19 +171,32 @@ static int cand_cmp(const void *x, const void *y)
     return 0;
 }
 
+/* A3: distance of two nodes from their left-to-right sums <a,b>, <a,a>, <b,b>.
+ * cosine (default): 1 - max(0, <a,b> / (sqrt<a,a> sqrt<b,b>)), GRAPH_VARIABLES.md:7,37.
+ * l2 / l2sq [UNPINNED variants]: the Gram form (<a,a> + <b,b>) - 2<a,b>, clamped at 0, and its square root. */
+static inline double node_distance(double dot, double saa, double sbb, double na, double nb, int distance)
+{
+    if (distance != ORC_DISTANCE_COSINE) {
+        double d2 = (saa + sbb) - 2.0 * dot;
+        if (!(d2 > 0.0)) d2 = 0.0;
+        return distance == ORC_DISTANCE_L2 ? sqrt(d2) : d2;
+    }
+    double c = 0.0;                                       /* A3: c := 0 if a norm is 0 */
+    if (na != 0.0 && nb != 0.0) c = dot / (na * nb);
+    return 1.0 - (c > 0.0 ? c : 0.0);
+}
+
 /* A3 + A4 for one node a given its dot products with every node.
  * Writes up to kk (d, b) pairs, ascending by (d, b); returns the count. */
-static int64_t select_neighbours(const double *dots, const double *norm, int64_t m, int64_t a,
-                                 double eps, int64_t kk, cand_t *heap)
+static int64_t select_neighbours(const double *dots, const double *norm, const double *nsq, int64_t m, int64_t a,
+                                 double eps, int64_t kk, int distance, cand_t *heap)
 {
     int64_t cnt = 0;
     if (kk <= 0) return 0;
     const double na = norm[a];
     for (int64_t b = 0; b < m; ++b) {
         if (b == a) continue;
-        double c = 0.0;                                   /* A3: c := 0 if a norm is 0 */
-        if (na != 0.0 && norm[b] != 0.0) c = dots[b] / (na * norm[b]);
-        const double dist = 1.0 - (c > 0.0 ? c : 0.0);    /* GRAPH_VARIABLES.md:7,37 */
+        const double dist = node_distance(dots[b], nsq[a], nsq[b], na, norm[b], distance);
         if (!(dist <= eps)) continue;                     /* GRAPH_VARIABLES.md:7 */
         cand_t cd = { dist, b };
         if (cnt < kk) {                                   /* GRAPH_VARIABLES.md:8: k-cap */
@@ -214,9 +232,19 @@ static int edge_cmp(const void *x, const void *y)
     return 0;
 }
 
-/* A6 + A7: symmetrise W = max(W, W^T), L = D - W, CSR with sorted columns and the diagonal. */
+static int list_has(const int64_t *nbr, const int64_t *cnt, int64_t kk, int64_t row, int64_t v)
+{
+    for (int64_t j = 0; j < cnt[row]; ++j)
+        if (nbr[row * kk + j] == v) return 1;
+    return 0;
+}
+
+/* A6 + A7: symmetrise (default W = max(W, W^T)), L = D - W (or a normalised variant), CSR with sorted columns and the
+ * diagonal.  d is symmetric, so an edge selected by both endpoints carries the same weight in both lists: the rules only
+ * differ on ONE-SIDED edges -- max keeps them in both directions, avg halves them, min drops them, none keeps the
+ * selecting direction only. */
 static int assemble_laplacian(int64_t m, int64_t kk, const int64_t *cnt, const int64_t *nbr,
-                              const double *wgt, orc_graph *g)
+                              const double *wgt, const orc_switches *sw, orc_graph *g)
 {
     int64_t ne = 0;
     for (int64_t a = 0; a < m; ++a) ne += cnt[a];
@@ -226,32 +254,37 @@ static int assemble_laplacian(int64_t m, int64_t kk, const int64_t *cnt, const i
     for (int64_t a = 0; a < m; ++a)
         for (int64_t j = 0; j < cnt[a]; ++j) {
             const int64_t b = nbr[a * kk + j];
-            const double w = wgt[a * kk + j];
+            double w = wgt[a * kk + j];
+            if (!(w > 0.0)) continue;                     /* W entries that underflowed to 0 are not edges (A7) */
+            int mirror = 1;
+            if (sw->symmetrise != ORC_SYM_MAX) {
+                const int mutual = list_has(nbr, cnt, kk, b, a);
+                if (sw->symmetrise == ORC_SYM_NONE) mirror = 0;
+                else if (!mutual && sw->symmetrise == ORC_SYM_MIN) continue;
+                else if (!mutual && sw->symmetrise == ORC_SYM_AVG) w = 0.5 * w;
+            }
             e[q].r = a; e[q].c = b; e[q].w = w; ++q;
-            e[q].r = b; e[q].c = a; e[q].w = w; ++q;
+            if (mirror) { e[q].r = b; e[q].c = a; e[q].w = w; ++q; }
         }
     qsort(e, (size_t)q, sizeof(edge_t), edge_cmp);
     int64_t u = 0;                                        /* dedupe, first (= max) wins */
     for (int64_t i = 0; i < q; ++i)
         if (u == 0 || e[i].r != e[u - 1].r || e[i].c != e[u - 1].c) e[u++] = e[i];
-    /* W entries that underflowed to 0 are not edges ("edge set" = W_ab > 0, A7) */
-    int64_t v = 0;
-    for (int64_t i = 0; i < u; ++i)
-        if (e[i].w > 0.0) e[v++] = e[i];
-    u = v;
 
     g->nnodes = m;
     g->nnz = u + m;
     g->indptr = (int64_t *)malloc((size_t)(m + 1) * sizeof(int64_t));
     g->indices = (int32_t *)malloc((size_t)(g->nnz) * sizeof(int32_t));
     g->data = (double *)malloc((size_t)(g->nnz) * sizeof(double));
-    if (!g->indptr || !g->indices || !g->data) { free(e); return ORC_ERR_NOMEM; }
+    double *degs = (double *)malloc((size_t)m * sizeof(double));
+    if (!g->indptr || !g->indices || !g->data || !degs) { free(e); free(degs); return ORC_ERR_NOMEM; }
     int64_t pos = 0, i = 0;
     for (int64_t a = 0; a < m; ++a) {
         g->indptr[a] = pos;
         int64_t j = i;
         double deg = 0.0;
         while (j < u && e[j].r == a) { deg += e[j].w; ++j; }   /* ascending column order */
+        degs[a] = deg;
         int diag_done = 0;
         for (int64_t t = i; t < j; ++t) {
             if (!diag_done && e[t].c > a) {
@@ -264,6 +297,20 @@ static int assemble_laplacian(int64_t m, int64_t kk, const int64_t *cnt, const i
     }
     g->indptr[m] = pos;
     free(e);
+    /* A7 variants [UNPINNED]: sym  L_ab = -w_ab / sqrt(deg_a deg_b), L_aa = [deg_a > 0];  rw  L_ab = -w_ab / deg_a.
+     * Entries towards a node of degree 0 (possible with symmetrise = none) become explicit zeros. */
+    if (sw->laplacian != ORC_LAPLACIAN_COMBINATORIAL)
+        for (int64_t a = 0; a < m; ++a)
+            for (int64_t t = g->indptr[a]; t < g->indptr[a + 1]; ++t) {
+                const int64_t b = g->indices[t];
+                if (b == a) { g->data[t] = degs[a] > 0.0 ? 1.0 : 0.0; continue; }
+                const double w = -g->data[t];
+                double v = 0.0;
+                if (sw->laplacian == ORC_LAPLACIAN_SYM) { if (degs[a] > 0.0 && degs[b] > 0.0) v = -(w / sqrt(degs[a] * degs[b])); }
+                else if (degs[a] > 0.0) v = -(w / degs[a]);
+                g->data[t] = v;
+            }
+    free(degs);
     return ORC_OK;
 }
 
@@ -275,22 +322,27 @@ int orc_graph_from_nodes_t(const double *nt, int64_t d, int64_t m, const orc_par
     orc_switches sw;
     if (sw_in) sw = *sw_in; else orc_default_switches(&sw);
 
+    /* A4 neighbour cap + the unpinned conventions: min(k, topk) when topk prunes, minus the node itself when k counts it */
     int64_t kk = gp->k;
+    if (sw.topk_prunes && gp->topk < kk) kk = gp->topk;
+    if (sw.k_counts_self) kk -= 1;
     if (kk > m - 1) kk = m - 1;
     if (kk < 0) kk = 0;
     const int64_t kalloc = kk > 0 ? kk : 1;
 
     double *norm = (double *)malloc((size_t)m * sizeof(double));
+    double *nsq = (double *)malloc((size_t)m * sizeof(double));
     int64_t *cnt = (int64_t *)calloc((size_t)m, sizeof(int64_t));
     int64_t *nbr = (int64_t *)malloc((size_t)(m * kalloc) * sizeof(int64_t));
     double *wgt = (double *)malloc((size_t)(m * kalloc) * sizeof(double));
-    if (!norm || !cnt || !nbr || !wgt) { free(norm); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
+    if (!norm || !nsq || !cnt || !nbr || !wgt) { free(norm); free(nsq); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
 
     /* A3: norms, sqrt of the sequential sum of squares */
 #pragma omp parallel for schedule(static)
     for (int64_t a = 0; a < m; ++a) {
         double s = 0.0;
         for (int64_t t = 0; t < d; ++t) { const double v = nt[t * m + a]; s += v * v; }
+        nsq[a] = s;
         norm[a] = sqrt(s);
     }
 
@@ -305,7 +357,7 @@ int orc_graph_from_nodes_t(const double *nt, int64_t d, int64_t m, const orc_par
             const int64_t a0 = ib * blk, a1 = (a0 + blk < m) ? a0 + blk : m;
             dots_block_full(nt, d, m, a0, a1, acc);
             for (int64_t a = a0; a < a1; ++a) {
-                const int64_t c = select_neighbours(acc + (a - a0) * m, norm, m, a, gp->eps, kk, heap);
+                const int64_t c = select_neighbours(acc + (a - a0) * m, norm, nsq, m, a, gp->eps, kk, sw.distance, heap);
                 cnt[a] = c;
                 for (int64_t j = 0; j < c; ++j) {
                     nbr[a * kalloc + j] = heap[j].b;
@@ -318,11 +370,11 @@ int orc_graph_from_nodes_t(const double *nt, int64_t d, int64_t m, const orc_par
     }
 
     orc_graph *g = (orc_graph *)calloc(1, sizeof(orc_graph));
-    if (!g) { free(norm); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
+    if (!g) { free(norm); free(nsq); free(cnt); free(nbr); free(wgt); return ORC_ERR_NOMEM; }
     g->gp = *gp;
     g->sw = sw;
-    int rc = assemble_laplacian(m, kalloc, cnt, nbr, wgt, g);
-    free(norm); free(cnt); free(nbr); free(wgt);
+    int rc = assemble_laplacian(m, kalloc, cnt, nbr, wgt, &sw, g);
+    free(norm); free(nsq); free(cnt); free(nbr); free(wgt);
     if (rc != ORC_OK) { orc_free_graph(g); return rc; }
     *out_graph = g;
     return ORC_OK;
@@ -378,13 +430,21 @@ static int taumode_one(const orc_graph *g, const orc_switches *sw, const double 
     const double eb = e / (e + tau);
     double lam = eb;
     if (sw->lambda_form == ORC_LAMBDA_SYNTHETIC) {        /* TAUMODE.md:8,26-27 */
+        /* edgewise Dirichlet energies on the coefficients of the symmetrised form, c_ab = -(L_ab + L_ba)/2, for which
+         * x^T L x = sum_{a<b} c_ab (x_a - x_b)^2 holds (c_ab = w_ab for the default symmetric Laplacian) */
         double tot = 0.0, sq = 0.0;
         for (int64_t a = 0; a < m; ++a)
             for (int64_t j = g->indptr[a]; j < g->indptr[a + 1]; ++j) {
                 const int64_t b = g->indices[j];
-                if (b <= a) continue;
+                if (b == a) continue;
+                double lba = 0.0;
+                int have_ba = 0;
+                for (int64_t t = g->indptr[b]; t < g->indptr[b + 1]; ++t)
+                    if (g->indices[t] == a) { lba = g->data[t]; have_ba = 1; break; }
+                if (b < a && have_ba) continue;           /* the pair was handled from row b */
+                const double cab = (b > a) ? (-0.5 * g->data[j]) + (-0.5 * lba) : (-0.5 * lba) + (-0.5 * g->data[j]);
                 const double df = x[a] - x[b];
-                const double en = -g->data[j] * (df * df);
+                const double en = cab * (df * df);
                 tot += en;
                 sq += en * en;
             }

@@ -51,13 +51,24 @@ enum { ORC_NODES_FEATURE_COLUMNS = 0, ORC_NODES_ITEMS = 1 };
 enum { ORC_KERNEL_INV_POWER = 0, ORC_KERNEL_GAUSSIAN = 1 };
 enum { ORC_TAU_MEDIAN = 0, ORC_TAU_MEDIAN_ABS = 1, ORC_TAU_MEAN = 2, ORC_TAU_FIXED = 3 };
 enum { ORC_LAMBDA_BOUNDED = 0, ORC_LAMBDA_SYNTHETIC = 1 };
+enum { ORC_SYM_MAX = 0, ORC_SYM_AVG = 1, ORC_SYM_MIN = 2, ORC_SYM_NONE = 3 };
+enum { ORC_LAPLACIAN_COMBINATORIAL = 0, ORC_LAPLACIAN_SYM = 1, ORC_LAPLACIAN_RW = 2 };
+enum { ORC_DISTANCE_COSINE = 0, ORC_DISTANCE_L2 = 1, ORC_DISTANCE_L2SQ = 2 };
 
+/* Every switch is an UNPINNED choice of SURVEY.md 8(c); zero = the default spec of Appendix A.  The profile
+ * {symmetrise none, laplacian sym, k_counts_self 1, topk_prunes 1} ("kat12", found by tools/fit_switches.py) reproduces
+ * all 12 indices of /root/reference/tests/test_0.py:29-61; the default spec reproduces 11. */
 typedef struct {
-    int32_t nodes;        /* ORC_NODES_*   (A2) */
-    int32_t kernel;       /* ORC_KERNEL_*  (A5) */
-    int32_t tau_mode;     /* ORC_TAU_*     (A8) */
-    int32_t lambda_form;  /* ORC_LAMBDA_*  (A8) */
-    double  tau_fixed;    /* used when tau_mode == ORC_TAU_FIXED */
+    int32_t nodes;         /* ORC_NODES_*     (A2) */
+    int32_t kernel;        /* ORC_KERNEL_*    (A5) */
+    int32_t tau_mode;      /* ORC_TAU_*       (A8) */
+    int32_t lambda_form;   /* ORC_LAMBDA_*    (A8) */
+    double  tau_fixed;     /* used when tau_mode == ORC_TAU_FIXED */
+    int32_t symmetrise;    /* ORC_SYM_*       (A6): max(W,W^T) | (W+W^T)/2 | min(W,W^T) | W as selected (directed) */
+    int32_t laplacian;     /* ORC_LAPLACIAN_* (A7): D-W | I - D^-1/2 W D^-1/2 | I - D^-1 W, D = row sums of W */
+    int32_t k_counts_self; /* (A4) 1: the node is its own first neighbour: k keeps k-1 others */
+    int32_t topk_prunes;   /* (A4) 1: the neighbour cap is min(k, topk) */
+    int32_t distance;      /* ORC_DISTANCE_*  (A3): 1-max(0,cos) | sqrt(<a,a>+<b,b>-2<a,b>) | its square */
 } orc_switches;
 
 typedef struct orc_space orc_space;   /* items (copied), norms, lambdas */

@@ -34,41 +34,65 @@ def resolve_sigma(eps, sigma):
     return eps * 0.5 if sigma is None else float(sigma)      # helpers.rs:68-72
 
 
-def build_graph(nodes, eps, k, p, sigma, kernel="inv_power", laplacian="combinatorial"):
-    """nodes: (M, D) array, one node vector per row. Returns dense W, dense L, edge set."""
+def build_graph(nodes, eps, k, p, sigma, kernel="inv_power", laplacian="combinatorial", symmetrise="max",
+                k_counts_self=False, topk_prunes=False, topk=None, distance="cosine"):
+    """nodes: (M, D) array, one node vector per row. Returns dense W, dense L, edge set.
+
+    The keyword switches are the UNPINNED choices of SURVEY.md 8(c) (same names / meaning as oracle.h)."""
     nodes = np.asarray(nodes, dtype=np.float64)
     M = nodes.shape[0]
-    norm = [math.sqrt(_seq_dot(nodes[a], nodes[a])) for a in range(M)]
+    nsq = [_seq_dot(nodes[a], nodes[a]) for a in range(M)]
+    norm = [math.sqrt(v) for v in nsq]
     d = np.ones((M, M))
     for a in range(M):
         for b in range(M):
             if a == b:
                 continue
-            den = norm[a] * norm[b]
-            c = 0.0 if (norm[a] == 0.0 or norm[b] == 0.0) else _seq_dot(nodes[a], nodes[b]) / den
-            d[a, b] = 1.0 - max(0.0, c)                         # GRAPH_VARIABLES.md:7
-    W = np.zeros((M, M))
+            dot = _seq_dot(nodes[a], nodes[b])
+            if distance == "cosine":
+                den = norm[a] * norm[b]
+                c = 0.0 if (norm[a] == 0.0 or norm[b] == 0.0) else dot / den
+                d[a, b] = 1.0 - max(0.0, c)                     # GRAPH_VARIABLES.md:7
+            else:
+                d2 = max(0.0, (nsq[a] + nsq[b]) - 2.0 * dot)
+                d[a, b] = math.sqrt(d2) if distance == "l2" else d2
+    cap = k
+    if topk_prunes and topk is not None:
+        cap = min(cap, topk)
+    if k_counts_self:
+        cap -= 1
+    cap = max(0, min(cap, M - 1))
+    sel = np.zeros((M, M))                                      # directed selections
     for a in range(M):
         cand = sorted((d[a, b], b) for b in range(M) if b != a and d[a, b] <= eps)
-        for dist, b in cand[:k]:                                # GRAPH_VARIABLES.md:8
+        for dist, b in cand[:cap]:                              # GRAPH_VARIABLES.md:8
             t = (dist / sigma) ** p
-            w = 1.0 / (1.0 + t) if kernel == "inv_power" else math.exp(-t)   # :3,9
-            W[a, b] = max(W[a, b], w)
-            W[b, a] = max(W[b, a], w)                           # symmetrise (A6)
-    deg = np.array([sum(W[a, b] for b in range(M)) for a in range(M)])
+            sel[a, b] = 1.0 / (1.0 + t) if kernel == "inv_power" else math.exp(-t)   # :3,9
+    if symmetrise == "max":
+        W = np.maximum(sel, sel.T)
+    elif symmetrise == "avg":
+        W = 0.5 * sel + 0.5 * sel.T
+    elif symmetrise == "min":
+        W = np.minimum(sel, sel.T)
+    else:
+        W = sel
+    deg = np.array([sum(W[a, b] for b in range(M) if W[a, b] != 0.0) for a in range(M)])
     if laplacian == "combinatorial":
         L = -W.copy()
         for a in range(M):
             L[a, a] = deg[a]
-    else:                                                        # sym-normalised variant
+    else:                                                        # normalised variants
         L = np.zeros((M, M))
         for a in range(M):
             for b in range(M):
                 if a == b:
                     L[a, a] = 1.0 if deg[a] > 0 else 0.0
                 elif W[a, b] != 0.0:
-                    L[a, b] = -W[a, b] / math.sqrt(deg[a] * deg[b])
-    edges = sorted((a, b) for a in range(M) for b in range(a + 1, M) if W[a, b] > 0.0)
+                    if laplacian == "sym":
+                        L[a, b] = -(W[a, b] / math.sqrt(deg[a] * deg[b])) if (deg[a] > 0 and deg[b] > 0) else 0.0
+                    else:
+                        L[a, b] = -(W[a, b] / deg[a]) if deg[a] > 0 else 0.0
+    edges = sorted((a, b) for a in range(M) for b in range(a + 1, M) if W[a, b] > 0.0 or W[b, a] > 0.0)
     return W, L, edges
 
 
@@ -111,8 +135,9 @@ def taumode_lambda(x, L, tau_mode="median", tau_fixed=0.0, lambda_form="bounded"
     sq = 0.0
     for a in range(F):
         for b in range(a + 1, F):
-            if L[a, b] != 0.0:
-                e = -L[a, b] * (float(x[a]) - float(x[b])) ** 2
+            if L[a, b] != 0.0 or L[b, a] != 0.0:
+                cab = (-0.5 * L[a, b]) + (-0.5 * L[b, a])       # coefficient of the symmetrised form
+                e = cab * (float(x[a]) - float(x[b])) ** 2
                 tot += e
                 sq += e * e
     G = 0.0 if tot == 0.0 else min(1.0, max(0.0, sq / (tot * tot)))   # TAUMODE.md:26-27
@@ -136,7 +161,8 @@ def build(items, eps, k, topk, p, sigma=None, nodes="feature_columns", **sw):
     items = np.asarray(items, dtype=np.float64)
     sigma = resolve_sigma(eps, sigma)
     node_mat = items.T if nodes == "feature_columns" else items
-    gkw = {k_: sw[k_] for k_ in ("kernel", "laplacian") if k_ in sw}
+    gkw = {k_: sw[k_] for k_ in ("kernel", "laplacian", "symmetrise", "k_counts_self", "topk_prunes", "distance") if k_ in sw}
+    gkw["topk"] = topk
     lkw = {k_: sw[k_] for k_ in ("tau_mode", "tau_fixed", "lambda_form") if k_ in sw}
     W, L, edges = build_graph(node_mat, eps, k, p, sigma, **gkw)
     lam = None

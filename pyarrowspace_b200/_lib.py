@@ -26,6 +26,20 @@ ROW_UNIT = 32
 
 KERNEL = {"inv_power": 0, "gaussian": 1}
 TAU_MODE = {"median": 0, "median_abs": 1, "mean": 2, "fixed": 3}
+LAMBDA_FORM = {"bounded": 0, "synthetic": 1}
+SYMMETRISE = {"max": 0, "avg": 1, "min": 2, "none": 3}
+LAPLACIAN = {"combinatorial": 0, "sym": 1, "rw": 2}
+DISTANCE = {"cosine": 0, "l2": 1, "l2sq": 2}
+
+# Named sets of the switches the reference's tests cannot pin.  "default" is the documented recipe
+# (GRAPH_VARIABLES.md:3,7-10; TAUMODE.md:18-19,24-25); "kat12" is the set that reproduces all 12
+# indices of /root/reference/tests/test_0.py:29-61.
+PROFILES = {
+    "default": {},
+    "kat12": {"symmetrise": "none", "laplacian": "sym", "k_counts_self": True, "topk_prunes": True},
+}
+SWITCH_KEYS = ("kernel", "tau_mode", "tau_fixed", "lambda_form", "symmetrise", "laplacian", "k_counts_self", "topk_prunes",
+               "distance", "profile")
 
 
 class GraphParams(C.Structure):
@@ -34,7 +48,9 @@ class GraphParams(C.Structure):
 
 
 class Switches(C.Structure):
-    _fields_ = [("kernel", C.c_int32), ("tau_mode", C.c_int32), ("tau_fixed", C.c_double)]
+    _fields_ = [("kernel", C.c_int32), ("tau_mode", C.c_int32), ("tau_fixed", C.c_double), ("lambda_form", C.c_int32),
+                ("symmetrise", C.c_int32), ("laplacian", C.c_int32), ("k_counts_self", C.c_int32),
+                ("topk_prunes", C.c_int32), ("distance", C.c_int32)]
 
 
 class LibraryError(RuntimeError):
@@ -63,6 +79,9 @@ SYMBOLS = {
     "asp_shard_rows": (_int, [_i64, _int, _int, C.POINTER(_i64), C.POINTER(_i64)]),
     "asp_space_create": (_int, [_vp, _vp, _i64, _i32, _i64, _int, _int, C.POINTER(_vp)]),
     "asp_space_adopt": (_int, [_vp, _vp, _i64, _i32, C.POINTER(_vp)]),
+    "asp_space_adopt_shard": (_int, [_vp, _vp, _i64, _i32, _i64, _int, _int, C.POINTER(_vp)]),
+    "asp_space_import_lambdas": (_int, [_vp, _vp, _vp]),
+    "asp_ctx_trim": (_int, [_vp, C.c_size_t]),
     "asp_space_gram_partials": (_int, [_vp, _vp]),
     "asp_graph_from_gram": (_int, [_vp, _vp, _i32, _i64, C.POINTER(GraphParams), C.POINTER(Switches),
                                    _vp, _vp, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_vp)]),
@@ -81,7 +100,7 @@ SYMBOLS = {
     "asp_peer_exchange_bytes": (C.c_size_t, [_int, _i64, _i64]),
     "asp_peer_merge": (_int, [_vp, _int, _int, C.POINTER(C.c_uint64), _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp]),
     "asp_item_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
-    "asp_item_knn_rows": (_int, [_vp, C.POINTER(GraphParams), _i64, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "asp_item_knn_rows": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), _i64, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
     "asp_graph_from_knn": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
     "asp_free_space": (None, [_vp]),
     "asp_free_graph": (None, [_vp]),
@@ -134,5 +153,17 @@ def make_params(eps, k, topk, p, sigma):
                        0 if sigma is None else 1)
 
 
-def make_switches(kernel="inv_power", tau_mode="median", tau_fixed=0.0):
-    return Switches(KERNEL[kernel], TAU_MODE[tau_mode], float(tau_fixed))
+def make_switches(kernel="inv_power", tau_mode="median", tau_fixed=0.0, lambda_form="bounded", symmetrise="max",
+                  laplacian="combinatorial", k_counts_self=False, topk_prunes=False, distance="cosine", profile=None):
+    if profile is not None:
+        kw = dict(kernel=kernel, tau_mode=tau_mode, tau_fixed=tau_fixed, lambda_form=lambda_form, symmetrise=symmetrise,
+                  laplacian=laplacian, k_counts_self=k_counts_self, topk_prunes=topk_prunes, distance=distance)
+        kw.update(PROFILES[profile])
+        return make_switches(**kw)
+    return Switches(KERNEL[kernel], TAU_MODE[tau_mode], float(tau_fixed), LAMBDA_FORM[lambda_form], SYMMETRISE[symmetrise],
+                    LAPLACIAN[laplacian], int(bool(k_counts_self)), int(bool(topk_prunes)), DISTANCE[distance])
+
+
+def switches_from(extras):
+    """asp_switches from the keyword-only extras of the build entry points (unknown keys are left to the caller)."""
+    return make_switches(**{k: extras[k] for k in SWITCH_KEYS if k in extras})

@@ -153,11 +153,12 @@ class ArrowSpace:
         raise ValueError("ArrowSpace cannot be constructed directly; use ArrowSpaceBuilder.build")
 
     @classmethod
-    def _wrap(cls, handle, ctx, group=None):
+    def _wrap(cls, handle, ctx, group=None, grid=None):
         self = object.__new__(cls)
         self._h = handle
         self._ctx = ctx
-        self._group = group          # torch.distributed group for sharded spaces, else None
+        self._group = group          # torch.distributed group the per-shard results are merged over (item shards > 1), else None
+        self._grid = grid            # multi-GPU layout (distributed.regroup): R item shards x C query slots
         return self
 
     def __del__(self):
@@ -238,6 +239,8 @@ class ArrowSpace:
 
     def _search_batch(self, queries, gl, tau, want_lambda):
         import time
+        if self._grid is not None and self._grid["C"] > 1:
+            return self._search_batch_grid(queries, gl, tau)
         t_a = time.perf_counter()
         lib = _lib.load()
         f = self.nfeatures
@@ -301,6 +304,85 @@ class ArrowSpace:
             idx, score, lam = _to_host(idx, host_out and host_out[0]), _to_host(score, host_out and host_out[1]), \
                 _to_host(lam, host_out and host_out[2])
         return idx, score, lam
+
+    def _search_batch_grid(self, queries, gl, tau):
+        """R item shards x C query slots (distributed.regroup): this rank answers rows [a, b) of the batch against its item
+        shard; R > 1: the R ranks of the slot merge their lists (K5); the C slots all-gather the finished slices, so every
+        rank returns the whole batch.  Host batches: this rank uploads only ITS slice (over its own PCIe link)."""
+        import threading
+        import torch
+        import torch.distributed as dist
+        from .distributed import query_slice
+        lib = _lib.load()
+        g = self._grid
+        f = self.nfeatures
+        topk = gl.graph_params["topk"]
+        dev = torch.device("cuda", lib.asp_ctx_device(self._ctx))
+        host_in = not _is_device_tensor(queries)
+        if host_in:
+            q = np.ascontiguousarray(queries, dtype=np.float64)
+            if q.ndim != 2 or q.shape[1] != f:
+                raise ValueError("query length %d must match nfeatures %d" % (q.shape[-1], f))
+        else:
+            if queries.dim() != 2 or queries.shape[1] != f:
+                raise ValueError("query length %d must match nfeatures %d" % (queries.shape[-1], f))
+            q = queries.contiguous()
+            if q.dtype != torch.float64:
+                raise TypeError("queries must be float64")
+        nq = q.shape[0]
+        a, b, per = query_slice(nq, g["C"], g["c"])
+        host_out, toucher = None, None
+        if host_in and nq * max(topk, 1) >= 65536:      # first touch of the caller's result pages while the kernels run
+            host_out = (np.empty((nq, topk), dtype=np.int64), np.empty((nq, topk), dtype=np.float64), np.empty(nq, dtype=np.float64))
+            toucher = threading.Thread(target=lambda: [arr.fill(0) for arr in host_out])
+            toucher.start()
+        # one packed exchange buffer per slot: [per + 1] rows of (topk indices, topk scores, lambda_q) as 8-byte words;
+        # the extra row carries this rank's status so that every rank raises the same error
+        w = 2 * topk + 1
+        part = torch.empty((per + 1, w), dtype=torch.int64, device=dev)
+        part[:, :topk] = -1
+        part[:, topk:].view(torch.float64).fill_(float("nan"))
+        part[per] = 0
+        idx_p, sc_p, lam_p = part[:per, :topk], part[:per, topk:2 * topk].view(torch.float64), part[:per, 2 * topk].view(torch.float64)
+        err = None
+        if b > a:
+            idx_c = torch.empty((b - a, topk), dtype=torch.int64, device=dev)
+            sc_c = torch.empty((b - a, topk), dtype=torch.float64, device=dev)
+            lam_c = torch.empty(b - a, dtype=torch.float64, device=dev)
+            qp = q[a:b].ctypes.data if host_in else q[a:b].data_ptr()
+            torch.cuda.current_stream(dev).synchronize()                 # the library runs on its own stream
+            rc = lib.asp_search_batch(self._h, gl._h, qp, b - a, tau, idx_c.data_ptr(), sc_c.data_ptr(), lam_c.data_ptr())
+            if rc != _lib.ASP_OK:
+                msg = lib.asp_last_error()
+                err = LibraryError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")
+                part[per, 0] = rc
+            else:
+                idx_p[: b - a], sc_p[: b - a], lam_p[: b - a] = idx_c, sc_c, lam_c
+        if g["R"] > 1:
+            m_idx, m_sc = _merge_across_ranks(self, idx_p.contiguous(), sc_p.contiguous(), per, topk)
+            idx_p.copy_(m_idx)
+            sc_p.copy_(m_sc)
+        full = torch.empty((g["C"] * (per + 1), w), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(full, part, group=g["item_group"])
+        full = full.view(g["C"], per + 1, w)
+        codes = full[:, per, 0].cpu().tolist()
+        if toucher is not None:
+            toucher.join()
+        bad = [int(cd) for cd in codes if cd != 0]
+        if bad:
+            code = bad[0]
+            message = err.message if err is not None else ("a rank of the query grid failed with error %d" % code)
+            if code == _lib.ASP_ERR_LAMBDA_ZERO:
+                raise PanicException("assertion `left != right` failed: The lambdas are zero, check the magnitude of items and eps.\n  left: 0.0\n right: 0.0")
+            if code == _lib.ASP_ERR_ZERO_VECTOR:
+                raise PanicException(message)
+            raise LibraryError(code, message)
+        rows = full[:, :per, :].reshape(g["C"] * per, w)[:nq]
+        idx, score, lam = rows[:, :topk], rows[:, topk:2 * topk].view(torch.float64), rows[:, 2 * topk].view(torch.float64)
+        if host_in:
+            return (_to_host(idx.contiguous(), host_out and host_out[0]), _to_host(score.contiguous(), host_out and host_out[1]),
+                    _to_host(lam.contiguous(), host_out and host_out[2]))
+        return idx.contiguous(), score.contiguous(), lam.contiguous()
 
     # ------------------------------------------------------------------ out of scope (SURVEY.md 8(f))
     def search_hybrid(self, item, gl, tau):
@@ -408,7 +490,9 @@ class ArrowSpaceBuilder:
     def build(graph_params, items, **extras):
         """Feature graph + Laplacian + per-item lambdas.  src/lib.rs:270-300.
 
-        keyword-only extras (never positional): device=int, kernel=, tau_mode=, tau_fixed=.
+        keyword-only extras (never positional): device=int and the switches of the choices the
+        reference's tests cannot pin (include/arrowspace_b200.h asp_switches): kernel=, tau_mode=, tau_fixed=,
+        lambda_form=, symmetrise=, laplacian=, k_counts_self=, topk_prunes=, distance=, or a named set profile="kat12".
         """
         lib = _lib.load()
         dbg_println("Convert pyarray2 and Vec<Vec>")
@@ -440,8 +524,7 @@ class ArrowSpaceBuilder:
         if gp is None:
             gp = dict(DEFAULT_GRAPH_PARAMS)
         cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
-        sw = _lib.make_switches(extras.get("kernel", "inv_power"), extras.get("tau_mode", "median"),
-                                extras.get("tau_fixed", 0.0))
+        sw = _lib.switches_from(extras)
         ctx = _lib.context(extras.get("device"))
         dbg_println("Building from rows")
         hs, hg = C.c_void_p(), C.c_void_p()
@@ -482,7 +565,7 @@ class ArrowSpaceBuilder:
         n, f = x.shape
         gp = parse_graph_params(graph_params) or dict(DEFAULT_GRAPH_PARAMS)
         cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
-        sw = _lib.make_switches(extras.get("kernel", "inv_power"))
+        sw = _lib.switches_from(extras)
         ctx = _lib.context(extras.get("device"))
         hs, hg = C.c_void_p(), C.c_void_p()
         _lib.check(lib.asp_space_create(ctx, ptr, n, f, n, 1, 0, C.byref(hs)))

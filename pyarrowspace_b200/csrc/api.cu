@@ -102,9 +102,21 @@ int asp_abi_version(void) { return ASP_ABI_VERSION; }
 
 void asp_default_switches(asp_switches *sw)
 {
+    memset(sw, 0, sizeof(*sw));          // every switch's default is its zero value
     sw->kernel = ASP_KERNEL_INV_POWER;
     sw->tau_mode = ASP_TAU_MEDIAN;
     sw->tau_fixed = 0.0;
+}
+
+// range check of caller-supplied switches
+static int check_switches(const asp_switches *sw)
+{
+    if (sw->kernel < 0 || sw->kernel > ASP_KERNEL_GAUSSIAN || sw->tau_mode < 0 || sw->tau_mode > ASP_TAU_FIXED ||
+        sw->lambda_form < 0 || sw->lambda_form > ASP_LAMBDA_SYNTHETIC || sw->symmetrise < 0 || sw->symmetrise > ASP_SYM_NONE ||
+        sw->laplacian < 0 || sw->laplacian > ASP_LAPLACIAN_RW || sw->distance < 0 || sw->distance > ASP_DISTANCE_L2SQ ||
+        (sw->k_counts_self != 0 && sw->k_counts_self != 1) || (sw->topk_prunes != 0 && sw->topk_prunes != 1))
+        ASP_FAIL(ASP_ERR_ARG, "asp_switches: value out of range");
+    return ASP_OK;
 }
 
 int asp_ctx_create(int device, asp_ctx **out)
@@ -126,10 +138,13 @@ int asp_ctx_create(int device, asp_ctx **out)
     ctx->num_sms = prop.multiProcessorCount;
     ASP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {   // keep freed blocks in the stream-ordered pool: every build/search reuses its scratch instead of
-        // going back to the driver (cudaMalloc/cudaFree of GB-sized buffers cost milliseconds and synchronise)
+        // going back to the driver (cudaMalloc/cudaFree of GB-sized buffers cost milliseconds and synchronise).
+        // Bounded (a quarter of the device by default, ASP_POOL_KEEP_GB overrides) so that another allocator in the
+        // same process (PyTorch's) is not starved; asp_ctx_trim() gives the cached blocks back explicitly.
         cudaMemPool_t pool;
         ASP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = UINT64_MAX;
+        uint64_t keep = (uint64_t)prop.totalGlobalMem / 4;
+        if (const char *e = getenv("ASP_POOL_KEEP_GB")) { const double gb = atof(e); if (gb >= 0.0) keep = (uint64_t)(gb * 1073741824.0); }
         ASP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     ASP_CUDA(cudaEventCreate(&ctx->ev0));
@@ -178,6 +193,17 @@ int asp_ctx_synchronize(asp_ctx *ctx)
 }
 
 int64_t asp_ctx_launch_count(const asp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int asp_ctx_trim(asp_ctx *ctx, size_t keep_bytes)
+{
+    if (!ctx) ASP_FAIL(ASP_ERR_ARG, "ctx is NULL");
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    ASP_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    ASP_CUDA(cudaMemPoolTrimTo(pool, keep_bytes));
+    return ASP_OK;
+}
 
 double asp_ctx_stat(const asp_ctx *ctx, const char *key)
 {
@@ -239,29 +265,56 @@ int asp_space_create(asp_ctx *ctx, const double *items_shard, int64_t n_local, i
     return ASP_OK;
 }
 
-// World-1 space over a device buffer the CALLER keeps alive (n x f f64 row-major, f a multiple of 4, 16-byte aligned): no
-// copy.  For the multi-GPU item graph, where the all-gathered item matrix (C5: 54 GB per rank) must not exist twice.
-int asp_space_adopt(asp_ctx *ctx, double *items_dev, int64_t n, int32_t f, asp_space **out)
+// Space over a device buffer the CALLER keeps alive (n_local x f f64 row-major, f a multiple of 4, 16-byte aligned): no
+// copy.  For the multi-GPU paths, where a gathered item matrix (C5: 54 GB per rank) must not exist twice.
+int asp_space_adopt_shard(asp_ctx *ctx, double *items_dev, int64_t n_local, int32_t f, int64_t n_total, int world, int rank,
+                          asp_space **out)
 {
-    if (!ctx || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_adopt: NULL argument");
-    if (!items_dev || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    if (!ctx || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_adopt_shard: NULL argument");
+    if (!items_dev || n_local <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
     if (!asp_is_device_ptr(items_dev) || (f & 3) != 0 || (reinterpret_cast<uintptr_t>(items_dev) & 15) != 0)
         ASP_FAIL(ASP_ERR_ARG, "asp_space_adopt: needs 16-byte aligned device memory and a feature count that is a multiple of 4 (got %d)", f);
+    int64_t r0 = 0, r1 = 0;
+    ASP_CHECK(asp_shard_rows(n_total, world, rank, &r0, &r1));
+    if (r1 - r0 != n_local)
+        ASP_FAIL(ASP_ERR_ARG, "rank %d of %d owns rows [%lld,%lld) of %lld, got %lld rows", rank, world, (long long)r0,
+                 (long long)r1, (long long)n_total, (long long)n_local);
     ASP_CUDA(cudaSetDevice(ctx->device));
     asp_space *s = new asp_space();
     s->ctx = ctx;
-    s->n_local = n; s->row0 = 0; s->n_total = n;
+    s->n_local = n_local; s->row0 = r0; s->n_total = n_total;
     s->f = f; s->fp = f;
-    s->world = 1; s->rank = 0;
+    s->world = world; s->rank = rank;
     s->items = items_dev;
     s->owns_items = false;
-    ASP_CUDA(cudaMallocAsync(&s->norms, sizeof(double) * n, ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&s->inv_norms, sizeof(double) * n, ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&s->lambdas, sizeof(double) * n, ctx->stream));
-    int rc = asp_make_items_tmap(&s->tmap_gram, s->items, n, s->fp, ASP_ROW_UNIT, 32);
-    if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n, s->fp, 128, 4);
+    ASP_CUDA(cudaMallocAsync(&s->norms, sizeof(double) * n_local, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->inv_norms, sizeof(double) * n_local, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&s->lambdas, sizeof(double) * n_local, ctx->stream));
+    int rc = asp_make_items_tmap(&s->tmap_gram, s->items, n_local, s->fp, ASP_ROW_UNIT, 32);
+    if (rc == ASP_OK) rc = asp_make_items_tmap(&s->tmap_rows, s->items, n_local, s->fp, 128, 4);
     if (rc != ASP_OK) { asp_free_space(s); return rc; }
     *out = s;
+    return ASP_OK;
+}
+
+int asp_space_adopt(asp_ctx *ctx, double *items_dev, int64_t n, int32_t f, asp_space **out)
+{
+    return asp_space_adopt_shard(ctx, items_dev, n, f, n, 1, 0, out);
+}
+
+// Per-item lambdas and norms computed elsewhere (the rank that owned the rows at build time): the multi-GPU regrouping
+// all-gathers them next to the item rows instead of recomputing.  norms must be the left-to-right ones (asp_space_norms).
+int asp_space_import_lambdas(asp_space *s, const double *lambdas, const double *norms)
+{
+    if (!s || !lambdas || !norms) ASP_FAIL(ASP_ERR_ARG, "asp_space_import_lambdas: NULL argument");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    ASP_CHECK(asp_copy_in(ctx, s->lambdas, lambdas, sizeof(double) * s->n_local));
+    ASP_CHECK(asp_copy_in(ctx, s->norms, norms, sizeof(double) * s->n_local));
+    ASP_CHECK(asp_launch_reciprocal(ctx, s->norms, s->n_local, s->inv_norms));
+    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    asp_free_tc_cache(s);                                           // operands in lambda order depend on the lambdas
+    s->have_lambdas = true;
     return ASP_OK;
 }
 
@@ -283,7 +336,8 @@ void asp_free_graph(asp_graph *g)
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     cudaStream_t st = g->ctx->stream;
-    void *bufs[] = {g->d_indptr, g->d_indices, g->d_data, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, g->d_tm_chunks};
+    asp_graph_free_upper(g);
+    void *bufs[] = {g->d_indptr, g->d_indices, g->d_data};
     for (void *b : bufs)
         if (b) cudaFreeAsync(b, st);
     delete g;
@@ -311,6 +365,7 @@ int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f
     ASP_CUDA(cudaSetDevice(ctx->device));
     asp_switches sw;
     if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    ASP_CHECK(check_switches(&sw));
     cudaStream_t st = ctx->stream;
     if (n_need) *n_need = 0;
     StageTimer timer(ctx, "graph_ms");
@@ -343,14 +398,16 @@ int asp_graph_from_gram(asp_ctx *ctx, const double *gram_segments_dev, int32_t f
         ASP_CUDA(cudaStreamSynchronize(st));
     }
 
-    const int64_t dev_cap = 1 << 16;
+    // room for every column pair (data with many duplicate columns puts most pairs inside the band), bounded at 16M pairs
+    const int64_t all_pairs = (int64_t)f * (f - 1) / 2;
+    const int64_t dev_cap = std::max<int64_t>(1, std::min<int64_t>(all_pairs * 2, (int64_t)1 << 24));
     int32_t *d_need = nullptr, *d_need_count = nullptr;
     ASP_CUDA(cudaMallocAsync(&d_need, sizeof(int32_t) * 2 * dev_cap, st));
     ASP_CUDA(cudaMallocAsync(&d_need_count, sizeof(int32_t), st));
     ASP_CUDA(cudaMemsetAsync(d_need_count, 0, sizeof(int32_t), st));
 
     asp_knn_lists lists;
-    int rc = asp_feature_select(ctx, gram, f, n_total, gp, d_pairs, d_sums, n_exact, &lists, d_need, dev_cap, d_need_count);
+    int rc = asp_feature_select(ctx, gram, f, n_total, gp, &sw, d_pairs, d_sums, n_exact, &lists, d_need, dev_cap, d_need_count);
     int32_t need_count = 0;
     if (rc == ASP_OK) {
         ASP_CUDA(cudaMemcpyAsync(&need_count, d_need_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -470,13 +527,19 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
         double graph_ms = 0.0;
         std::vector<int32_t> pairs;
         std::vector<double> sums;
-        const int64_t cap = 1 << 16;
+        int64_t cap = 1 << 16;
         std::vector<int32_t> need(2 * cap);
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = 0; pass < 6; ++pass) {
             int64_t n_need = 0;
             rc = asp_graph_from_gram(ctx, segs, f, n, gp, sw, pairs.data(), sums.data(), (int64_t)(pairs.size() / 2),
                                      need.data(), cap, &n_need, &g);
             graph_ms += ctx->stats["graph_ms"];
+            if (rc == ASP_ERR_ARG && n_need > cap) {               // more undecided pairs than the list holds: grow it, same pass again
+                cap = n_need;
+                need.resize(2 * cap);
+                rc = ASP_NEED_EXACT;
+                continue;
+            }
             if (rc != ASP_NEED_EXACT) break;
             std::vector<double> add(3 * n_need, 0.0);
             rc = asp_space_exact_pairs(s, need.data(), n_need, add.data());
@@ -819,8 +882,13 @@ int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches 
     ASP_CUDA(cudaSetDevice(ctx->device));
     asp_switches sw;
     if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    ASP_CHECK(check_switches(&sw));
+    if (sw.distance != ASP_DISTANCE_COSINE)
+        ASP_FAIL(ASP_ERR_UNSUPPORTED, "the item graph (tensor-core candidates) supports the rectified-cosine distance only");
     asp_knn_lists lists;
-    ASP_CHECK(asp_item_knn(s, gp, &lists));
+    asp_graph_params gpe = *gp;
+    gpe.k = asp_neighbour_cap(gp, &sw, s->n_total);               // k convention switches (k_counts_self, topk_prunes)
+    ASP_CHECK(asp_item_knn(s, &gpe, &lists));
     asp_graph *g = new asp_graph();
     g->ctx = ctx;
     g->gp = *gp;
@@ -836,14 +904,21 @@ int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches 
     return ASP_OK;
 }
 
-int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, int64_t row_begin, int64_t row_end, int32_t *out_idx,
-                      double *out_dist, int32_t *out_cnt, int32_t *out_kk)
+int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, const asp_switches *sw_in, int64_t row_begin, int64_t row_end,
+                      int32_t *out_idx, double *out_dist, int32_t *out_cnt, int32_t *out_kk)
 {
     if (!s || !gp || !out_cnt || !out_kk) ASP_FAIL(ASP_ERR_ARG, "asp_item_knn_rows: NULL argument");
     asp_ctx *ctx = s->ctx;
     ASP_CUDA(cudaSetDevice(ctx->device));
+    asp_switches sw;
+    if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    ASP_CHECK(check_switches(&sw));
+    if (sw.distance != ASP_DISTANCE_COSINE)
+        ASP_FAIL(ASP_ERR_UNSUPPORTED, "the item graph (tensor-core candidates) supports the rectified-cosine distance only");
     asp_knn_lists lists;
-    int rc = asp_item_knn_rows_impl(s, gp, row_begin, row_end, &lists);
+    asp_graph_params gpe = *gp;
+    gpe.k = asp_neighbour_cap(gp, &sw, s->n_total);
+    int rc = asp_item_knn_rows_impl(s, &gpe, row_begin, row_end, &lists);
     if (rc == ASP_OK) {
         const size_t rows = (size_t)lists.m;
         *out_kk = lists.kk;
@@ -866,6 +941,7 @@ int asp_graph_from_knn(asp_ctx *ctx, int64_t m, int32_t kk, const int32_t *idx, 
     cudaStream_t st = ctx->stream;
     asp_switches sw;
     if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    ASP_CHECK(check_switches(&sw));
     asp_knn_lists lists;
     lists.m = m; lists.kk = kk;
     ASP_CUDA(cudaMallocAsync(&lists.idx, sizeof(int32_t) * (size_t)m * kk, st));

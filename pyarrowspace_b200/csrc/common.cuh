@@ -80,21 +80,25 @@ struct asp_graph {
     std::vector<int64_t> h_indptr;
     std::vector<int32_t> h_indices;
     std::vector<double>  h_data;
-    // strictly-upper adjacency W (a<b) + degrees, device: what the lambda kernel consumes
-    int32_t *d_uptr = nullptr;           // nnodes+1
-    int32_t *d_ucol = nullptr;
-    double  *d_uval = nullptr;
-    double  *d_deg = nullptr;            // nnodes
-    int64_t  unnz = 0;
-    // row chunks of the upper adjacency the lambda kernel stages through shared memory (taumode.cu), built on first use
-    mutable void *d_tm_chunks = nullptr;
-    mutable int   n_tm_chunks = 0;
+    // graph-only inputs of the lambda pass (taumode.cu: the symmetrised quadratic form, pre-cut into chunks); feature graphs only
+    void *tm_blob = nullptr;
 };
 
 // ------------------------------------------------------------------ launch bookkeeping
 #define ASP_LAUNCHED(ctx) ((ctx)->launches++)
 
 static inline int64_t asp_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// neighbour cap of one node (SURVEY.md Appendix A4 + the unpinned conventions): min(k, topk) when topk prunes, minus the
+// node itself when k counts it; never more than m - 1 others
+static inline int64_t asp_neighbour_cap(const asp_graph_params *gp, const asp_switches *sw, int64_t m)
+{
+    int64_t kk = gp->k;
+    if (sw && sw->topk_prunes && gp->topk < kk) kk = gp->topk;
+    if (sw && sw->k_counts_self) kk -= 1;
+    if (kk > m - 1) kk = m - 1;
+    return kk < 0 ? 0 : kk;
+}
 
 // host helpers implemented in api.cu
 int  asp_copy_in(asp_ctx *ctx, void *dst_dev, const void *src, size_t bytes);
@@ -115,18 +119,19 @@ struct asp_knn_lists {                    // device buffers, m rows x kk slots
     int32_t *idx = nullptr; double *dist = nullptr; int32_t *cnt = nullptr;
 };
 int asp_feature_select(asp_ctx *ctx, const double *gram_dev, int32_t f, int64_t n_total,
-                       const asp_graph_params *gp, const int32_t *exact_pairs_dev,
+                       const asp_graph_params *gp, const asp_switches *sw, const int32_t *exact_pairs_dev,
                        const double *exact_sums_dev, int64_t n_exact, asp_knn_lists *lists,
                        int32_t *need_pairs_dev, int64_t need_cap, int32_t *need_count_dev);
 int asp_launch_exact_pairs(asp_space *s, const int32_t *pairs_dev, int64_t n_pairs, double *sums_dev);
 
 // csr.cu
 int asp_graph_host_mirror(asp_graph *g);
-int asp_graph_upload_upper(asp_graph *g);
 int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_graph_params *gp,
                            const asp_switches *sw, asp_graph *g);
 
 // taumode.cu
+int asp_graph_upload_upper(asp_graph *g);
+void asp_graph_free_upper(asp_graph *g);
 int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const double *x_dev,
                        int64_t n, int32_t f, int32_t pitch, double *out_energy, double *out_tau,
                        double *out_lambda, double *out_norm, double *out_inv_norm, int *zero_flag_dev);

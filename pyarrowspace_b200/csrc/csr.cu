@@ -6,11 +6,15 @@
 // Bound: HBM, ~60*M*k bytes: lists in, mirrored edges, CSR out.
 //
 //   1. weights_compact   w = 1/(1+(d/sigma)^p) | exp(-(d/sigma)^p); drop w == 0; compact each list
+//  1b. symmetrise rule   (asp_switches.symmetrise, UNPINNED): max = union (default) | avg: a one-sided edge weighs w/2 in both
+//                        directions | min: one-sided edges are dropped | none: the directed lists are the graph
 //   2. count_mirror      for edge a->b: is a in list(b)?  if not, row b grows by one (atomic count)
 //   3. exclusive scan    row lengths (own + mirrored + diagonal) -> indptr   (3-kernel block scan)
 //   4. fill              own edges at their slot, mirrored edges through an atomic cursor
 //   5. sort_rows         segmented sort by column (warp bitonic <= 64, block bitonic otherwise),
 //                        degree = sum of weights in ascending column order, values -> -w, diag -> deg
+//   6. normalise         (asp_switches.laplacian, UNPINNED): sym  L_ab = -w_ab / sqrt(deg_a deg_b), L_aa = [deg_a > 0]
+//                        rw   L_ab = -w_ab / deg_a; entries towards a node of degree 0 become explicit zeros
 // The atomics only decide slots inside a row; the sort makes the result deterministic.
 #include "common.cuh"
 
@@ -49,6 +53,32 @@ __device__ __forceinline__ bool list_contains(const int32_t *idx, int kk, const 
     for (int j = 0; j < c; ++j)
         if (idx[row * kk + j] == v) return true;
     return false;
+}
+
+// one-sided edges (a -> b with a not in list(b)): halved (avg) or marked dead with a negative weight (min)
+__global__ void symmetrise_mark_kernel(int64_t m, int kk, const int32_t *idx, double *val, const int32_t *cnt, int mode)
+{
+    const int64_t total = m * kk;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = e / kk;
+        if ((int)(e % kk) >= cnt[a]) continue;
+        if (list_contains(idx, kk, cnt, idx[e], (int32_t)a)) continue;
+        val[e] = (mode == ASP_SYM_AVG) ? 0.5 * val[e] : -1.0;
+    }
+}
+
+__global__ void drop_marked_kernel(int64_t m, int kk, int32_t *idx, double *val, int32_t *cnt)
+{
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < m; a += (int64_t)gridDim.x * blockDim.x) {
+        const int c = cnt[a];
+        int o = 0;
+        for (int j = 0; j < c; ++j) {
+            const double w = val[a * kk + j];
+            const int32_t b = idx[a * kk + j];
+            if (w >= 0.0) { idx[a * kk + o] = b; val[a * kk + o] = w; ++o; }
+        }
+        cnt[a] = o;
+    }
 }
 
 __global__ void count_mirror_kernel(int64_t m, int kk, const int32_t *idx, const int32_t *cnt, int32_t *extra)
@@ -118,7 +148,7 @@ __global__ void scan_add_kernel(int64_t m, int64_t *indptr, const int64_t *block
 }
 
 __global__ void fill_kernel(int64_t m, int kk, const int32_t *idx, const double *val, const int32_t *cnt,
-                            const int64_t *indptr, int32_t *cursor, int32_t *col, double *data)
+                            const int64_t *indptr, int32_t *cursor, int32_t *col, double *data, int mirror)
 {
     const int64_t total = m * kk;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -134,7 +164,7 @@ __global__ void fill_kernel(int64_t m, int kk, const int32_t *idx, const double 
         const double w = val[e];
         col[indptr[a] + j] = b;
         data[indptr[a] + j] = w;
-        if (!list_contains(idx, kk, cnt, b, (int32_t)a)) {
+        if (mirror && !list_contains(idx, kk, cnt, b, (int32_t)a)) {
             const int slot = atomicAdd(&cursor[b], 1);
             const int64_t pos = indptr[b] + cnt[b] + slot;
             col[pos] = (int32_t)a;
@@ -254,25 +284,34 @@ __global__ void sort_rows_block_kernel(const int64_t *long_rows, const int32_t *
     }
 }
 
-}  // namespace
-
-static void build_upper(asp_graph *g, std::vector<int32_t> &uptr, std::vector<int32_t> &ucol, std::vector<double> &uval,
-                        std::vector<double> &deg)
+__global__ void extract_degree_kernel(int64_t m, const int64_t *indptr, const int32_t *col, const double *data, double *deg)
 {
-    const int64_t m = g->nnodes;
-    uptr.assign(m + 1, 0);
-    deg.assign(m, 0.0);
-    ucol.clear();
-    uval.clear();
-    for (int64_t a = 0; a < m; ++a) {
-        for (int64_t j = g->h_indptr[a]; j < g->h_indptr[a + 1]; ++j) {
-            const int32_t c = g->h_indices[j];
-            if (c == a) deg[a] = g->h_data[j];
-            else if (c > a) { ucol.push_back(c); uval.push_back(-g->h_data[j]); }
+    for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < m; a += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t j = indptr[a]; j < indptr[a + 1]; ++j)
+            if (col[j] == (int32_t)a) deg[a] = data[j];
+}
+
+// one warp per row: the row's entries are rewritten from the degrees of both endpoints (oracle.c normalise_laplacian)
+__global__ void normalise_kernel(int64_t m, const int64_t *indptr, const int32_t *col, double *data, const double *deg, int mode)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t a = warp; a < m; a += nwarps) {
+        const double da = deg[a];
+        for (int64_t j = indptr[a] + lane; j < indptr[a + 1]; j += 32) {
+            const int32_t b = col[j];
+            if (b == (int32_t)a) { data[j] = da > 0.0 ? 1.0 : 0.0; continue; }
+            const double w = -data[j], db = deg[b];
+            double v = 0.0;
+            if (mode == ASP_LAPLACIAN_SYM) { if (da > 0.0 && db > 0.0) v = -__ddiv_rn(w, __dsqrt_rn(__dmul_rn(da, db))); }
+            else if (da > 0.0) v = -__ddiv_rn(w, da);
+            data[j] = v;
         }
-        uptr[a + 1] = (int32_t)ucol.size();
     }
 }
+
+}  // namespace
 
 int asp_graph_host_mirror(asp_graph *g)
 {
@@ -288,29 +327,6 @@ int asp_graph_host_mirror(asp_graph *g)
     return ASP_OK;
 }
 
-int asp_graph_upload_upper(asp_graph *g)
-{
-    asp_ctx *ctx = g->ctx;
-    ASP_CHECK(asp_graph_host_mirror(g));
-    std::vector<int32_t> uptr, ucol;
-    std::vector<double> uval, deg;
-    build_upper(g, uptr, ucol, uval, deg);
-    g->unnz = (int64_t)ucol.size();
-    const size_t un = ucol.size() > 0 ? ucol.size() : 1;
-    ASP_CUDA(cudaMallocAsync(&g->d_uptr, sizeof(int32_t) * (g->nnodes + 1), ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&g->d_ucol, sizeof(int32_t) * un, ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&g->d_uval, sizeof(double) * un, ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&g->d_deg, sizeof(double) * g->nnodes, ctx->stream));
-    ASP_CUDA(cudaMemcpyAsync(g->d_uptr, uptr.data(), sizeof(int32_t) * (g->nnodes + 1), cudaMemcpyHostToDevice, ctx->stream));
-    if (!ucol.empty()) {
-        ASP_CUDA(cudaMemcpyAsync(g->d_ucol, ucol.data(), sizeof(int32_t) * ucol.size(), cudaMemcpyHostToDevice, ctx->stream));
-        ASP_CUDA(cudaMemcpyAsync(g->d_uval, uval.data(), sizeof(double) * uval.size(), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    ASP_CUDA(cudaMemcpyAsync(g->d_deg, deg.data(), sizeof(double) * g->nnodes, cudaMemcpyHostToDevice, ctx->stream));
-    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
-    return ASP_OK;
-}
-
 int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_graph_params *gp, const asp_switches *sw,
                            asp_graph *g)
 {
@@ -322,6 +338,15 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
 
     weights_compact_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->dist, lists->cnt, sigma, gp->p, sw->kernel);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    if (sw->symmetrise == ASP_SYM_AVG || sw->symmetrise == ASP_SYM_MIN) {
+        symmetrise_mark_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->dist, lists->cnt, sw->symmetrise);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        if (sw->symmetrise == ASP_SYM_MIN) {
+            drop_marked_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->dist, lists->cnt);
+            ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        }
+    }
+    const int mirror = (sw->symmetrise == ASP_SYM_NONE || sw->symmetrise == ASP_SYM_MIN) ? 0 : 1;
 
     int32_t *extra = nullptr, *cursor = nullptr, *long_count = nullptr;
     int64_t *block_sums = nullptr, *total = nullptr, *long_rows = nullptr;
@@ -336,8 +361,10 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
     ASP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * m, st));
     ASP_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int32_t), st));
 
-    count_mirror_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->cnt, extra);
-    ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    if (mirror) {
+        count_mirror_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->cnt, extra);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+    }
 
     ASP_CUDA(cudaMallocAsync(&g->d_indptr, sizeof(int64_t) * (m + 1), st));
     scan_blocks_kernel<<<(unsigned)nblocks, SCAN_BLOCK, 0, st>>>(m, lists->cnt, extra, g->d_indptr, block_sums);
@@ -356,7 +383,7 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
     ASP_CUDA(cudaMallocAsync(&g->d_data, sizeof(double) * (nnz > 0 ? nnz : 1), st));
 
     fill_kernel<<<grid, 256, 0, st>>>(m, kk, lists->idx, lists->dist, lists->cnt, g->d_indptr, cursor, g->d_indices,
-                                      g->d_data);
+                                      g->d_data, mirror);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
 
     sort_rows_warp_kernel<<<grid, 256, 0, st>>>(m, g->d_indptr, g->d_indices, g->d_data, long_rows, long_count);
@@ -368,6 +395,16 @@ int asp_assemble_laplacian(asp_ctx *ctx, const asp_knn_lists *lists, const asp_g
     sort_rows_block_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(long_rows, long_count, g->d_indptr, g->d_indices, g->d_data,
                                                              scratch_col, scratch_w);
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+
+    if (sw->laplacian != ASP_LAPLACIAN_COMBINATORIAL) {
+        double *deg = nullptr;
+        ASP_CUDA(cudaMallocAsync(&deg, sizeof(double) * m, st));
+        extract_degree_kernel<<<grid, 256, 0, st>>>(m, g->d_indptr, g->d_indices, g->d_data, deg);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        normalise_kernel<<<grid, 256, 0, st>>>(m, g->d_indptr, g->d_indices, g->d_data, deg, sw->laplacian);
+        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
+        ASP_CUDA(cudaFreeAsync(deg, st));
+    }
 
     ASP_CUDA(cudaFreeAsync(scratch_col, st));
     ASP_CUDA(cudaFreeAsync(scratch_w, st));

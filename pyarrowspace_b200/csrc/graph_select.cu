@@ -14,6 +14,11 @@
 //                 exact values fills the remaining slots (proof in DESIGN.md).
 // The band is always derived from the approximate values only, so the request set is the same
 // on every pass and the host loop terminates after at most three passes.
+//
+// Distance variants (asp_switches.distance, an UNPINNED choice of SURVEY.md 8(c)): besides the documented rectified cosine
+// (GRAPH_VARIABLES.md:7) the Gram-form Euclidean distance d^2 = <a,a> + <b,b> - 2<a,b> (clamped at 0) and its square
+// root.  Their rounding band is per pair, 2 rel (<a,a> + <b,b>) on d^2 (and d~ - sqrt(d~^2 - band) on d); the
+// row uses the largest band of its pairs, which keeps the uniform-band argument above valid.
 #include "common.cuh"
 
 #include <math.h>
@@ -45,13 +50,40 @@ __device__ void block_bitonic_sort(Key *keys, int p2)
     __syncthreads();
 }
 
-// exact d from left-to-right sums, the oracle's own expression (oracle.c select_neighbours)
-__device__ __forceinline__ double exact_distance(double sab, double saa, double sbb)
+// exact d from left-to-right sums, the oracle's own expression (oracle.c node_distance)
+__device__ __forceinline__ double exact_distance(double sab, double saa, double sbb, int distance)
 {
+    if (distance != ASP_DISTANCE_COSINE) {
+        double d2 = __dsub_rn(__dadd_rn(saa, sbb), __dmul_rn(2.0, sab));
+        if (!(d2 > 0.0)) d2 = 0.0;
+        return distance == ASP_DISTANCE_L2 ? __dsqrt_rn(d2) : d2;
+    }
     const double na = __dsqrt_rn(saa), nb = __dsqrt_rn(sbb);
     double c = 0.0;
     if (na != 0.0 && nb != 0.0) c = __ddiv_rn(sab, __dmul_rn(na, nb));
     return __dsub_rn(1.0, c > 0.0 ? c : 0.0);
+}
+
+// approximate distance of the pair from the (DMMA) Gram + the band that contains the oracle's value
+__device__ __forceinline__ double approx_distance(double gab, double gaa, double gbb, int distance, double rel, double *band,
+                                                  bool *surely_one)
+{
+    *surely_one = false;
+    if (distance != ASP_DISTANCE_COSINE) {
+        double d2 = (gaa + gbb) - 2.0 * gab;
+        if (!(d2 > 0.0)) d2 = 0.0;
+        const double b2 = rel * 2.0 * (gaa + gbb) + 1e-300;       // 2 sum|x_a x_b| <= <a,a> + <b,b>
+        if (distance == ASP_DISTANCE_L2SQ) { *band = b2; return d2; }
+        const double d = sqrt(d2), lo2 = d2 - b2;
+        *band = (d - (lo2 > 0.0 ? sqrt(lo2) : 0.0)) * (1.0 + 1e-12) + 8.0 * 1.1102230246251565e-16 * d + 1e-300;
+        return d;
+    }
+    *band = rel;
+    const double na = sqrt(gaa), nb = sqrt(gbb);
+    if (na == 0.0 || nb == 0.0) { *surely_one = true; return 1.0; }
+    const double c = gab / (na * nb);
+    if (c < -rel) *surely_one = true;                                   // surely rectified: d == 1 exactly
+    return 1.0 - (c > 0.0 ? c : 0.0);
 }
 
 __device__ int find_exact(const int32_t *pairs, int64_t n, int a, int b)
@@ -74,8 +106,8 @@ __device__ void emit_need(int a, int b, int32_t *need_pairs, int64_t need_cap, i
     if (slot < need_cap) { need_pairs[2 * slot] = a; need_pairs[2 * slot + 1] = b; }
 }
 
-// One block per node a.  smem: Key keys[p2]; double vexact[f] (NaN = none); unsigned char flags[f]
-__global__ void feature_select_kernel(const double *__restrict__ gram, int f, double eps, int kk, double delta,
+// One block per node a.  smem: Key keys[p2]; double vexact[f] (NaN = none)
+__global__ void feature_select_kernel(const double *__restrict__ gram, int f, double eps, int kk, double rel, int distance,
                                       const int32_t *__restrict__ exact_pairs, const double *__restrict__ exact_sums,
                                       int64_t n_exact, int p2, int32_t *__restrict__ out_idx,
                                       double *__restrict__ out_dist, int32_t *__restrict__ out_cnt,
@@ -86,33 +118,41 @@ __global__ void feature_select_kernel(const double *__restrict__ gram, int f, do
     double *vexact = reinterpret_cast<double *>(keys + p2);
     __shared__ int s_incomplete, s_cnt, s_band;
     __shared__ double s_T;
+    __shared__ unsigned long long s_delta;
 
     const int a = blockIdx.x;
-    if (threadIdx.x == 0) { s_incomplete = 0; s_cnt = 0; s_band = 0; }
+    if (threadIdx.x == 0) { s_incomplete = 0; s_cnt = 0; s_band = 0; s_delta = 0ull; }
     __syncthreads();
 
     const double gaa = gram[(size_t)a * f + a];
-    const double na = sqrt(gaa);
+
+    // ---- A0: the row's band = the largest band of its pairs (non-negative doubles order like their bit patterns)
+    double delta = rel;
+    if (distance != ASP_DISTANCE_COSINE) {
+        double mx = 0.0;
+        for (int b = threadIdx.x; b < f; b += blockDim.x) {
+            if (b == a) continue;
+            double band; bool one;
+            approx_distance(gram[(size_t)a * f + b], gaa, gram[(size_t)b * f + b], distance, rel, &band, &one);
+            mx = fmax(mx, band);
+        }
+        atomicMax(&s_delta, (unsigned long long)__double_as_longlong(mx));
+        __syncthreads();
+        delta = __longlong_as_double((long long)s_delta);
+    }
 
     // ---- A: approximate distance, exact value if known, eps status
     for (int b = threadIdx.x; b < p2; b += blockDim.x) {
         Key k; k.d = INFINITY; k.idx = 0x7fffffff;
         if (b < f) vexact[b] = NAN;
         if (b < f && b != a) {
-            const double gbb = gram[(size_t)b * f + b];
-            const double nb = sqrt(gbb);
-            double c = 0.0;
+            double band;
             bool known = false;          // exact value known without a resolve pass
-            double dex = NAN;
-            if (na == 0.0 || nb == 0.0) { known = true; dex = 1.0; }
-            else {
-                c = gram[(size_t)a * f + b] / (na * nb);
-                if (c < -delta) { known = true; dex = 1.0; }     // surely rectified: d == 1 exactly
-            }
-            const double dap = 1.0 - (c > 0.0 ? c : 0.0);
+            const double dap = approx_distance(gram[(size_t)a * f + b], gaa, gram[(size_t)b * f + b], distance, rel, &band, &known);
+            double dex = known ? 1.0 : NAN;
             if (!known && n_exact > 0) {
                 const int e = find_exact(exact_pairs, n_exact, a, b);
-                if (e >= 0) { known = true; dex = exact_distance(exact_sums[3 * e], exact_sums[3 * e + 1], exact_sums[3 * e + 2]); }
+                if (e >= 0) { known = true; dex = exact_distance(exact_sums[3 * e], exact_sums[3 * e + 1], exact_sums[3 * e + 2], distance); }
             }
             bool in;
             if (known) in = (dex <= eps);
@@ -198,13 +238,11 @@ __global__ void exact_pairs_kernel(const double *__restrict__ items, int64_t n_l
 }  // namespace
 
 int asp_feature_select(asp_ctx *ctx, const double *gram_dev, int32_t f, int64_t n_total, const asp_graph_params *gp,
-                       const int32_t *exact_pairs_dev, const double *exact_sums_dev, int64_t n_exact,
+                       const asp_switches *sw, const int32_t *exact_pairs_dev, const double *exact_sums_dev, int64_t n_exact,
                        asp_knn_lists *lists, int32_t *need_pairs_dev, int64_t need_cap, int32_t *need_count_dev)
 {
     if (f > 8192) ASP_FAIL(ASP_ERR_UNSUPPORTED, "feature graph supports at most 8192 features (got %d)", f);
-    int64_t kk = gp->k;
-    if (kk > f - 1) kk = f - 1;
-    if (kk < 0) kk = 0;
+    const int64_t kk = asp_neighbour_cap(gp, sw, f);
     lists->m = f;
     lists->kk = (int32_t)(kk > 0 ? kk : 1);
     ASP_CUDA(cudaMallocAsync(&lists->idx, sizeof(int32_t) * (size_t)f * lists->kk, ctx->stream));
@@ -222,7 +260,7 @@ int asp_feature_select(asp_ctx *ctx, const double *gram_dev, int32_t f, int64_t 
     while (p2 < f) p2 <<= 1;
     const size_t smem = (size_t)p2 * sizeof(Key) + (size_t)f * sizeof(double);
     ASP_CUDA(cudaFuncSetAttribute(feature_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    feature_select_kernel<<<f, 256, smem, ctx->stream>>>(gram_dev, f, gp->eps, (int)kk, delta, exact_pairs_dev,
+    feature_select_kernel<<<f, 256, smem, ctx->stream>>>(gram_dev, f, gp->eps, (int)kk, delta, sw ? sw->distance : 0, exact_pairs_dev,
                                                          exact_sums_dev, n_exact, p2, lists->idx, lists->dist,
                                                          lists->cnt, need_pairs_dev, need_cap, need_count_dev);
     ASP_CUDA(cudaGetLastError());

@@ -1,39 +1,66 @@
 // taumode.cu -- K3: per-vector taumode lambda (items at build time, queries at search time).
-//   E = x^T L x / x^T x,  tau = max(median(x), 1e-9),  lambda = E / (E + tau)
-// (TAUMODE.md:18-19,24-25; replaces the lambda pass of
-// ArrowSpaceBuilder::build and ArrowSpace::prepare_query_item, /root/reference/src/lib.rs:289,154).
+//   E = x^T L x / x^T x,  tau = max(median(x), 1e-9),  lambda = E / (E + tau)          (bounded form)
+//   lambda = tau * E/(E+tau) + (1 - tau) * G(x),  G = clamp(sum e_ab^2 / (sum e_ab)^2)  (synthetic form, TAUMODE.md:8,26-27)
+// (TAUMODE.md:18-19,24-27; replaces the lambda pass of ArrowSpaceBuilder::build and
+// ArrowSpace::prepare_query_item, /root/reference/src/lib.rs:289,154).
 //
-// Formulation: L = D - W is symmetric, so  x^T L x = sum_a x_a (deg_a x_a - 2 sum_{b>a} w_ab x_b):
-// only the strictly-upper adjacency is walked (half the gathers of a CSR SpMM).
-// Bound: HBM (8*n*f bytes, X read once) while nnz(L)/f is small; for k = 25 the gathers from the
-// shared-memory X tile dominate (8 bytes per nonzero per item) -- see DESIGN.md.
+// Formulation.  For ANY square L,  x^T L x = sum_a x_a (L_aa x_a - 2 sum_{b>a} c_ab x_b)  with  c_ab = -(L_ab + L_ba) / 2
+// (the symmetrised quadratic form; c_ab = w_ab for the combinatorial Laplacian).  Only these strictly-upper coefficients
+// are walked: half the gathers of a CSR SpMM, and the random-walk / unsymmetrised Laplacians of the unpinned switches
+// need no second code path.
 //
-// Two kernels:
-//  median_kernel   one warp per vector, order-preserving 64-bit keys in registers, MSB-first radix selection through a
-//                  256-bin shared-memory histogram per warp (2-3 passes for F = 384); streaming, high occupancy
-//  taumode_kernel  CTA = 256 threads, one tile of T = 16*R items at a time, grid-stride (persistent):
-//   A. warp w loads item rows (coalesced) and stores them transposed into shared memory
-//      xs[feature][item] (row stride T+1: conflict free both ways)
-//   A' thread t < T: left-to-right sum of squares (the norm the search kernel divides by; same
-//      order as the oracle) and, for tau_mode = mean, the left-to-right sum
-//   B. thread (part p = tid/16, lane-group g = tid%16) owns items g+16r (r < R) and the graph rows
-//      a = p, p+16, ...; the upper adjacency is staged through shared memory in chunks; each
-//      nonzero costs one broadcast LDS (col, weight) and R conflict-free LDS.64 of x
-//   C. the 16 partial energies of an item are summed in part order; E, tau, lambda written.
+// ONE kernel, one pass over X (round 1 had a separate median kernel that read X a second time):
+//   CTA = THR compute threads + 8 auxiliary warps + 1 producer warp, persistent over tiles of T = 16*R vectors.
+//   compute warps   A. load the tile's rows (coalesced, two rows in flight per warp) and store them transposed into shared
+//                      memory xs[feature][item] (row stride T+1: conflict free both ways)
+//                   B. walk the graph: a (part p = tid/16, lane group g = tid%16) pair owns items g+16r (r < R) and the row
+//                      pieces p, p+NP, ... of the current graph chunk; per FOUR non-zeros: one 8-byte load of 4 columns, two
+//                      16-byte loads of 4 coefficients (broadcasts), 4*R conflict-free 8-byte gathers of x
+//                   C. partial energies: half-warp pairs by shuffle, warps through shared memory in warp order
+//   auxiliary warps the per-vector median (tau) from the rows in L2 -- selection on order-preserving 64-bit keys, either
+//                      ALU-only (packed counters + warp reductions: no shared-memory traffic, the gathers own that pipe) or
+//                      through a shared-memory histogram (ASP_TM_MEDIAN=hist) -- and the left-to-right sums of squares (the
+//                      norm the search divides by, the oracle's order; one thread per item)
+//   producer warp   streams the graph, pre-cut into fixed-size chunks (cp.async.bulk + mbarrier, two buffers), and asks L2
+//                      for the next tile's rows (cp.async.bulk.prefetch.L2) so that phase A finds them there
+// Bound: HBM 8*n*f bytes while nnz(L)/f is small; at k = 25 (nnz/f = 41) the 8-byte shared-memory
+// gather per upper non-zero per item binds (128 B/clk/SM), see DESIGN.md section 4.
+//
+// Vectors longer than 1500 features do not fit a transposed tile: taumode_wide_kernel (one CTA per vector, the row in
+// shared memory, block-wide selection) covers them up to 16384 features.
 #include "common.cuh"
+#include "ptx.cuh"
 
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 
 namespace {
 
-constexpr int CH_NNZ_MAX = 1536; // upper-adjacency entries staged per chunk (>= longest row); per-variant value CHN below
-constexpr int CH_ROWS = 256;
 constexpr double TAU_FLOOR = 1e-9;
 
-struct TmChunk { int row_begin; int row_end; };
+// ---- graph blob: row pieces of the upper coefficients in fixed-size chunks (one bulk copy each)
+constexpr int TM_PIECE = 16;                                 // entries per row piece (multiple of 4)
+constexpr int TM_CH_ENT = 512;                               // entries per chunk
+constexpr int TM_CH_ROWS = 64;                               // pieces per chunk
+constexpr int TM_OFF_W = 0;                                  // double  [TM_CH_ENT]   coefficient c_ab
+constexpr int TM_OFF_COL = TM_OFF_W + TM_CH_ENT * 8;         // uint16  [TM_CH_ENT]   column b
+constexpr int TM_OFF_DIAG = TM_OFF_COL + TM_CH_ENT * 2;      // double  [TM_CH_ROWS]  L_aa on the first piece of a row, else 0
+constexpr int TM_OFF_PIECE = TM_OFF_DIAG + TM_CH_ROWS * 8;   // uint16x4[TM_CH_ROWS]  {row a, first entry, end entry, 0}
+constexpr int TM_OFF_HDR = TM_OFF_PIECE + TM_CH_ROWS * 8;    // int32   [4]           {pieces in this chunk, 0, 0, 0}
+constexpr int TM_CHUNK_BYTES = TM_OFF_HDR + 16;
+static_assert(TM_CHUNK_BYTES % 16 == 0 && TM_OFF_COL % 16 == 0 && TM_OFF_DIAG % 16 == 0, "bulk copies move 16-byte units");
+constexpr int TM_AUX_WARPS = 8;
 
-// ---- radix selection on order-preserving 64-bit keys (the streaming median kernel below)
+struct TmBlob {
+    void *d_chunks = nullptr;
+    int nchunks = 0;
+    // plain upper CSR + diagonal of the same form, for taumode_wide_kernel
+    int32_t *d_uptr = nullptr, *d_ucol = nullptr;
+    double *d_uval = nullptr, *d_diag = nullptr;
+};
+
+// ---- order-preserving 64-bit keys
 // key(x) is monotone in x for every non-NaN double (-0.0 is folded into +0.0 first); absent elements carry the largest key.
 __device__ __forceinline__ unsigned long long f64_key(double x)
 {
@@ -46,15 +73,10 @@ __device__ __forceinline__ double key_f64(unsigned long long k)
     return __longlong_as_double((long long)b);
 }
 
-// rank-th smallest key (0-based) of the n present keys held as k[j] of lane l = element l + 32 j.  MSB-first radix
-// selection, 8 bits per pass through a 256-bin histogram in shared memory (one per warp); the bytes all present keys
-// share are skipped (embeddings of one scale share sign, exponent and often the first mantissa bits), and the walk
-// stops as soon as the selected bin holds one key -- two or three passes for F = 384.  *count_le = number of keys <= result.
+// identical leading bits of the n present keys (64: all equal); k0 = key of element 0
 template <int FPL>
-__device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FPL], int n, int rank, int lane,
-                                                uint32_t *hist /* [256] of this warp */, int *count_le)
+__device__ __forceinline__ int warp_common_lead(const unsigned long long (&k)[FPL], int n, int lane, unsigned long long *k0_out)
 {
-    // common leading bytes
     uint32_t dhi = 0, dlo = 0;
     const unsigned long long k0 = __shfl_sync(0xffffffffu, k[0], 0);            // element 0 is always present
 #pragma unroll
@@ -66,17 +88,99 @@ __device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FP
     }
     dhi = __reduce_or_sync(0xffffffffu, dhi);
     dlo = __reduce_or_sync(0xffffffffu, dlo);
-    if ((dhi | dlo) == 0u) { *count_le = n; return k0; }                         // all keys equal
-    const int lead = dhi ? __clz(dhi) : 32 + __clz(dlo);                         // identical leading bits
-    // the first digit is the 8 most significant bits that VARY (not a byte boundary): the keys spread over all 256 bins,
-    // so the shared-memory atomics of the first -- and only populous -- pass hardly collide
+    *k0_out = k0;
+    if ((dhi | dlo) == 0u) return 64;
+    return dhi ? __clz(dhi) : 32 + __clz(dlo);
+}
+
+// the single key under (mask, prefix): fetched from the lane that holds it
+template <int FPL>
+__device__ __forceinline__ unsigned long long warp_fetch_unique(const unsigned long long (&k)[FPL], int n, int lane,
+                                                                unsigned long long mask, unsigned long long prefix)
+{
+    unsigned long long mine = 0ull;
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < FPL; ++j) {
+        const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
+        if (act) { mine = k[j]; have = true; }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, have)) - 1;
+    return __shfl_sync(0xffffffffu, mine, src);
+}
+
+// rank-th smallest key (0-based) of the n present keys held as k[j] of lane l = element l + 32 j.  MSB-first radix
+// selection, 4 bits per pass, NO shared memory: every lane counts its keys into sixteen 8-bit fields of two 64-bit
+// registers, eight warp reductions (redux.sync) add the lanes, every lane scans the 16 totals.  The bits all keys share
+// are skipped and the walk stops as soon as the selected bin holds one key (3-4 passes for F = 384).
+// *count_le = number of keys <= result.
+template <int FPL>
+__device__ unsigned long long warp_select_alu(const unsigned long long (&k)[FPL], int n, int rank, int lane, int *count_le)
+{
+    static_assert(FPL <= 255, "8-bit per-lane counters");
+    unsigned long long k0;
+    const int lead = warp_common_lead<FPL>(k, n, lane, &k0);
+    if (lead == 64) { *count_le = n; return k0; }
     const int top = 64 - lead;                                                   // low bits that may differ, >= 1
+    int shift = top > 4 ? top - 4 : 0;
+    int width = top - shift;
+    unsigned long long prefix = (top == 64) ? 0ull : (k0 >> top) << top;
+    unsigned long long mask = (top == 64) ? 0ull : ~0ull << top;
+    int below = 0, r = rank;
+    for (;;) {
+        unsigned long long ca = 0ull, cb = 0ull;                                 // bins 0-7 / 8-15, 8 bits each
+        const uint32_t dmask = (1u << width) - 1u;
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) {
+            const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
+            const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
+            const unsigned long long inc = act ? (1ull << (8 * (d & 7u))) : 0ull;
+            if (d & 8u) cb += inc; else ca += inc;
+        }
+        uint32_t c[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t wa = (uint32_t)((ca >> (16 * i)) & 0xffull) | ((uint32_t)((ca >> (16 * i + 8)) & 0xffull) << 16);
+            const uint32_t wb = (uint32_t)((cb >> (16 * i)) & 0xffull) | ((uint32_t)((cb >> (16 * i + 8)) & 0xffull) << 16);
+            const uint32_t ta = __reduce_add_sync(0xffffffffu, wa), tb = __reduce_add_sync(0xffffffffu, wb);
+            c[2 * i] = ta & 0xffffu; c[2 * i + 1] = ta >> 16;
+            c[8 + 2 * i] = tb & 0xffffu; c[8 + 2 * i + 1] = tb >> 16;
+        }
+        uint32_t run = 0, digit = 0, cnt = 0, before = 0;
+        bool found = false;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const bool here = !found && (run + c[b] > (uint32_t)r);
+            if (here) { digit = b; cnt = c[b]; before = run; found = true; }
+            run += c[b];
+        }
+        below += (int)before;
+        r -= (int)before;
+        prefix |= (unsigned long long)digit << shift;
+        mask |= (unsigned long long)dmask << shift;
+        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }         // cnt equal keys
+        if (cnt == 1u) { *count_le = below + 1; return warp_fetch_unique<FPL>(k, n, lane, mask, prefix); }
+        const int next = shift > 4 ? shift - 4 : 0;
+        width = shift - next;
+        shift = next;
+    }
+}
+
+// the same selection, 8 bits per pass through a 256-bin shared-memory histogram of the warp (round 1's median kernel);
+// kept for the A/B (ASP_TM_MEDIAN=hist): its shared-memory atomics compete with the gathers of the compute warps.
+template <int FPL>
+__device__ unsigned long long warp_select_hist(const unsigned long long (&k)[FPL], int n, int rank, int lane,
+                                               uint32_t *hist /* [256] of this warp */, int *count_le)
+{
+    unsigned long long k0;
+    const int lead = warp_common_lead<FPL>(k, n, lane, &k0);
+    if (lead == 64) { *count_le = n; return k0; }
+    const int top = 64 - lead;
     int shift = top > 8 ? top - 8 : 0;
     int width = top - shift;
     unsigned long long prefix = (top == 64) ? 0ull : (k0 >> top) << top;
     unsigned long long mask = (top == 64) ? 0ull : ~0ull << top;
-    int below = 0;                                                               // keys smaller than every key under the prefix
-    int r = rank;
+    int below = 0, r = rank;
     for (;;) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0u;
@@ -87,8 +191,7 @@ __device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FP
             if (act) atomicAdd(&hist[(uint32_t)(k[j] >> shift) & ((1u << width) - 1u)], 1u);
         }
         __syncwarp();
-        // lane l owns bins 8l .. 8l+7
-        uint32_t c[8];
+        uint32_t c[8];                                                           // lane l owns bins 8l .. 8l+7
         const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 8 * lane), h1 = *reinterpret_cast<const uint4 *>(hist + 8 * lane + 4);
         c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
         uint32_t tot = 0;
@@ -101,7 +204,7 @@ __device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FP
             if (lane >= off) incl += t;
         }
         const unsigned owners = __ballot_sync(0xffffffffu, incl > (uint32_t)r);
-        const int owner = __ffs(owners) - 1;                                     // first lane whose inclusive count exceeds r
+        const int owner = __ffs(owners) - 1;
         uint32_t run = incl - tot, digit = 0, cnt = 0, before = 0;
         if (lane == owner) {
             bool found = false;
@@ -119,32 +222,23 @@ __device__ unsigned long long warp_radix_select(const unsigned long long (&k)[FP
         r -= (int)before;
         prefix |= (unsigned long long)digit << shift;
         mask |= (unsigned long long)((1u << width) - 1u) << shift;
-        __syncwarp();                                                            // the histogram is reused by the next pass
-        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }         // cnt equal keys
-        if (cnt == 1u) {                                                         // one key left under the prefix: fetch it
-            unsigned long long mine = 0ull;
-            bool have = false;
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) {
-                const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
-                if (act) { mine = k[j]; have = true; }
-            }
-            const int src = __ffs(__ballot_sync(0xffffffffu, have)) - 1;
-            *count_le = below + 1;
-            return __shfl_sync(0xffffffffu, mine, src);
-        }
+        __syncwarp();
+        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }
+        if (cnt == 1u) { *count_le = below + 1; return warp_fetch_unique<FPL>(k, n, lane, mask, prefix); }
         const int next = shift > 8 ? shift - 8 : 0;
         width = shift - next;
         shift = next;
     }
 }
 
-template <int FPL>
-__device__ double warp_median_radix(const unsigned long long (&k)[FPL], int n, int lane, uint32_t *hist)
+// median of the n present keys: the middle one, or the mean of the two middle ones (oracle.c median_of)
+template <int FPL, bool HIST>
+__device__ double warp_median(const unsigned long long (&k)[FPL], int n, int lane, uint32_t *hist)
 {
     int cle = 0;
-    if (n & 1) return key_f64(warp_radix_select<FPL>(k, n, n / 2, lane, hist, &cle));
-    const unsigned long long klo = warp_radix_select<FPL>(k, n, n / 2 - 1, lane, hist, &cle);
+    const int r0 = (n & 1) ? n / 2 : n / 2 - 1;
+    const unsigned long long klo = HIST ? warp_select_hist<FPL>(k, n, r0, lane, hist, &cle) : warp_select_alu<FPL>(k, n, r0, lane, &cle);
+    if (n & 1) return key_f64(klo);
     unsigned long long khi = klo;
     if (cle < n / 2 + 1) {                   // the next order statistic is the smallest key > klo
         unsigned long long m = ~0ull;
@@ -158,262 +252,504 @@ __device__ double warp_median_radix(const unsigned long long (&k)[FPL], int n, i
         }
         khi = m;
     }
-    return 0.5 * (key_f64(klo) + key_f64(khi));   // oracle.c median_of: 0.5 * (s[n/2-1] + s[n/2])
+    return 0.5 * (key_f64(klo) + key_f64(khi));
 }
 
-// K3a: per-vector median (tau before flooring), one warp per vector, grid-stride.  A pure streaming pass with a small
-// footprint (1 KB of shared memory per warp, FPL 64-bit keys per lane): many resident warps hide the latency of the
-// selection, which the tile kernel below (1 CTA / SM, 222 KB of shared memory) cannot.
-// PF (ASP_MEDIAN_PREFETCH=1, not yet the default: written after the GPU budget of round 1 was spent): the row of the warp's
-// NEXT item is requested before the selection on the current one, so the loads -- 59 % of this kernel's stall samples -- overlap
-// the selection instead of preceding it.  Costs FPL more 64-bit registers (3 instead of 4 CTAs per SM at F <= 384).
-template <int FPL, bool PF>
-__global__ void __launch_bounds__(256, FPL <= 12 ? (PF ? 3 : 4) : 1)     // 64 registers: 32 warps per SM hide the selection's latency
-median_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, int use_abs, double *__restrict__ out_median)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {
-    __shared__ __align__(16) uint32_t s_hist[8][256];
-    const int lane = threadIdx.x & 31;
-    uint32_t *hist = s_hist[threadIdx.x >> 5];
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    double nv[FPL];                                                      // PF: the next item's values, in flight
-    if (PF && warp < n) {
-        const double *row = x + warp * pitch;
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; nv[j] = (ff < f) ? row[ff] : 0.0; }
-    }
-    for (int64_t item = warp; item < n; item += nwarps) {
-        const double *row = x + item * pitch;
-        unsigned long long k[FPL];
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) {
-            const int ff = lane + 32 * j;
-            double v = PF ? nv[j] : ((ff < f) ? row[ff] : 0.0);
-            if (use_abs) v = fabs(v);
-            k[j] = (ff < f) ? f64_key(v) : ~0ull;
-        }
-        if (PF && item + nwarps < n) {
-            const double *nrow = x + (item + nwarps) * pitch;
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; nv[j] = (ff < f) ? nrow[ff] : 0.0; }
-        }
-        const double med = warp_median_radix<FPL>(k, f, lane, hist);
-        if (lane == 0) out_median[item] = med;
-    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(asp::smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(asp::smem_u32(bar))
+                 : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_sync(int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"n"(ID), "r"(nthreads) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void named_arrive(int nthreads) { asm volatile("bar.arrive %0, %1;\n" ::"n"(ID), "r"(nthreads) : "memory"); }
 
-// THR compute threads + AUXW auxiliary warps.  The left-to-right sums of phase A' are one dependent chain per item (the
-// oracle's order), i.e. T busy threads for ~10 us per tile; they run on the auxiliary warps WHILE the compute warps walk
-// the graph (phase B only needs the transposed tile), and meet them again at the reduction (phase C).
-template <int R>
-struct TmAux { static constexpr int T = 16 * R; static constexpr int WARPS = (T + 31) / 32; };
-
-template <int FPL, int R, int CHN, int THR, bool PF>
-__global__ void __launch_bounds__(THR + 32 * TmAux<R>::WARPS, 1)
-taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
-               const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ deg,
-               const TmChunk *__restrict__ chunks, int nchunks, int tau_mode, double tau_fixed,
-               const double *__restrict__ medians, double *__restrict__ out_energy, double *__restrict__ out_tau, double *__restrict__ out_lambda,
-               double *__restrict__ out_norm, double *__restrict__ out_inv_norm, int *zero_flag)
+template <int FPL, int R, int THR, bool SYN, bool HIST>
+__global__ void __launch_bounds__(THR + 32 * TM_AUX_WARPS + 32, 1)
+taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const unsigned char *__restrict__ blob, int nchunks,
+               int tau_mode, double tau_fixed, double *__restrict__ out_energy, double *__restrict__ out_tau,
+               double *__restrict__ out_lambda, double *__restrict__ out_norm, double *__restrict__ out_inv_norm, int *zero_flag)
 {
     constexpr int T = 16 * R;
     constexpr int XS = T + 1;
+    constexpr int NW = THR / 32;                                       // compute warps
+    constexpr int NP = THR / 16;                                       // parts: row pieces in flight
+    constexpr int NAUX = 32 * TM_AUX_WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *xs = reinterpret_cast<double *>(smem_raw);                 // f * XS
-    double *s_val = xs + (size_t)f * XS;                               // CHN   (aliased by red[(THR / 16)][T])
-    int32_t *s_col = reinterpret_cast<int32_t *>(s_val + CHN);         // CHN
-    int32_t *s_rptr = s_col + CHN;                                     // CH_ROWS + 1
-    double *s_deg = reinterpret_cast<double *>(s_rptr + CH_ROWS + 2);  // CH_ROWS
-    double *s_tau = s_deg + CH_ROWS;                                   // T
-    double *s_n2 = s_tau + T;                                          // T
-    double *red = s_val;
+    double *xs = reinterpret_cast<double *>(smem_raw);                                          // f * XS
+    unsigned char *cbuf = smem_raw + (((size_t)f * XS * 8 + 15) & ~(size_t)15);               // 2 * TM_CHUNK_BYTES
+    double *red = reinterpret_cast<double *>(cbuf + 2 * TM_CHUNK_BYTES);                        // NW * T
+    double *s_tau = red + NW * T;                                                               // T
+    double *s_n2 = s_tau + T;                                                                   // T
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_n2 + T);                                  // HIST: TM_AUX_WARPS * 256
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
 
-    const bool is_aux = threadIdx.x >= THR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = threadIdx.x & 15, p = threadIdx.x >> 4;
+    const bool is_compute = threadIdx.x < THR;
+    const bool is_aux = !is_compute && threadIdx.x < THR + NAUX;
     const int64_t ntiles = (n + T - 1) / T;
-    auto compute_sync = []() { asm volatile("bar.sync 1, %0;\n" ::"n"(THR) : "memory"); };   // the compute warps only
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) { asp::mbar_init(&full_bar[b], 1); asp::mbar_init(&empty_bar[b], NW); }
+        asp::fence_barrier_init();
+    }
+    __syncthreads();
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t item0 = tile * T;
-        __syncthreads();                                               // previous tile fully consumed
-
-        // ---- A: load, transpose into shared memory (compute warps)
-        if (!is_aux) {
-            for (int t = warp; t < T; t += THR / 32) {
-                const int64_t item = item0 + t;
-                double v[FPL];
-                if (item < n) {
-                    const double *row = x + item * pitch;
-#pragma unroll
-                    for (int j = 0; j < FPL; ++j) {
-                        const int ff = lane + 32 * j;
-                        v[j] = (ff < f) ? row[ff] : INFINITY;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < FPL; ++j) v[j] = (lane + 32 * j < f) ? 0.0 : INFINITY;
+    if (!is_compute && !is_aux) {
+        // ===================== producer warp: graph chunks + L2 prefetch of the next tile's rows =====================
+        if (lane == 0) {
+            int64_t it = 0;
+            const bool can_prefetch = ((pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t nxt = tile + gridDim.x;
+                if (can_prefetch && nxt < ntiles) {
+                    const int64_t i0 = nxt * T, i1 = (i0 + T < n) ? i0 + T : n;
+                    bulk_prefetch_l2(x + i0 * pitch, (uint32_t)((i1 - i0) * pitch * 8));
                 }
-#pragma unroll
-                for (int j = 0; j < FPL; ++j) {
-                    const int ff = lane + 32 * j;
-                    if (ff < f) xs[ff * XS + t] = v[j];
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int b = (int)(it & 1);
+                    asp::mbar_wait(&empty_bar[b], (uint32_t)(((it >> 1) & 1) ^ 1));
+                    asp::mbar_arrive_expect_tx(&full_bar[b], TM_CHUNK_BYTES);
+                    bulk_g2s(cbuf + b * TM_CHUNK_BYTES, blob + (size_t)c * TM_CHUNK_BYTES, TM_CHUNK_BYTES, &full_bar[b]);
                 }
             }
         }
-        __syncthreads();
+        return;
+    }
 
-        double en[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) en[r] = 0.0;
+    const int g = threadIdx.x & 15, p = threadIdx.x >> 4;               // compute: lane group / part
+    const int aw = warp - NW;                                           // auxiliary warp index
+    int64_t it = 0;                                                     // chunk sequence number (compute warps)
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t item0 = tile * T;
         if (is_aux) {
-            // ---- A': left-to-right sums (norm^2; mean), one thread per item
-            const int t = threadIdx.x - THR;
-            if (t < T) {
-                double n2 = 0.0, sm = 0.0;
-#pragma unroll 8
-                for (int ff = 0; ff < f; ++ff) {                       // loads and products run ahead; only the adds are a chain
-                    const double xv = xs[ff * XS + t];
-                    n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
-                    sm = __dadd_rn(sm, xv);
+            // ---- tau (median / mean / fixed) of this warp's items, rows read from L2; independent of the transposed tile
+            for (int t = aw; t < T; t += TM_AUX_WARPS) {
+                const int64_t item = item0 + t;
+                double tau = 1.0;
+                if (item < n) {
+                    if (tau_mode == ASP_TAU_MEDIAN || tau_mode == ASP_TAU_MEDIAN_ABS) {
+                        const double *row = x + item * pitch;
+                        unsigned long long k[FPL];
+#pragma unroll
+                        for (int j = 0; j < FPL; ++j) {
+                            const int ff = lane + 32 * j;
+                            double v = (ff < f) ? asp::ld_nc_f64(row + ff) : 0.0;
+                            if (tau_mode == ASP_TAU_MEDIAN_ABS) v = fabs(v);
+                            k[j] = (ff < f) ? f64_key(v) : ~0ull;
+                        }
+                        tau = warp_median<FPL, HIST>(k, f, lane, HIST ? s_hist + aw * 256 : nullptr);
+                    } else if (tau_mode == ASP_TAU_FIXED) {
+                        tau = tau_fixed;
+                    }
                 }
-                s_n2[t] = n2;
-                double tau;
-                if (tau_mode == ASP_TAU_MEAN) tau = sm / (double)f;
-                else if (tau_mode == ASP_TAU_FIXED) tau = tau_fixed;
-                else tau = (item0 + t < n) ? medians[item0 + t] : 1.0;
-                s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
+                if (lane == 0 && tau_mode != ASP_TAU_MEAN) s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
+            }
+            // ---- left-to-right sums (norm^2; mean), one thread per item, once the transposed tile is complete
+            const int t = threadIdx.x - THR;
+            if (t < ((T + 31) & ~31)) {
+                named_sync<3>(THR + ((T + 31) & ~31));
+                if (t < T) {
+                    double n2 = 0.0, sm = 0.0;
+#pragma unroll 8
+                    for (int ff = 0; ff < f; ++ff) {                   // loads and products run ahead; only the adds are a chain
+                        const double xv = xs[ff * XS + t];
+                        n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
+                        sm = __dadd_rn(sm, xv);
+                    }
+                    s_n2[t] = n2;
+                    if (tau_mode == ASP_TAU_MEAN) { const double tau = sm / (double)f; s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR; }
+                }
             }
         } else {
-            // ---- B: x^T L x through the strictly-upper adjacency
-            // PF (ASP_TM_PREFETCH=1, not yet the default: written after the GPU budget of round 1 was spent): the adjacency of
-            // chunk c+1 is fetched into registers while chunk c is walked, so the L2 round trip of the staging -- 24 % of this
-            // kernel's stall samples -- is no longer exposed between two barriers.
-            constexpr int NPF = (CHN + THR - 1) / THR;
-            int32_t pf_col[NPF], pf_rptr = 0;
-            double pf_val[NPF], pf_deg = 0.0;
-            int pf_ra0 = 0, pf_ra1 = 0, pf_e0 = 0, pf_e1 = 0;
-            auto fetch = [&](int c) {
-                pf_ra0 = chunks[c].row_begin; pf_ra1 = chunks[c].row_end;
-                pf_e0 = uptr[pf_ra0]; pf_e1 = uptr[pf_ra1];
+            // ---- A: rows -> transposed tile, two rows in flight per warp (one when a row is more than 24 registers wide)
+            constexpr bool TWO = FPL <= 24;
+            for (int t0 = warp; t0 < T; t0 += (TWO ? 2 : 1) * NW) {
+                const int t1 = t0 + NW;
+                double v0[FPL], v1[TWO ? FPL : 1];
+                const bool in0 = item0 + t0 < n, in1 = TWO && (t1 < T) && (item0 + t1 < n);
+                const double *row0 = x + (item0 + t0) * pitch, *row1 = x + (item0 + t1) * pitch;
 #pragma unroll
-                for (int u = 0; u < NPF; ++u) {
-                    const int i = (int)threadIdx.x + u * THR;
-                    if (i < pf_e1 - pf_e0) { pf_col[u] = ucol[pf_e0 + i]; pf_val[u] = uval[pf_e0 + i]; }
+                for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; v0[j] = (in0 && ff < f) ? row0[ff] : 0.0; }
+                if constexpr (TWO) {
+#pragma unroll
+                    for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; v1[j] = (in1 && ff < f) ? row1[ff] : 0.0; }
                 }
-                if ((int)threadIdx.x <= pf_ra1 - pf_ra0) pf_rptr = uptr[pf_ra0 + threadIdx.x] - pf_e0;
-                if ((int)threadIdx.x < pf_ra1 - pf_ra0) pf_deg = deg[pf_ra0 + threadIdx.x];
-            };
-            if (PF) fetch(0);
-            for (int c = 0; c < nchunks; ++c) {
-                int ra0, ra1;
-                if (PF) {
-                    ra0 = pf_ra0; ra1 = pf_ra1;
-                    const int ne = pf_e1 - pf_e0;
-                    compute_sync();                                    // the previous chunk is consumed
 #pragma unroll
-                    for (int u = 0; u < NPF; ++u) {
-                        const int i = (int)threadIdx.x + u * THR;
-                        if (i < ne) { s_col[i] = pf_col[u]; s_val[i] = pf_val[u]; }
+                for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; if (ff < f) xs[ff * XS + t0] = v0[j]; }
+                if constexpr (TWO) {
+                    if (t1 < T) {
+#pragma unroll
+                        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; if (ff < f) xs[ff * XS + t1] = v1[j]; }
                     }
-                    if ((int)threadIdx.x <= ra1 - ra0) s_rptr[threadIdx.x] = pf_rptr;
-                    if ((int)threadIdx.x < ra1 - ra0) s_deg[threadIdx.x] = pf_deg;
-                    if (c + 1 < nchunks) fetch(c + 1);                 // in flight during the walk below
-                } else {
-                    ra0 = chunks[c].row_begin; ra1 = chunks[c].row_end;
-                    const int e0 = uptr[ra0], e1 = uptr[ra1];
-                    compute_sync();
-                    for (int i = threadIdx.x; i < e1 - e0; i += THR) { s_col[i] = ucol[e0 + i]; s_val[i] = uval[e0 + i]; }
-                    for (int i = threadIdx.x; i <= ra1 - ra0; i += THR) s_rptr[i] = uptr[ra0 + i] - e0;
-                    for (int i = threadIdx.x; i < ra1 - ra0; i += THR) s_deg[i] = deg[ra0 + i];
                 }
-                compute_sync();
-                for (int a = ra0 + p; a < ra1; a += (THR / 16)) {
+            }
+            named_sync<1>(THR);                                        // the tile is complete (compute warps)
+            named_arrive<3>(THR + ((T + 31) & ~31));                   // ... and the norm threads may start
+
+            // ---- B: x^T L x through the upper coefficients, chunk by chunk
+            double en[R], tot[SYN ? R : 1], sq[SYN ? R : 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) en[r] = 0.0;
+#pragma unroll
+            for (int r = 0; r < (SYN ? R : 1); ++r) { tot[r] = 0.0; sq[r] = 0.0; }
+            const double *xg = xs + g;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int b = (int)(it & 1);
+                asp::mbar_wait(&full_bar[b], (uint32_t)((it >> 1) & 1));
+                const unsigned char *cb = cbuf + b * TM_CHUNK_BYTES;
+                const double *cw = reinterpret_cast<const double *>(cb + TM_OFF_W);
+                const uint16_t *cc = reinterpret_cast<const uint16_t *>(cb + TM_OFF_COL);
+                const double *cdiag = reinterpret_cast<const double *>(cb + TM_OFF_DIAG);
+                const uint2 *cpiece = reinterpret_cast<const uint2 *>(cb + TM_OFF_PIECE);
+                const int npieces = *reinterpret_cast<const int *>(cb + TM_OFF_HDR);
+                for (int slot = p; slot < npieces; slot += NP) {
+                    const uint2 pc = cpiece[slot];
+                    const int a = (int)(pc.x & 0xffffu), jb = (int)(pc.x >> 16), je = (int)(pc.y & 0xffffu);
                     double xa[R], s[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) { xa[r] = xs[a * XS + g + 16 * r]; s[r] = 0.0; }
-                    const int jb = s_rptr[a - ra0], je = s_rptr[a - ra0 + 1];
-                    for (int j = jb; j < je; ++j) {
-                        const int b = s_col[j];
-                        const double w = s_val[j];
+                    for (int r = 0; r < R; ++r) { xa[r] = xg[a * XS + 16 * r]; s[r] = 0.0; }
+                    for (int j = jb; j < je; j += 4) {
+                        const uint2 c4 = *reinterpret_cast<const uint2 *>(cc + j);
+                        const double2 w01 = *reinterpret_cast<const double2 *>(cw + j), w23 = *reinterpret_cast<const double2 *>(cw + j + 2);
+                        const double *x0 = xg + (int)(c4.x & 0xffffu) * XS, *x1 = xg + (int)(c4.x >> 16) * XS;
+                        const double *x2 = xg + (int)(c4.y & 0xffffu) * XS, *x3 = xg + (int)(c4.y >> 16) * XS;
 #pragma unroll
-                        for (int r = 0; r < R; ++r) s[r] = fma(w, xs[b * XS + g + 16 * r], s[r]);
+                        for (int r = 0; r < R; ++r) {
+                            const double b0 = x0[16 * r], b1 = x1[16 * r], b2 = x2[16 * r], b3 = x3[16 * r];
+                            s[r] = fma(w01.x, b0, s[r]);
+                            s[r] = fma(w01.y, b1, s[r]);
+                            s[r] = fma(w23.x, b2, s[r]);
+                            s[r] = fma(w23.y, b3, s[r]);
+                            if (SYN) {                                 // edgewise Dirichlet energies e = c (x_a - x_b)^2
+                                const double d0 = xa[r] - b0, d1 = xa[r] - b1, d2 = xa[r] - b2, d3 = xa[r] - b3;
+                                const double e0 = w01.x * d0 * d0, e1 = w01.y * d1 * d1, e2 = w23.x * d2 * d2, e3 = w23.y * d3 * d3;
+                                tot[r] += (e0 + e1) + (e2 + e3);
+                                sq[r] = fma(e0, e0, fma(e1, e1, fma(e2, e2, fma(e3, e3, sq[r]))));
+                            }
+                        }
                     }
-                    const double dg = s_deg[a - ra0];
+                    const double dg = cdiag[slot];
 #pragma unroll
                     for (int r = 0; r < R; ++r) en[r] = fma(xa[r], fma(dg, xa[r], -2.0 * s[r]), en[r]);
                 }
+                __syncwarp();
+                if (lane == 0) asp::mbar_arrive(&empty_bar[b]);
             }
-            compute_sync();                                            // the staged weights are dead: red[] aliases them
-            // ---- C: the parts' partial energies
+            // ---- C: the two parts of a warp by shuffle, the warps through shared memory (summed in warp order below)
 #pragma unroll
-            for (int r = 0; r < R; ++r) red[p * T + g + 16 * r] = en[r];
-        }
-        __syncthreads();                                               // partial energies, norms and taus are in shared memory
-        if (threadIdx.x < T) {
-            const int t = threadIdx.x;
-            const int64_t item = item0 + t;
-            if (item < n) {
-                double num = 0.0;
-                for (int q = 0; q < (THR / 16); ++q) num += red[q * T + t];
-                const double n2 = s_n2[t];
-                const double tau = s_tau[t];
-                double e = NAN, lam = NAN;
-                if (n2 == 0.0) atomicExch(zero_flag, 1);                 // TAUMODE.md:13
-                else { e = num / n2; lam = e / (e + tau); }
-                if (out_energy) out_energy[item] = e;
-                if (out_tau) out_tau[item] = tau;
-                if (out_lambda) out_lambda[item] = lam;
-                const double nr = sqrt(n2);
-                if (out_norm) out_norm[item] = nr;
-                if (out_inv_norm) out_inv_norm[item] = (nr > 0.0) ? 1.0 / nr : 0.0;
+            for (int r = 0; r < R; ++r) {
+                en[r] += __shfl_xor_sync(0xffffffffu, en[r], 16);
+                if (lane < 16) red[warp * T + g + 16 * r] = en[r];
             }
+            if (SYN) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) { tot[r] += __shfl_xor_sync(0xffffffffu, tot[r], 16); sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], 16); }
+            }
+            double num = 0.0, gt = 0.0, gs = 0.0;
+            named_sync<2>(THR + NAUX);                                 // partial energies, norms and taus are in shared memory
+            if (threadIdx.x < T) for (int q = 0; q < NW; ++q) num += red[q * T + threadIdx.x];
+            if (SYN) {                                                 // two more rounds through the same buffer
+                named_sync<1>(THR);
+#pragma unroll
+                for (int r = 0; r < R; ++r) if (lane < 16) red[warp * T + g + 16 * r] = tot[r];
+                named_sync<1>(THR);
+                if (threadIdx.x < T) for (int q = 0; q < NW; ++q) gt += red[q * T + threadIdx.x];
+                named_sync<1>(THR);
+#pragma unroll
+                for (int r = 0; r < R; ++r) if (lane < 16) red[warp * T + g + 16 * r] = sq[r];
+                named_sync<1>(THR);
+                if (threadIdx.x < T) for (int q = 0; q < NW; ++q) gs += red[q * T + threadIdx.x];
+            }
+            if (threadIdx.x < T) {
+                const int t = threadIdx.x;
+                const int64_t item = item0 + t;
+                if (item < n) {
+                    const double n2 = s_n2[t];
+                    const double tau = s_tau[t];
+                    double e = NAN, lam = NAN;
+                    if (n2 == 0.0) atomicExch(zero_flag, 1);             // TAUMODE.md:13
+                    else {
+                        e = num / n2;
+                        lam = e / (e + tau);                             // TAUMODE.md:19,25
+                        if (SYN) {                                       // TAUMODE.md:8,26-27
+                            double gd = (gt == 0.0) ? 0.0 : gs / (gt * gt);
+                            gd = gd < 0.0 ? 0.0 : (gd > 1.0 ? 1.0 : gd);
+                            lam = tau * lam + (1.0 - tau) * gd;
+                        }
+                    }
+                    if (out_energy) out_energy[item] = e;
+                    if (out_tau) out_tau[item] = tau;
+                    if (out_lambda) out_lambda[item] = lam;
+                    const double nr = sqrt(n2);
+                    if (out_norm) out_norm[item] = nr;
+                    if (out_inv_norm) out_inv_norm[item] = (nr > 0.0) ? 1.0 / nr : 0.0;
+                }
+            }
+        }
+        if (is_aux) named_sync<2>(THR + NAUX);                         // (the compute warps passed theirs before the reduction)
+        named_sync<4>(THR + NAUX);                                     // the tile is fully consumed: xs / s_tau / s_n2 / red reusable
+    }
+}
+
+// ---- vectors of more than 1500 features: one CTA per vector, the row in shared memory
+constexpr int TW_THREADS = 256;
+
+__global__ void __launch_bounds__(TW_THREADS)
+taumode_wide_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const int32_t *__restrict__ uptr,
+                    const int32_t *__restrict__ ucol, const double *__restrict__ uval, const double *__restrict__ diag,
+                    int tau_mode, double tau_fixed, int synthetic, double *__restrict__ out_energy, double *__restrict__ out_tau,
+                    double *__restrict__ out_lambda, double *__restrict__ out_norm, double *__restrict__ out_inv_norm, int *zero_flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *xr = reinterpret_cast<double *>(smem_raw);                 // f
+    __shared__ double s_part[3][TW_THREADS / 32];
+    __shared__ uint32_t s_cnt[16];
+    __shared__ double s_n2, s_mean;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t item = blockIdx.x; item < n; item += gridDim.x) {
+        __syncthreads();
+        const double *row = x + item * pitch;
+        for (int j = threadIdx.x; j < f; j += TW_THREADS) xr[j] = row[j];
+        __syncthreads();
+        // left-to-right sums on one thread (the oracle's order) while the other warps walk the graph
+        if (threadIdx.x == 0) {
+            double n2 = 0.0, sm = 0.0;
+            for (int j = 0; j < f; ++j) { const double v = xr[j]; n2 = __dadd_rn(n2, __dmul_rn(v, v)); sm = __dadd_rn(sm, v); }
+            s_n2 = n2; s_mean = sm / (double)f;
+        }
+        double en = 0.0, tot = 0.0, sq = 0.0;
+        if (warp > 0) {
+            for (int a = warp - 1; a < f; a += TW_THREADS / 32 - 1) {
+                const double xa = xr[a];
+                double s = 0.0;
+                for (int j = uptr[a] + lane; j < uptr[a + 1]; j += 32) {
+                    const double w = uval[j], xb = xr[ucol[j]];
+                    s = fma(w, xb, s);
+                    if (synthetic) { const double d = xa - xb, e = w * d * d; tot += e; sq = fma(e, e, sq); }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                en = fma(xa, fma(diag[a], xa, -2.0 * s), en);          // identical on every lane
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, off); sq += __shfl_xor_sync(0xffffffffu, sq, off); }
+        if (lane == 0) { s_part[0][warp] = en; s_part[1][warp] = tot; s_part[2][warp] = sq; }
+        // block-wide radix selection of the median (4 bits per pass over the keys in shared memory)
+        double tau = tau_fixed;
+        if (tau_mode == ASP_TAU_MEDIAN || tau_mode == ASP_TAU_MEDIAN_ABS) {
+            const bool use_abs = tau_mode == ASP_TAU_MEDIAN_ABS;
+            double med[2];
+            const int ranks[2] = {(f & 1) ? f / 2 : f / 2 - 1, f / 2};
+            for (int which = 0; which < ((f & 1) ? 1 : 2); ++which) {
+                unsigned long long prefix = 0ull, mask = 0ull;
+                int r = ranks[which];
+                for (int shift = 60; shift >= 0; shift -= 4) {
+                    __syncthreads();
+                    if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
+                    __syncthreads();
+                    uint32_t loc[16];
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) loc[b] = 0u;
+                    for (int j = threadIdx.x; j < f; j += TW_THREADS) {
+                        const unsigned long long key = f64_key(use_abs ? fabs(xr[j]) : xr[j]);
+                        if ((key & mask) == prefix) {
+                            const uint32_t d = (uint32_t)(key >> shift) & 15u;
+#pragma unroll
+                            for (int b = 0; b < 16; ++b) loc[b] += (d == (uint32_t)b) ? 1u : 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) {
+                        const uint32_t t = __reduce_add_sync(0xffffffffu, loc[b]);
+                        if (lane == 0 && t) atomicAdd(&s_cnt[b], t);
+                    }
+                    __syncthreads();
+                    uint32_t run = 0, digit = 0;
+                    bool found = false;
+                    for (int b = 0; b < 16; ++b) {
+                        const uint32_t cbin = s_cnt[b];
+                        if (!found && run + cbin > (uint32_t)r) { digit = b; r -= (int)run; found = true; }
+                        run += cbin;
+                    }
+                    prefix |= (unsigned long long)digit << shift;
+                    mask |= 15ull << shift;
+                }
+                med[which] = key_f64(prefix);
+            }
+            tau = (f & 1) ? med[0] : 0.5 * (med[0] + med[1]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (tau_mode == ASP_TAU_MEAN) tau = s_mean;
+            tau = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
+            double num = 0.0, gt = 0.0, gs = 0.0;
+            for (int w = 0; w < TW_THREADS / 32; ++w) { num += s_part[0][w]; gt += s_part[1][w]; gs += s_part[2][w]; }
+            const double n2 = s_n2;
+            double e = NAN, lam = NAN;
+            if (n2 == 0.0) atomicExch(zero_flag, 1);
+            else {
+                e = num / n2;
+                lam = e / (e + tau);
+                if (synthetic) {
+                    double gd = (gt == 0.0) ? 0.0 : gs / (gt * gt);
+                    gd = gd < 0.0 ? 0.0 : (gd > 1.0 ? 1.0 : gd);
+                    lam = tau * lam + (1.0 - tau) * gd;
+                }
+            }
+            if (out_energy) out_energy[item] = e;
+            if (out_tau) out_tau[item] = tau;
+            if (out_lambda) out_lambda[item] = lam;
+            const double nr = sqrt(n2);
+            if (out_norm) out_norm[item] = nr;
+            if (out_inv_norm) out_inv_norm[item] = (nr > 0.0) ? 1.0 / nr : 0.0;
         }
     }
 }
 
-template <int FPL, int R, int CHN, int THR>
-int launch_tm(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const double *x, int64_t n, int f, int pitch,
-              const TmChunk *d_chunks, int nchunks, double *oe, double *ot, double *ol, double *on, double *oi,
-              int *zero_flag)
+template <int FPL, int R, int THR>
+int launch_tm(asp_ctx *ctx, const TmBlob *blob, const asp_switches *sw, const double *x, int64_t n, int f, int pitch,
+              double *oe, double *ot, double *ol, double *on, double *oi, int *zero_flag)
 {
     constexpr int T = 16 * R;
-    double *medians = nullptr;
-    if (sw->tau_mode == ASP_TAU_MEDIAN || sw->tau_mode == ASP_TAU_MEDIAN_ABS) {
-        ASP_CUDA(cudaMallocAsync(&medians, sizeof(double) * n, ctx->stream));
-        const int64_t want = asp_ceil_div(n, 8);
-        const int mgrid = (int)(want < (int64_t)ctx->num_sms * 8 ? want : (int64_t)ctx->num_sms * 8);
-        const char *mpf = getenv("ASP_MEDIAN_PREFETCH");
-        auto mk = (mpf && mpf[0] == '1') ? median_kernel<FPL, true> : median_kernel<FPL, false>;
-        mk<<<mgrid, 256, 0, ctx->stream>>>(x, n, f, pitch, sw->tau_mode == ASP_TAU_MEDIAN_ABS ? 1 : 0, medians);
-        ASP_CUDA(cudaGetLastError());
-        ASP_LAUNCHED(ctx);
-    }
-    static_assert((size_t)CHN * 12 >= (size_t)(THR / 16) * T * 8, "the part reduction aliases the staged weights and columns");
-    const size_t smem = (size_t)f * (T + 1) * 8 + (size_t)CHN * 12 + (CH_ROWS + 2) * 4 + (size_t)CH_ROWS * 8 +
-                        (size_t)T * 16 + 64;
+    constexpr int NTHREADS = THR + 32 * TM_AUX_WARPS + 32;
+    const char *menv = getenv("ASP_TM_MEDIAN");
+    const bool hist = menv && menv[0] == 'h';
+    const bool syn = sw->lambda_form == ASP_LAMBDA_SYNTHETIC;
+    const size_t smem = (((size_t)f * (T + 1) * 8 + 15) & ~(size_t)15) + 2 * (size_t)TM_CHUNK_BYTES + (size_t)(THR / 32) * T * 8 +
+                        (size_t)T * 16 + (hist ? (size_t)TM_AUX_WARPS * 1024 : 0);
     if (smem > 227 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "taumode kernel: %d features do not fit in shared memory", f);
-    // the register-prefetch variant needs one thread per staged row pointer (CH_ROWS + 1 <= THR)
-    const char *pf_env = getenv("ASP_TM_PREFETCH");
-    const bool pf = (THR > CH_ROWS) && pf_env && pf_env[0] == '1';
-    auto kern = pf ? taumode_kernel<FPL, R, CHN, THR, (THR > CH_ROWS)> : taumode_kernel<FPL, R, CHN, THR, false>;
+    auto kern = syn ? taumode_kernel<FPL, R, THR, true, false>
+                    : hist ? taumode_kernel<FPL, R, THR, false, true> : taumode_kernel<FPL, R, THR, false, false>;
     ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;                                                       // resident CTAs per SM: their load / gather phases overlap
-    constexpr int NTHREADS = THR + 32 * TmAux<R>::WARPS;
     ASP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
     if (occ < 1) occ = 1;
     const int64_t ntiles = (n + T - 1) / T;
     const int64_t slots = (int64_t)ctx->num_sms * occ;
     const int grid = (int)(ntiles < slots ? ntiles : slots);
-    kern<<<grid, NTHREADS, smem, ctx->stream>>>(x, n, f, pitch, g->d_uptr, g->d_ucol, g->d_uval, g->d_deg, d_chunks,
-                                                  nchunks, sw->tau_mode, sw->tau_fixed, medians, oe, ot, ol, on, oi, zero_flag);
+    kern<<<grid, NTHREADS, smem, ctx->stream>>>(x, n, f, pitch, static_cast<const unsigned char *>(blob->d_chunks), blob->nchunks,
+                                                  sw->tau_mode, sw->tau_fixed, oe, ot, ol, on, oi, zero_flag);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
-    if (medians) ASP_CUDA(cudaFreeAsync(medians, ctx->stream));
+    return ASP_OK;
+}
+
+// Symmetrised quadratic form of the host CSR, cut into pieces and chunks (see the top of the file).
+int build_tm_blob(asp_ctx *ctx, const asp_graph *g, TmBlob *out)
+{
+    const int64_t m = g->nnodes;
+    if (m > 65535) ASP_FAIL(ASP_ERR_UNSUPPORTED, "the lambda pass supports at most 65535 graph nodes (got %lld)", (long long)m);
+    std::vector<std::vector<std::pair<int32_t, double>>> up(m);
+    std::vector<double> diag(m, 0.0);
+    for (int64_t a = 0; a < m; ++a)
+        for (int64_t j = g->h_indptr[a]; j < g->h_indptr[a + 1]; ++j) {
+            const int32_t c = g->h_indices[j];
+            if (c == a) { diag[a] += g->h_data[j]; continue; }
+            const int64_t lo = c < a ? c : a;
+            const int32_t hi = c < a ? (int32_t)a : c;
+            up[lo].push_back({hi, -0.5 * g->h_data[j]});               // c_ab = -(L_ab + L_ba) / 2
+        }
+    std::vector<int32_t> uptr(m + 1, 0), ucol;
+    std::vector<double> uval;
+    for (int64_t a = 0; a < m; ++a) {
+        auto &v = up[a];
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<int32_t, double> &x, const std::pair<int32_t, double> &y) { return x.first < y.first; });
+        size_t o = 0;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (o > 0 && v[o - 1].first == v[i].first) v[o - 1].second += v[i].second;    // row a's entry first, then row b's
+            else v[o++] = v[i];
+        }
+        v.resize(o);
+        for (auto &e : v) { ucol.push_back(e.first); uval.push_back(e.second); }
+        uptr[a + 1] = (int32_t)ucol.size();
+    }
+    // pieces, longest first (equal lengths inside a chunk balance the parts)
+    struct Piece { int32_t row, beg, len; double diag; };
+    std::vector<Piece> pieces;
+    for (int64_t a = 0; a < m; ++a) {
+        const int32_t len = uptr[a + 1] - uptr[a];
+        if (len == 0) { if (diag[a] != 0.0) pieces.push_back({(int32_t)a, uptr[a], 0, diag[a]}); continue; }
+        for (int32_t o = 0; o < len; o += TM_PIECE)
+            pieces.push_back({(int32_t)a, uptr[a] + o, std::min<int32_t>(TM_PIECE, len - o), o == 0 ? diag[a] : 0.0});
+    }
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece &x, const Piece &y) { return x.len > y.len; });
+    std::vector<unsigned char> blob;
+    int nchunks = 0;
+    size_t i = 0;
+    while (i < pieces.size() || nchunks == 0) {
+        blob.resize((size_t)(nchunks + 1) * TM_CHUNK_BYTES, 0);
+        unsigned char *cb = blob.data() + (size_t)nchunks * TM_CHUNK_BYTES;
+        double *cw = reinterpret_cast<double *>(cb + TM_OFF_W);
+        uint16_t *cc = reinterpret_cast<uint16_t *>(cb + TM_OFF_COL);
+        double *cd = reinterpret_cast<double *>(cb + TM_OFF_DIAG);
+        uint16_t *cp = reinterpret_cast<uint16_t *>(cb + TM_OFF_PIECE);
+        int np = 0, ne = 0;
+        while (i < pieces.size() && np < TM_CH_ROWS) {
+            const Piece &pc = pieces[i];
+            const int padded = (pc.len + 3) & ~3;
+            if (ne + padded > TM_CH_ENT) break;
+            cp[4 * np + 0] = (uint16_t)pc.row; cp[4 * np + 1] = (uint16_t)ne; cp[4 * np + 2] = (uint16_t)(ne + padded); cp[4 * np + 3] = 0;
+            cd[np] = pc.diag;
+            for (int e = 0; e < padded; ++e) {
+                cw[ne + e] = e < pc.len ? uval[pc.beg + e] : 0.0;      // padding: coefficient 0 on the row's own column
+                cc[ne + e] = (uint16_t)(e < pc.len ? ucol[pc.beg + e] : pc.row);
+            }
+            ne += padded; ++np; ++i;
+        }
+        *reinterpret_cast<int32_t *>(cb + TM_OFF_HDR) = np;
+        ++nchunks;
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t un = ucol.empty() ? 1 : ucol.size();
+    ASP_CUDA(cudaMallocAsync(&out->d_chunks, blob.size(), st));
+    ASP_CUDA(cudaMallocAsync(&out->d_uptr, sizeof(int32_t) * (m + 1), st));
+    ASP_CUDA(cudaMallocAsync(&out->d_ucol, sizeof(int32_t) * un, st));
+    ASP_CUDA(cudaMallocAsync(&out->d_uval, sizeof(double) * un, st));
+    ASP_CUDA(cudaMallocAsync(&out->d_diag, sizeof(double) * m, st));
+    ASP_CUDA(cudaMemcpyAsync(out->d_chunks, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    ASP_CUDA(cudaMemcpyAsync(out->d_uptr, uptr.data(), sizeof(int32_t) * (m + 1), cudaMemcpyHostToDevice, st));
+    if (!ucol.empty()) {
+        ASP_CUDA(cudaMemcpyAsync(out->d_ucol, ucol.data(), sizeof(int32_t) * ucol.size(), cudaMemcpyHostToDevice, st));
+        ASP_CUDA(cudaMemcpyAsync(out->d_uval, uval.data(), sizeof(double) * uval.size(), cudaMemcpyHostToDevice, st));
+    }
+    ASP_CUDA(cudaMemcpyAsync(out->d_diag, diag.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    ASP_CUDA(cudaStreamSynchronize(st));                               // the host vectors go out of scope
+    out->nchunks = nchunks;
     return ASP_OK;
 }
 
 }  // namespace
+
+// Called once per feature graph (asp_graph_from_gram): the graph-only inputs of the lambda pass.  A per-call upload would
+// queue behind the query uploads of a pipelined search.
+int asp_graph_upload_upper(asp_graph *g)
+{
+    ASP_CHECK(asp_graph_host_mirror(g));
+    TmBlob *b = new TmBlob();
+    const int rc = build_tm_blob(g->ctx, g, b);
+    if (rc != ASP_OK) { delete b; return rc; }
+    g->tm_blob = b;
+    return ASP_OK;
+}
+
+void asp_graph_free_upper(asp_graph *g)
+{
+    if (!g->tm_blob) return;
+    TmBlob *b = static_cast<TmBlob *>(g->tm_blob);
+    cudaStream_t st = g->ctx->stream;
+    void *bufs[] = {b->d_chunks, b->d_uptr, b->d_ucol, b->d_uval, b->d_diag};
+    for (void *p : bufs)
+        if (p) cudaFreeAsync(p, st);
+    delete b;
+    g->tm_blob = nullptr;
+}
 
 int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, const double *x_dev, int64_t n,
                        int32_t f, int32_t pitch, double *out_energy, double *out_tau, double *out_lambda,
@@ -421,43 +757,21 @@ int asp_launch_taumode(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw,
 {
     if (n == 0) return ASP_OK;
     if (f != g->nnodes) ASP_FAIL(ASP_ERR_ARG, "vector length %d must equal the graph's node count %lld", f, (long long)g->nnodes);
-    if (!g->d_uptr) ASP_FAIL(ASP_ERR_ARG, "graph has no upper adjacency (not a feature graph)");
-    // chunk the upper adjacency by rows: <= chn entries and <= CH_ROWS rows per chunk.  The table depends on the graph
-    // only: it is built and uploaded once (a per-call H2D copy would queue behind the query uploads of a pipelined search)
-    if (!g->d_tm_chunks) {
-        const int chn = CH_NNZ_MAX;
-        std::vector<TmChunk> chunks;
-        std::vector<int32_t> uptr(g->nnodes + 1);
-        // host mirror of uptr: rebuild from the host CSR (cheap, f rows)
-        int32_t acc = 0;
-        uptr[0] = 0;
-        for (int64_t a = 0; a < g->nnodes; ++a) {
-            for (int64_t j = g->h_indptr[a]; j < g->h_indptr[a + 1]; ++j)
-                if (g->h_indices[j] > a) ++acc;
-            uptr[a + 1] = acc;
-        }
-        int a0 = 0;
-        while (a0 < g->nnodes) {
-            int a1 = a0;
-            while (a1 < g->nnodes && (a1 - a0) < CH_ROWS && (uptr[a1 + 1] - uptr[a0]) <= chn) ++a1;
-            if (a1 == a0) ASP_FAIL(ASP_ERR_UNSUPPORTED, "graph row %d has more than %d upper neighbours", a0, chn);
-            chunks.push_back(TmChunk{a0, a1});
-            a0 = a1;
-        }
-        void *d = nullptr;
-        ASP_CUDA(cudaMallocAsync(&d, sizeof(TmChunk) * chunks.size(), ctx->stream));
-        ASP_CUDA(cudaMemcpyAsync(d, chunks.data(), sizeof(TmChunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
-        ASP_CUDA(cudaStreamSynchronize(ctx->stream));     // chunks vector goes out of scope
-        g->d_tm_chunks = d;
-        g->n_tm_chunks = (int)chunks.size();
-    }
-    const TmChunk *d_chunks = static_cast<const TmChunk *>(g->d_tm_chunks);
-    int rc;
-    const int nch = g->n_tm_chunks;
-    if (f <= 128)       rc = launch_tm<4, 4, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 384)  rc = launch_tm<12, 4, CH_NNZ_MAX, 512>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 768)  rc = launch_tm<24, 2, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else if (f <= 1500) rc = launch_tm<48, 1, CH_NNZ_MAX, 256>(ctx, g, sw, x_dev, n, f, pitch, d_chunks, nch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
-    else { rc = ASP_ERR_UNSUPPORTED; asp_set_error("taumode kernel supports at most 1500 features (got %d)", f); }
-    return rc;
+    if (!g->tm_blob) ASP_FAIL(ASP_ERR_ARG, "graph has no upper adjacency (not a feature graph)");
+    const TmBlob *b = static_cast<const TmBlob *>(g->tm_blob);
+    if (f <= 128)  return launch_tm<4, 4, 256>(ctx, b, sw, x_dev, n, f, pitch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f <= 384)  return launch_tm<12, 4, 512>(ctx, b, sw, x_dev, n, f, pitch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f <= 768)  return launch_tm<24, 2, 256>(ctx, b, sw, x_dev, n, f, pitch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f <= 1024) return launch_tm<32, 1, 256>(ctx, b, sw, x_dev, n, f, pitch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f <= 1500) return launch_tm<47, 1, 128>(ctx, b, sw, x_dev, n, f, pitch, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    if (f > 16384) ASP_FAIL(ASP_ERR_UNSUPPORTED, "the lambda pass supports at most 16384 features (got %d)", f);
+    const size_t smem = (size_t)f * 8;
+    ASP_CUDA(cudaFuncSetAttribute(taumode_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (int64_t)ctx->num_sms * 4;
+    taumode_wide_kernel<<<(unsigned)(n < want ? n : want), TW_THREADS, smem, ctx->stream>>>(
+        x_dev, n, f, pitch, b->d_uptr, b->d_ucol, b->d_uval, b->d_diag, sw->tau_mode, sw->tau_fixed,
+        sw->lambda_form == ASP_LAMBDA_SYNTHETIC ? 1 : 0, out_energy, out_tau, out_lambda, out_norm, out_inv_norm, zero_flag_dev);
+    ASP_CUDA(cudaGetLastError());
+    ASP_LAUNCHED(ctx);
+    return ASP_OK;
 }

@@ -10,6 +10,12 @@ The path shards by rows: rank r owns the rows of Gram s
   item graph (nodes = items)
           4. all-gather of the item shards (the "halo rows": every rank scores ITS rows against ALL items)
           5. all-gather of the per-rank neighbour lists (12 * N * k bytes), Laplacian assembled on every rank
+  regrouping (item_shards = R < world = G; `regroup`)
+          6. the build is always row-partitioned G ways; for the search the G ranks form an R x C grid (C = G / R): the C
+             consecutive ranks of item shard r all-gather their rows, lambdas and norms (once, at build time), and every
+             rank then answers 1/C of each query batch against item shard r.  Per-query work (lambda_q, operand
+             projection, stage 2, merge) is divided by C instead of being replicated G times; R = 1 needs no cross-GPU
+             merge at all.  R = G is the fully item-sharded layout (every rank scores every query).
 
 The summation tree of the Gram is fixed (segments -> slices), so every world size produces
 bit-identical graphs, lambdas and result lists.
@@ -49,6 +55,17 @@ class CudaEngine:
         return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
 
     def space_create(self, shard, n_total, world, rank):
+        """Copies the row shard into the library (host ndarray or device tensor, any strides; float64 only)."""
+        if hasattr(shard, "data_ptr"):
+            if shard.dtype != self.torch.float64 or shard.dim() != 2:
+                raise TypeError("argument 'items': expected a 2-D float64 tensor")
+            shard = shard.contiguous()
+            if shard.is_cuda:
+                self.torch.cuda.current_stream(shard.device).synchronize()      # the library runs on its own stream
+        else:
+            if shard.dtype != np.float64 or shard.ndim != 2:
+                raise TypeError("argument 'items': expected 2-D numpy.ndarray of float64")
+            shard = np.ascontiguousarray(shard)
         n_local, f = shard.shape
         h = C.c_void_p()
         _lib.check(self.lib.asp_space_create(self.ctx, self._ptr(shard), n_local, f, n_total, world, rank, C.byref(h)))
@@ -64,14 +81,19 @@ class CudaEngine:
     def graph_from_gram(self, segs, f, n_total, cgp, sw, pairs, sums):
         """-> (graph handle | None, need_pairs int32[m, 2])"""
         cap = 1 << 16
-        need = np.empty((cap, 2), dtype=np.int32)
-        n_need = C.c_int64(0)
-        hg = C.c_void_p()
         n_exact = 0 if pairs is None else len(pairs)
         pp = pairs.ctypes.data if n_exact else None
         sp = sums.ctypes.data if n_exact else None
-        rc = self.lib.asp_graph_from_gram(self.ctx, segs.data_ptr(), f, n_total, C.byref(cgp), C.byref(sw), pp, sp,
-                                          n_exact, need.ctypes.data, cap, C.byref(n_need), C.byref(hg))
+        while True:
+            need = np.empty((cap, 2), dtype=np.int32)
+            n_need = C.c_int64(0)
+            hg = C.c_void_p()
+            rc = self.lib.asp_graph_from_gram(self.ctx, segs.data_ptr(), f, n_total, C.byref(cgp), C.byref(sw), pp, sp,
+                                              n_exact, need.ctypes.data, cap, C.byref(n_need), C.byref(hg))
+            if rc == _lib.ASP_ERR_ARG and n_need.value > cap:       # more undecided pairs than the list holds: grow it
+                cap = n_need.value
+                continue
+            break
         if rc == _lib.ASP_NEED_EXACT:
             return None, need[: n_need.value].copy()
         _lib.check(rc)
@@ -83,6 +105,43 @@ class CudaEngine:
 
     def compute_lambdas(self, space, graph):
         _lib.check(self.lib.asp_space_compute_lambdas(space, graph))
+
+    # ---- regrouping (item_shards < world)
+    def lambdas_norms(self, space, n_local):
+        """-> (lambdas, norms) of the space's rows as device tensors."""
+        t = self.torch
+        lam = t.empty(n_local, dtype=t.float64, device=self.device)
+        nrm = t.empty(n_local, dtype=t.float64, device=self.device)
+        t.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_space_lambdas(space, lam.data_ptr()))
+        _lib.check(self.lib.asp_space_norms(space, nrm.data_ptr()))
+        _lib.check(self.lib.asp_ctx_synchronize(self.ctx))
+        return lam, nrm
+
+    def space_from_gathered(self, x, lam, nrm, n_total, shards, shard):
+        """Space over the gathered rows of item shard `shard` of `shards` with imported lambdas / norms.  The library
+        works on the tensor itself when it can (no second copy); the caller keeps `self.adopted` alive."""
+        n_local, f = x.shape
+        h = C.c_void_p()
+        self.torch.cuda.current_stream(self.device).synchronize()
+        if f % 4 == 0 and x.is_contiguous() and x.data_ptr() % 16 == 0:
+            _lib.check(self.lib.asp_space_adopt_shard(self.ctx, x.data_ptr(), n_local, f, n_total, shards, shard, C.byref(h)))
+            self.adopted = x
+        else:
+            _lib.check(self.lib.asp_space_create(self.ctx, x.data_ptr(), n_local, f, n_total, shards, shard, C.byref(h)))
+            self.adopted = None
+        _lib.check(self.lib.asp_space_import_lambdas(h, lam.contiguous().data_ptr(), nrm.contiguous().data_ptr()))
+        return h
+
+    def free_space(self, space):
+        self.lib.asp_free_space(space)
+
+    def device_rows(self, shard):
+        """The caller's row shard as a contiguous device tensor (uploaded when it is host memory)."""
+        t = self.torch
+        if hasattr(shard, "data_ptr") and hasattr(shard, "is_cuda"):
+            return shard.to(self.device).contiguous()
+        return t.from_numpy(np.ascontiguousarray(shard, dtype=np.float64)).to(self.device)
 
     # ---- item graph
     def full_space(self, x_full):
@@ -100,7 +159,7 @@ class CudaEngine:
             self.adopted = None
         return h
 
-    def knn_rows(self, space, cgp, r0, r1):
+    def knn_rows(self, space, cgp, r0, r1, sw=None):
         """-> (idx int32[rows, kk], dist f64[rows, kk], cnt int32[rows]) device tensors."""
         t = self.torch
         rows = r1 - r0
@@ -110,7 +169,8 @@ class CudaEngine:
         cnt = t.zeros((max(rows, 1),), dtype=t.int32, device=self.device)
         kk = C.c_int32(0)
         t.cuda.current_stream(self.device).synchronize()
-        _lib.check(self.lib.asp_item_knn_rows(space, C.byref(cgp), r0, r1, idx.data_ptr(), dist.data_ptr(), cnt.data_ptr(), C.byref(kk)))
+        _lib.check(self.lib.asp_item_knn_rows(space, C.byref(cgp), C.byref(sw) if sw is not None else None, r0, r1,
+                                              idx.data_ptr(), dist.data_ptr(), cnt.data_ptr(), C.byref(kk)))
         if kk.value != kmax:                       # k was capped at n - 1: the library wrote rows of kk entries
             idx = idx.reshape(-1)[: rows * kk.value].reshape(rows, kk.value)
             dist = dist.reshape(-1)[: rows * kk.value].reshape(rows, kk.value)
@@ -168,7 +228,7 @@ def sharded_build(engine, shard, n_total, cgp, sw, group=None):
     pairs = np.empty((0, 2), dtype=np.int32)
     sums = np.empty((0, 3), dtype=np.float64)
     graph = None
-    for _ in range(4):
+    for _ in range(6):
         graph, need = engine.graph_from_gram(segs, f, n_total, cgp, sw, pairs if len(pairs) else None,
                                              sums if len(sums) else None)
         if graph is not None:
@@ -188,6 +248,78 @@ def sharded_build(engine, shard, n_total, cgp, sw, group=None):
         raise RuntimeError("exact-pair resolution did not converge")
     engine.compute_lambdas(space, graph)
     return space, graph
+
+
+_GRIDS = {}
+
+
+def grid_layout(world, rank, item_shards):
+    """R x C grid of the search: (R, C, item shard r, query slot c) of `rank`; ranks of one item shard are consecutive."""
+    r_ = int(item_shards)
+    if r_ < 1 or world % r_ != 0 or _lib.GRAM_SEGMENTS % r_ != 0:
+        raise ValueError("item_shards = %d must divide the world size %d and %d" % (r_, world, _lib.GRAM_SEGMENTS))
+    c_ = world // r_
+    return r_, c_, rank // c_, rank % c_
+
+
+def query_slice(nq, slots, slot):
+    """Rows [a, b) of a batch of nq queries answered by query slot `slot` of `slots`; `per` = rows of a full slice."""
+    per = (nq + slots - 1) // slots
+    a = min(slot * per, nq)
+    return a, min(a + per, nq), per
+
+
+def grid_groups(world, item_shards):
+    """Process groups of the grid, created collectively (every rank creates every group, in the same order) and cached:
+    -> (item_groups[r] = the C ranks holding item shard r, merge_groups[c] = the R ranks answering query slot c)."""
+    dist = _dist()
+    key = (world, int(item_shards))
+    if key not in _GRIDS:
+        r_, c_, _, _ = grid_layout(world, 0, item_shards)
+        item_groups = [dist.new_group([r * c_ + c for c in range(c_)]) if c_ > 1 else None for r in range(r_)]
+        merge_groups = [dist.new_group([r * c_ + c for r in range(r_)]) if (r_ > 1 and c_ > 1) else None for c in range(c_)]
+        _GRIDS[key] = (item_groups, merge_groups)
+    return _GRIDS[key]
+
+
+def auto_item_shards(world, n_total, f, free_bytes):
+    """Fewest item shards whose share of the items (f64 rows + fp16 operands of both split terms + emission scratch)
+    takes at most half of the free device memory: replicate when it fits, shard when it must."""
+    for r_ in (1, 2, 4, 8):
+        if r_ > world or world % r_:
+            continue
+        need = (n_total / r_) * (8.0 * f + 4.0 * (f + 64)) + 6e9
+        if need <= 0.5 * free_bytes:
+            return r_
+    return world
+
+
+def regroup(engine, space, rows_dev, n_total, item_shards, group=None):
+    """Step 6 above.  `space` = this rank's build-time space (rows of asp_shard_rows(n_total, world, rank), lambdas computed),
+    rows_dev = the same rows as a device tensor.  Returns (space over item shard r with imported lambdas, grid dict);
+    the build-time space is freed."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    r_, c_, r, c = grid_layout(world, rank, item_shards)
+    grid = dict(R=r_, C=c_, r=r, c=c, item_group=None, merge_group=None)
+    if c_ == 1:
+        grid["merge_group"] = group
+        return space, grid
+    if group is not None and group is not dist.group.WORLD:
+        raise ValueError("item_shards < world needs the default process group")
+    item_groups, merge_groups = grid_groups(world, r_)
+    grid["item_group"], grid["merge_group"] = item_groups[r], merge_groups[c]
+    lam, nrm = engine.lambdas_norms(space, rows_dev.shape[0])
+    counts = [shard_rows(n_total, world, r * c_ + j) for j in range(c_)]
+    counts = [b - a for a, b in counts]
+    x = _all_gather_rows(rows_dev, counts, item_groups[r])
+    lam = _all_gather_rows(lam, counts, item_groups[r])
+    nrm = _all_gather_rows(nrm, counts, item_groups[r])
+    if hasattr(engine, "after_collective"):
+        engine.after_collective()
+    new_space = engine.space_from_gathered(x, lam, nrm, n_total, r_, r)
+    engine.free_space(space)
+    return new_space, grid
 
 
 def _all_gather_ragged(t_local, counts, group):
@@ -232,7 +364,7 @@ def sharded_item_graph(engine, shard, n_total, row0, cgp, sw, group=None):
     if hasattr(engine, "after_collective"):
         engine.after_collective()
     space = engine.full_space(x_full)
-    idx, dst, cnt = engine.knn_rows(space, cgp, row0, row0 + counts[rank])
+    idx, dst, cnt = engine.knn_rows(space, cgp, row0, row0 + counts[rank], sw)
     if world > 1:
         idx = _all_gather_rows(idx.contiguous(), counts, group)
         dst = _all_gather_rows(dst.contiguous(), counts, group)
@@ -250,7 +382,7 @@ def build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=Non
     import torch
     gp = api.parse_graph_params(graph_params) or dict(api.DEFAULT_GRAPH_PARAMS)
     cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
-    sw = _lib.make_switches(extras.get("kernel", "inv_power"))
+    sw = _lib.switches_from(extras)
     engine = CudaEngine(extras.get("device"))
     if not (hasattr(items_shard, "data_ptr") and items_shard.is_cuda):
         items_shard = torch.from_numpy(np.ascontiguousarray(items_shard, dtype=np.float64)).to(engine.device)
@@ -263,17 +395,31 @@ def build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=Non
     return aspace, api.GraphLaplacian._wrap(graph)
 
 
-def build_sharded(graph_params, items_shard, n_total, group=None, **extras):
+def build_sharded(graph_params, items_shard, n_total, group=None, item_shards=None, **extras):
+    """One process per GPU; every rank passes ITS rows (api.shard_rows).  The build is row-partitioned over all ranks.
+    item_shards = R (a divisor of the world size; None = the fewest shards that fit the device memory) chooses the layout
+    of the search: R item shards x world / R query slots (see `regroup`)."""
     from . import api
+    import torch
     gp = api.parse_graph_params(graph_params) or dict(api.DEFAULT_GRAPH_PARAMS)
     cgp = _lib.make_params(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
-    sw = _lib.make_switches(extras.get("kernel", "inv_power"), extras.get("tau_mode", "median"),
-                            extras.get("tau_fixed", 0.0))
+    sw = _lib.switches_from(extras)
     engine = CudaEngine(extras.get("device"))
     if not (hasattr(items_shard, "data_ptr") and items_shard.is_cuda):
         items_shard = np.ascontiguousarray(items_shard, dtype=np.float64)
     dist = _dist()
     if group is None:
         group = dist.group.WORLD
-    space, graph = sharded_build(engine, items_shard, int(n_total), cgp, sw, group)
-    return api.ArrowSpace._wrap(space, engine.ctx, group), api.GraphLaplacian._wrap(graph)
+    world = dist.get_world_size(group)
+    if item_shards is None:
+        free_bytes, _ = torch.cuda.mem_get_info(engine.device)
+        t = torch.tensor([float(free_bytes)], dtype=torch.float64, device=engine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)          # every rank must take the same decision
+        item_shards = auto_item_shards(world, int(n_total), items_shard.shape[1], float(t.item()))
+    grid_layout(world, 0, item_shards)                                  # validates
+    rows_dev = engine.device_rows(items_shard) if item_shards < world else None
+    space, graph = sharded_build(engine, items_shard if rows_dev is None else rows_dev, int(n_total), cgp, sw, group)
+    space, grid = regroup(engine, space, rows_dev, int(n_total), item_shards, group)
+    aspace = api.ArrowSpace._wrap(space, engine.ctx, grid["merge_group"] if grid["R"] > 1 else None, grid)
+    aspace._keepalive = getattr(engine, "adopted", None)              # the adopted item matrix outlives the space handle
+    return aspace, api.GraphLaplacian._wrap(graph)

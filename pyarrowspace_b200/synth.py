@@ -16,10 +16,11 @@ CONFIGS = {
 }
 
 
-def make_items(n, f, seed, scale=100.0, n_clusters=256, rows=None, dtype=np.float64):
+def make_items(n, f, seed, scale=100.0, n_clusters=256, rows=None, dtype=np.float64, shift=0.25):
     """Rows [rows[0], rows[1]) of the n x f item matrix (whole matrix when rows is None).
 
-    Row i depends only on (seed, i // block), so shards generated on different ranks agree."""
+    Row i depends only on (seed, i // block), so shards generated on different ranks agree.  shift = 0 gives the
+    MEAN-ZERO variant (unit rows x scale, entries of both signs: what sentence-embedding models produce)."""
     rng = np.random.default_rng(seed)
     centres = rng.standard_normal((n_clusters, f))
     r0, r1 = (0, n) if rows is None else rows
@@ -37,7 +38,8 @@ def make_items(n, f, seed, scale=100.0, n_clusters=256, rows=None, dtype=np.floa
     # unit rows in hundreds of dimensions have entries well inside (-0.25, 0.25): a FIXED shift (not the
     # matrix minimum) keeps every entry positive and the matrix independent of how it is sharded
     out *= scale
-    out += 0.25 * scale
+    if shift:
+        out += shift * scale
     return out
 
 
@@ -47,6 +49,17 @@ def make_queries(items, nq, seed, scale=100.0, noise=0.01):
     sel = rng.integers(0, items.shape[0], size=nq)
     q = items[sel] / scale + noise * rng.standard_normal((nq, items.shape[1]))
     return np.ascontiguousarray(q), sel
+
+
+def make_fresh_queries(f, nq, seed, n_clusters=256):
+    """Queries that are NOT copies of items: fresh unit-norm draws from the same cluster mixture (cosine ~0.92 to the
+    items of their cluster, no exact neighbour), unscaled.  Returns (queries, cluster labels)."""
+    centres = np.random.default_rng(seed).standard_normal((n_clusters, f))
+    rng = np.random.default_rng([seed, 11])
+    lab = rng.integers(0, n_clusters, size=nq)
+    q = centres[lab] + 0.3 * rng.standard_normal((nq, f))
+    q /= np.sqrt((q * q).sum(axis=1, keepdims=True))
+    return np.ascontiguousarray(q), lab
 
 
 def config(name):

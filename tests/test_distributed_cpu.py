@@ -153,7 +153,7 @@ class NumpyKnnEngine:
     def full_space(self, x_full):
         return {"x": x_full.numpy().copy()}
 
-    def knn_rows(self, space, cgp, r0, r1):
+    def knn_rows(self, space, cgp, r0, r1, sw=None):
         x = space["x"]
         n = x.shape[0]
         kk = min(int(cgp.k), n - 1)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libarrowspace_b200.so lacks %s" % name
     assert sorted(_lib.SYMBOLS) == declared, "ctypes table and header disagree"
-    assert lib.asp_abi_version() == 1
+    assert lib.asp_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (asp_[a-z0-9_]+)", out))
     assert set(declared) <= exported

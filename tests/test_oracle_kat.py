@@ -56,6 +56,25 @@ def test_test0_tau09_third_place_reference(oracle_mod, kat):
     assert hits[2][0] == 0
 
 
+@pytest.mark.parametrize("tau", ["1.0", "0.9", "0.6", "0.55"])
+def test_test0_all_twelve_indices_under_profile_kat12(oracle_mod, kat, tau):
+    """The passing sibling of the xfail above: the named switch set `kat12` (symmetrise none, laplacian sym, k counts
+    self, topk prunes -- found by tools/fit_switches.py) reproduces every index tests/test_0.py:29-61 asserts."""
+    t = kat["test_0"]
+    items = np.array(t["items"])
+    s, g = oracle_mod.build(t["graph_params"], items, profile="kat12")
+    hits = s.search(items[t["query_item"]] * t["query_scale"], g, float(tau))
+    assert [i for i, _ in hits] == t["expected_top3"][tau]
+
+
+def test_readme_kat_bit_exact_under_profile_kat12(oracle_mod, kat):
+    """README.md:69 is tau = 1 (pure cosine): bit exact whatever the graph switches are."""
+    r = kat["readme"]
+    s, g = oracle_mod.build(r["graph_params"], np.array(r["items"]), profile="kat12")
+    hits = s.search(np.array(r["query"]), g, r["tau"])
+    assert [(i, sc) for i, sc in hits] == [(i, sc) for i, sc in r["hits"]]
+
+
 def test_appendix_a_self_check(oracle_mod, kat):
     """SURVEY.md Appendix A expected intermediate values on test_0."""
     t = kat["test_0"]
@@ -121,6 +140,34 @@ def test_switches_match_mirror(oracle_mod, tau_mode, lambda_form):
     s, g = oracle_mod.build(gp, x, tau_mode=tau_mode, lambda_form=lambda_form, tau_fixed=0.2)
     m = oracle_np.build(x, 1.0, 3, 4, 2.0, 0.5, tau_mode=tau_mode, lambda_form=lambda_form, tau_fixed=0.2)
     np.testing.assert_allclose(s.lambdas(), m["lambdas"], rtol=1e-13, atol=0)
+
+
+GRAPH_SWITCH_CASES = [
+    dict(symmetrise="avg"), dict(symmetrise="min"), dict(symmetrise="none"),
+    dict(laplacian="sym"), dict(laplacian="rw"), dict(symmetrise="none", laplacian="sym"), dict(symmetrise="none", laplacian="rw"),
+    dict(k_counts_self=True), dict(topk_prunes=True), dict(k_counts_self=True, topk_prunes=True),
+    dict(distance="l2"), dict(distance="l2sq"), dict(profile="kat12"),
+    dict(symmetrise="avg", laplacian="sym", lambda_form="synthetic"), dict(symmetrise="none", lambda_form="synthetic"),
+]
+
+
+@pytest.mark.parametrize("case", GRAPH_SWITCH_CASES, ids=lambda c: ",".join("%s=%s" % kv for kv in c.items()))
+def test_graph_switches_match_mirror(oracle_mod, case):
+    """Every unpinned graph switch: C oracle == independent numpy restatement (L entry by entry, lambdas 1e-12)."""
+    rng = np.random.default_rng(5)
+    x = np.abs(rng.normal(size=(31, 17))) + 0.05
+    gp = {"eps": 0.6, "k": 5, "topk": 3, "p": 2.0, "sigma": 0.3}
+    if "distance" in case:
+        gp["eps"], gp["sigma"] = (4.0, 2.0) if case["distance"] == "l2" else (16.0, 8.0)
+    sw = dict(oracle_mod.PROFILES[case["profile"]]) if "profile" in case else dict(case)
+    s, g = oracle_mod.build(gp, x, **case)
+    m = oracle_np.build(x, gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"], **sw)
+    import scipy.sparse as sp
+    ip, ix, dt = g.csr()
+    L = sp.csr_matrix((dt, ix, ip), shape=(g.nnodes, g.nnodes)).toarray()
+    assert np.array_equal(L, m["L"])
+    assert len(g.edges()) > 0
+    np.testing.assert_allclose(s.lambdas(), m["lambdas"], rtol=1e-12, atol=0)
 
 
 def test_graph_properties(oracle_mod):

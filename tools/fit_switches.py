@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Which settings of the UNPINNED switches reproduce all 12 indices of the reference's tests/test_0.py:29-61?
+
+TEST / ANALYSIS TOOL (CPU only, numpy): enumerates the switches SURVEY.md section 8(c) lists as unpinned
+(symmetrisation, k convention, topk pruning, Laplacian normalisation, kernel, tau source, lambda form) on the
+reference's own known-answer data (tests/golden/kat.json, transcribed from /root/reference/tests/test_0.py:4-61) and
+prints, per combination, how many of the 12 expected indices it reproduces and the smallest decisive score margin.
+The README example (README.md:69) is tau = 1, i.e. independent of every switch here.
+
+    python tools/fit_switches.py            # table of the 12/12 combinations, most robust first
+"""
+import itertools
+import json
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def graph(nodes, eps, k, topk, p, sigma, kernel, symmetrise, k_counts_self, topk_prunes, laplacian, distance):
+    M = nodes.shape[0]
+    G = nodes @ nodes.T
+    nrm = np.sqrt(np.diag(G))
+    if distance == "cosine":
+        c = G / np.outer(nrm, nrm)
+        d = 1.0 - np.maximum(0.0, c)
+    else:
+        d2 = np.maximum(0.0, np.add.outer(np.diag(G), np.diag(G)) - 2.0 * G)
+        d = np.sqrt(d2) if distance == "l2" else d2
+    keep = k - 1 if k_counts_self else k
+    if topk_prunes:
+        keep = min(keep, topk)
+    W = np.zeros((M, M))
+    for a in range(M):
+        cand = sorted((d[a, b], b) for b in range(M) if b != a and d[a, b] <= eps)
+        for dist, b in cand[:max(keep, 0)]:
+            t = (dist / sigma) ** p
+            W[a, b] = 1.0 / (1.0 + t) if kernel == "inv_power" else math.exp(-t)
+    if symmetrise == "max":
+        W = np.maximum(W, W.T)
+    elif symmetrise == "avg":
+        W = 0.5 * (W + W.T)
+    elif symmetrise == "min":
+        W = np.minimum(W, W.T)
+    deg = W.sum(axis=1)
+    if laplacian == "combinatorial":
+        L = np.diag(deg) - W
+    elif laplacian == "sym":
+        s = np.where(deg > 0, 1.0 / np.sqrt(np.where(deg > 0, deg, 1.0)), 0.0)
+        L = np.diag((deg > 0).astype(float)) - W * np.outer(s, s)
+    else:
+        s = np.where(deg > 0, 1.0 / np.where(deg > 0, deg, 1.0), 0.0)
+        L = np.diag((deg > 0).astype(float)) - W * s[:, None]
+    return L
+
+
+def lam_of(x, L, tau_mode, lambda_form):
+    e = float(x @ L @ x) / float(x @ x)
+    if tau_mode == "median":
+        t = float(np.median(x))
+    elif tau_mode == "median_abs":
+        t = float(np.median(np.abs(x)))
+    else:
+        t = float(np.mean(x))
+    t = max(t, 1e-9)
+    eb = e / (e + t)
+    if lambda_form == "bounded":
+        return eb
+    Ms = -0.5 * (L + L.T)
+    iu = np.triu_indices(len(x), 1)
+    en = Ms[iu] * (x[iu[0]] - x[iu[1]]) ** 2
+    tot = en.sum()
+    g = 0.0 if tot == 0.0 else min(1.0, max(0.0, float((en * en).sum() / (tot * tot))))
+    return t * eb + (1.0 - t) * g
+
+
+def main():
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))["test_0"]
+    X = np.array(kat["items"])
+    gp = kat["graph_params"]
+    q = X[kat["query_item"]] * kat["query_scale"]
+    expect = {float(t): v for t, v in kat["expected_top3"].items()}
+    cosv = (X @ q) / (np.linalg.norm(X, axis=1) * np.linalg.norm(q))
+    space = dict(
+        kernel=["inv_power", "gaussian"], symmetrise=["max", "avg", "min", "none"], k_counts_self=[0, 1],
+        topk_prunes=[0, 1], laplacian=["combinatorial", "sym", "rw"], distance=["cosine", "l2", "l2sq"],
+        tau_mode=["median", "median_abs", "mean"], lambda_form=["bounded", "synthetic"])
+    if "--no-distance" in sys.argv:
+        space["distance"] = ["cosine"]
+    keys = list(space)
+    rows = []
+    for combo in itertools.product(*[space[k] for k in keys]):
+        sw = dict(zip(keys, combo))
+        L = graph(X.T, gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"], sw["kernel"], sw["symmetrise"],
+                  sw["k_counts_self"], sw["topk_prunes"], sw["laplacian"], sw["distance"])
+        lam = np.array([lam_of(x, L, sw["tau_mode"], sw["lambda_form"]) for x in X])
+        lq = lam_of(q, L, sw["tau_mode"], sw["lambda_form"])
+        hits, margin = 0, np.inf
+        for tau, want in expect.items():
+            s = tau * cosv + (1.0 - tau) / (1.0 + np.abs(lq - lam))
+            order = sorted(range(len(s)), key=lambda i: (-s[i], i))
+            hits += sum(int(a == b) for a, b in zip(order[:3], want))
+            if order[:3] == want:
+                ss = [s[i] for i in order[:4]]
+                margin = min(margin, min(ss[j] - ss[j + 1] for j in range(3)))
+        rows.append((hits, margin if np.isfinite(margin) else 0.0, sw))
+    rows.sort(key=lambda r: (-r[0], -r[1]))
+    full = [r for r in rows if r[0] == 12]
+    print("%d combinations, %d reproduce 12/12" % (len(rows), len(full)))
+    default = [r for r in rows if all(r[2][k] == space[k][0] for k in keys)][0]
+    print("default spec: %d/12" % default[0])
+    for hits, margin, sw in full[:40]:
+        diff = {k: v for k, v in sw.items() if v != space[k][0]}
+        print("12/12  min margin %.2e  changed: %s" % (margin, diff))
+
+
+if __name__ == "__main__":
+    main()
