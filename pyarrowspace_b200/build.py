@@ -1,7 +1,7 @@
 """Builds pyarrowspace_b200/libarrowspace_b200.so from csrc/*.cu with nvcc for sm_100a.
 
 In-tree build (the .so travels to the GPU box with the repo snapshot).  Usage:
-    python -m pyarrowspace_b200.build [--force] [--verbose]
+    python -m pyarrowspace_b200.build [--force] [--verbose] [--profiling]
 """
 import concurrent.futures
 import os
@@ -30,14 +30,20 @@ def _deps_mtime():
     return m
 
 
-def _compile(src, verbose):
+def _compile(src, verbose, profiling=False):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DASP_PROFILING"] if profiling else []) + \
+        ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, r.returncode, r.stdout + r.stderr
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, profiling=False):
+    """profiling=True (--profiling) compiles the diagnostic kernel variants in (ASP_TC_VARIANT: results are wrong under
+    them); the default build has none.  A profiling build forces a full recompile, and so does the next default build."""
+    marker = os.path.join(OBJ, ".profiling")
+    if profiling or os.path.exists(marker):
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     hdr = _deps_mtime()
     todo = []
@@ -47,11 +53,15 @@ def build(force=False, verbose=False):
             todo.append(src)
     if todo:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(todo))) as ex:
-            for src, rc, out in ex.map(lambda s: _compile(s, verbose), todo):
+            for src, rc, out in ex.map(lambda s: _compile(s, verbose, profiling), todo):
                 if verbose or rc != 0:
                     sys.stderr.write("---- %s\n%s\n" % (src, out))
                 if rc != 0:
                     raise RuntimeError("nvcc failed on %s" % src)
+    if profiling:
+        open(marker, "w").close()
+    elif os.path.exists(marker):
+        os.remove(marker)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if todo or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
@@ -64,4 +74,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profiling="--profiling" in sys.argv))

@@ -703,6 +703,7 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     if (g->nnodes != s->f)
         ASP_FAIL(ASP_ERR_ARG, "graph has %lld nodes but items have %d features", (long long)g->nnodes, s->f);
     if (nq == 0) return ASP_OK;
+    if (s->f > 6144) ASP_FAIL(ASP_ERR_UNSUPPORTED, "search supports at most 6144 features (got %d)", s->f);
     asp_ctx *ctx = s->ctx;
     ASP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

@@ -468,7 +468,7 @@ int asp_search_impl(const asp_space *s, const asp_graph *g, const double *q_dev,
     double *cand_score = nullptr;
     int32_t *cand_idx = nullptr;
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));
-    if (nq <= GV_MAXQ) {
+    if (nq <= GV_MAXQ && f <= 1536) {            // the GEMV kernel keeps a query in registers: wider vectors take the DMMA tile kernel
         int64_t want = asp_ceil_div(s->n_local, GV_WARPS * 16);
         nparts = (int)(want < ctx->num_sms * 2 ? (want > 0 ? want : 1) : ctx->num_sms * 2);
         ASP_CUDA(cudaMallocAsync(&cand_score, sizeof(double) * (size_t)nq * nparts * LISTSEL, st));

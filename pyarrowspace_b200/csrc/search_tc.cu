@@ -1171,16 +1171,26 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
                         2 * TN * sizeof(float) + 1024;
     const int64_t grid_x = pair ? (qblocks + 1) / 2 * 2 : qblocks;
     dim3 grid((unsigned)grid_x, nchunks);
-    const char *var = getenv("ASP_TC_VARIANT");                   // profiling only: results are wrong for 2 / 3 / 4
+    // Profiling variants (epilogue / MMA switched off: the results are WRONG) exist only in builds with -DASP_PROFILING
+    // (python -m pyarrowspace_b200.build --profiling); the shipped library has no knob that changes a result.
+#ifdef ASP_PROFILING
+    const char *var = getenv("ASP_TC_VARIANT");
     const int v = (var && !dump_dev && !wide) ? atoi(var) : 0;
+#else
+    const int v = 0;
+#endif
     void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
         dump_dev ? (ares ? tc_gemm_kernel<true, 0, true, false, 16> : tc_gemm_kernel<true, 0, false, false, 16>)
         : wide ? (ares ? tc_gemm_kernel<false, 0, true, false, 32> : tc_gemm_kernel<false, 0, false, false, 32>)
+#ifdef ASP_PROFILING
         : pair ? ((v == 2) ? tc_gemm_kernel<false, 2, true, true, 16> : (v == 3) ? tc_gemm_kernel<false, 3, true, true, 16>
                   : (v == 4) ? tc_gemm_kernel<false, 4, true, true, 16> : tc_gemm_kernel<false, 0, true, true, 16>)
         : (v == 4 && ares) ? tc_gemm_kernel<false, 4, true, false, 16>
         : (v == 2) ? (ares ? tc_gemm_kernel<false, 2, true, false, 16> : tc_gemm_kernel<false, 2, false, false, 16>)
         : (v == 3) ? (ares ? tc_gemm_kernel<false, 3, true, false, 16> : tc_gemm_kernel<false, 3, false, false, 16>)
+#else
+        : pair ? tc_gemm_kernel<false, 0, true, true, 16>
+#endif
         : (ares ? tc_gemm_kernel<false, 0, true, false, 16> : tc_gemm_kernel<false, 0, false, false, 16>);
     ASP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASP_CUDA(cudaEventRecord(ctx->ev0, st));

@@ -10,19 +10,22 @@
 // need no second code path.
 //
 // ONE kernel, one pass over X (round 1 had a separate median kernel that read X a second time):
-//   CTA = THR compute threads + 8 auxiliary warps + 1 producer warp, persistent over tiles of T = 16*R vectors.
-//   compute warps   A. load the tile's rows (coalesced, two rows in flight per warp) and store them transposed into shared
-//                      memory xs[feature][item] (row stride T+1: conflict free both ways)
+//   CTA = THR compute threads + 3 auxiliary warps + 1 producer warp, persistent over tiles of T = 16*R vectors.
+//   compute warps   A. load the tile's rows (coalesced, two rows in flight per warp), store them transposed into shared
+//                      memory xs[feature][item] (row stride T+1: conflict free both ways) and select the row's MEDIAN (tau)
+//                      from the registers that still hold it: interpolation search on the empirical distribution
+//                      (~8 passes of 12 compares + one warp reduction; exact, radix selection as fallback)
 //                   B. walk the graph: a (part p = tid/16, lane group g = tid%16) pair owns items g+16r (r < R) and the row
 //                      pieces p, p+NP, ... of the current graph chunk; per FOUR non-zeros: one 8-byte load of 4 columns, two
 //                      16-byte loads of 4 coefficients (broadcasts), 4*R conflict-free 8-byte gathers of x
 //                   C. partial energies: half-warp pairs by shuffle, warps through shared memory in warp order
-//   auxiliary warps the per-vector median (tau) from the rows in L2 -- selection on order-preserving 64-bit keys, either
-//                      ALU-only (packed counters + warp reductions: no shared-memory traffic, the gathers own that pipe) or
-//                      through a shared-memory histogram (ASP_TM_MEDIAN=hist) -- and the left-to-right sums of squares (the
-//                      norm the search divides by, the oracle's order; one thread per item)
+//   auxiliary warps the left-to-right sums of squares (the norm the search divides by, the oracle's order; one thread per item)
+//                      under the graph walk
 //   producer warp   streams the graph, pre-cut into fixed-size chunks (cp.async.bulk + mbarrier, two buffers), and asks L2
 //                      for the next tile's rows (cp.async.bulk.prefetch.L2) so that phase A finds them there
+// Why the median sits in phase A: during the walk the LSU / MIO pipe is ~94 % busy with gathers (ncu), and every
+// warp-collective instruction of a selection (redux, shuffles, shared-memory atomics) queues behind them -- medians on
+// auxiliary warps next to the walk cost 1.9 - 3.7 ms per 1M items whatever the algorithm (profiles/k3_r02.md).
 // Bound: HBM 8*n*f bytes while nnz(L)/f is small; at k = 25 (nnz/f = 41) the 8-byte shared-memory
 // gather per upper non-zero per item binds (128 B/clk/SM), see DESIGN.md section 4.
 //
@@ -46,11 +49,11 @@ constexpr int TM_CH_ROWS = 64;                               // pieces per chunk
 constexpr int TM_OFF_W = 0;                                  // double  [TM_CH_ENT]   coefficient c_ab
 constexpr int TM_OFF_COL = TM_OFF_W + TM_CH_ENT * 8;         // uint16  [TM_CH_ENT]   column b
 constexpr int TM_OFF_DIAG = TM_OFF_COL + TM_CH_ENT * 2;      // double  [TM_CH_ROWS]  L_aa on the first piece of a row, else 0
-constexpr int TM_OFF_PIECE = TM_OFF_DIAG + TM_CH_ROWS * 8;   // uint16x4[TM_CH_ROWS]  {row a, first entry, end entry, 0}
+constexpr int TM_OFF_PIECE = TM_OFF_DIAG + TM_CH_ROWS * 8;   // uint16x4[TM_CH_ROWS]  {row a, first entry (multiple of 4), end entry, 0}
 constexpr int TM_OFF_HDR = TM_OFF_PIECE + TM_CH_ROWS * 8;    // int32   [4]           {pieces in this chunk, 0, 0, 0}
 constexpr int TM_CHUNK_BYTES = TM_OFF_HDR + 16;
 static_assert(TM_CHUNK_BYTES % 16 == 0 && TM_OFF_COL % 16 == 0 && TM_OFF_DIAG % 16 == 0, "bulk copies move 16-byte units");
-constexpr int TM_AUX_WARPS = 8;
+constexpr int TM_AUX_WARPS = 3;                               // norm chains (one thread per item, T <= 64); + 1 producer warp = 4 warps
 
 struct TmBlob {
     void *d_chunks = nullptr;
@@ -109,150 +112,198 @@ __device__ __forceinline__ unsigned long long warp_fetch_unique(const unsigned l
     return __shfl_sync(0xffffffffu, mine, src);
 }
 
-// rank-th smallest key (0-based) of the n present keys held as k[j] of lane l = element l + 32 j.  MSB-first radix
-// selection, 4 bits per pass, NO shared memory: every lane counts its keys into sixteen 8-bit fields of two 64-bit
-// registers, eight warp reductions (redux.sync) add the lanes, every lane scans the 16 totals.  The bits all keys share
-// are skipped and the walk stops as soon as the selected bin holds one key (3-4 passes for F = 384).
-// *count_le = number of keys <= result.
+// One MSB-first radix pass over the keys under (mask, prefix): which digit of `width` bits at `shift` holds the r-th of them.
+// ALU form, NO shared memory: every lane counts its keys into sixteen 8-bit fields of two 64-bit registers, eight warp
+// reductions (redux.sync) add the lanes, every lane scans the 16 totals.  width <= 4.
 template <int FPL>
-__device__ unsigned long long warp_select_alu(const unsigned long long (&k)[FPL], int n, int rank, int lane, int *count_le)
+__device__ __forceinline__ void radix_pass_alu(const unsigned long long (&k)[FPL], int n, int lane, unsigned long long mask,
+                                               unsigned long long prefix, int shift, int width, int r, uint32_t *digit,
+                                               uint32_t *cnt, uint32_t *before)
 {
     static_assert(FPL <= 255, "8-bit per-lane counters");
-    unsigned long long k0;
-    const int lead = warp_common_lead<FPL>(k, n, lane, &k0);
-    if (lead == 64) { *count_le = n; return k0; }
-    const int top = 64 - lead;                                                   // low bits that may differ, >= 1
-    int shift = top > 4 ? top - 4 : 0;
-    int width = top - shift;
-    unsigned long long prefix = (top == 64) ? 0ull : (k0 >> top) << top;
-    unsigned long long mask = (top == 64) ? 0ull : ~0ull << top;
-    int below = 0, r = rank;
-    for (;;) {
-        unsigned long long ca = 0ull, cb = 0ull;                                 // bins 0-7 / 8-15, 8 bits each
-        const uint32_t dmask = (1u << width) - 1u;
+    unsigned long long ca = 0ull, cb = 0ull;                                     // bins 0-7 / 8-15, 8 bits each
+    const uint32_t dmask = (1u << width) - 1u;
 #pragma unroll
-        for (int j = 0; j < FPL; ++j) {
-            const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
-            const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
-            const unsigned long long inc = act ? (1ull << (8 * (d & 7u))) : 0ull;
-            if (d & 8u) cb += inc; else ca += inc;
-        }
-        uint32_t c[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t wa = (uint32_t)((ca >> (16 * i)) & 0xffull) | ((uint32_t)((ca >> (16 * i + 8)) & 0xffull) << 16);
-            const uint32_t wb = (uint32_t)((cb >> (16 * i)) & 0xffull) | ((uint32_t)((cb >> (16 * i + 8)) & 0xffull) << 16);
-            const uint32_t ta = __reduce_add_sync(0xffffffffu, wa), tb = __reduce_add_sync(0xffffffffu, wb);
-            c[2 * i] = ta & 0xffffu; c[2 * i + 1] = ta >> 16;
-            c[8 + 2 * i] = tb & 0xffffu; c[8 + 2 * i + 1] = tb >> 16;
-        }
-        uint32_t run = 0, digit = 0, cnt = 0, before = 0;
-        bool found = false;
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            const bool here = !found && (run + c[b] > (uint32_t)r);
-            if (here) { digit = b; cnt = c[b]; before = run; found = true; }
-            run += c[b];
-        }
-        below += (int)before;
-        r -= (int)before;
-        prefix |= (unsigned long long)digit << shift;
-        mask |= (unsigned long long)dmask << shift;
-        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }         // cnt equal keys
-        if (cnt == 1u) { *count_le = below + 1; return warp_fetch_unique<FPL>(k, n, lane, mask, prefix); }
-        const int next = shift > 4 ? shift - 4 : 0;
-        width = shift - next;
-        shift = next;
+    for (int j = 0; j < FPL; ++j) {
+        const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
+        const uint32_t d = (uint32_t)(k[j] >> shift) & dmask;
+        const unsigned long long inc = act ? (1ull << (8 * (d & 7u))) : 0ull;
+        if (d & 8u) cb += inc; else ca += inc;
     }
+    uint32_t c[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t wa = (uint32_t)((ca >> (16 * i)) & 0xffull) | ((uint32_t)((ca >> (16 * i + 8)) & 0xffull) << 16);
+        const uint32_t wb = (uint32_t)((cb >> (16 * i)) & 0xffull) | ((uint32_t)((cb >> (16 * i + 8)) & 0xffull) << 16);
+        const uint32_t ta = __reduce_add_sync(0xffffffffu, wa), tb = __reduce_add_sync(0xffffffffu, wb);
+        c[2 * i] = ta & 0xffffu; c[2 * i + 1] = ta >> 16;
+        c[8 + 2 * i] = tb & 0xffffu; c[8 + 2 * i + 1] = tb >> 16;
+    }
+    uint32_t run = 0, dg = 0, cn = 0, bf = 0;
+    bool found = false;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const bool here = !found && (run + c[b] > (uint32_t)r);
+        if (here) { dg = b; cn = c[b]; bf = run; found = true; }
+        run += c[b];
+    }
+    *digit = dg; *cnt = cn; *before = bf;
 }
 
-// the same selection, 8 bits per pass through a 256-bin shared-memory histogram of the warp (round 1's median kernel);
-// kept for the A/B (ASP_TM_MEDIAN=hist): its shared-memory atomics compete with the gathers of the compute warps.
+// rank-th smallest key (0-based) of the n present keys held as k[j] of lane l = element l + 32 j.  MSB-first radix
+// selection, 4 bits per pass; the bits all keys share are skipped and the walk stops as soon as the selected bin holds one
+// key.  Exact for ANY input (ties, signed zeros, hundreds of binades): the fallback of the interpolation search below.
+// *count_le = number of keys <= result.
 template <int FPL>
-__device__ unsigned long long warp_select_hist(const unsigned long long (&k)[FPL], int n, int rank, int lane,
-                                               uint32_t *hist /* [256] of this warp */, int *count_le)
+__device__ unsigned long long warp_select(const unsigned long long (&k)[FPL], int n, int rank, int lane, int *count_le)
 {
     unsigned long long k0;
     const int lead = warp_common_lead<FPL>(k, n, lane, &k0);
     if (lead == 64) { *count_le = n; return k0; }
-    const int top = 64 - lead;
-    int shift = top > 8 ? top - 8 : 0;
-    int width = top - shift;
-    unsigned long long prefix = (top == 64) ? 0ull : (k0 >> top) << top;
-    unsigned long long mask = (top == 64) ? 0ull : ~0ull << top;
+    int remaining = 64 - lead;                                                   // low bits that may differ, >= 1
+    unsigned long long prefix = (remaining == 64) ? 0ull : (k0 >> remaining) << remaining;
+    unsigned long long mask = (remaining == 64) ? 0ull : ~0ull << remaining;
     int below = 0, r = rank;
     for (;;) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0u;
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) {
-            const bool act = ((lane + 32 * j) < n) && ((k[j] & mask) == prefix);
-            if (act) atomicAdd(&hist[(uint32_t)(k[j] >> shift) & ((1u << width) - 1u)], 1u);
-        }
-        __syncwarp();
-        uint32_t c[8];                                                           // lane l owns bins 8l .. 8l+7
-        const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 8 * lane), h1 = *reinterpret_cast<const uint4 *>(hist + 8 * lane + 4);
-        c[0] = h0.x; c[1] = h0.y; c[2] = h0.z; c[3] = h0.w; c[4] = h1.x; c[5] = h1.y; c[6] = h1.z; c[7] = h1.w;
-        uint32_t tot = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) tot += c[b];
-        uint32_t incl = tot;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        const unsigned owners = __ballot_sync(0xffffffffu, incl > (uint32_t)r);
-        const int owner = __ffs(owners) - 1;
-        uint32_t run = incl - tot, digit = 0, cnt = 0, before = 0;
-        if (lane == owner) {
-            bool found = false;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool here = !found && (run + c[b] > (uint32_t)r);
-                if (here) { digit = 8 * lane + b; cnt = c[b]; before = run; found = true; }
-                run += c[b];
-            }
-        }
-        digit = __shfl_sync(0xffffffffu, digit, owner);
-        cnt = __shfl_sync(0xffffffffu, cnt, owner);
-        before = __shfl_sync(0xffffffffu, before, owner);
+        const int shift = remaining > 4 ? remaining - 4 : 0;
+        const int width = remaining - shift;
+        uint32_t digit, cnt, before;
+        radix_pass_alu<FPL>(k, n, lane, mask, prefix, shift, width, r, &digit, &cnt, &before);
         below += (int)before;
         r -= (int)before;
         prefix |= (unsigned long long)digit << shift;
         mask |= (unsigned long long)((1u << width) - 1u) << shift;
-        __syncwarp();
-        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }
+        if (shift == 0) { *count_le = below + (int)cnt; return prefix; }         // cnt equal keys
         if (cnt == 1u) { *count_le = below + 1; return warp_fetch_unique<FPL>(k, n, lane, mask, prefix); }
-        const int next = shift > 8 ? shift - 8 : 0;
-        width = shift - next;
-        shift = next;
+        remaining = shift;
     }
 }
 
-// median of the n present keys: the middle one, or the mean of the two middle ones (oracle.c median_of)
-template <int FPL, bool HIST>
-__device__ double warp_median(const unsigned long long (&k)[FPL], int n, int lane, uint32_t *hist)
+// warp minimum / maximum of per-lane doubles through their order-preserving keys: four redux.sync, no shuffles
+__device__ __forceinline__ double warp_min_f64(double v)
 {
-    int cle = 0;
-    const int r0 = (n & 1) ? n / 2 : n / 2 - 1;
-    const unsigned long long klo = HIST ? warp_select_hist<FPL>(k, n, r0, lane, hist, &cle) : warp_select_alu<FPL>(k, n, r0, lane, &cle);
-    if (n & 1) return key_f64(klo);
-    unsigned long long khi = klo;
-    if (cle < n / 2 + 1) {                   // the next order statistic is the smallest key > klo
-        unsigned long long m = ~0ull;
+    const unsigned long long k = f64_key(v);
+    const uint32_t hi = __reduce_min_sync(0xffffffffu, (uint32_t)(k >> 32));
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, ((uint32_t)(k >> 32) == hi) ? (uint32_t)k : 0xffffffffu);
+    return key_f64(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ double warp_max_f64(double v)
+{
+    const unsigned long long k = f64_key(v);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(k >> 32));
+    const uint32_t lo = __reduce_max_sync(0xffffffffu, ((uint32_t)(k >> 32) == hi) ? (uint32_t)k : 0u);
+    return key_f64(((unsigned long long)hi << 32) | lo);
+}
+
+// Exact selection by INTERPOLATION SEARCH on the empirical distribution, NV rows of one warp in lock step (NV = 2 gives the
+// dependent chain of a pass -- compare, count, interpolate -- a second independent instance to overlap with).
+// v[i][j] of lane l = element l + 32 j of row i (absent elements: NaN).  Per row: a bracket (lo, hi] that contains the wanted
+// order statistic, c(lo) = #{v <= lo} <= rank < c(hi); the pivot is the linear interpolation of the rank inside the bracket;
+// one pass counts #{v <= pivot} (12 compares per row at F = 384, the lane counts of both rows packed in one register and
+// summed by a 5-step shuffle butterfly) and shrinks the bracket; a bracket that holds exactly one element ends the search
+// and the element is fetched from the lane that owns it.  ~8 passes for embedding rows (C4 data: mean 8.2, p95 13) against
+// ~2500 instructions for the radix selection.  ok[i] = false when row i was not isolated within MAX_PASSES (duplicates around
+// the wanted rank, values spanning hundreds of binades, non-finite entries): the caller falls back to the radix selection.
+template <int FPL, int NV>
+__device__ void warp_select_interp(const double (&v)[NV][FPL], const bool (&want)[NV], int n, int rank, int lane,
+                                   double (&result)[NV], int (&count_le)[NV], bool (&ok)[NV])
+{
+    constexpr int MAX_PASSES = 16;
+    double lo[NV], hi[NV];
+    int clo[NV], chi[NV];
+    bool active[NV];
 #pragma unroll
-        for (int j = 0; j < FPL; ++j)
-            if ((lane + 32 * j) < n && k[j] > klo && k[j] < m) m = k[j];
+    for (int i = 0; i < NV; ++i) {
+        ok[i] = false;
+        active[i] = want[i];
+        // bracket from the high words of the extreme keys: lo strictly below every element, hi at or above every element
+        double mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, off);
-            m = (o < m) ? o : m;
-        }
-        khi = m;
+        for (int j = 0; j < FPL; ++j) { mn = fmin(mn, v[i][j]); mx = fmax(mx, v[i][j]); }   // fmin / fmax skip the NaN of absent elements
+        const uint32_t kmn = __reduce_min_sync(0xffffffffu, (uint32_t)(f64_key(mn) >> 32));
+        const uint32_t kmx = __reduce_max_sync(0xffffffffu, (uint32_t)(f64_key(mx) >> 32));
+        lo[i] = key_f64((((unsigned long long)kmn) << 32) - 1ull);
+        hi[i] = key_f64((((unsigned long long)kmx) << 32) | 0xffffffffull);
+        clo[i] = 0;
+        chi[i] = n;
+        if (!(hi[i] - lo[i] < INFINITY) || kmn == 0u) active[i] = false;         // non-finite entries / overflowing range: radix decides
     }
-    return 0.5 * (key_f64(klo) + key_f64(khi));
+    for (int pass = 0; pass < MAX_PASSES; ++pass) {
+        bool any = false;
+        double p[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            p[i] = hi[i];
+            if (!active[i]) continue;
+            if (chi[i] - clo[i] == 1) {                                          // exactly one element in (lo, hi]: fetch it
+                double mine = 0.0;
+                bool have = false;
+#pragma unroll
+                for (int j = 0; j < FPL; ++j) { const bool in = (v[i][j] > lo[i]) && (v[i][j] <= hi[i]); if (in) { mine = v[i][j]; have = true; } }
+                const int src = __ffs(__ballot_sync(0xffffffffu, have)) - 1;
+                result[i] = __shfl_sync(0xffffffffu, mine, src) + 0.0;           // (-0.0 folded like the keys)
+                count_le[i] = chi[i];
+                ok[i] = true;
+                active[i] = false;
+                continue;
+            }
+            const float frac = __fdividef((float)(rank - clo[i]) + 0.5f, (float)(chi[i] - clo[i]));
+            double q = fma(hi[i] - lo[i], (double)frac, lo[i]);
+            if (!(q > lo[i] && q < hi[i])) q = lo[i] + 0.5 * (hi[i] - lo[i]);
+            if (!(q > lo[i] && q < hi[i])) { active[i] = false; continue; }      // no double strictly inside: equal values, radix decides
+            p[i] = q;
+            any = true;
+        }
+        if (!any) return;
+        uint32_t c = 0;                                                          // lane counts of the rows, 16 bits each
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) c += (v[i][j] <= p[i]) ? (1u << (16 * i)) : 0u;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (!active[i]) continue;
+            const int ci = (int)((c >> (16 * i)) & 0xffffu);
+            if (ci > rank) { hi[i] = p[i]; chi[i] = ci; } else { lo[i] = p[i]; clo[i] = ci; }
+        }
+    }
+}
+
+// medians of NV rows: the middle element, or the mean of the two middle ones (oracle.c median_of).  v[i][j] of lane l =
+// element l + 32 j of row i (NaN when absent, already |.|-ed for median_abs).  use_interp: interpolation search first, radix
+// selection as its fallback; else the radix selection only (A/B).
+template <int FPL, int NV>
+__device__ void warp_medians(const double (&v)[NV][FPL], const bool (&want)[NV], int n, int lane, int use_interp, double (&med)[NV])
+{
+    static_assert(NV <= 2 && FPL * 32 < 65536, "lane counts are packed 16 bits per row");
+    const int r0 = (n & 1) ? n / 2 : n / 2 - 1;
+    double vlo[NV];
+    int cle[NV];
+    bool ok[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { ok[i] = false; vlo[i] = 0.0; cle[i] = 0; }
+    if (use_interp) warp_select_interp<FPL, NV>(v, want, n, r0, lane, vlo, cle, ok);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (!want[i]) { med[i] = 1.0; continue; }
+        if (!ok[i]) {
+            unsigned long long k[FPL];
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) k[j] = ((lane + 32 * j) < n) ? f64_key(v[i][j]) : ~0ull;
+            vlo[i] = key_f64(warp_select<FPL>(k, n, r0, lane, &cle[i]));
+        }
+        double vhi = vlo[i];
+        if (!(n & 1) && cle[i] < n / 2 + 1) {    // the next order statistic is the smallest value > vlo
+            double m = INFINITY;
+#pragma unroll
+            for (int j = 0; j < FPL; ++j)
+                if (v[i][j] > vlo[i]) m = fmin(m, v[i][j]);
+            vhi = warp_min_f64(m) + 0.0;
+        }
+        med[i] = (n & 1) ? vlo[i] : 0.5 * (vlo[i] + vhi);
+    }
 }
 
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
@@ -270,10 +321,10 @@ __device__ __forceinline__ void named_sync(int nthreads) { asm volatile("bar.syn
 template <int ID>
 __device__ __forceinline__ void named_arrive(int nthreads) { asm volatile("bar.arrive %0, %1;\n" ::"n"(ID), "r"(nthreads) : "memory"); }
 
-template <int FPL, int R, int THR, bool SYN, bool HIST>
+template <int FPL, int R, int THR, bool SYN>
 __global__ void __launch_bounds__(THR + 32 * TM_AUX_WARPS + 32, 1)
 taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const unsigned char *__restrict__ blob, int nchunks,
-               int tau_mode, double tau_fixed, double *__restrict__ out_energy, double *__restrict__ out_tau,
+               int tau_mode, double tau_fixed, int use_interp, double *__restrict__ out_energy, double *__restrict__ out_tau,
                double *__restrict__ out_lambda, double *__restrict__ out_norm, double *__restrict__ out_inv_norm, int *zero_flag)
 {
     constexpr int T = 16 * R;
@@ -287,7 +338,6 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     double *red = reinterpret_cast<double *>(cbuf + 2 * TM_CHUNK_BYTES);                        // NW * T
     double *s_tau = red + NW * T;                                                               // T
     double *s_n2 = s_tau + T;                                                                   // T
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_n2 + T);                                  // HIST: TM_AUX_WARPS * 256
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,69 +378,67 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t item0 = tile * T;
         if (is_aux) {
-            // ---- tau (median / mean / fixed) of this warp's items, rows read from L2; independent of the transposed tile
-            for (int t = aw; t < T; t += TM_AUX_WARPS) {
-                const int64_t item = item0 + t;
-                double tau = 1.0;
-                if (item < n) {
-                    if (tau_mode == ASP_TAU_MEDIAN || tau_mode == ASP_TAU_MEDIAN_ABS) {
-                        const double *row = x + item * pitch;
-                        unsigned long long k[FPL];
-#pragma unroll
-                        for (int j = 0; j < FPL; ++j) {
-                            const int ff = lane + 32 * j;
-                            double v = (ff < f) ? asp::ld_nc_f64(row + ff) : 0.0;
-                            if (tau_mode == ASP_TAU_MEDIAN_ABS) v = fabs(v);
-                            k[j] = (ff < f) ? f64_key(v) : ~0ull;
-                        }
-                        tau = warp_median<FPL, HIST>(k, f, lane, HIST ? s_hist + aw * 256 : nullptr);
-                    } else if (tau_mode == ASP_TAU_FIXED) {
-                        tau = tau_fixed;
-                    }
-                }
-                if (lane == 0 && tau_mode != ASP_TAU_MEAN) s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
-            }
-            // ---- left-to-right sums (norm^2; mean), one thread per item, once the transposed tile is complete
-            const int t = threadIdx.x - THR;
-            if (t < ((T + 31) & ~31)) {
-                named_sync<3>(THR + ((T + 31) & ~31));
-                if (t < T) {
-                    double n2 = 0.0, sm = 0.0;
+            named_sync<3>(THR + NAUX);                                 // the transposed tile is complete
+            // ---- left-to-right sums (norm^2; mean), one thread per item
+            const int ct = threadIdx.x - THR;
+            if (ct < T) {
+                double n2 = 0.0, sm = 0.0;
 #pragma unroll 8
-                    for (int ff = 0; ff < f; ++ff) {                   // loads and products run ahead; only the adds are a chain
-                        const double xv = xs[ff * XS + t];
-                        n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
-                        sm = __dadd_rn(sm, xv);
-                    }
-                    s_n2[t] = n2;
-                    if (tau_mode == ASP_TAU_MEAN) { const double tau = sm / (double)f; s_tau[t] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR; }
+                for (int ff = 0; ff < f; ++ff) {                       // loads and products run ahead; only the adds are a chain
+                    const double xv = xs[ff * XS + ct];
+                    n2 = __dadd_rn(n2, __dmul_rn(xv, xv));
+                    sm = __dadd_rn(sm, xv);
+                }
+                s_n2[ct] = n2;
+                if (tau_mode == ASP_TAU_MEAN || tau_mode == ASP_TAU_FIXED) {     // (the medians come from the compute warps, phase A)
+                    const double tau = (tau_mode == ASP_TAU_MEAN) ? sm / (double)f : tau_fixed;
+                    s_tau[ct] = (tau > TAU_FLOOR) ? tau : TAU_FLOOR;
                 }
             }
         } else {
-            // ---- A: rows -> transposed tile, two rows in flight per warp (one when a row is more than 24 registers wide)
-            constexpr bool TWO = FPL <= 24;
-            for (int t0 = warp; t0 < T; t0 += (TWO ? 2 : 1) * NW) {
-                const int t1 = t0 + NW;
-                double v0[FPL], v1[TWO ? FPL : 1];
-                const bool in0 = item0 + t0 < n, in1 = TWO && (t1 < T) && (item0 + t1 < n);
-                const double *row0 = x + (item0 + t0) * pitch, *row1 = x + (item0 + t1) * pitch;
+            // ---- A: rows -> transposed tile, two rows in flight per warp (one when a row is more than 24 registers wide).
+            // The per-vector median (tau) is selected HERE, from the registers that hold the row: in this phase the LSU /
+            // MIO pipe is idle (the warps wait for L2), whereas during the graph walk every warp-collective instruction of
+            // a selection (redux, shuffles, shared-memory atomics) queues behind the gathers -- measured: 64 medians on
+            // auxiliary warps next to the walk cost 1.9 - 3.7 ms per 1M items whatever the selection algorithm.
+            const bool want_median = (tau_mode == ASP_TAU_MEDIAN || tau_mode == ASP_TAU_MEDIAN_ABS);
+            constexpr int NV = (FPL <= 24) ? 2 : 1;
+            for (int t0 = warp; t0 < T; t0 += NV * NW) {
+                double vv[NV][FPL];
+                bool in[NV];
 #pragma unroll
-                for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; v0[j] = (in0 && ff < f) ? row0[ff] : 0.0; }
-                if constexpr (TWO) {
+                for (int i = 0; i < NV; ++i) {
+                    const int t = t0 + i * NW;
+                    in[i] = (t < T) && (item0 + t < n);
+                    const double *row = x + (item0 + t) * pitch;
 #pragma unroll
-                    for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; v1[j] = (in1 && ff < f) ? row1[ff] : 0.0; }
+                    for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; vv[i][j] = (in[i] && ff < f) ? row[ff] : 0.0; }
                 }
 #pragma unroll
-                for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; if (ff < f) xs[ff * XS + t0] = v0[j]; }
-                if constexpr (TWO) {
-                    if (t1 < T) {
+                for (int i = 0; i < NV; ++i) {
+                    const int t = t0 + i * NW;
+                    if (t < T) {
 #pragma unroll
-                        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; if (ff < f) xs[ff * XS + t1] = v1[j]; }
+                        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; if (ff < f) xs[ff * XS + t] = vv[i][j]; }
+                    }
+                }
+                if (want_median) {
+                    const bool ab = tau_mode == ASP_TAU_MEDIAN_ABS;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i)
+#pragma unroll
+                        for (int j = 0; j < FPL; ++j) { const int ff = lane + 32 * j; vv[i][j] = (ff < f) ? (ab ? fabs(vv[i][j]) : vv[i][j]) : NAN; }
+                    double med[NV];
+                    warp_medians<FPL, NV>(vv, in, f, lane, use_interp, med);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const int t = t0 + i * NW;
+                        if (lane == 0 && t < T) s_tau[t] = (med[i] > TAU_FLOOR) ? med[i] : TAU_FLOOR;
                     }
                 }
             }
             named_sync<1>(THR);                                        // the tile is complete (compute warps)
-            named_arrive<3>(THR + ((T + 31) & ~31));                   // ... and the norm threads may start
+            named_arrive<3>(THR + NAUX);                               // ... and the auxiliary warps may start
 
             // ---- B: x^T L x through the upper coefficients, chunk by chunk
             double en[R], tot[SYN ? R : 1], sq[SYN ? R : 1];
@@ -414,7 +462,8 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
                     double xa[R], s[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) { xa[r] = xg[a * XS + 16 * r]; s[r] = 0.0; }
-                    for (int j = jb; j < je; j += 4) {
+                    int j = jb;
+                    for (; j + 4 <= je; j += 4) {
                         const uint2 c4 = *reinterpret_cast<const uint2 *>(cc + j);
                         const double2 w01 = *reinterpret_cast<const double2 *>(cw + j), w23 = *reinterpret_cast<const double2 *>(cw + j + 2);
                         const double *x0 = xg + (int)(c4.x & 0xffffu) * XS, *x1 = xg + (int)(c4.x >> 16) * XS;
@@ -432,6 +481,16 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
                                 tot[r] += (e0 + e1) + (e2 + e3);
                                 sq[r] = fma(e0, e0, fma(e1, e1, fma(e2, e2, fma(e3, e3, sq[r]))));
                             }
+                        }
+                    }
+                    for (; j < je; ++j) {                              // the 0-3 entries left of the piece, one at a time
+                        const double w = cw[j];
+                        const double *x0 = xg + (int)cc[j] * XS;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const double b0 = x0[16 * r];
+                            s[r] = fma(w, b0, s[r]);
+                            if (SYN) { const double d0 = xa[r] - b0, e0 = w * d0 * d0; tot[r] += e0; sq[r] = fma(e0, e0, sq[r]); }
                         }
                     }
                     const double dg = cdiag[slot];
@@ -619,14 +678,15 @@ int launch_tm(asp_ctx *ctx, const TmBlob *blob, const asp_switches *sw, const do
 {
     constexpr int T = 16 * R;
     constexpr int NTHREADS = THR + 32 * TM_AUX_WARPS + 32;
-    const char *menv = getenv("ASP_TM_MEDIAN");
-    const bool hist = menv && menv[0] == 'h';
+    // median selection (A/B knob ASP_TM_MEDIAN = interp | alu): interpolation search with the ALU radix selection as its
+    // fallback, or the radix selection alone; both select the same element, so the knob cannot change a result.
+    int use_interp = 1;
+    if (const char *menv = getenv("ASP_TM_MEDIAN")) { if (menv[0] == 'a') use_interp = 0; }
     const bool syn = sw->lambda_form == ASP_LAMBDA_SYNTHETIC;
     const size_t smem = (((size_t)f * (T + 1) * 8 + 15) & ~(size_t)15) + 2 * (size_t)TM_CHUNK_BYTES + (size_t)(THR / 32) * T * 8 +
-                        (size_t)T * 16 + (hist ? (size_t)TM_AUX_WARPS * 1024 : 0);
+                        (size_t)T * 16;
     if (smem > 227 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "taumode kernel: %d features do not fit in shared memory", f);
-    auto kern = syn ? taumode_kernel<FPL, R, THR, true, false>
-                    : hist ? taumode_kernel<FPL, R, THR, false, true> : taumode_kernel<FPL, R, THR, false, false>;
+    auto kern = syn ? taumode_kernel<FPL, R, THR, true> : taumode_kernel<FPL, R, THR, false>;
     ASP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;                                                       // resident CTAs per SM: their load / gather phases overlap
     ASP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem));
@@ -635,7 +695,7 @@ int launch_tm(asp_ctx *ctx, const TmBlob *blob, const asp_switches *sw, const do
     const int64_t slots = (int64_t)ctx->num_sms * occ;
     const int grid = (int)(ntiles < slots ? ntiles : slots);
     kern<<<grid, NTHREADS, smem, ctx->stream>>>(x, n, f, pitch, static_cast<const unsigned char *>(blob->d_chunks), blob->nchunks,
-                                                  sw->tau_mode, sw->tau_fixed, oe, ot, ol, on, oi, zero_flag);
+                                                  sw->tau_mode, sw->tau_fixed, use_interp, oe, ot, ol, on, oi, zero_flag);
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
     return ASP_OK;
@@ -695,10 +755,10 @@ int build_tm_blob(asp_ctx *ctx, const asp_graph *g, TmBlob *out)
             const Piece &pc = pieces[i];
             const int padded = (pc.len + 3) & ~3;
             if (ne + padded > TM_CH_ENT) break;
-            cp[4 * np + 0] = (uint16_t)pc.row; cp[4 * np + 1] = (uint16_t)ne; cp[4 * np + 2] = (uint16_t)(ne + padded); cp[4 * np + 3] = 0;
+            cp[4 * np + 0] = (uint16_t)pc.row; cp[4 * np + 1] = (uint16_t)ne; cp[4 * np + 2] = (uint16_t)(ne + pc.len); cp[4 * np + 3] = 0;
             cd[np] = pc.diag;
             for (int e = 0; e < padded; ++e) {
-                cw[ne + e] = e < pc.len ? uval[pc.beg + e] : 0.0;      // padding: coefficient 0 on the row's own column
+                cw[ne + e] = e < pc.len ? uval[pc.beg + e] : 0.0;      // storage padding (pieces start on 4-entry boundaries), never walked
                 cc[ne + e] = (uint16_t)(e < pc.len ? ucol[pc.beg + e] : pc.row);
             }
             ne += padded; ++np; ++i;

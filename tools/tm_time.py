@@ -22,8 +22,8 @@ lab = torch.randint(0, 256, (n,), generator=g, device="cuda")
 x = centres[lab] + 0.3 * torch.randn(n, f, generator=g, device="cuda", dtype=torch.float64)
 x = x / x.norm(dim=1, keepdim=True) * 100.0 + 25.0
 gp = {"eps": 10.0, "k": k, "topk": 10, "p": 2.0, "sigma": None}
-cases = [("median_alu", {}, {}), ("median_hist", {"ASP_TM_MEDIAN": "hist"}, {}), ("mean", {}, {"tau_mode": "mean"}),
-         ("fixed", {}, {"tau_mode": "fixed", "tau_fixed": 0.3}), ("synthetic", {}, {"lambda_form": "synthetic", "tau_mode": "mean"})]
+cases = [("median_interp", {}, {}), ("median_alu", {"ASP_TM_MEDIAN": "alu"}, {}), ("median_abs_interp", {}, {"tau_mode": "median_abs"}),
+         ("mean", {}, {"tau_mode": "mean"}), ("synthetic", {}, {"lambda_form": "synthetic", "tau_mode": "mean"})]
 out = {"n": n, "f": f, "k": k}
 ref = None
 for rnd in range(4):
@@ -35,11 +35,11 @@ for rnd in range(4):
         out.setdefault(name, []).append(api.stat("lambda_ms"))
         if rnd == 0:
             lam = aspace.lambdas()
-            if name == "median_alu":
+            if name == "median_interp":
                 ref = lam
                 out["upper_nnz"] = (gl.nnz - f) // 2
-            if name == "median_hist":
-                out["hist_equals_alu_bitwise"] = bool(np.array_equal(lam, ref))
+            elif name.startswith("median"):
+                out[name + "_equals_interp_bitwise"] = bool(np.array_equal(lam, ref))
         del aspace, gl
 for name, _, _ in cases:
     out[name + "_median_ms"] = float(np.median(out[name][1:]))
