@@ -465,8 +465,12 @@ def _merge_across_ranks(space, idx, score, nq, topk):
         out_sc = torch.empty((nq, topk), dtype=torch.float64, device=dev)
         t_idx, t_sc = t_idx.contiguous(), t_sc.contiguous()
         torch.cuda.current_stream(dev).synchronize()
-        _lib.check(lib.asp_peer_merge(space._ctx, world, dist.get_rank(group), st["ptrs"], st["cap"], st["epoch"],
-                                      t_idx.data_ptr(), t_sc.data_ptr(), nq, topk, out_idx.data_ptr(), out_sc.data_ptr()))
+        try:
+            _lib.check(lib.asp_peer_merge(space._ctx, world, dist.get_rank(group), st["ptrs"], st["cap"], st["epoch"],
+                                          t_idx.data_ptr(), t_sc.data_ptr(), nq, topk, out_idx.data_ptr(), out_sc.data_ptr()))
+        except LibraryError:
+            space._peer = None          # flags / epochs are out of step now: the next call re-rendezvouses (zeroed flags + barrier)
+            raise
         if was_numpy:
             return out_idx.cpu().numpy(), out_sc.cpu().numpy()
         return out_idx, out_sc

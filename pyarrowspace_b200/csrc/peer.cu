@@ -9,7 +9,8 @@
 //      (st.release.sys), and
 //   2. merges as soon as the flags of all ranks show the current epoch (ld.acquire.sys on its own memory).
 // No rank waits on another before it has published its own lists, so the wait cannot deadlock; it is bounded anyway
-// (a few seconds of clock64) and reports a timeout instead of hanging the GPU.
+// (60 s of clock64 by default) and reports a timeout instead of hanging the GPU; after a timeout the Python layer drops the
+// exchange buffer, so the next call re-rendezvouses on zeroed flags behind a barrier.
 //
 // Buffer layout (the same on every rank; `cap` = queries the buffer was sized for):
 //   [0, 4096)                                   uint32 flag[2 parities][ASP_PEER_MAX_WORLD]
@@ -26,6 +27,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -42,6 +44,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// the exchange buffer is written by REMOTE GPUs while this kernel runs: no const / __restrict__ on it (the compiler could
+// emit ld.global.nc, undefined for data modified during the kernel's lifetime) and system-scope relaxed loads after the acquire
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -84,7 +95,7 @@ __device__ __forceinline__ bool pkey_better(const PKey &x, const PKey &y) { retu
 
 // step 2: one block per query; waits for all flags, then the same bitonic merge as topk_merge_kernel (search.cu)
 __global__ void __launch_bounds__(128)
-peer_merge_kernel(const unsigned char *__restrict__ own, int world, int parity, uint32_t epoch, int64_t nq, int64_t cap,
+peer_merge_kernel(unsigned char *own, int world, int parity, uint32_t epoch, int64_t nq, int64_t cap,
                   int topk, int p2, long long timeout_cycles, int64_t *__restrict__ out_idx, double *__restrict__ out_score,
                   int *status)
 {
@@ -115,8 +126,8 @@ peer_merge_kernel(const unsigned char *__restrict__ own, int world, int parity, 
             const int p = i / topk, j = i % topk;
             const int64_t *pi = reinterpret_cast<const int64_t *>(own + PEER_HEADER + ((size_t)parity * world + p) * slot);
             const double *ps = reinterpret_cast<const double *>(pi + (size_t)cap * topk);
-            const int64_t id = pi[qi * topk + j];
-            if (id >= 0) { k.s = ps[qi * topk + j]; k.i = id; }
+            const int64_t id = (int64_t)ld_relaxed_sys_u64(pi + qi * topk + j);
+            if (id >= 0) { k.s = __longlong_as_double((long long)ld_relaxed_sys_u64(ps + qi * topk + j)); k.i = id; }
         }
         keys[i] = k;
     }
@@ -179,7 +190,11 @@ int asp_peer_merge(asp_ctx *ctx, int world, int rank, const uint64_t *peer_bases
     ASP_CUDA(cudaGetLastError());
     ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaFuncSetAttribute(peer_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long timeout_cycles = 4000000000LL;                       // ~2 s at 2 GHz: a missing rank is an error, not a hang
+    // a missing rank is an error, not a hang -- but ordinary rank skew (a first-call cache build, page faults, a GC pause on
+    // another rank) is not an error: 60 s by default, ASP_PEER_TIMEOUT_S overrides
+    double timeout_s = 60.0;
+    if (const char *e = getenv("ASP_PEER_TIMEOUT_S")) { const double v = atof(e); if (v > 0.0) timeout_s = v; }
+    const long long timeout_cycles = (long long)(timeout_s * 2.0e9);
     peer_merge_kernel<<<(unsigned)nq, 128, smem, st>>>(pp.base[rank], world, parity, e32, nq, cap, (int)topk, p2, timeout_cycles,
                                                        out_idx_dev, out_score_dev, reinterpret_cast<int *>(scratch + 1));
     ASP_CUDA(cudaGetLastError());
