@@ -170,6 +170,7 @@ int asp_search_slow_path(const asp_space *s, const double *q_dev, int32_t qpitch
                          const double *qnorm_dev, double tau, int64_t topk, const int32_t *slow_list_dev, int nslow,
                          int64_t *out_idx_dev, double *out_score_dev);
 int asp_make_f16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows);
+int asp_make_f16_tmap_narrow(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows, int nw);
 
 // knn.cu
 int asp_item_knn(asp_space *s, const asp_graph_params *gp, asp_knn_lists *lists);

@@ -20,6 +20,20 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// one lane of the (fully active) warp: the same lane every time
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -179,9 +193,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Arrive on an mbarrier of a peer CTA.  Default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): the
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of every arrive (22 % of the epilogue warps' samples in
+// the CTA-pair kernel, profiles/tc_pair_r02.md); what the consumer waits for here -- TMEM reads having completed -- is ordered
+// by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tiled load whose completion is credited to an mbarrier that may live in the peer CTA (cluster address)
 __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1)

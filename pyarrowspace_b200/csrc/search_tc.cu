@@ -323,6 +323,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
+// The same for a NARROW K-major tile: rows of `row_bytes` = 32 or 64 bytes (16 / 32 halves, what TMA wrote with
+// SWIZZLE_32B / SWIZZLE_64B), 8-row groups 8 * row_bytes apart, layout type 6 / 4 (cute/arch/mma_sm100_desc.hpp).
+__device__ __forceinline__ uint64_t make_kmajor_narrow_desc(uint32_t smem_addr, int row_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(row_bytes == 32 ? 6 : 4) << 61;
+    return d;
+}
+
 // kind::f16: D f32 (bit 4), A f16 (bits 7-9 = 0), B f16 (bits 10-12 = 0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t IDESC_F16_128x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
 constexpr uint32_t IDESC_F16_256x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TQ) >> 4) << 24);   // cta_group::2
@@ -354,6 +367,8 @@ struct TcParams {
     int nterms;                   // 1: single fp16 term of the residuals; 3: two-term split (lo.hi, hi.lo, hi.hi)
     int kb_lo, kb_hi;             // 64-wide k blocks of the lo terms (residual columns only) / of hi.hi (all columns)
     int sub_lo_last, sub_hi_last; // K=16 MMA steps in the last block of each
+    int nw_hi;                    // > 0: the last hi.hi block (it holds the 3 rank-1 columns: 16 useful columns of 64 at F = 384) is
+                                  // loaded as a NARROW box of nw_hi = 16 | 32 halves (SWIZZLE_32B | 64B): -11 % operand bytes per tile
     const float *lam_x, *lam_q;   // lam_x in visiting (lambda) order
     const float *tile_lo, *tile_hi;
     const int32_t *perm;          // visiting position -> local item index
@@ -378,7 +393,8 @@ struct TcParams {
 template <bool DUMP, int VARIANT, bool ARES, bool PAIR, int LISTN>   // LISTN: running list per thread (>= topk); VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued, 4 epilogue loads TMEM only
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
-               const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, const TcParams p)
+               const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+               const __grid_constant__ CUtensorMap map_q_nw, const __grid_constant__ CUtensorMap map_x_nw, const TcParams p)
 {
     static_assert(!PAIR || ARES, "the CTA-pair kernel keeps the query operand resident");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -428,9 +444,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     asp::tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
+    // Both single-thread roles run as WARP-UNIFORM loops (all 32 lanes walk the tiles and wait on the barriers); only the
+    // asynchronous instructions themselves sit under one elected lane.  With the whole role under `if (lane == 0)` the
+    // compiler wraps every uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR) in an ELECT / BRA.U.ANY loop and the
+    // issuing thread needs ~100 instructions per k block -- as long as the 4 MMAs it feeds (ncu: tensor pipe 56 % active,
+    // the issuer never waiting for operands).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        const bool el = asp::elect_one();
+        if (el) {
             asp::tma_prefetch_desc(&map_q_hi); asp::tma_prefetch_desc(&map_q_lo);
             asp::tma_prefetch_desc(&map_x_hi); asp::tma_prefetch_desc(&map_x_lo);
             if (PAIR) {
@@ -439,15 +461,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                 if (leader) asp::mbar_arrive_expect_tx(&a_full, (uint32_t)(2 * p.kb_hi * A_BYTES));
                 for (int kb = 0; kb < p.kb_hi; ++kb) asp::tma_load_2d_pair(a_res + (size_t)kb * A_BYTES, &map_q_hi, a_bar, kb * TKB, qb * TQ);
             } else if (ARES) {
-                asp::mbar_arrive_expect_tx(&a_full, (uint32_t)(p.kb_hi * A_BYTES));
-                for (int kb = 0; kb < p.kb_hi; ++kb) asp::tma_load_2d(a_res + (size_t)kb * A_BYTES, &map_q_hi, &a_full, kb * TKB, qb * TQ);
+                const int a_last = p.nw_hi ? TQ * p.nw_hi * 2 : A_BYTES;             // bytes of the last (maybe narrow) block
+                asp::mbar_arrive_expect_tx(&a_full, (uint32_t)((p.kb_hi - 1) * A_BYTES + a_last));
+                for (int kb = 0; kb < p.kb_hi; ++kb)
+                    asp::tma_load_2d(a_res + (size_t)kb * A_BYTES, (p.nw_hi && kb == p.kb_hi - 1) ? &map_q_nw : &map_q_hi, &a_full, kb * TKB, qb * TQ);
             }
-            int64_t it = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int item0 = tile_of(t) * TN;
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = (int)(it % NST);
-                    asp::mbar_wait_suspend(&empty_bar[s], (uint32_t)(((it / NST) & 1) ^ 1), 4000);
+        }
+        int s = 0;
+        uint32_t ph = 1;                                                         // parity of the "stage free" wait (first round passes)
+        for (int t = 0; t < ntiles; ++t) {
+            const int item0 = tile_of(t) * TN;
+            for (int ki = 0; ki < kiters; ++ki) {
+                asp::mbar_wait_suspend(&empty_bar[s], ph, 4000);
+                if (el) {
                     const int seg = (ki < klo) ? 0 : (ki < 2 * klo) ? 1 : 2;
                     const int kc = (ki - seg * klo) * TKB;
                     // small terms first: (q_lo, x_hi), (q_hi, x_lo), then (q_hi, x_hi)
@@ -457,44 +483,57 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                     if (PAIR) {                                                  // this CTA's half of the item tile (map_x_lo = half-box map)
                         if (leader) asp::mbar_arrive_expect_tx(&full_bar[s], 2 * STB);
                         asp::tma_load_2d_pair(dst, &map_x_lo, asp::mapa_shared(asp::smem_u32(&full_bar[s]), 0), kc, item0 + (int)cta_rank * (TN / 2));
+                    } else if (p.nw_hi && ki == kiters - 1) {                    // narrow last block of hi.hi
+                        asp::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((ARES ? 0 : TQ * p.nw_hi * 2) + TN * p.nw_hi * 2));
+                        if (!ARES) asp::tma_load_2d(dst, &map_q_nw, &full_bar[s], kc, qb * TQ);
+                        asp::tma_load_2d(dst + (ARES ? 0 : A_BYTES), &map_x_nw, &full_bar[s], kc, item0);
                     } else {
                         asp::mbar_arrive_expect_tx(&full_bar[s], STB);
                         if (!ARES) asp::tma_load_2d(dst, ma, &full_bar[s], kc, qb * TQ);
                         asp::tma_load_2d(dst + (ARES ? 0 : A_BYTES), mb, &full_bar[s], kc, item0);
                     }
                 }
+                if (++s == NST) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (PAIR: the leader CTA only) =====================
-        if (lane == 0 && leader) {
-            int64_t it = 0;
+        if (leader) {
+            const bool el = asp::elect_one();
             if (ARES) { asp::mbar_wait(&a_full, 0); asp::tc_fence_after(); }
+            int s = 0;
+            uint32_t ph = 0;                                                     // parity of the "stage full" wait
             for (int t = 0; t < ntiles; ++t) {
                 const int acc = (int)(t & 1);
                 asp::mbar_wait(&tmem_empty[acc], (uint32_t)((((t >> 1) & 1)) ^ 1));
                 asp::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TN);
-                for (int ki = 0; ki < kiters; ++ki, ++it) {
-                    const int s = (int)(it % NST);
-                    asp::mbar_wait(&full_bar[s], (uint32_t)((it / NST) & 1));
+                for (int ki = 0; ki < kiters; ++ki) {
+                    asp::mbar_wait(&full_bar[s], ph);
                     asp::tc_fence_after();
-                    const uint32_t st_addr = asp::smem_u32(stages + (size_t)s * STB);
-                    const uint64_t da = make_kmajor_sw128_desc(ARES ? asp::smem_u32(a_res + (size_t)ki * A_BYTES) : st_addr);
-                    const uint64_t db = make_kmajor_sw128_desc(ARES ? st_addr : st_addr + A_BYTES);
-                    // K = 16 halves per MMA = 32 B = +2 in the address field; the last block of a term may be short
-                    const int nsub = (ki == klo - 1 || ki == 2 * klo - 1) ? p.sub_lo_last : (ki == kiters - 1) ? p.sub_hi_last : TKB / 16;
-                    if (VARIANT != 3) {
+                    if (el) {
+                        const uint32_t st_addr = asp::smem_u32(stages + (size_t)s * STB);
+                        const uint32_t a_addr = ARES ? asp::smem_u32(a_res + (size_t)ki * A_BYTES) : st_addr;
+                        const uint32_t b_addr = ARES ? st_addr : st_addr + A_BYTES;
+                        const bool narrow = !PAIR && p.nw_hi && ki == kiters - 1;
+                        const uint64_t da = narrow ? make_kmajor_narrow_desc(a_addr, 2 * p.nw_hi) : make_kmajor_sw128_desc(a_addr);
+                        const uint64_t db = narrow ? make_kmajor_narrow_desc(b_addr, 2 * p.nw_hi) : make_kmajor_sw128_desc(b_addr);
+                        // K = 16 halves per MMA = 32 B = +2 in the address field; the last block of a term may be short
+                        const int nsub = (ki == klo - 1 || ki == 2 * klo - 1) ? p.sub_lo_last : (ki == kiters - 1) ? p.sub_hi_last : TKB / 16;
+                        if (VARIANT != 3) {
 #pragma unroll
-                        for (int k = 0; k < TKB / 16; ++k)
-                            if (k < nsub) {
-                                if (PAIR) asp::umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_256x256, (ki > 0 || k > 0) ? 1u : 0u);
-                                else asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
-                            }
+                            for (int k = 0; k < TKB / 16; ++k)
+                                if (k < nsub) {
+                                    if (PAIR) asp::umma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_256x256, (ki > 0 || k > 0) ? 1u : 0u);
+                                    else asp::umma_f16(tmem_d, da + 2 * k, db + 2 * k, IDESC_F16_128x256, (ki > 0 || k > 0) ? 1u : 0u);
+                                }
+                        }
+                        if (PAIR) asp::umma_commit_pair(&empty_bar[s]); else asp::umma_commit(&empty_bar[s]);   // stage reusable when these MMAs retire
+                        if (ki == kiters - 1) { if (PAIR) asp::umma_commit_pair(&tmem_full[acc]); else asp::umma_commit(&tmem_full[acc]); }   // accumulator complete
                     }
-                    if (PAIR) asp::umma_commit_pair(&empty_bar[s]); else asp::umma_commit(&empty_bar[s]);   // stage reusable when these MMAs retire
+                    __syncwarp();
+                    if (++s == NST) { s = 0; ph ^= 1u; }
                 }
-                if (PAIR) asp::umma_commit_pair(&tmem_full[acc]); else asp::umma_commit(&tmem_full[acc]);   // accumulator complete
             }
         }
     } else {
@@ -906,6 +945,8 @@ struct asp_tc_cache {               // per-space fp16 operands in lambda order, 
     double rho_max = 1.0;           // largest residual norm |x^ - (m.x^) m| of the shard
     int kp = 0;                     // operand row: f residual columns + 3 rank-1 columns, padded to a multiple of 64
     CUtensorMap map_hi, map_lo, map_hi_half;      // boxes of 256 item rows; 128 for the CTA-pair kernel
+    CUtensorMap map_hi_nw;                        // narrow box (16 | 32 halves) over the last k block, see TcParams::nw_hi
+    int nw = 0;
 };
 
 static int device_max(asp_ctx *ctx, const double *v_dev, int64_t n, double *out)
@@ -1006,6 +1047,13 @@ static int ensure_tc_cache(const asp_space *s, asp_tc_cache **out)
     ASP_CHECK(asp_make_f16_tmap(&c->map_hi, c->hi, n, c->kp, TN));
     ASP_CHECK(asp_make_f16_tmap(&c->map_hi_half, c->hi, n, c->kp, TN / 2));
     c->map_lo = c->map_hi;
+    {   // the last k block holds (f + 3) - 64 * (kp / 64 - 1) useful columns: 16 or 32 of them travel as a narrow box
+        const int used = s->f + 3 - (c->kp / TKB - 1) * TKB;
+        c->nw = (used <= 16) ? 16 : (used <= 32) ? 32 : 0;
+        if (const char *e = getenv("ASP_TC_NARROW")) { if (atoi(e) == 0) c->nw = 0; }     // A/B knob (same results either way)
+        c->map_hi_nw = c->map_hi;
+        if (c->nw) ASP_CHECK(asp_make_f16_tmap_narrow(&c->map_hi_nw, c->hi, n, c->kp, TN, c->nw));
+    }
     ms->tc_cache = c;
     *out = c;
     return ASP_OK;
@@ -1118,9 +1166,11 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
                                                                                (int)asp_ceil_div(s->n_local, TN), b->center);
         ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     }
-    CUtensorMap map_q_hi, map_q_lo;
+    CUtensorMap map_q_hi, map_q_lo, map_q_nw;
     ASP_CHECK(asp_make_f16_tmap(&map_q_hi, q_hi, nq, kp, TQ));
     ASP_CHECK(asp_make_f16_tmap(&map_q_lo, q_lo, nq, kp, TQ));
+    map_q_nw = map_q_hi;
+    if (c->nw) ASP_CHECK(asp_make_f16_tmap_narrow(&map_q_nw, q_hi, nq, kp, TQ, c->nw));
 
     // grid: query blocks x item chunks, whole waves of SMs
     const int64_t tiles_total = asp_ceil_div(s->n_local, TN);
@@ -1151,6 +1201,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     p.kb_lo = (s->f + TKB - 1) / TKB; p.kb_hi = kp / TKB;
     p.sub_lo_last = (s->f - (p.kb_lo - 1) * TKB + 15) / 16;
     p.sub_hi_last = (s->f + 3 - (p.kb_hi - 1) * TKB + 15) / 16;
+    p.nw_hi = c->nw;
     p.lam_x = c->lam32; p.lam_q = b->lam_q32; p.tile_lo = c->tile_lo; p.tile_hi = c->tile_hi; p.perm = c->perm; p.center = b->center;
     p.theta_glob = nullptr; p.emit_sc = nullptr; p.emit_ix = nullptr; p.emit_cnt = nullptr; p.dump = dump_dev;
     if (!dump_dev) {
@@ -1179,7 +1230,8 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
 #else
     const int v = 0;
 #endif
-    void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
+    if (pair) p.nw_hi = 0;                                        // (the CTA-pair kernel keeps full boxes)
+    void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
         dump_dev ? (ares ? tc_gemm_kernel<true, 0, true, false, 16> : tc_gemm_kernel<true, 0, false, false, 16>)
         : wide ? (ares ? tc_gemm_kernel<false, 0, true, false, 32> : tc_gemm_kernel<false, 0, false, false, 32>)
 #ifdef ASP_PROFILING
@@ -1201,9 +1253,9 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        ASP_CUDA(cudaLaunchKernelEx(&cfg, k, map_q_hi, map_q_lo, c->map_hi, c->map_hi_half, p));
+        ASP_CUDA(cudaLaunchKernelEx(&cfg, k, map_q_hi, map_q_lo, c->map_hi, c->map_hi_half, map_q_nw, c->map_hi_nw, p));
     } else {
-        k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, p);
+        k<<<grid, TC_THREADS, smem, st>>>(map_q_hi, map_q_lo, c->map_hi, c->map_lo, map_q_nw, c->map_hi_nw, p);
     }
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));

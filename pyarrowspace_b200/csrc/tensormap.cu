@@ -62,3 +62,22 @@ int asp_make_f16_tmap(CUtensorMap *out, const void *base, int64_t rows, int32_t 
     if (r != CUDA_SUCCESS) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r);
     return ASP_OK;
 }
+
+// Narrow box over the same operand: `nw` = 16 or 32 elements (32 / 64 bytes) x box_rows, SWIZZLE_32B / SWIZZLE_64B: the
+// canonical K-major layout of a 32- / 64-byte-row tile (UMMA layout types 6 / 4).  For the last k block of the tcgen05
+// candidate pass, which holds only the 3 rank-1 columns (+ padding) when the feature count is a multiple of 64.
+int asp_make_f16_tmap_narrow(CUtensorMap *out, const void *base, int64_t rows, int32_t kp, int box_rows, int nw)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if (kp % 64 != 0 || (nw != 16 && nw != 32)) ASP_FAIL(ASP_ERR_ARG, "narrow fp16 box must be 16 or 32 elements wide");
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)nw, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, nw == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) ASP_FAIL(ASP_ERR_CUDA, "cuTensorMapEncodeTiled (narrow fp16) failed with CUresult %d", (int)r);
+    return ASP_OK;
+}
