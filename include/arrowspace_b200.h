@@ -166,8 +166,17 @@ int asp_space_dims(const asp_space *s, int64_t *n_local, int32_t *f, int64_t *ro
 int asp_space_lambdas(const asp_space *s, double *out /* n_local, host or device */);
 int asp_space_norms(const asp_space *s, double *out /* n_local */);
 int asp_space_get_item(const asp_space *s, int64_t local_idx, double *out_features /* f */, double *out_lambda);
+int asp_space_items(const asp_space *s, double *out /* n_local x f row-major, host or device: the stored rows (persistence) */);
 int asp_graph_info(const asp_graph *g, int64_t *nnodes, int64_t *nnz, asp_graph_params *gp);
 int asp_graph_csr(const asp_graph *g, int64_t *indptr /* nnodes+1 */, int32_t *indices /* nnz */, double *data /* nnz */);
+
+/* ---- persistence (no reference counterpart: the pyo3 objects cannot be pickled) ------------------
+ * A graph handle from a stored Laplacian (the arrays asp_graph_csr exported; host or device).  feature_graph != 0 also
+ * prepares the lambda pass, so the handle serves asp_query_lambda / asp_search_batch like the graph it was saved from.
+ * Together with asp_space_create + asp_space_import_lambdas this restores a built (aspace, gl) pair without rebuilding. */
+int asp_graph_from_csr(asp_ctx *ctx, int64_t nnodes, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *data,
+                       const asp_graph_params *gp, const asp_switches *sw, int feature_graph, asp_graph **out_graph);
+int asp_graph_switches(const asp_graph *g, asp_switches *sw);
 
 /* ---- search -------------------------------------------------------------------------------- */
 

@@ -91,8 +91,11 @@ SYMBOLS = {
     "asp_space_lambdas": (_int, [_vp, _vp]),
     "asp_space_norms": (_int, [_vp, _vp]),
     "asp_space_get_item": (_int, [_vp, _i64, _vp, _vp]),
+    "asp_space_items": (_int, [_vp, _vp]),
     "asp_graph_info": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(GraphParams)]),
     "asp_graph_csr": (_int, [_vp, _vp, _vp, _vp]),
+    "asp_graph_from_csr": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(GraphParams), C.POINTER(Switches), _int, C.POINTER(_vp)]),
+    "asp_graph_switches": (_int, [_vp, C.POINTER(Switches)]),
     "asp_query_lambda": (_int, [_vp, _vp, C.POINTER(Switches), _vp, _i64, _vp, _vp, _vp]),
     "asp_search_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "asp_debug_tc_dots": (_int, [_vp, _vp, _i64, _vp]),

@@ -384,6 +384,12 @@ class ArrowSpace:
                     _to_host(lam.contiguous(), host_out and host_out[2]))
         return idx.contiguous(), score.contiguous(), lam.contiguous()
 
+    # ------------------------------------------------------------------ persistence (extension)
+    def save(self, path, gl, items=None):
+        """Write this space and its graph to `path` (.npz); ArrowSpaceBuilder.load restores the pair without rebuilding."""
+        from . import persist
+        return persist.save(path, self, gl, items)
+
     # ------------------------------------------------------------------ out of scope (SURVEY.md 8(f))
     def search_hybrid(self, item, gl, tau):
         raise NotImplementedError("search_hybrid is outside the build-and-search hot path (src/lib.rs:182-219)")
@@ -583,6 +589,12 @@ class ArrowSpaceBuilder:
         (halo rows), every rank resolves its rows on the tensor cores, all-gather of the neighbour lists."""
         from .distributed import build_item_graph_sharded
         return build_item_graph_sharded(graph_params, items_shard, n_total, row0, group=group, **extras)
+
+    @staticmethod
+    def load(path, **extras):
+        """Extension: (ArrowSpace, GraphLaplacian) from a file written by ArrowSpace.save -- no build kernel runs."""
+        from . import persist
+        return persist.load(path, extras.get("device"))
 
     @staticmethod
     def build_energy(items, energy_params=None, graph_params=None):

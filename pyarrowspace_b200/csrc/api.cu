@@ -586,6 +586,17 @@ int asp_space_norms(const asp_space *s, double *out)
     return asp_copy_out(s->ctx, out, s->norms, sizeof(double) * s->n_local);
 }
 
+int asp_space_items(const asp_space *s, double *out)
+{
+    if (!s || !out) ASP_FAIL(ASP_ERR_ARG, "asp_space_items: NULL argument");
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    ASP_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * s->f, s->items, sizeof(double) * s->fp, sizeof(double) * s->f, (size_t)s->n_local,
+                               cudaMemcpyDefault, ctx->stream));
+    ASP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ASP_OK;
+}
+
 int asp_space_get_item(const asp_space *s, int64_t local_idx, double *out_features, double *out_lambda)
 {
     if (!s) ASP_FAIL(ASP_ERR_ARG, "space is NULL");
@@ -873,6 +884,49 @@ int asp_topk_merge(asp_ctx *ctx, const int64_t *idx, const double *score, int pa
     cudaFreeAsync(d_oidx, st);
     cudaFreeAsync(d_osc, st);
     return rc;
+}
+
+// Persistence: a graph handle from a stored Laplacian (what asp_graph_csr exported).  feature_graph != 0 also prepares the
+// lambda pass (the graph then serves asp_query_lambda / asp_search_batch exactly like the one it was saved from).
+int asp_graph_from_csr(asp_ctx *ctx, int64_t nnodes, int64_t nnz, const int64_t *indptr, const int32_t *indices, const double *data,
+                       const asp_graph_params *gp, const asp_switches *sw_in, int feature_graph, asp_graph **out_graph)
+{
+    if (!ctx || !indptr || !indices || !data || !gp || !out_graph || nnodes <= 0 || nnz < 0)
+        ASP_FAIL(ASP_ERR_ARG, "asp_graph_from_csr: bad argument");
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    asp_switches sw;
+    if (sw_in) sw = *sw_in; else asp_default_switches(&sw);
+    ASP_CHECK(check_switches(&sw));
+    asp_graph *g = new asp_graph();
+    g->ctx = ctx;
+    g->gp = *gp;
+    if (!g->gp.has_sigma) { g->gp.sigma = gp->eps * 0.5; g->gp.has_sigma = 1; }
+    g->sw = sw;
+    g->nnodes = nnodes;
+    g->nnz = nnz;
+    int rc = ASP_OK;
+    if (cudaMallocAsync(&g->d_indptr, sizeof(int64_t) * (nnodes + 1), st) != cudaSuccess ||
+        cudaMallocAsync(&g->d_indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1), st) != cudaSuccess ||
+        cudaMallocAsync(&g->d_data, sizeof(double) * (nnz > 0 ? nnz : 1), st) != cudaSuccess) {
+        asp_set_error("out of device memory for the stored Laplacian");
+        rc = ASP_ERR_NOMEM;
+    }
+    if (rc == ASP_OK) rc = asp_copy_in(ctx, g->d_indptr, indptr, sizeof(int64_t) * (nnodes + 1));
+    if (rc == ASP_OK) rc = asp_copy_in(ctx, g->d_indices, indices, sizeof(int32_t) * nnz);
+    if (rc == ASP_OK) rc = asp_copy_in(ctx, g->d_data, data, sizeof(double) * nnz);
+    if (rc == ASP_OK && cudaStreamSynchronize(st) != cudaSuccess) { asp_set_error("upload of the stored Laplacian failed"); rc = ASP_ERR_CUDA; }
+    if (rc == ASP_OK && feature_graph) rc = asp_graph_upload_upper(g);
+    if (rc != ASP_OK) { asp_free_graph(g); return rc; }
+    *out_graph = g;
+    return ASP_OK;
+}
+
+int asp_graph_switches(const asp_graph *g, asp_switches *sw)
+{
+    if (!g || !sw) ASP_FAIL(ASP_ERR_ARG, "asp_graph_switches: NULL argument");
+    *sw = g->sw;
+    return ASP_OK;
 }
 
 int asp_item_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw_in, asp_graph **out_graph)

@@ -531,7 +531,10 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
             rows_direct3 += nq;
             continue;
         }
-        rc = run_batch(s->items + b0 * s->fp, s->norms + b0, nq, b0, nullptr, 0, slow1, counts, &terms_pass1);
+        // the first batch picks the number of MMA terms from its residual norms; the later batches are held to the same
+        // choice (their per-row bands stay valid either way), so that `slow1` holds rows of ONE kind: all of them still owed
+        // the two-term pass (1 term) or all of them owed the exact scan (3 terms)
+        rc = run_batch(s->items + b0 * s->fp, s->norms + b0, nq, b0, nullptr, b0 == row_begin ? 0 : terms_pass1, slow1, counts, &terms_pass1);
         if (rc == ASP_OK && b0 == row_begin && terms_pass1 == 1 && b0 + batch < row_end) {
             ASP_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
             ASP_CUDA(cudaStreamSynchronize(st));

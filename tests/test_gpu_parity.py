@@ -918,3 +918,37 @@ def test_small_batches_on_the_tensor_core_route(oracle_mod):
         np.testing.assert_allclose([v for _, v in one], osc[5], rtol=RTOL, atol=0)
     finally:
         _force_stage1(None)
+
+
+def test_save_and_load_restore_the_index_bit_for_bit(oracle_mod, tmp_path):
+    """Persistence: ArrowSpace.save / ArrowSpaceBuilder.load -- the restored pair gives the same CSR, lambdas
+    and search results as the one it was saved from (bit for bit) without running a build kernel, under a non-default switch
+    set too; and the evaluation harness writes the donor's files from it."""
+    import csv
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, evalharness, synth
+    x = synth.make_items(3000, 96, 17, n_clusters=12)
+    q, _ = synth.make_queries(x, 300, 18)
+    gp = {"eps": 0.6, "k": 6, "topk": 20, "p": 2.0, "sigma": 0.3}
+    for sw in ({}, {"profile": "kat12", "tau_mode": "median_abs"}):
+        aspace, gl = ArrowSpaceBuilder.build(gp, x, **sw)
+        idx, sc = aspace.search_batch(q, gl, 0.62)
+        path = str(tmp_path / ("index_%d.npz" % len(sw)))
+        aspace.save(path, gl)                                             # rows read back from the device
+        launches = api.launch_count()
+        a2, g2 = ArrowSpaceBuilder.load(path)
+        assert api.launch_count() - launches <= 2                          # reciprocal norms only: no build kernel
+        assert a2.nitems == 3000 and a2.nfeatures == 96 and g2.graph_params == gl.graph_params
+        assert all(np.array_equal(u, v) for u, v in zip(g2.csr(), gl.csr()))
+        assert np.array_equal(a2.lambdas(), aspace.lambdas()) and np.array_equal(a2.norms(), aspace.norms())
+        assert np.array_equal(a2.get_item(7)[0], x[7])
+        idx2, sc2 = a2.search_batch(q, g2, 0.62)
+        assert np.array_equal(idx2, idx) and np.array_equal(sc2, sc)
+        assert a2.search(q[3], g2, 0.8) == aspace.search(q[3], gl, 0.8)
+    sweep = evalharness.run_tau_sweep(a2, g2, q[:5])
+    texts = ["query %d" % i for i in range(5)]
+    evalharness.write_search_results(tmp_path / "res.csv", texts, sweep, ["id%d" % i for i in range(3000)], ["t%d" % i for i in range(3000)])
+    rows = list(csv.DictReader(open(tmp_path / "res.csv", encoding="utf-8")))
+    assert len(rows) == 5 * 3 * 20
+    rec = evalharness.compare(sweep, texts)
+    assert all(abs(r["ndcg"][0]) <= 1.0 + 1e-12 for r in rec) and all(len(r["tail_metrics"]) == 3 for r in rec)
