@@ -1217,7 +1217,10 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     bool ares = (nterms == 1) && (p.kb_hi <= 7);
     if (const char *e = getenv("ASP_TC_ARES")) ares = ares && atoi(e) != 0;
     const bool wide = topk > 16;                                  // 32-entry running lists
-    const bool pair = ares && !dump_dev && !wide && getenv("ASP_TC_PAIR") && atoi(getenv("ASP_TC_PAIR")) != 0;
+    // CTA pairs (cta_group::2: two query blocks share one M = 256 MMA, each SM loads half of every item tile) whenever there
+    // are two query blocks to pair: -18 % stage-1 time at C4 / 64k queries (ASP_TC_PAIR=0: the 1-SM kernel, same bits)
+    bool pair = ares && !dump_dev && !wide && qblocks >= 2;
+    if (const char *e = getenv("ASP_TC_PAIR")) pair = pair && atoi(e) != 0;
     const size_t smem = (ares ? (size_t)p.kb_hi * A_BYTES + 3 * (size_t)B_BYTES : (size_t)TC_STAGES * STAGE_BYTES) +
                         2 * TN * sizeof(float) + 1024;
     const int64_t grid_x = pair ? (qblocks + 1) / 2 * 2 : qblocks;

@@ -762,22 +762,26 @@ def test_tc_error_band_at_c4_scale():
 
 
 def test_cta_pair_kernel_matches(oracle_mod):
-    """The experimental cta_group::2 candidate kernel (ASP_TC_PAIR=1: two CTAs share one M = 256 MMA) returns the same
-    bits as the default 1-SM kernel."""
+    """The cta_group::2 candidate kernel (the default whenever a batch has two query blocks: two CTAs share one M = 256 MMA and
+    each SM loads half of every item tile) returns the same bits as the 1-SM kernel (ASP_TC_PAIR=0) and the oracle's answer."""
     from arrowspace import ArrowSpaceBuilder
     from pyarrowspace_b200 import api, synth
     x = synth.make_items(30_000, 384, 9, n_clusters=12)
     q, _ = synth.make_queries(x, 700, 9)                                 # odd number of query blocks: a padded pair
-    aspace, gl = ArrowSpaceBuilder.build({"eps": 0.6, "k": 6, "topk": 10, "p": 2.0, "sigma": 0.3}, x)
-    idx0, sc0 = aspace.search_batch(q, gl, 0.62)
-    assert api.stat("search_cta_pair") == 0.0
-    os.environ["ASP_TC_PAIR"] = "1"
+    gp = {"eps": 0.6, "k": 6, "topk": 10, "p": 2.0, "sigma": 0.3}
+    aspace, gl = ArrowSpaceBuilder.build(gp, x)
+    idx1, sc1 = aspace.search_batch(q, gl, 0.62)
+    assert api.stat("search_cta_pair") == 1.0
+    os.environ["ASP_TC_PAIR"] = "0"
     try:
-        idx1, sc1 = aspace.search_batch(q, gl, 0.62)
-        assert api.stat("search_cta_pair") == 1.0
+        idx0, sc0 = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_cta_pair") == 0.0
     finally:
         os.environ.pop("ASP_TC_PAIR", None)
     assert np.array_equal(idx0, idx1) and np.array_equal(sc0, sc1)
+    s, g = oracle_mod.build(gp, x)
+    oidx, osc, _ = s.search_batch(q, g, 0.62)
+    _assert_hits_equal(idx1, sc1, oidx, osc)
 
 
 def test_pipelined_host_batches_equal_single_shot(oracle_mod):
