@@ -1219,7 +1219,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     const bool wide = topk > 16;                                  // 32-entry running lists
     // CTA pairs (cta_group::2: two query blocks share one M = 256 MMA, each SM loads half of every item tile) whenever there
     // are two query blocks to pair: -18 % stage-1 time at C4 / 64k queries (ASP_TC_PAIR=0: the 1-SM kernel, same bits)
-    bool pair = ares && !dump_dev && !wide && qblocks >= 2;
+    bool pair = ares && !dump_dev && qblocks >= 2;
     if (const char *e = getenv("ASP_TC_PAIR")) pair = pair && atoi(e) != 0;
     const size_t smem = (ares ? (size_t)p.kb_hi * A_BYTES + 3 * (size_t)B_BYTES : (size_t)TC_STAGES * STAGE_BYTES) +
                         2 * TN * sizeof(float) + 1024;
@@ -1236,7 +1236,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     if (pair) p.nw_hi = 0;                                        // (the CTA-pair kernel keeps full boxes)
     void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
         dump_dev ? (ares ? tc_gemm_kernel<true, 0, true, false, 16> : tc_gemm_kernel<true, 0, false, false, 16>)
-        : wide ? (ares ? tc_gemm_kernel<false, 0, true, false, 32> : tc_gemm_kernel<false, 0, false, false, 32>)
+        : wide ? (pair ? tc_gemm_kernel<false, 0, true, true, 32> : ares ? tc_gemm_kernel<false, 0, true, false, 32> : tc_gemm_kernel<false, 0, false, false, 32>)
 #ifdef ASP_PROFILING
         : pair ? ((v == 2) ? tc_gemm_kernel<false, 2, true, true, 16> : (v == 3) ? tc_gemm_kernel<false, 3, true, true, 16>
                   : (v == 4) ? tc_gemm_kernel<false, 4, true, true, 16> : tc_gemm_kernel<false, 0, true, true, 16>)
