@@ -8,8 +8,9 @@ step     : one pass of the search hot path over one batch of Q = 65536 synthetic
            the search runs on an R x C grid (R item shards x C query slots, --item-shards, default: replicate the items when
            they fit, i.e. R = 1 for C4) and every rank ends with the whole result; strong scaling (fixed N and Q).
 value    : whole-job queries/s with items and queries resident in HBM.
-e2e      : the same through the public API (ArrowSpace.search_batch) with HOST buffers: pinned host -> device copy of
-           the batch and device -> host read of (idx, score) inside the timed region.
+e2e      : the same through the public API (ArrowSpace.search_batch(q, gl, tau, out=...)) with HOST buffers: pinned host ->
+           device copy of the batch and device -> host read of (idx, score) into the caller's pinned result buffers, every
+           step, inside the timed region.
 roofline : dominant kernel = tc_gemm_kernel (tcgen05.mma kind::f16 candidate pass): ALGORITHMIC 2*Q*N_local*F FLOP per
            launch (SURVEY.md 8(d) K4) / its CUDA-event duration, against MEASURED_PEAKS.json's dense 16-bit tensor figure;
            the executed FLOP (K padded to 16, extra split terms) are reported next to it.  The build's kernels are reported
@@ -317,19 +318,22 @@ def main():
             st = {k: api.stat(k, local) for k in ("search_slow_queries", "search_stage1_is_tc", "search_rescored_per_query", "search_terms",
                                                  "search_stage2_ms", "search_a_resident", "search_delta_cos_max", "search_rho_q_max",
                                                  "search_rho_x_max", "search_exact_per_query")}
+            # the caller's result buffers: pinned host memory reused from step to step (search_batch(out=...))
+            out_h = (torch.empty((q_host[0].shape[0], topk), dtype=torch.int64).pin_memory().numpy(),
+                     torch.empty((q_host[0].shape[0], topk), dtype=torch.float64).pin_memory().numpy())
             for w in range(2 if warmup else 0):
-                aspace.search_batch(q_host[w % nb].numpy(), gl, tau)
+                aspace.search_batch(q_host[w % nb].numpy(), gl, tau, out=out_h)
             barrier_sync()
             e0.record(stream)
             for k in range(steps):
-                idx_h, sc_h = aspace.search_batch(q_host[k % nb].numpy(), gl, tau)
+                idx_h, sc_h = aspace.search_batch(q_host[k % nb].numpy(), gl, tau, out=out_h)
             e1.record(stream)
             barrier_sync()
             e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
         clk = clocks.stop() if rank == 0 else None
         return {"step_ms": step_ms, "e2e_ms": e2e_ms, "launches": int(launches), "stage1_ms": max_over_ranks(float(np.mean(stage1))),
                 "stats": st, "clocks": clk, "last_batch": (steps - 1) % nb,
-                "idx": idx.cpu().numpy(), "sc": sc.cpu().numpy(), "idx_h": np.asarray(idx_h), "sc_h": np.asarray(sc_h)}
+                "idx": idx.cpu().numpy(), "sc": sc.cpu().numpy(), "idx_h": np.array(idx_h), "sc_h": np.array(sc_h)}
 
     # ---- synthetic inputs: this rank's row shard (identical bytes to what the oracle sees)
     r0, r1 = shard_rows(n, world, rank)

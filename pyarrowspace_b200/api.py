@@ -232,15 +232,27 @@ class ArrowSpace:
         dbg_println("search: qlen=%d, lambda_q=%.6f" % (item.shape[0], lam_q[0]))
         return [(int(i), float(s)) for i, s in zip(idx[0], score[0]) if i >= 0]
 
-    def search_batch(self, queries, gl, tau):
-        """Extension: (idx int64[Q, topk], score f64[Q, topk]); rows padded with -1 / NaN."""
-        idx, score, _ = self._search_batch(queries, gl, float(tau), want_lambda=False)
+    def search_batch(self, queries, gl, tau, out=None):
+        """Extension: (idx int64[Q, topk], score f64[Q, topk]); rows padded with -1 / NaN.
+        out = (idx, score) host arrays to fill (C-contiguous, right shapes / dtypes; e.g. pinned memory that the caller
+        reuses from call to call: the device -> host read then runs at the PCIe rate instead of the page-fault rate of
+        freshly allocated memory).  Host query batches only."""
+        if out is not None:
+            topk = gl.graph_params["topk"]
+            nq = queries.shape[0]
+            oi, os_ = out
+            if not (isinstance(oi, np.ndarray) and isinstance(os_, np.ndarray) and oi.dtype == np.int64 and os_.dtype == np.float64
+                    and oi.shape == (nq, topk) and os_.shape == (nq, topk) and oi.flags.c_contiguous and os_.flags.c_contiguous):
+                raise ValueError("out must be (int64[%d, %d], float64[%d, %d]) C-contiguous host arrays" % (nq, topk, nq, topk))
+            if _is_device_tensor(queries):
+                raise ValueError("out= is for host query batches (device batches return device tensors)")
+        idx, score, _ = self._search_batch(queries, gl, float(tau), want_lambda=False, out=out)
         return idx, score
 
-    def _search_batch(self, queries, gl, tau, want_lambda):
+    def _search_batch(self, queries, gl, tau, want_lambda, out=None):
         import time
         if self._grid is not None and self._grid["C"] > 1:
-            return self._search_batch_grid(queries, gl, tau)
+            return self._search_batch_grid(queries, gl, tau, out)
         t_a = time.perf_counter()
         lib = _lib.load()
         f = self.nfeatures
@@ -254,7 +266,9 @@ class ArrowSpace:
             if q_np.ndim != 2 or q_np.shape[1] != f:
                 raise ValueError("query length %d must match nfeatures %d" % (q_np.shape[-1], f))
             queries = _upload_queries_sharded(self, q_np)
-            if q_np.shape[0] * max(topk, 1) >= 65536:
+            if out is not None:
+                host_out = (out[0], out[1], np.empty(q_np.shape[0], dtype=np.float64))
+            elif q_np.shape[0] * max(topk, 1) >= 65536:
                 # result arrays for the caller: freshly allocated pageable memory page-faults on first touch (~3 GB/s, 3 ms
                 # for 64k x 10 results).  A helper thread touches them while this thread sits in the library (ctypes drops
                 # the GIL), so the final D2H copy lands in resident pages.
@@ -281,8 +295,8 @@ class ArrowSpace:
             if q.ndim != 2 or q.shape[1] != f:
                 raise ValueError("query length %d must match nfeatures %d" % (q.shape[-1], f))
             nq = q.shape[0]
-            idx = np.empty((nq, topk), dtype=np.int64)
-            score = np.empty((nq, topk), dtype=np.float64)
+            idx = out[0] if out is not None else np.empty((nq, topk), dtype=np.int64)
+            score = out[1] if out is not None else np.empty((nq, topk), dtype=np.float64)
             lam = np.empty(nq, dtype=np.float64)
             qp, ip, sp, lp = q.ctypes.data, idx.ctypes.data, score.ctypes.data, lam.ctypes.data
         t_b = time.perf_counter()
@@ -305,7 +319,7 @@ class ArrowSpace:
                 _to_host(lam, host_out and host_out[2])
         return idx, score, lam
 
-    def _search_batch_grid(self, queries, gl, tau):
+    def _search_batch_grid(self, queries, gl, tau, out=None):
         """R item shards x C query slots (distributed.regroup): this rank answers rows [a, b) of the batch against its item
         shard; R > 1: the R ranks of the slot merge their lists (K5); the C slots all-gather the finished slices, so every
         rank returns the whole batch.  Host batches: this rank uploads only ITS slice (over its own PCIe link)."""
@@ -332,40 +346,37 @@ class ArrowSpace:
         nq = q.shape[0]
         a, b, per = query_slice(nq, g["C"], g["c"])
         host_out, toucher = None, None
-        if host_in and nq * max(topk, 1) >= 65536:      # first touch of the caller's result pages while the kernels run
+        if host_in and out is not None:
+            host_out = (out[0], out[1], np.empty(nq, dtype=np.float64))
+        elif host_in and nq * max(topk, 1) >= 65536:    # first touch of the caller's result pages while the kernels run
             host_out = (np.empty((nq, topk), dtype=np.int64), np.empty((nq, topk), dtype=np.float64), np.empty(nq, dtype=np.float64))
             toucher = threading.Thread(target=lambda: [arr.fill(0) for arr in host_out])
             toucher.start()
-        # one packed exchange buffer per slot: [per + 1] rows of (topk indices, topk scores, lambda_q) as 8-byte words;
-        # the extra row carries this rank's status so that every rank raises the same error
-        w = 2 * topk + 1
-        part = torch.empty((per + 1, w), dtype=torch.int64, device=dev)
-        part[:, :topk] = -1
-        part[:, topk:].view(torch.float64).fill_(float("nan"))
-        part[per] = 0
-        idx_p, sc_p, lam_p = part[:per, :topk], part[:per, topk:2 * topk].view(torch.float64), part[:per, 2 * topk].view(torch.float64)
+        # this slot's slice, padded to `per` rows; lam carries one extra element: this rank's status, so that every rank
+        # raises the same error
+        idx_p = torch.full((per, topk), -1, dtype=torch.int64, device=dev)
+        sc_p = torch.full((per, topk), float("nan"), dtype=torch.float64, device=dev)
+        lam_p = torch.full((per + 1,), float("nan"), dtype=torch.float64, device=dev)
+        lam_p[per] = 0.0
         err = None
         if b > a:
-            idx_c = torch.empty((b - a, topk), dtype=torch.int64, device=dev)
-            sc_c = torch.empty((b - a, topk), dtype=torch.float64, device=dev)
-            lam_c = torch.empty(b - a, dtype=torch.float64, device=dev)
             qp = q[a:b].ctypes.data if host_in else q[a:b].data_ptr()
             torch.cuda.current_stream(dev).synchronize()                 # the library runs on its own stream
-            rc = lib.asp_search_batch(self._h, gl._h, qp, b - a, tau, idx_c.data_ptr(), sc_c.data_ptr(), lam_c.data_ptr())
+            rc = lib.asp_search_batch(self._h, gl._h, qp, b - a, tau, idx_p.data_ptr(), sc_p.data_ptr(), lam_p.data_ptr())
             if rc != _lib.ASP_OK:
                 msg = lib.asp_last_error()
                 err = LibraryError(rc, msg.decode("utf-8", "replace") if msg else "unknown error")
-                part[per, 0] = rc
-            else:
-                idx_p[: b - a], sc_p[: b - a], lam_p[: b - a] = idx_c, sc_c, lam_c
+                lam_p[per] = float(rc)
         if g["R"] > 1:
-            m_idx, m_sc = _merge_across_ranks(self, idx_p.contiguous(), sc_p.contiguous(), per, topk)
-            idx_p.copy_(m_idx)
-            sc_p.copy_(m_sc)
-        full = torch.empty((g["C"] * (per + 1), w), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(full, part, group=g["item_group"])
-        full = full.view(g["C"], per + 1, w)
-        codes = full[:, per, 0].cpu().tolist()
+            idx_p, sc_p = _merge_across_ranks(self, idx_p, sc_p, per, topk)
+        idx = torch.empty((g["C"] * per, topk), dtype=torch.int64, device=dev)
+        score = torch.empty((g["C"] * per, topk), dtype=torch.float64, device=dev)
+        lam = torch.empty((g["C"] * (per + 1),), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(idx, idx_p, group=g["item_group"])
+        dist.all_gather_into_tensor(score, sc_p, group=g["item_group"])
+        dist.all_gather_into_tensor(lam, lam_p, group=g["item_group"])
+        lam = lam.view(g["C"], per + 1)
+        codes = lam[:, per].cpu().tolist()
         if toucher is not None:
             toucher.join()
         bad = [int(cd) for cd in codes if cd != 0]
@@ -377,12 +388,11 @@ class ArrowSpace:
             if code == _lib.ASP_ERR_ZERO_VECTOR:
                 raise PanicException(message)
             raise LibraryError(code, message)
-        rows = full[:, :per, :].reshape(g["C"] * per, w)[:nq]
-        idx, score, lam = rows[:, :topk], rows[:, topk:2 * topk].view(torch.float64), rows[:, 2 * topk].view(torch.float64)
+        idx, score, lam = idx[:nq], score[:nq], lam[:, :per].reshape(-1)[:nq]
         if host_in:
-            return (_to_host(idx.contiguous(), host_out and host_out[0]), _to_host(score.contiguous(), host_out and host_out[1]),
+            return (_to_host(idx, host_out and host_out[0]), _to_host(score, host_out and host_out[1]),
                     _to_host(lam.contiguous(), host_out and host_out[2]))
-        return idx.contiguous(), score.contiguous(), lam.contiguous()
+        return idx, score, lam.contiguous()
 
     # ------------------------------------------------------------------ persistence (extension)
     def save(self, path, gl, items=None):
@@ -399,7 +409,7 @@ class ArrowSpace:
 
 
 def _to_host(t, out=None):
-    """Device tensor -> numpy; into `out` (already resident pages) when given."""
+    """Device tensor -> numpy; into `out` (already resident pages, or the caller's pinned buffer) when given."""
     if out is None:
         return t.cpu().numpy()
     import torch
