@@ -17,6 +17,8 @@
 // (32 rows x 128 features for the a-block and for the b-block).  Shared-memory stage layout
 // [feature/4][row][4] (tensormap.cu) makes every fragment load 256 contiguous bytes per warp.
 #include "common.cuh"
+
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace {
@@ -225,29 +227,37 @@ int asp_launch_gram_partials(asp_space *s, double *out_dev)
     const int ntile = (int)asp_ceil_div(s->fp, TILE);
     const int ntu = ntile * (ntile + 1) / 2;
 
+    // The slice partials are scratch of nslices * ntu * 128 KB: 151 MB at F = 384, but quadratic in F (13 GB at 4096, 52 GB at
+    // 8192 for a whole-matrix shard).  Segments are independent, so they are processed in groups whose scratch stays
+    // under 2 GB (one group -- one launch -- for the usual feature counts).
+    const size_t seg_bytes = sizeof(double) * (size_t)ASP_GRAM_SLICES * ntu * TILE * TILE;
+    int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)nseg, ((size_t)2 << 30) / seg_bytes));
     SliceRange *d_slices = nullptr;
     double *d_partial = nullptr;
     ASP_CUDA(cudaMallocAsync(&d_slices, sizeof(SliceRange) * nslices, ctx->stream));
-    ASP_CUDA(cudaMallocAsync(&d_partial, sizeof(double) * (size_t)nslices * ntu * TILE * TILE, ctx->stream));
+    ASP_CUDA(cudaMallocAsync(&d_partial, seg_bytes * group, ctx->stream));
     ASP_CUDA(cudaMemcpyAsync(d_slices, h_slices.data(), sizeof(SliceRange) * nslices, cudaMemcpyHostToDevice,
                              ctx->stream));
 
     const size_t smem = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
-    dim3 grid(ntu, nslices);
-    if (ctx->use_tma) {
-        ASP_CUDA(cudaFuncSetAttribute(gram_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_slice_kernel<true><<<grid, NUM_MMA_WARPS * 32, smem, ctx->stream>>>(
-            s->tmap_gram, s->items, s->n_local, s->fp, ntile, d_slices, d_partial);
-    } else {
-        ASP_CUDA(cudaFuncSetAttribute(gram_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_slice_kernel<false><<<grid, NUM_MMA_WARPS * 32, smem, ctx->stream>>>(
-            s->tmap_gram, s->items, s->n_local, s->fp, ntile, d_slices, d_partial);
+    for (int e0 = 0; e0 < nseg; e0 += group) {
+        const int ne = std::min(group, nseg - e0);
+        dim3 grid(ntu, ne * ASP_GRAM_SLICES);
+        if (ctx->use_tma) {
+            ASP_CUDA(cudaFuncSetAttribute(gram_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gram_slice_kernel<true><<<grid, NUM_MMA_WARPS * 32, smem, ctx->stream>>>(
+                s->tmap_gram, s->items, s->n_local, s->fp, ntile, d_slices + (size_t)e0 * ASP_GRAM_SLICES, d_partial);
+        } else {
+            ASP_CUDA(cudaFuncSetAttribute(gram_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gram_slice_kernel<false><<<grid, NUM_MMA_WARPS * 32, smem, ctx->stream>>>(
+                s->tmap_gram, s->items, s->n_local, s->fp, ntile, d_slices + (size_t)e0 * ASP_GRAM_SLICES, d_partial);
+        }
+        ASP_CUDA(cudaGetLastError());
+        ASP_LAUNCHED(ctx);
+        gram_segment_reduce<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_partial, ntile, s->f, ne, seg0 + e0, out_dev);
+        ASP_CUDA(cudaGetLastError());
+        ASP_LAUNCHED(ctx);
     }
-    ASP_CUDA(cudaGetLastError());
-    ASP_LAUNCHED(ctx);
-    gram_segment_reduce<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_partial, ntile, s->f, nseg, seg0, out_dev);
-    ASP_CUDA(cudaGetLastError());
-    ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaFreeAsync(d_partial, ctx->stream));
     ASP_CUDA(cudaFreeAsync(d_slices, ctx->stream));
     return ASP_OK;

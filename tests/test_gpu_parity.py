@@ -226,12 +226,12 @@ def test_test0_script_all_twelve_indices_under_profile_kat12(kat, oracle_mod, ta
     np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL)
 
 
-@pytest.mark.parametrize("f", [1024, 1536, 2048, 3072])
+@pytest.mark.parametrize("f", [1024, 1536, 2048, 3072, 4096])
 def test_wide_embeddings(oracle_mod, f):
     """1536 / 3072-dimensional embeddings (the reference has no feature limit): the lambda pass takes the transposed-tile
     kernel up to 1500 features and taumode_wide_kernel (one CTA per vector) above."""
     from pyarrowspace_b200 import synth
-    n = 1500
+    n = 1500 if f < 4096 else 600              # (f = 4096: the Gram's slice partials are processed in segment groups)
     x = synth.make_items(n, f, 77, n_clusters=6)
     q, _ = synth.make_queries(x, 40, 78)
     gp = {"eps": 0.5, "k": 6, "topk": 8, "p": 2.0, "sigma": 0.25}
