@@ -231,3 +231,88 @@ def test_sharded_item_graph_over_gloo(world, oracle_mod):
     for r in res:
         assert r[2] == (n, f)
         assert [tuple(e) for e in r[1]] == want
+
+
+# ----------------------------------------------------------------------------- search grid (R item shards x C query slots)
+
+def test_grid_arithmetic():
+    from pyarrowspace_b200.distributed import auto_item_shards, grid_layout, query_slice
+    assert grid_layout(8, 5, 2) == (2, 4, 1, 1)            # ranks 4..7 hold item shard 1; rank 5 answers query slot 1
+    assert grid_layout(8, 5, 8) == (8, 1, 5, 0) and grid_layout(8, 5, 1) == (1, 8, 0, 5)
+    with pytest.raises(ValueError):
+        grid_layout(8, 0, 3)
+    # the slices of a batch tile it exactly, in slot order, whatever the remainder
+    for nq, slots in ((65536, 8), (10, 4), (3, 8), (0, 2), (1000, 3)):
+        cuts = [query_slice(nq, slots, c) for c in range(slots)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == nq and all(cuts[i][1] == cuts[i + 1][0] for i in range(slots - 1))
+        assert all(b - a <= per for a, b, per in cuts) and len({per for _, _, per in cuts}) == 1
+    assert auto_item_shards(8, 1_000_000, 384, 170e9) == 1          # C4: replicate
+    assert auto_item_shards(8, 8_800_000, 768, 170e9) == 2          # C5: two shards
+    assert auto_item_shards(8, 40_000_000, 768, 170e9) == 8
+    assert auto_item_shards(2, 40_000_000, 768, 170e9) == 2
+
+
+class _GridEngine:
+    """The regrouping half of CudaEngine on CPU tensors: a space is a dict of numpy arrays."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def lambdas_norms(self, space, n_local):
+        return self.torch.from_numpy(space["lam"].copy()), self.torch.from_numpy(space["nrm"].copy())
+
+    def space_from_gathered(self, x, lam, nrm, n_total, shards, shard):
+        return {"x": x.numpy(), "lam": lam.numpy(), "nrm": nrm.numpy(), "shards": shards, "shard": shard}
+
+    def free_space(self, space):
+        space["freed"] = True
+
+
+def _regroup_worker(rank, world, port, n, f, item_shards, q):
+    import torch
+    import torch.distributed as dist
+    try:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        from pyarrowspace_b200 import shard_rows
+        from pyarrowspace_b200.distributed import regroup
+        r0, r1 = shard_rows(n, world, rank)
+        x = np.arange(n * f, dtype=np.float64).reshape(n, f)
+        space = {"lam": x[r0:r1, 0] * 0.5, "nrm": x[r0:r1, 1] + 1.0}
+        new_space, grid = regroup(_GridEngine(), space, torch.from_numpy(x[r0:r1].copy()), n, item_shards, None)
+        q.put((rank, grid["R"], grid["C"], grid["r"], grid["c"], new_space.get("x"), new_space["lam"], new_space["nrm"],
+               space.get("freed", False)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:                                              # pragma: no cover
+        q.put((rank, "error", repr(e)))
+        raise
+
+
+@pytest.mark.parametrize("world,item_shards", [(4, 1), (4, 2), (2, 2)])
+def test_regroup_over_gloo(world, item_shards):
+    """distributed.regroup: the C ranks of an item shard end up with the shard's rows, lambdas and norms in row order (the
+    all-gathers of the R x C search grid), the build-time space is released; item_shards == world is a no-op."""
+    import torch.multiprocessing as mp
+    from pyarrowspace_b200 import shard_rows
+    n, f = 1000, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_regroup_worker, args=(r, world, port, n, f, item_shards, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] != "error" for r in res), res
+    x = np.arange(n * f, dtype=np.float64).reshape(n, f)
+    c_ = world // item_shards
+    for rank, R, C_, r, c, gx, lam, nrm, freed in res:
+        assert (R, C_, r, c) == (item_shards, c_, rank // c_, rank % c_)
+        if c_ == 1:
+            assert gx is None and not freed                              # untouched
+            continue
+        a, b = shard_rows(n, item_shards, r)
+        assert freed and np.array_equal(gx, x[a:b]) and np.array_equal(lam, x[a:b, 0] * 0.5) and np.array_equal(nrm, x[a:b, 1] + 1.0)
