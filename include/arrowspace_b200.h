@@ -248,6 +248,58 @@ int asp_item_knn_rows(asp_space *s, const asp_graph_params *gp, const asp_switch
 int asp_graph_from_knn(asp_ctx *ctx, int64_t m, int32_t kk, const int32_t *idx, const double *dist, const int32_t *cnt,
                        const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
 
+/* ---- pre-graph reduction --------------------------------------------------------------------------
+ * What the crate runs inside ArrowSpaceBuilder::build before graph construction (with_dims_reduction / with_seed,
+ * src/lib.rs:282-283; log evidence tests/output/1760705545_v0_16/suggested_eps.md:3-11: "Simple random sampler with keep
+ * rate 60.0%", "Two-NN mean ratio: 1.3560, estimated ID: 3", "Testing K in range [178, 179]" for N = 313841): the items
+ * are sampled, clustered, and the graph is built on the CENTROID matrix (n_clusters x f) instead of the item matrix;
+ * lambdas are still computed for every item.  The crate's arithmetic and RNG stream are not in the reference, so this is a
+ * deterministic restatement (PARITY UNPINNED against the crate; GPU == oracle bit for bit on the centroids):
+ *   R1 sample   row i is kept iff u(seed, i) < sample_rate, u = (splitmix64(seed + (i+1)*0x9E3779B97F4A7C15) >> 11) * 2^-53;
+ *               sample_rate >= 1 keeps every row.  S = kept rows, ascending.
+ *   R2 two-NN   probes = S[floor(j*|S|/P)], P = min(probes, |S|); r1 <= r2 = the two smallest Euclidean distances from a
+ *               probe to the other rows of S (squared distances summed left to right, ties by position); probes with
+ *               r1 == 0 are skipped; mean ratio = mean(r2/r1) in probe order; intrinsic dimension = trunc(m/(m-1))
+ *               clamped to [1, f] (the mean of a Pareto(d) variable is d/(d-1); 1.3560 -> 3 as in the log).
+ *   R3 K        n_clusters if > 0, else ceil(sqrt(n_total/10)) (the one published data point: 313841 -> 178), at most |S|.
+ *   R4 k-means  centroid j starts at row S[floor(j*|S|/K)]; Lloyd iterations: assign every row of S to the nearest centroid
+ *               (squared Euclidean, left to right, ties -> smaller centroid), stop when no assignment changed, else
+ *               centroid = (sum of its rows in ascending row order) / count (an empty cluster keeps its centroid); at most
+ *               max_iters updates.
+ *   R5 graph    the usual recipe (asp_graph_params / asp_switches) with nodes = the f columns of the centroid matrix.
+ *   R6 lambdas  per item, from that Laplacian.
+ * Not restated: the crate's optional JL projection (with_dims_reduction(true, Some(eps))) -- searched vectors stay raw. */
+typedef struct {
+    double   sample_rate;   /* default 0.6 */
+    uint64_t seed;          /* default 42 (src/lib.rs:283) */
+    int32_t  n_clusters;    /* 0 = rule R3 */
+    int32_t  max_iters;     /* default 10 */
+    int32_t  probes;        /* default 2048; 0 = skip the two-NN estimate */
+    int32_t  reserved;
+} asp_reduction;
+typedef struct {
+    int64_t n_sampled;
+    int64_t n_probes;          /* probes that entered the mean (r1 > 0) */
+    double  two_nn_mean_ratio; /* NaN when skipped */
+    int32_t intrinsic_dim;     /* 0 when skipped */
+    int32_t n_clusters;
+    int32_t iters;             /* centroid updates done */
+    int32_t converged;         /* 1: an assignment pass changed nothing */
+} asp_reduction_info;
+void asp_default_reduction(asp_reduction *red);
+/* R1 on the host: kept rows of [row0, row0 + n_local) as LOCAL indices, ascending; out_rows holds n_local entries. */
+int asp_reduction_sample(const asp_reduction *red, int64_t row0, int64_t n_local, int32_t *out_rows, int64_t *out_count);
+/* R1-R4 on a resident space (world 1): a new space whose rows are the centroids (read them with asp_space_items).
+ * n_total_for_k = the N of rule R3 (0: the space's own row count). */
+int asp_space_reduce(asp_space *s, const asp_reduction *red, int64_t n_total_for_k, asp_reduction_info *info,
+                     asp_space **out_centroids);
+/* R5: the feature graph of the rows of a space (what asp_build does between upload and lambdas). */
+int asp_space_feature_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph);
+/* R1-R6 in one call; out_centroids may be NULL. */
+int asp_build_reduced(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp_graph_params *gp,
+                      const asp_switches *sw, const asp_reduction *red, asp_space **out_space, asp_graph **out_graph,
+                      asp_reduction_info *info, asp_space **out_centroids);
+
 /* ---- teardown / stats ---------------------------------------------------------------------- */
 void asp_free_space(asp_space *s);
 void asp_free_graph(asp_graph *g);
