@@ -60,6 +60,28 @@ class _Switches(C.Structure):
                 ("distance", C.c_int32)]
 
 
+class _Reduction(C.Structure):
+    _fields_ = [("sample_rate", C.c_double), ("seed", C.c_uint64), ("n_clusters", C.c_int32), ("max_iters", C.c_int32),
+                ("probes", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _ReductionInfo(C.Structure):
+    _fields_ = [("n_sampled", C.c_int64), ("n_probes", C.c_int64), ("two_nn_mean_ratio", C.c_double),
+                ("intrinsic_dim", C.c_int32), ("n_clusters", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32)]
+
+
+def make_reduction(reduction=None):
+    """True / None -> the defaults (keep rate 0.6, seed 42, K by rule, 10 iterations, 2048 probes); dict overrides."""
+    red = _Reduction()
+    lib().orc_default_reduction(C.byref(red))
+    if isinstance(reduction, dict):
+        for key, val in reduction.items():
+            if key not in dict(_Reduction._fields_) or key == "reserved":
+                raise ValueError("unknown reduction option %r" % key)
+            setattr(red, key, val)
+    return red
+
+
 def build_library(force=False):
     """Compile oracle.c (gcc) -- building the checker is not using it."""
     if force or not os.path.exists(_LIB_PATH) or \
@@ -97,6 +119,15 @@ def lib():
         L.orc_gram_columns.restype = None
         L.orc_scores.argtypes = [vp, vp, C.c_double, C.c_double, vp]
         L.orc_scores.restype = None
+        L.orc_default_reduction.argtypes = [C.POINTER(_Reduction)]
+        L.orc_default_reduction.restype = None
+        L.orc_reduction_sample.argtypes = [C.POINTER(_Reduction), C.c_int64, C.c_int64, vp]
+        L.orc_reduction_sample.restype = C.c_int64
+        L.orc_reduce.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(_Reduction), C.c_int64, C.POINTER(_ReductionInfo), vp,
+                                 C.c_int64]
+        L.orc_build_reduced.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(_Params), C.POINTER(_Switches),
+                                        C.POINTER(_Reduction), C.POINTER(vp), C.POINTER(vp), C.POINTER(_ReductionInfo), vp,
+                                        C.c_int64]
         L.orc_free_space.argtypes = [vp]
         L.orc_free_graph.argtypes = [vp]
         L.orc_free_space.restype = None
@@ -246,6 +277,47 @@ def build(graph_params, items, **switch_kw):
     _check(lib().orc_build(x.ctypes.data, x.shape[0], x.shape[1], C.byref(gp), C.byref(sw),
                            C.byref(hs), C.byref(hg)))
     return Space(hs, sw), Graph(hg, gp)
+
+
+def _info_dict(info):
+    return {name: getattr(info, name) for name, _ in _ReductionInfo._fields_}
+
+
+def reduction_sample(n, reduction=None, row0=0):
+    """R1: the kept rows of [row0, row0 + n) as local indices."""
+    red = make_reduction(reduction)
+    rows = np.empty(n, dtype=np.int32)
+    cnt = lib().orc_reduction_sample(C.byref(red), int(row0), int(n), rows.ctypes.data)
+    return rows[:cnt].copy()
+
+
+def reduce(items, reduction=None, n_total_for_k=0):
+    """R1-R4: (centroids K x f, info dict)."""
+    x = _f64(items, 2)
+    red = make_reduction(reduction)
+    cap = min(x.shape[0], 65535)
+    cent = np.empty((cap, x.shape[1]))
+    info = _ReductionInfo()
+    _check(lib().orc_reduce(x.ctypes.data, x.shape[0], x.shape[1], C.byref(red), int(n_total_for_k), C.byref(info),
+                            cent.ctypes.data, cap))
+    return cent[:info.n_clusters].copy(), _info_dict(info)
+
+
+def build_reduced(graph_params, items, reduction=None, **switch_kw):
+    """ArrowSpaceBuilder.build with the pre-graph reduction: (Space, Graph, centroids, info)."""
+    x = _f64(items)
+    if x.ndim != 2 or x.shape[0] == 0 or x.shape[1] == 0:
+        raise OracleError(1)
+    gp = resolve_params(graph_params)
+    sw = make_switches(**switch_kw)
+    red = make_reduction(reduction)
+    cap = min(x.shape[0], 65535)
+    cent = np.empty((cap, x.shape[1]))
+    info = _ReductionInfo()
+    hs, hg = C.c_void_p(), C.c_void_p()
+    _check(lib().orc_build_reduced(x.ctypes.data, x.shape[0], x.shape[1], C.byref(gp), C.byref(sw), C.byref(red),
+                                   C.byref(hs), C.byref(hg), C.byref(info), cent.ctypes.data, cap))
+    return Space(hs, sw), Graph(hg, gp), cent[:info.n_clusters].copy(), _info_dict(info)
 
 
 def graph_from_nodes(nodes, graph_params, **switch_kw):

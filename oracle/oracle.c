@@ -529,6 +529,207 @@ int orc_build(const double *items, int64_t n, int32_t f, const orc_params *gp,
     return ORC_OK;
 }
 
+/* ---------------------------------------------------------------- pre-graph reduction (R1-R6) */
+
+void orc_default_reduction(orc_reduction *red)
+{
+    red->sample_rate = 0.6;   /* suggested_eps.md:6 "keep rate 60.0%" */
+    red->seed = 42;           /* src/lib.rs:283 */
+    red->n_clusters = 0;
+    red->max_iters = 10;
+    red->probes = 2048;
+    red->reserved = 0;
+}
+
+static uint64_t splitmix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+int64_t orc_reduction_sample(const orc_reduction *red, int64_t row0, int64_t n, int32_t *out_rows)
+{
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (red->sample_rate < 1.0) {
+            const uint64_t z = splitmix64(red->seed + (uint64_t)(row0 + i + 1) * 0x9E3779B97F4A7C15ULL);
+            const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+            if (!(u < red->sample_rate)) continue;
+        }
+        out_rows[cnt++] = (int32_t)i;
+    }
+    return cnt;
+}
+
+/* squared Euclidean distance, left to right: difference, product rounded, then added */
+static double seq_sqdist(const double *a, const double *b, int64_t f)
+{
+    double s = 0.0;
+    for (int64_t t = 0; t < f; ++t) {
+        const double d = a[t] - b[t];
+        s += d * d;
+    }
+    return s;
+}
+
+int orc_reduce(const double *items, int64_t n, int32_t f, const orc_reduction *red_in, int64_t n_total_for_k,
+               orc_reduction_info *info, double *centroids_out, int64_t cap_clusters)
+{
+    if (!items || !centroids_out) return ORC_ERR_ARG;
+    if (n <= 0 || f <= 0) return ORC_ERR_EMPTY;
+    orc_reduction red;
+    if (red_in) red = *red_in; else orc_default_reduction(&red);
+    if (!(red.sample_rate > 0.0) || red.max_iters < 0 || red.n_clusters < 0 || red.probes < 0) return ORC_ERR_ARG;
+
+    /* R1 */
+    int32_t *rows = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+    if (!rows) return ORC_ERR_NOMEM;
+    int64_t ns = orc_reduction_sample(&red, 0, n, rows);
+    if (ns == 0) { for (int64_t i = 0; i < n; ++i) rows[i] = (int32_t)i; ns = n; }   /* an empty sample keeps every row */
+
+    orc_reduction_info inf;
+    memset(&inf, 0, sizeof(inf));
+    inf.n_sampled = ns;
+    inf.two_nn_mean_ratio = NAN;
+
+    /* R2 */
+    if (red.probes > 0 && ns >= 3) {
+        const int64_t P = red.probes < ns ? red.probes : ns;
+        double *r12 = (double *)malloc((size_t)(2 * P) * sizeof(double));
+        if (!r12) { free(rows); return ORC_ERR_NOMEM; }
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int64_t j = 0; j < P; ++j) {
+            const int64_t pos = (j * ns) / P;
+            const double *x = items + (int64_t)rows[pos] * f;
+            double d1 = INFINITY, d2 = INFINITY;              /* ties by position: a later equal distance never displaces */
+            for (int64_t b = 0; b < ns; ++b) {
+                if (b == pos) continue;
+                const double d = seq_sqdist(x, items + (int64_t)rows[b] * f, f);
+                if (d < d1) { d2 = d1; d1 = d; }
+                else if (d < d2) d2 = d;
+            }
+            r12[2 * j] = d1; r12[2 * j + 1] = d2;
+        }
+        double acc = 0.0;
+        int64_t used = 0;
+        for (int64_t j = 0; j < P; ++j) {
+            const double r1 = sqrt(r12[2 * j]), r2 = sqrt(r12[2 * j + 1]);
+            if (!(r1 > 0.0) || !isfinite(r2)) continue;        /* duplicates carry no scale information */
+            acc += r2 / r1;
+            ++used;
+        }
+        free(r12);
+        inf.n_probes = used;
+        if (used > 0) {
+            const double m = acc / (double)used;
+            inf.two_nn_mean_ratio = m;
+            double d = (m > 1.0) ? m / (m - 1.0) : (double)f;  /* mean of a Pareto(d) ratio is d/(d-1); 1.3560 -> 3 (suggested_eps.md:9) */
+            if (!(d < (double)f)) d = (double)f;
+            inf.intrinsic_dim = d < 1.0 ? 1 : (int32_t)d;
+        }
+    }
+
+    /* R3: the one published data point is N = 313841 -> "Testing K in range [178, 179]" (suggested_eps.md:11) */
+    int64_t K = red.n_clusters;
+    if (K <= 0) {
+        const int64_t N = n_total_for_k > 0 ? n_total_for_k : n;
+        K = (int64_t)ceil(sqrt((double)N / 10.0));
+    }
+    if (K > ns) K = ns;
+    if (K < 1) K = 1;
+    if (K > cap_clusters) { free(rows); return ORC_ERR_ARG; }
+    inf.n_clusters = (int32_t)K;
+
+    /* R4 */
+    double *C = centroids_out;
+    for (int64_t j = 0; j < K; ++j)
+        memcpy(C + j * f, items + (int64_t)rows[(j * ns) / K] * f, (size_t)f * sizeof(double));
+    int32_t *assign = (int32_t *)malloc((size_t)ns * sizeof(int32_t));
+    double *sum = (double *)malloc((size_t)f * sizeof(double));
+    if (!assign || !sum) { free(rows); free(assign); free(sum); return ORC_ERR_NOMEM; }
+    for (int64_t i = 0; i < ns; ++i) assign[i] = -1;
+    for (int it = 0; it < red.max_iters; ++it) {
+        int64_t changed = 0;
+#pragma omp parallel for schedule(static) reduction(+ : changed)
+        for (int64_t i = 0; i < ns; ++i) {
+            const double *x = items + (int64_t)rows[i] * f;
+            double best = INFINITY;
+            int32_t bj = 0;
+            for (int64_t j = 0; j < K; ++j) {
+                const double d = seq_sqdist(x, C + j * f, f);
+                if (d < best) { best = d; bj = (int32_t)j; }   /* ties -> smaller centroid */
+            }
+            if (bj != assign[i]) { assign[i] = bj; ++changed; }
+        }
+        if (changed == 0) { inf.converged = 1; break; }
+        for (int64_t j = 0; j < K; ++j) {                      /* rows added in ascending order, then one division */
+            int64_t cnt = 0;
+            for (int32_t t = 0; t < f; ++t) sum[t] = 0.0;
+            for (int64_t i = 0; i < ns; ++i) {
+                if (assign[i] != (int32_t)j) continue;
+                const double *x = items + (int64_t)rows[i] * f;
+                for (int32_t t = 0; t < f; ++t) sum[t] += x[t];
+                ++cnt;
+            }
+            if (cnt > 0)
+                for (int32_t t = 0; t < f; ++t) C[j * f + t] = sum[t] / (double)cnt;
+        }
+        inf.iters = it + 1;
+    }
+    free(rows); free(assign); free(sum);
+    if (info) *info = inf;
+    return ORC_OK;
+}
+
+int orc_build_reduced(const double *items, int64_t n, int32_t f, const orc_params *gp, const orc_switches *sw_in,
+                      const orc_reduction *red, orc_space **out_space, orc_graph **out_graph, orc_reduction_info *info,
+                      double *centroids_out, int64_t cap_clusters)
+{
+    if (!items || !gp || !out_space || !out_graph) return ORC_ERR_ARG;
+    if (n <= 0 || f <= 0) return ORC_ERR_EMPTY;
+    orc_switches sw;
+    if (sw_in) sw = *sw_in; else orc_default_switches(&sw);
+    if (sw.nodes != ORC_NODES_FEATURE_COLUMNS) return ORC_ERR_ARG;
+    orc_reduction_info inf;
+    int64_t cap = cap_clusters;
+    double *C = centroids_out;
+    if (!C) {
+        cap = n < 65535 ? n : 65535;
+        C = (double *)malloc((size_t)(cap * f) * sizeof(double));
+        if (!C) return ORC_ERR_NOMEM;
+    }
+    int rc = orc_reduce(items, n, f, red, n, &inf, C, cap);
+    orc_space *s = NULL;
+    orc_graph *g = NULL;
+    if (rc == ORC_OK) {
+        s = (orc_space *)calloc(1, sizeof(orc_space));
+        if (!s) rc = ORC_ERR_NOMEM;
+    }
+    if (rc == ORC_OK) {
+        s->n = n; s->f = f;
+        s->items = (double *)malloc((size_t)(n * f) * sizeof(double));
+        s->norms = (double *)malloc((size_t)n * sizeof(double));
+        s->lambdas = (double *)malloc((size_t)n * sizeof(double));
+        if (!s->items || !s->norms || !s->lambdas) rc = ORC_ERR_NOMEM;
+    }
+    if (rc == ORC_OK) {
+        memcpy(s->items, items, (size_t)(n * f) * sizeof(double));
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i)
+            s->norms[i] = sqrt(seq_dot(s->items + i * f, s->items + i * f, f));
+        /* R5: node a = column a of the centroid matrix (K x f row-major IS the transposed node matrix, d = K, m = f) */
+        rc = orc_graph_from_nodes_t(C, inf.n_clusters, f, gp, &sw, &g);
+    }
+    if (rc == ORC_OK) rc = orc_taumode(g, &sw, s->items, n, NULL, NULL, s->lambdas);   /* R6 */
+    if (!centroids_out) free(C);
+    if (rc != ORC_OK) { orc_free_space(s); orc_free_graph(g); return rc; }
+    if (info) *info = inf;
+    *out_space = s;
+    *out_graph = g;
+    return ORC_OK;
+}
+
 /* ---------------------------------------------------------------- search (A9) */
 
 void orc_scores(const orc_space *s, const double *q, double lambda_q, double tau, double *out)

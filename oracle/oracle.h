@@ -124,6 +124,39 @@ void orc_gram_columns(const double *x, int64_t n, int64_t m, double *out);
 /* All n scores of one query (A9), no top-k. */
 void orc_scores(const orc_space *s, const double *q, double lambda_q, double tau, double *out);
 
+/* ---- pre-graph reduction: the deterministic restatement R1-R6 of include/arrowspace_b200.h.
+ * What the crate does here (sampler at 60 %, two-NN intrinsic dimension, optimal-K clustering: log evidence
+ * /root/reference/tests/output/1760705545_v0_16/suggested_eps.md:3-11; call sites src/lib.rs:282-283) depends on its RNG
+ * stream and on arithmetic that is not in the reference: PARITY UNPINNED against the crate.  This restatement is the arbiter
+ * of the CUDA path only. */
+typedef struct {
+    double   sample_rate;
+    uint64_t seed;
+    int32_t  n_clusters;
+    int32_t  max_iters;
+    int32_t  probes;
+    int32_t  reserved;
+} orc_reduction;
+typedef struct {
+    int64_t n_sampled;
+    int64_t n_probes;
+    double  two_nn_mean_ratio;
+    int32_t intrinsic_dim;
+    int32_t n_clusters;
+    int32_t iters;
+    int32_t converged;
+} orc_reduction_info;
+void orc_default_reduction(orc_reduction *red);
+/* R1: kept rows of [row0, row0 + n) as local indices, ascending. */
+int64_t orc_reduction_sample(const orc_reduction *red, int64_t row0, int64_t n, int32_t *out_rows);
+/* R1-R4: centroids_out holds up to cap_clusters x f doubles (info->n_clusters rows are written). */
+int orc_reduce(const double *items, int64_t n, int32_t f, const orc_reduction *red, int64_t n_total_for_k,
+               orc_reduction_info *info, double *centroids_out, int64_t cap_clusters);
+/* R1-R6: space over the items, graph on the centroid matrix, lambdas of every item from it. */
+int orc_build_reduced(const double *items, int64_t n, int32_t f, const orc_params *gp, const orc_switches *sw,
+                      const orc_reduction *red, orc_space **out_space, orc_graph **out_graph, orc_reduction_info *info,
+                      double *centroids_out, int64_t cap_clusters);
+
 void orc_free_space(orc_space *s);
 void orc_free_graph(orc_graph *g);
 int  orc_num_threads(void);

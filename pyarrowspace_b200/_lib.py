@@ -53,6 +53,20 @@ class Switches(C.Structure):
                 ("topk_prunes", C.c_int32), ("distance", C.c_int32)]
 
 
+class Reduction(C.Structure):
+    """asp_reduction: sampler keep rate, seed, cluster count (0 = rule), Lloyd iterations, two-NN probes."""
+    _fields_ = [("sample_rate", C.c_double), ("seed", C.c_uint64), ("n_clusters", C.c_int32), ("max_iters", C.c_int32),
+                ("probes", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ReductionInfo(C.Structure):
+    _fields_ = [("n_sampled", C.c_int64), ("n_probes", C.c_int64), ("two_nn_mean_ratio", C.c_double),
+                ("intrinsic_dim", C.c_int32), ("n_clusters", C.c_int32), ("iters", C.c_int32), ("converged", C.c_int32)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 class LibraryError(RuntimeError):
     """A call into libarrowspace_b200.so failed (code + the library's message)."""
 
@@ -105,6 +119,12 @@ SYMBOLS = {
     "asp_item_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
     "asp_item_knn_rows": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), _i64, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
     "asp_graph_from_knn": (_int, [_vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
+    "asp_default_reduction": (None, [C.POINTER(Reduction)]),
+    "asp_reduction_sample": (_int, [C.POINTER(Reduction), _i64, _i64, _vp, C.POINTER(_i64)]),
+    "asp_space_reduce": (_int, [_vp, C.POINTER(Reduction), _i64, C.POINTER(ReductionInfo), C.POINTER(_vp)]),
+    "asp_space_feature_graph": (_int, [_vp, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(_vp)]),
+    "asp_build_reduced": (_int, [_vp, _vp, _i64, _i32, C.POINTER(GraphParams), C.POINTER(Switches), C.POINTER(Reduction),
+                                 C.POINTER(_vp), C.POINTER(_vp), C.POINTER(ReductionInfo), C.POINTER(_vp)]),
     "asp_free_space": (None, [_vp]),
     "asp_free_graph": (None, [_vp]),
     "asp_ctx_stat": (_dbl, [_vp, C.c_char_p]),
@@ -165,6 +185,22 @@ def make_switches(kernel="inv_power", tau_mode="median", tau_fixed=0.0, lambda_f
         return make_switches(**kw)
     return Switches(KERNEL[kernel], TAU_MODE[tau_mode], float(tau_fixed), LAMBDA_FORM[lambda_form], SYMMETRISE[symmetrise],
                     LAPLACIAN[laplacian], int(bool(k_counts_self)), int(bool(topk_prunes)), DISTANCE[distance])
+
+
+def make_reduction(reduction):
+    """asp_reduction from the `reduction=` extra: True -> the defaults (keep rate 0.6, seed 42, K by rule, 10 Lloyd
+    iterations, 2048 two-NN probes); a dict overrides single fields."""
+    red = Reduction()
+    load().asp_default_reduction(C.byref(red))
+    if isinstance(reduction, dict):
+        known = {name for name, _ in Reduction._fields_} - {"reserved"}
+        for key, val in reduction.items():
+            if key not in known:
+                raise ValueError("unknown reduction option %r (known: %s)" % (key, ", ".join(sorted(known))))
+            setattr(red, key, val)
+    elif reduction is not True:
+        raise TypeError("reduction= expects True or a dict of options")
+    return red
 
 
 def switches_from(extras):

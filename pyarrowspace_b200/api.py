@@ -98,6 +98,8 @@ class GraphLaplacian:
     def _wrap(cls, handle):
         self = object.__new__(cls)
         self._h = handle
+        self.reduction = None            # extension: outcome of the pre-graph reduction (ArrowSpaceBuilder.build(reduction=))
+        self._centroids = None
         return self
 
     def __del__(self):
@@ -105,6 +107,12 @@ class GraphLaplacian:
         if h and _lib is not None and getattr(_lib, "_lib", None) is not None:
             _lib._lib.asp_free_graph(h)
             self._h = None
+
+    def centroids(self):
+        """Extension: the n_clusters x nfeatures centroid matrix the graph was built on (None without reduction=)."""
+        if self._centroids is None:
+            return None
+        return persist_items(self._centroids)
 
     def _info(self):
         n, nnz, gp = C.c_int64(), C.c_int64(), _lib.GraphParams()
@@ -408,6 +416,14 @@ class ArrowSpace:
         raise NotImplementedError("search_energy belongs to the energy pipeline (src/lib.rs:232-262)")
 
 
+def persist_items(space):
+    """The stored rows of a space as a host array (asp_space_items)."""
+    n, f = space.nitems_local, space.nfeatures
+    out = np.empty((n, f), dtype=np.float64)
+    _lib.check(_lib.load().asp_space_items(space._h, out.ctypes.data))
+    return out
+
+
 def _to_host(t, out=None):
     """Device tensor -> numpy; into `out` (already resident pages, or the caller's pinned buffer) when given."""
     if out is None:
@@ -513,6 +529,11 @@ class ArrowSpaceBuilder:
         keyword-only extras (never positional): device=int and the switches of the choices the
         reference's tests cannot pin (include/arrowspace_b200.h asp_switches): kernel=, tau_mode=, tau_fixed=,
         lambda_form=, symmetrise=, laplacian=, k_counts_self=, topk_prunes=, distance=, or a named set profile="kat12".
+
+        reduction=True | {"sample_rate": 0.6, "seed": 42, "n_clusters": 0, "max_iters": 10, "probes": 2048} runs the
+        pre-graph reduction the crate runs inside this call (src/lib.rs:282-283): rows sampled, two-NN
+        intrinsic dimension, k-means; the graph is built on the centroid matrix, lambdas for every item.  The outcome is
+        on `gl.reduction` (dict) and the centroids on `gl.centroids()`.  Default: off (the documented recipe on all rows).
         """
         lib = _lib.load()
         dbg_println("Convert pyarray2 and Vec<Vec>")
@@ -547,14 +568,24 @@ class ArrowSpaceBuilder:
         sw = _lib.switches_from(extras)
         ctx = _lib.context(extras.get("device"))
         dbg_println("Building from rows")
-        hs, hg = C.c_void_p(), C.c_void_p()
+        hs, hg, hc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        reduction = extras.get("reduction")
+        info = _lib.ReductionInfo()
         try:
-            _lib.check(lib.asp_build(ctx, ptr, n, f, C.byref(cgp), C.byref(sw), C.byref(hs), C.byref(hg)))
+            if reduction:
+                red = _lib.make_reduction(reduction)
+                _lib.check(lib.asp_build_reduced(ctx, ptr, n, f, C.byref(cgp), C.byref(sw), C.byref(red), C.byref(hs),
+                                                 C.byref(hg), C.byref(info), C.byref(hc)))
+            else:
+                _lib.check(lib.asp_build(ctx, ptr, n, f, C.byref(cgp), C.byref(sw), C.byref(hs), C.byref(hg)))
         except LibraryError as e:
             if e.code in (_lib.ASP_ERR_ZERO_VECTOR, _lib.ASP_ERR_EMPTY):
                 raise PanicException(e.message)
             raise
         aspace, gl = ArrowSpace._wrap(hs, ctx), GraphLaplacian._wrap(hg)
+        if reduction:
+            gl.reduction = info.as_dict()
+            gl._centroids = ArrowSpace._wrap(hc, ctx)
         dbg_println("built ArrowSpace: nitems=%d, nfeatures=%d, lambdas_len=%d" % (n, f, n))
         return aspace, gl
 

@@ -504,25 +504,22 @@ int asp_space_compute_lambdas(asp_space *s, const asp_graph *g)
     return ASP_OK;
 }
 
-int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp_graph_params *gp, const asp_switches *sw,
-              asp_space **out_space, asp_graph **out_graph)
+// K1 (API orientation) + K2 for the rows of a world-1 space: Gram partials, selection with the exact-pair loop, Laplacian.
+int asp_space_feature_graph(asp_space *s, const asp_graph_params *gp, const asp_switches *sw, asp_graph **out_graph)
 {
-    if (!ctx || !gp || !out_space || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_build: NULL argument");
-    if (!items || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
-    asp_space *s = nullptr;
-    {
-        StageTimer t(ctx, "upload_ms");
-        ASP_CHECK(asp_space_create(ctx, items, n, f, n, 1, 0, &s));
-        t.stop();
-    }
+    if (!s || !gp || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_space_feature_graph: NULL argument");
+    if (s->world != 1) ASP_FAIL(ASP_ERR_UNSUPPORTED, "asp_space_feature_graph: needs a world-1 space (the sharded build exchanges the Gram segments itself)");
+    asp_ctx *ctx = s->ctx;
+    const int32_t f = s->f;
+    const int64_t n = s->n_local;
+    ASP_CUDA(cudaSetDevice(ctx->device));
     double *segs = nullptr;
     asp_graph *g = nullptr;
-    int rc = ASP_OK;
     if (cudaMallocAsync(&segs, sizeof(double) * (size_t)ASP_GRAM_SEGMENTS * f * f, ctx->stream) != cudaSuccess) {
-        asp_set_error("out of device memory for the Gram segments");
-        rc = ASP_ERR_NOMEM;
+        cudaGetLastError();
+        ASP_FAIL(ASP_ERR_NOMEM, "out of device memory for the Gram segments");
     }
-    if (rc == ASP_OK) rc = asp_space_gram_partials(s, segs);
+    int rc = asp_space_gram_partials(s, segs);
     if (rc == ASP_OK) {
         double graph_ms = 0.0;
         std::vector<int32_t> pairs;
@@ -551,9 +548,56 @@ int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp
         if (rc == ASP_NEED_EXACT) { asp_set_error("exact-pair resolution did not converge"); rc = ASP_ERR_CUDA; }
         ctx->stats["graph_ms"] = graph_ms;
     }
+    cudaFreeAsync(segs, ctx->stream);
+    if (rc != ASP_OK) { asp_free_graph(g); return rc; }
+    *out_graph = g;
+    return ASP_OK;
+}
+
+int asp_build(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp_graph_params *gp, const asp_switches *sw,
+              asp_space **out_space, asp_graph **out_graph)
+{
+    if (!ctx || !gp || !out_space || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_build: NULL argument");
+    if (!items || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    asp_space *s = nullptr;
+    {
+        StageTimer t(ctx, "upload_ms");
+        ASP_CHECK(asp_space_create(ctx, items, n, f, n, 1, 0, &s));
+        t.stop();
+    }
+    asp_graph *g = nullptr;
+    int rc = asp_space_feature_graph(s, gp, sw, &g);
     if (rc == ASP_OK) rc = asp_space_compute_lambdas(s, g);
-    if (segs) cudaFreeAsync(segs, ctx->stream);
     if (rc != ASP_OK) { asp_free_space(s); asp_free_graph(g); return rc; }
+    *out_space = s;
+    *out_graph = g;
+    return ASP_OK;
+}
+
+// sample -> two-NN -> k-means (reduce.cu), graph on the centroid matrix, lambdas of every item from it.
+int asp_build_reduced(asp_ctx *ctx, const double *items, int64_t n, int32_t f, const asp_graph_params *gp,
+                      const asp_switches *sw, const asp_reduction *red, asp_space **out_space, asp_graph **out_graph,
+                      asp_reduction_info *info, asp_space **out_centroids)
+{
+    if (!ctx || !gp || !out_space || !out_graph) ASP_FAIL(ASP_ERR_ARG, "asp_build_reduced: NULL argument");
+    if (!items || n <= 0 || f <= 0) ASP_FAIL(ASP_ERR_EMPTY, "items must be non-empty 2D array");
+    asp_space *s = nullptr, *cs = nullptr;
+    {
+        StageTimer t(ctx, "upload_ms");
+        ASP_CHECK(asp_space_create(ctx, items, n, f, n, 1, 0, &s));
+        t.stop();
+    }
+    asp_graph *g = nullptr;
+    int rc;
+    {
+        StageTimer t(ctx, "reduce_ms");
+        rc = asp_space_reduce(s, red, n, info, &cs);
+        t.stop();
+    }
+    if (rc == ASP_OK) rc = asp_space_feature_graph(cs, gp, sw, &g);
+    if (rc == ASP_OK) rc = asp_space_compute_lambdas(s, g);
+    if (rc != ASP_OK) { asp_free_space(s); asp_free_space(cs); asp_free_graph(g); return rc; }
+    if (out_centroids) *out_centroids = cs; else asp_free_space(cs);
     *out_space = s;
     *out_graph = g;
     return ASP_OK;

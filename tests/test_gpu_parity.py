@@ -956,3 +956,64 @@ def test_save_and_load_restore_the_index_bit_for_bit(oracle_mod, tmp_path):
     assert len(rows) == 5 * 3 * 20
     rec = evalharness.compare(sweep, texts)
     assert all(abs(r["ndcg"][0]) <= 1.0 + 1e-12 for r in rec) and all(len(r["tail_metrics"]) == 3 for r in rec)
+
+
+# ----------------------------------------------------------------------------- pre-graph reduction
+
+def _clustered(n, f, seed, n_clusters=12, spread=0.15, dup=0):
+    rng = np.random.default_rng(seed)
+    cent = rng.normal(size=(n_clusters, f))
+    x = np.abs(cent[rng.integers(0, n_clusters, n)] + spread * rng.normal(size=(n, f))) + 0.05
+    if dup:                                            # exact duplicates: two-NN probes with r1 == 0 must be skipped
+        x[n - dup:] = x[:dup]
+    return x
+
+
+def _assert_info_equal(a, b):
+    assert a.keys() == b.keys()
+    for key in a:
+        same = a[key] == b[key] or (isinstance(a[key], float) and np.isnan(a[key]) and np.isnan(b[key]))
+        assert same, (key, a, b)
+
+
+@pytest.mark.parametrize("n,f,red", [
+    (3000, 24, True),                                                   # defaults: keep rate 0.6, K by rule, 2048 probes
+    (5000, 96, {"n_clusters": 64, "max_iters": 6}),                     # 64-row centroid tiles
+    (2500, 50, {"sample_rate": 1.0, "n_clusters": 200, "probes": 300}),  # padded row pitch (50 -> 52), every row kept, 32-row tiles
+    (4000, 130, {"n_clusters": 37, "seed": 7, "max_iters": 25}),        # runs to convergence
+    (1500, 384, {"sample_rate": 0.3, "probes": 0}),                     # two-NN skipped
+    (2000, 33, {"n_clusters": 2000, "sample_rate": 0.9}),               # more clusters asked than rows kept
+])
+def test_reduced_build_gpu_equals_oracle(oracle_mod, n, f, red):
+    """sample -> two-NN -> k-means -> graph on the centroids -> lambdas of every item: centroids and the reported
+    statistics bit for bit, graph structure identical, lambdas / scores to 1e-9."""
+    from arrowspace import ArrowSpaceBuilder
+    x = _clustered(n, f, 100 + f, dup=40 if f == 24 else 0)
+    gp = {"eps": 0.6, "k": 5, "topk": 7, "p": 2.0, "sigma": 0.3}
+    aspace, gl = ArrowSpaceBuilder.build(gp, x, reduction=red)
+    s, g, cent, info = oracle_mod.build_reduced(gp, x, reduction=red)
+    _assert_info_equal(gl.reduction, info)
+    if f == 24:
+        assert info["n_probes"] < min(2048, info["n_sampled"])          # the duplicates were met
+    got = gl.centroids()
+    assert got.shape == cent.shape and np.array_equal(got, cent), "centroids differ"
+    _assert_graph_equal(gl, g)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=RTOL, atol=0)
+    q = x[::37] * 1.01
+    idx, sc = aspace.search_batch(q, gl, 0.7)
+    oidx, osc, _ = s.search_batch(q, g, 0.7)
+    _assert_hits_equal(idx, sc, oidx, osc)
+
+
+def test_reduction_off_is_the_plain_build(oracle_mod):
+    from arrowspace import ArrowSpaceBuilder
+    x = _clustered(1200, 48, 5)
+    gp = {"eps": 0.6, "k": 5, "topk": 7, "p": 2.0, "sigma": 0.3}
+    a0, g0 = ArrowSpaceBuilder.build(gp, x)
+    a1, g1 = ArrowSpaceBuilder.build(gp, x, reduction=None)
+    assert g0.reduction is None and g0.centroids() is None
+    assert all(np.array_equal(u, v) for u, v in zip(g0.csr(), g1.csr())) and np.array_equal(a0.lambdas(), a1.lambdas())
+    # one cluster per row, every row kept, no Lloyd update: the centroid matrix IS the item matrix -> the plain graph
+    a2, g2 = ArrowSpaceBuilder.build(gp, x, reduction={"sample_rate": 1.0, "n_clusters": 1200, "max_iters": 0, "probes": 0})
+    assert np.array_equal(g2.centroids(), x)
+    assert all(np.array_equal(u, v) for u, v in zip(g0.csr(), g2.csr())) and np.array_equal(a0.lambdas(), a2.lambdas())

@@ -181,3 +181,25 @@ def test_peer_exchange_buffer_size():
     assert lib.asp_peer_exchange_bytes(2, 1000, 3) == 4096 + 2 * 2 * 1000 * 3 * 16
     assert lib.asp_peer_exchange_bytes(9, 10, 10) == 0 and lib.asp_peer_exchange_bytes(0, 10, 10) == 0
     assert lib.asp_peer_exchange_bytes(2, 0, 10) == 0 and lib.asp_peer_exchange_bytes(2, 10, 0) == 0
+
+
+def test_reduction_sampler_is_the_oracles(oracle_mod):
+    """R1 of the pre-graph reduction is a host function of the C ABI (counter-based hash): same rows as the oracle's for any
+    shard offset, keep rate close to the one asked, and shards concatenate to the unsharded sample."""
+    import ctypes as C
+    from pyarrowspace_b200 import _lib
+    lib = _lib.load()
+    for rate, seed in ((0.6, 42), (0.25, 7), (1.0, 1)):
+        red = _lib.make_reduction({"sample_rate": rate, "seed": seed})
+        n = 50000
+        rows = np.empty(n, dtype=np.int32)
+        cnt = C.c_int64()
+        assert lib.asp_reduction_sample(C.byref(red), 0, n, rows.ctypes.data, C.byref(cnt)) == 0
+        want = oracle_mod.reduction_sample(n, {"sample_rate": rate, "seed": seed})
+        assert np.array_equal(rows[:cnt.value], want)
+        assert abs(cnt.value / n - rate) < 0.01
+        parts = []
+        for r0, r1 in ((0, 12345), (12345, 30000), (30000, n)):
+            assert lib.asp_reduction_sample(C.byref(red), r0, r1 - r0, rows.ctypes.data, C.byref(cnt)) == 0
+            parts.append(rows[:cnt.value].astype(np.int64) + r0)
+        assert np.array_equal(np.concatenate(parts), want)

@@ -218,3 +218,96 @@ def test_edge_cases(oracle_mod):
     with pytest.raises(oracle_mod.OracleError) as ei:
         oracle_mod.build({"eps": 1.0, "k": 2, "topk": 5, "p": 2.0}, np.array([[0.0, 0.0], [1.0, 2.0]]))
     assert ei.value.code == 2
+
+
+# ----------------------------------------------------------------------------- pre-graph reduction
+
+def _numpy_kmeans(S, K, iters):
+    """Independent restatement of R4 (strided start, left-to-right squared distances, in-order member sums)."""
+    ns, f = S.shape
+    cent = np.stack([S[(j * ns) // K] for j in range(K)])
+    assign = -np.ones(ns, dtype=np.int64)
+    done, conv = 0, 0
+    for _ in range(iters):
+        d = np.zeros((ns, K))
+        for t in range(f):
+            diff = S[:, t][:, None] - cent[:, t][None, :]
+            d += diff * diff
+        a = d.argmin(axis=1)                     # first minimum: ties -> smaller centroid
+        if np.array_equal(a, assign):
+            conv = 1
+            break
+        assign = a
+        for j in range(K):
+            m = S[assign == j]
+            if len(m):
+                acc = np.zeros(f)
+                for row in m:
+                    acc = acc + row
+                cent[j] = acc / len(m)
+        done += 1
+    return cent, done, conv
+
+
+@pytest.mark.parametrize("n,f,red", [(900, 12, {}), (700, 31, {"n_clusters": 9, "sample_rate": 1.0, "max_iters": 30}),
+                                     (500, 8, {"seed": 3, "sample_rate": 0.4, "max_iters": 3})])
+def test_reduction_matches_an_independent_restatement(oracle_mod, n, f, red):
+    rng = np.random.default_rng(n)
+    cent = rng.normal(size=(6, f))
+    x = cent[rng.integers(0, 6, n)] + 0.2 * rng.normal(size=(n, f))
+    got, info = oracle_mod.reduce(x, red)
+    rows = oracle_mod.reduction_sample(n, red)
+    assert info["n_sampled"] == len(rows)
+    K = red.get("n_clusters") or int(np.ceil(np.sqrt(n / 10.0)))
+    assert info["n_clusters"] == K
+    want, done, conv = _numpy_kmeans(x[rows], K, red.get("max_iters", 10))
+    assert np.array_equal(got, want)
+    assert (info["iters"], info["converged"]) == (done, conv)
+    # two-NN statistic, brute force
+    S = x[rows]
+    P = min(2048, len(S))
+    ratios = []
+    for j in range(P):
+        pos = (j * len(S)) // P
+        d = np.zeros(len(S))
+        for t in range(f):
+            diff = S[pos, t] - S[:, t]
+            d += diff * diff
+        d[pos] = np.inf
+        r = np.sqrt(np.sort(d)[:2])
+        if r[0] > 0:
+            ratios.append(r[1] / r[0])
+    acc = 0.0
+    for v in ratios:
+        acc += v
+    assert info["n_probes"] == len(ratios)
+    assert info["two_nn_mean_ratio"] == acc / len(ratios)
+    m = acc / len(ratios)
+    assert info["intrinsic_dim"] == max(1, int(min(m / (m - 1.0), f)))
+
+
+def test_reduction_rules_meet_the_published_data_point(oracle_mod):
+    """tests/output/1760705545_v0_16/suggested_eps.md:8-11: N = 313841 -> K tested in [178, 179]; mean two-NN ratio 1.3560
+    -> intrinsic dimension 3.  K rule on a small stand-in with n_total_for_k = 313841; the dimension rule on data of known
+    dimension (a 2-D sheet and a 5-D ball embedded in 20 dimensions)."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(400, 6))
+    _, info = oracle_mod.reduce(x, {"sample_rate": 1.0, "max_iters": 0, "probes": 0}, n_total_for_k=313841)
+    assert info["n_clusters"] == 178
+    assert int(1.3560 / (1.3560 - 1.0)) == 3
+    basis = np.linalg.qr(rng.normal(size=(20, 20)))[0]
+    for dim in (2, 5):
+        pts = rng.uniform(size=(4000, dim)) @ basis[:dim]
+        _, info = oracle_mod.reduce(pts, {"sample_rate": 1.0, "max_iters": 0, "probes": 1000})
+        assert abs(info["intrinsic_dim"] - dim) <= 1, info
+
+
+def test_reduced_build_uses_the_centroid_graph(oracle_mod):
+    rng = np.random.default_rng(2)
+    x = np.abs(rng.normal(size=(600, 16))) + 0.1
+    gp = {"eps": 0.8, "k": 4, "topk": 3, "p": 2.0, "sigma": 0.4}
+    s, g, cent, info = oracle_mod.build_reduced(gp, x, {"n_clusters": 20})
+    g2 = oracle_mod.graph_from_nodes(np.ascontiguousarray(cent.T), gp)          # nodes = columns of the centroid matrix
+    assert all(np.array_equal(a, b) for a, b in zip(g.csr(), g2.csr()))
+    _, _, lam = g.taumode(x)
+    assert np.array_equal(s.lambdas(), lam) and s.nitems == 600 and g.nnodes == 16
