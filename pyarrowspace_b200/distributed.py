@@ -106,6 +106,38 @@ class CudaEngine:
     def compute_lambdas(self, space, graph):
         _lib.check(self.lib.asp_space_compute_lambdas(space, graph))
 
+    # ---- pre-graph reduction
+    def sampled_rows(self, shard, red, row0):
+        """R1 for this rank's rows (global offset row0) -> the kept rows as a device tensor [m, f]."""
+        t = self.torch
+        n_local = shard.shape[0]
+        rows = np.empty(max(n_local, 1), dtype=np.int32)
+        cnt = C.c_int64(0)
+        _lib.check(self.lib.asp_reduction_sample(C.byref(red), int(row0), int(n_local), rows.ctypes.data, C.byref(cnt)))
+        sel = t.from_numpy(rows[:cnt.value].astype(np.int64))
+        if hasattr(shard, "is_cuda"):
+            return shard.to(self.device).index_select(0, sel.to(self.device)).contiguous()
+        return t.from_numpy(np.ascontiguousarray(shard[sel.numpy()])).to(self.device)
+
+    def reduce_rows(self, rows, red, n_total):
+        """R2-R4 on the gathered sample (every rank runs the same deterministic kernels on the same rows) ->
+        (space handle over the centroids, info dict)."""
+        h, hc = C.c_void_p(), C.c_void_p()
+        info = _lib.ReductionInfo()
+        n, f = rows.shape
+        self.torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.asp_space_create(self.ctx, rows.data_ptr(), n, f, n, 1, 0, C.byref(h)))
+        try:
+            _lib.check(self.lib.asp_space_reduce(h, C.byref(red), int(n_total), C.byref(info), C.byref(hc)))
+        finally:
+            self.lib.asp_free_space(h)
+        return hc, info.as_dict()
+
+    def feature_graph(self, space, cgp, sw):
+        hg = C.c_void_p()
+        _lib.check(self.lib.asp_space_feature_graph(space, C.byref(cgp), C.byref(sw), C.byref(hg)))
+        return hg
+
     # ---- regrouping (item_shards < world)
     def lambdas_norms(self, space, n_local):
         """-> (lambdas, norms) of the space's rows as device tensors."""
@@ -209,14 +241,55 @@ def _all_gather_blocks(t_local, world, group):
     return out
 
 
-def sharded_build(engine, shard, n_total, cgp, sw, group=None):
-    """Steps 1-2 above + lambdas.  Returns (space handle, graph handle)."""
+def _gather_ragged_rows(t_local, world, group):
+    """all-gather row blocks of different heights (same width), concatenated in rank order."""
+    import torch
+    if world == 1:
+        return t_local
+    cnt = torch.tensor([t_local.shape[0]], dtype=torch.int64, device=t_local.device)
+    counts = [int(c) for c in _all_gather_blocks(cnt, world, group).reshape(-1).tolist()]
+    if max(counts) == 0:
+        return t_local
+    return _all_gather_ragged(t_local, counts, group).contiguous()
+
+
+def sharded_reduction(engine, shard, n_total, row0, cgp, sw, red, group=None):
+    """SURVEY.md 8(f)-1 across ranks: every rank samples ITS rows (the hash runs on global row numbers), the kept rows
+    are all-gathered (C4: 0.6 x 3.07 GB), and every rank runs the same deterministic two-NN / k-means / centroid-graph
+    kernels on them -- replicas, no further collective; the result is the single-GPU one bit for bit.
+    Returns (graph handle, centroid space handle, info dict)."""
+    dist = _dist()
+    world = dist.get_world_size(group)
+    mine = engine.sampled_rows(shard, red, row0)
+    rows = _gather_ragged_rows(mine, world, group)
+    if rows.shape[0] == 0:                                   # an empty sample keeps every row
+        import torch
+        all_rows = shard if hasattr(shard, "is_cuda") else torch.from_numpy(np.ascontiguousarray(shard))
+        rows = _gather_ragged_rows(all_rows.to(mine.device).contiguous(), world, group)
+    if hasattr(engine, "after_collective"):
+        engine.after_collective()
+    whole = _lib.Reduction.from_buffer_copy(red)
+    whole.sample_rate = 1.0                                  # `rows` IS the sample
+    cspace, info = engine.reduce_rows(rows, whole, n_total)
+    graph = engine.feature_graph(cspace, cgp, sw)
+    return graph, cspace, info
+
+
+def sharded_build(engine, shard, n_total, cgp, sw, group=None, reduction=None):
+    """Steps 1-2 above + lambdas.  Returns (space handle, graph handle).  With `reduction` (an asp_reduction) the graph
+    comes from the centroid matrix instead (sharded_reduction) and (space, graph, centroid space, info) is returned."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if _lib.GRAM_SEGMENTS % world != 0:
         raise ValueError("world size %d must divide %d" % (world, _lib.GRAM_SEGMENTS))
     f = shard.shape[1]
     space = engine.space_create(shard, n_total, world, rank)
+    if reduction is not None:
+        from . import api
+        row0 = api.shard_rows(n_total, world, rank)[0]
+        graph, cspace, info = sharded_reduction(engine, shard, n_total, row0, cgp, sw, reduction, group)
+        engine.compute_lambdas(space, graph)
+        return space, graph, cspace, info
     segs = engine.gram_partials(space, f)                        # [8, f, f], own blocks filled
     per = _lib.GRAM_SEGMENTS // world
     if world > 1:
@@ -418,8 +491,17 @@ def build_sharded(graph_params, items_shard, n_total, group=None, item_shards=No
         item_shards = auto_item_shards(world, int(n_total), items_shard.shape[1], float(t.item()))
     grid_layout(world, 0, item_shards)                                  # validates
     rows_dev = engine.device_rows(items_shard) if item_shards < world else None
-    space, graph = sharded_build(engine, items_shard if rows_dev is None else rows_dev, int(n_total), cgp, sw, group)
+    reduction = extras.get("reduction")
+    src = items_shard if rows_dev is None else rows_dev
+    if reduction:
+        space, graph, cspace, info = sharded_build(engine, src, int(n_total), cgp, sw, group, _lib.make_reduction(reduction))
+    else:
+        space, graph = sharded_build(engine, src, int(n_total), cgp, sw, group)
     space, grid = regroup(engine, space, rows_dev, int(n_total), item_shards, group)
     aspace = api.ArrowSpace._wrap(space, engine.ctx, grid["merge_group"] if grid["R"] > 1 else None, grid)
     aspace._keepalive = getattr(engine, "adopted", None)              # the adopted item matrix outlives the space handle
-    return aspace, api.GraphLaplacian._wrap(graph)
+    gl = api.GraphLaplacian._wrap(graph)
+    if reduction:
+        gl.reduction = info
+        gl._centroids = api.ArrowSpace._wrap(cspace, engine.ctx)
+    return aspace, gl

@@ -316,3 +316,78 @@ def test_regroup_over_gloo(world, item_shards):
             continue
         a, b = shard_rows(n, item_shards, r)
         assert freed and np.array_equal(gx, x[a:b]) and np.array_equal(lam, x[a:b, 0] * 0.5) and np.array_equal(nrm, x[a:b, 1] + 1.0)
+
+
+# ----------------------------------------------------------------------------- pre-graph reduction across ranks
+
+class _ReduceEngine:
+    """Stands in for CudaEngine in sharded_reduction: the C ABI's host-side sampler, the oracle's reduction."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def sampled_rows(self, shard, red, row0):
+        import ctypes as C
+        from pyarrowspace_b200 import _lib
+        rows = np.empty(max(len(shard), 1), dtype=np.int32)
+        cnt = C.c_int64(0)
+        _lib.check(_lib.load().asp_reduction_sample(C.byref(red), int(row0), len(shard), rows.ctypes.data, C.byref(cnt)))
+        return self.torch.from_numpy(np.ascontiguousarray(shard[rows[:cnt.value]]))
+
+    def reduce_rows(self, rows, red, n_total):
+        import oracle
+        opts = {k: getattr(red, k) for k in ("sample_rate", "seed", "n_clusters", "max_iters", "probes")}
+        cent, info = oracle.reduce(rows.numpy(), opts, n_total_for_k=n_total)
+        return cent, info
+
+    def feature_graph(self, cspace, cgp, sw):
+        return {"centroids": cspace}
+
+
+def _reduce_worker(rank, world, port, n, f, opts, q):
+    import torch.distributed as dist
+    try:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        from pyarrowspace_b200 import _lib, shard_rows, synth
+        from pyarrowspace_b200.distributed import sharded_reduction
+        r0, r1 = shard_rows(n, world, rank)
+        shard = synth.make_items(n, f, 5, n_clusters=6, rows=(r0, r1))
+        red = _lib.make_reduction(opts)
+        graph, cent, info = sharded_reduction(_ReduceEngine(), shard, n, r0, _lib.make_params(0.5, 3, 4, 2.0, None),
+                                              _lib.make_switches(), red, None)
+        q.put((rank, cent, info, red.sample_rate))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:                                              # pragma: no cover
+        q.put((rank, "error", repr(e)))
+        raise
+
+
+@pytest.mark.parametrize("world,opts", [(2, {"max_iters": 5}), (4, {"sample_rate": 0.35, "seed": 9, "n_clusters": 11}),
+                                        (2, {"sample_rate": 1e-9, "n_clusters": 4, "probes": 64})])
+def test_sharded_reduction_over_gloo(world, opts, oracle_mod):
+    """Every rank samples its own rows (hash on GLOBAL row numbers), the kept rows are all-gathered in rank order, and the
+    replicated reduction on them equals the single-process reduction of the whole matrix bit for bit (the third case keeps
+    no row at all: the empty sample falls back to every row)."""
+    import torch.multiprocessing as mp
+    from pyarrowspace_b200 import synth
+    n, f = 1500, 10
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reduce_worker, args=(r, world, port, n, f, opts, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] is not None and not isinstance(r[1], str) for r in res), res
+    x = synth.make_items(n, f, 5, n_clusters=6)
+    want, info = oracle_mod.reduce(x, opts)
+    for r in res:
+        assert np.array_equal(r[1], want)
+        assert {k: v for k, v in r[2].items() if k != "two_nn_mean_ratio"} == {k: v for k, v in info.items() if k != "two_nn_mean_ratio"}
+        assert r[2]["two_nn_mean_ratio"] == info["two_nn_mean_ratio"] or np.isnan(info["two_nn_mean_ratio"])
+        assert r[3] == opts.get("sample_rate", 0.6)        # the caller's options are not modified

@@ -56,7 +56,21 @@ def main():
             s, g = oracle.build(gp, full)
             oidx, osc, _ = s.search_batch(q[pick], g, 0.62)
             ref = dict(idx1=idx1, sc1=sc1, lam1=a1.lambdas(), csr1=g1.csr(), pick=pick, oidx=oidx, osc=osc, olam=s.lambdas(), oedges=g.edges())
-            del a1, g1, s, g, full
+            ar, gr = ArrowSpaceBuilder.build(gp, full, device=local, reduction=True)      # pre-graph reduction, one GPU
+            ref.update(red_csr=gr.csr(), red_lam=ar.lambdas(), red_cent=gr.centroids(), red_info=gr.reduction)
+            del a1, g1, s, g, full, ar, gr
+        dist.barrier()
+        # pre-graph reduction across the ranks: sampled rows all-gathered, replicated k-means == the single-GPU one
+        aspace, gl = ArrowSpaceBuilder.build_sharded(gp, shard, n, device=local, item_shards=world, reduction=True)
+        cent, lam, lr0 = gl.centroids(), aspace.lambdas(), aspace.row_offset
+        same = True
+        if rank == 0:
+            same = (np.array_equal(cent, ref["red_cent"]) and all(np.array_equal(a, b) for a, b in zip(gl.csr(), ref["red_csr"]))
+                    and np.array_equal(lam, ref["red_lam"][lr0:lr0 + len(lam)]) and str(gl.reduction) == str(ref["red_info"]))
+            print("world %d n %d f %d reduced build (K = %d, %d rows sampled): centroids / graph / lambdas / statistics == single GPU "
+                  "(bitwise) %s" % (world, n, f, gl.reduction["n_clusters"], gl.reduction["n_sampled"], same), flush=True)
+        ok = ok and same
+        del aspace, gl
         dist.barrier()
         shards = [r for r in (world, 4, 2, 1) if r <= world and world % r == 0]
         for R in dict.fromkeys(shards):
