@@ -82,6 +82,7 @@ def parse_args():
     ap.add_argument("--item-shards", type=int, default=None, help="N > 1: item shards R of the search grid (default: fewest that fit; N: fully sharded)")
     ap.add_argument("--parity-queries", type=int, default=64, help="queries of the last step checked against the oracle's full scan (0: skip)")
     ap.add_argument("--no-regimes", action="store_true", help="skip the mean-zero regime")
+    ap.add_argument("--no-reduction", action="store_true", help="skip the build with the pre-graph reduction (SURVEY.md 8(f)-1)")
     return ap.parse_args()
 
 
@@ -469,6 +470,38 @@ def main():
                       "stage1_tflops": ig_exec / (ig_stats["knn_stage1_ms"] * 1e-3) / 1e12 if ig_stats["knn_stage1_ms"] > 0 else None,
                       "note": "rows of this rank against all %d items; N > 1: + all-gather of the item shards and of the lists" % n}
 
+    # ---- build with the pre-graph reduction the crate runs inside build: sample 60 %, two-NN intrinsic
+    # dimension, k-means, graph on the centroid matrix, lambdas of every item.  N > 1: sampled rows all-gathered, replicas.
+    reduced = None
+    if not args.no_reduction:
+        red_ms = []
+        with torch.cuda.stream(stream):
+            for rep in range(2):
+                barrier_sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if world == 1:
+                    a_rd, g_rd = ArrowSpaceBuilder.build(gp, x_dev, device=local, reduction=True)
+                else:
+                    a_rd, g_rd = ArrowSpaceBuilder.build_sharded(gp, x_dev, n, device=local, item_shards=world, reduction=True)
+                e1.record(stream)
+                barrier_sync()
+                red_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+                rd_info = g_rd.reduction
+                rd_stats = {k: api.stat(k, local) for k in ("reduce_two_nn_ms", "reduce_kmeans_ms", "reduce_assign_ms", "reduce_assign_passes")}
+                del a_rd, g_rd
+        dp_ops = 3.0 * rd_info["n_sampled"] * rd_info["n_clusters"] * f * rd_stats["reduce_assign_passes"]
+        reduced = {"ms": min(red_ms), "items_per_s": n / (min(red_ms) * 1e-3), "info": rd_info,
+                   "two_nn_ms": rd_stats["reduce_two_nn_ms"], "kmeans_ms": rd_stats["reduce_kmeans_ms"],
+                   "assign": {"kernel": "sqdist_min2_kernel (squared distances in the oracle's order: subtract, multiply, add -- no FMA "
+                                        "contraction under the parity contract; two smallest per row)",
+                              "ms": rd_stats["reduce_assign_ms"], "passes": rd_stats["reduce_assign_passes"], "bound": "fp64 issue",
+                              "dp_instructions": dp_ops, "achieved_per_s": dp_ops / (rd_stats["reduce_assign_ms"] * 1e-3),
+                              "peak_per_s_at_max_clock": 148 * 64 * 1.965e9,
+                              "frac_at_max_clock": dp_ops / (rd_stats["reduce_assign_ms"] * 1e-3) / (148 * 64 * 1.965e9)},
+                   "note": "centroids bit-identical to the oracle's at test sizes (tests/test_gpu_parity.py); the reference spends "
+                           "its ~2-minute build floor here (SURVEY.md section 6)"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()                                            # rank 0 runs the untimed oracle checks meanwhile
@@ -600,6 +633,7 @@ def main():
                              "gather": {"upper_nnz": upper_nnz, "smem_bytes": 8.0 * n_local * upper_nnz,
                                         "smem_floor_ms": gather_floor_ms, "frac_of_smem_floor": gather_floor_ms / lam_ms}}},
         "item_graph": item_graph,
+        "reduced_build": reduced,
         "single_query": single,
         "clocks": clk,
     }

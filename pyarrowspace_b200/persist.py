@@ -33,7 +33,11 @@ def save(path, aspace, gl, items=None):
     sw = _lib.Switches()
     _lib.check(_lib.load().asp_graph_switches(gl._h, C.byref(sw)))
     gp = gl.graph_params
-    np.savez(path, format_version=FORMAT_VERSION, items=items, lambdas=aspace.lambdas(), norms=aspace.norms(), indptr=indptr,
+    extra = {}
+    if gl.reduction is not None:                      # built with reduction=: keep the statistics and the centroid matrix
+        import json
+        extra = {"reduction": np.array(json.dumps(gl.reduction)), "centroids": gl.centroids()}
+    np.savez(path, **extra, format_version=FORMAT_VERSION, items=items, lambdas=aspace.lambdas(), norms=aspace.norms(), indptr=indptr,
              indices=indices, data=data, nnodes=gl.nnodes,
              graph_params=np.array([gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"]], dtype=np.float64),
              switches=np.array([float(getattr(sw, name)) for name in _SWITCH_FIELDS], dtype=np.float64),
@@ -68,4 +72,12 @@ def load(path, device=None):
     nnodes = int(z["nnodes"])
     _lib.check(lib.asp_graph_from_csr(ctx, nnodes, len(indices), indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
                                       C.byref(cgp), C.byref(sw), 1 if nnodes == f else 0, C.byref(hg)))
-    return aspace, api.GraphLaplacian._wrap(hg)
+    gl = api.GraphLaplacian._wrap(hg)
+    if "reduction" in z.files:
+        import json
+        gl.reduction = json.loads(str(z["reduction"]))
+        cent = np.ascontiguousarray(z["centroids"], dtype=np.float64)
+        hc = C.c_void_p()
+        _lib.check(lib.asp_space_create(ctx, cent.ctypes.data, cent.shape[0], f, cent.shape[0], 1, 0, C.byref(hc)))
+        gl._centroids = api.ArrowSpace._wrap(hc, ctx)
+    return aspace, gl

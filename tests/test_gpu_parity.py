@@ -1017,3 +1017,18 @@ def test_reduction_off_is_the_plain_build(oracle_mod):
     a2, g2 = ArrowSpaceBuilder.build(gp, x, reduction={"sample_rate": 1.0, "n_clusters": 1200, "max_iters": 0, "probes": 0})
     assert np.array_equal(g2.centroids(), x)
     assert all(np.array_equal(u, v) for u, v in zip(g0.csr(), g2.csr())) and np.array_equal(a0.lambdas(), a2.lambdas())
+
+
+def test_save_and_load_keep_the_reduction(tmp_path):
+    from arrowspace import ArrowSpaceBuilder
+    x = _clustered(1500, 40, 8)
+    gp = {"eps": 0.6, "k": 5, "topk": 7, "p": 2.0, "sigma": 0.3}
+    aspace, gl = ArrowSpaceBuilder.build(gp, x, reduction={"n_clusters": 25})
+    path = aspace.save(str(tmp_path / "reduced.npz"), gl)
+    a2, g2 = ArrowSpaceBuilder.load(path)
+    _assert_info_equal(g2.reduction, gl.reduction)
+    assert np.array_equal(g2.centroids(), gl.centroids())
+    q = x[::50] * 0.99
+    i1, s1 = aspace.search_batch(q, gl, 0.62)
+    i2, s2 = a2.search_batch(q, g2, 0.62)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
