@@ -716,6 +716,7 @@ static int search_device_batch(const asp_space *s, const asp_graph *g, const dou
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const int32_t f = s->f, fp = s->fp;
+    const double t_in = asp_now_us();
     ASP_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2, st));
     ASP_CHECK(asp_launch_taumode(ctx, g, &g->sw, dq, nq, f, fp, nullptr, nullptr, dlam, dnorm, nullptr, flags));
     zero_lambda_check_kernel<<<64, 256, 0, st>>>(dlam, nq, flags + 1);
@@ -725,6 +726,7 @@ static int search_device_batch(const asp_space *s, const asp_graph *g, const dou
     ASP_CUDA(cudaStreamSynchronize(st));
     if (h[0]) ASP_FAIL(ASP_ERR_ZERO_VECTOR, "a query vector is all zeros: its Rayleigh quotient is undefined");
     if (h[1]) ASP_FAIL(ASP_ERR_LAMBDA_ZERO, "The lambdas are zero, check the magnitude of items and eps.");   // src/lib.rs:156-159
+    ctx->stats["search_host_lambda_us"] = asp_now_us() - t_in;
     if (topk <= 0) return ASP_OK;
     // stage 1 on tcgen05 (fp16 split) for batches, FP64 DMMA / GEMV otherwise; same exact stage 2, same answers
     const char *force = getenv("ASP_SEARCH_STAGE1");
@@ -737,6 +739,7 @@ static int search_device_batch(const asp_space *s, const asp_graph *g, const dou
     else
         rc = asp_search_impl(s, g, dq, nq, fp, dlam, dnorm, tau, topk, didx, dscore);
     if (rc == ASP_OK) ASP_CUDA(cudaStreamSynchronize(st));
+    ctx->stats["search_host_device_batch_us"] = asp_now_us() - t_in;
     return rc;
 }
 
@@ -760,6 +763,8 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     if (nq == 0) return ASP_OK;
     if (s->f > 6144) ASP_FAIL(ASP_ERR_UNSUPPORTED, "search supports at most 6144 features (got %d)", s->f);
     asp_ctx *ctx = s->ctx;
+    const double t_call = asp_now_us();
+    struct CallTimer { asp_ctx *c; double t0; ~CallTimer() { c->stats["search_host_call_us"] = asp_now_us() - t0; } } call_timer{ctx, t_call};
     ASP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t topk = g->gp.topk;                              // src/lib.rs:169

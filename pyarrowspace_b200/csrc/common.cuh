@@ -84,6 +84,13 @@ struct asp_graph {
     void *tm_blob = nullptr;
 };
 
+// host wall clock in microseconds (diagnostic stats "search_host_*_us": where a call's time goes between the kernels)
+#include <chrono>
+static inline double asp_now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // ------------------------------------------------------------------ launch bookkeeping
 #define ASP_LAUNCHED(ctx) ((ctx)->launches++)
 

@@ -712,6 +712,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 constexpr int TR_WARPS = 4;
+constexpr int TR_MIN_CTAS = 8;    // throughput shape: 32 resident warps per SM (64 registers per thread)
 constexpr int TR_QUEUE = 96;       // survivor queue per warp (flushed in batches of 32)
 
 // WPQ warps per query.  See the header: (A) coalesced f64 re-scoring of every survivor, best 32 kept;
@@ -720,8 +721,8 @@ constexpr int TR_QUEUE = 96;       // survivor queue per warp (flushed in batche
 // reference's one-query-per-call `search`): one CTA per query, warp w takes the emission streams w, w + WPQ, ...; the
 // per-warp top lists are merged pairwise through shared memory.  Every quantity that decides the result (cut-off, fast
 // scores, the 32 kept, the band) is a function of the SET of emitted candidates, so all WPQ give bit-identical output.
-template <int WPQ>
-__global__ void __launch_bounds__((WPQ == 1 ? TR_WARPS : WPQ) * 32)
+template <int WPQ, int MINB = 1>   // MINB: resident CTAs per SM the register allocation must allow
+__global__ void __launch_bounds__((WPQ == 1 ? TR_WARPS : WPQ) * 32, MINB)
 tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const double *__restrict__ items, int64_t n_local,
                   int f, int pitch, int64_t row0, const double *__restrict__ norm_x, const double *__restrict__ lam_x,
                   const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk, int nstreams,
@@ -1105,6 +1106,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
 {
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    const double t_stage1 = asp_now_us();
     asp_tc_cache *c = nullptr;
     ASP_CHECK(ensure_tc_cache(s, &c));
     const int kp = c->kp;
@@ -1138,6 +1140,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     // model: fp16 roundings of both residuals, round-toward-zero f32 accumulation, truncated rank-1 split)
     double rho_q_max = 1.0;
     ASP_CHECK(device_max(ctx, b->rho_q, nq, &rho_q_max));
+    ctx->stats["search_host_prep_us"] = asp_now_us() - t_stage1;
     const double steps = (double)((s->f + 15) / 16);
     const double c_main1 = 2.0 * c->rho_max * (ldexp(1.0, -10) * (1.0 + ldexp(1.0, -11)) + steps * ldexp(1.0, -23));
     const double c_main3 = 2.0 * c->rho_max * (3.0 * ldexp(1.0, -22) + 3.0 * steps * ldexp(1.0, -23));
@@ -1185,7 +1188,11 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
         if (eff > best_eff + 1e-9) { best_eff = eff; best_chunks = cc; }
         if (eff >= 0.97 || cc == tiles_total) break;
     }
-    const int nchunks = (int)best_chunks;
+    int nchunks = (int)best_chunks;
+    if (const char *e = getenv("ASP_TC_CHUNKS")) {                   // tuning knob (same results for any split)
+        const long v = atol(e);
+        if (v >= 1 && v <= tiles_total) nchunks = (int)v;
+    }
     int capb = dump_dev ? 1 : (capb_override > 0 ? capb_override : 1024);   // per (query, chunk)
     if (const char *e = getenv("ASP_TC_CAPB")) {                     // test knob: shrink the emission buffers
         const int v = atoi(e);
@@ -1262,6 +1269,7 @@ int asp_tc_stage1(const asp_space *s, const double *q_dev, int64_t nq, int32_t q
     }
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev1, st));
+    ctx->stats["search_host_stage1_launched_us"] = asp_now_us() - t_stage1;
     b->variant = v;
     ctx->stats["search_cta_pair"] = pair ? 1.0 : 0.0;
     ctx->stats["search_a_resident"] = ares ? 1.0 : 0.0;
@@ -1321,7 +1329,8 @@ int asp_search_tc_impl(const asp_space *s, const double *q_dev, int64_t nq, int3
     };
     if (wpq == 32) ASP_CHECK(launch_rescore(tc_rescore_kernel<32>, 32, 1, (unsigned)nq));
     else if (wpq == 8) ASP_CHECK(launch_rescore(tc_rescore_kernel<8>, 8, 1, (unsigned)nq));
-    else ASP_CHECK(launch_rescore(tc_rescore_kernel<1>, TR_WARPS, TR_WARPS, (unsigned)asp_ceil_div(nq, TR_WARPS)));
+    else if (getenv("ASP_TC_RESCORE_OCC6")) ASP_CHECK(launch_rescore(tc_rescore_kernel<1>, TR_WARPS, TR_WARPS, (unsigned)asp_ceil_div(nq, TR_WARPS)));
+    else ASP_CHECK(launch_rescore(tc_rescore_kernel<1, TR_MIN_CTAS>, TR_WARPS, TR_WARPS, (unsigned)asp_ceil_div(nq, TR_WARPS)));
     ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
     ASP_CUDA(cudaEventRecord(ctx->ev2, st));
     int32_t nslow = 0;

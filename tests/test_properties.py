@@ -1,0 +1,106 @@
+"""Property tests of the path's invariants, on the oracle (CPU, hypothesis-generated inputs) and
+on the CUDA path (-m gpu, the same properties on seeded inputs).  None of them needs a reference value: they hold for any
+input, so they also hold at BASELINE.json's full sizes (tests/test_gpu_parity.py uses some of them there)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+from hypothesis.extra import numpy as hnp
+
+FAST = settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+
+shapes = st.tuples(st.integers(4, 40), st.integers(3, 12))
+seeds = st.integers(0, 2 ** 31 - 1)
+params = st.fixed_dictionaries({"eps": st.floats(0.05, 1.0), "k": st.integers(1, 6), "topk": st.integers(1, 5),
+                                "p": st.sampled_from([1.0, 2.0, 3.0]), "sigma": st.one_of(st.none(), st.floats(0.05, 1.0))})
+
+
+def _items(shape, seed):
+    rng = np.random.default_rng(seed)
+    return np.abs(rng.normal(size=shape)) + 0.05          # positive entries: the median tau stays off its floor
+
+
+def _dense(graph):
+    ip, ix, dt = graph.csr()
+    m = graph.nnodes
+    L = np.zeros((m, m))
+    for a in range(m):
+        L[a, ix[ip[a]:ip[a + 1]]] = dt[ip[a]:ip[a + 1]]
+    return L
+
+
+def _check_graph(L, gp, sw):
+    m = L.shape[0]
+    W = -(L - np.diag(np.diag(L)))
+    assert (W >= 0).all(), "off-diagonal entries of a Laplacian are <= 0"
+    if sw.get("laplacian", "combinatorial") == "combinatorial":
+        np.testing.assert_allclose(L.sum(axis=1), 0.0, atol=1e-12)           # rows sum to zero: L = D - W
+        if sw.get("symmetrise", "max") != "none":
+            assert np.array_equal(L, L.T), "symmetrised graph"
+        if sw.get("symmetrise", "max") == "min":                                # mutual edges only: the k cap holds per row
+            assert ((W > 0).sum(axis=1) <= gp["k"]).all()
+        assert ((W > 0).sum(axis=1) <= 2 * m).all()
+    if sw.get("laplacian") == "rw":
+        deg = (W > 0).sum(axis=1)
+        np.testing.assert_allclose(L.sum(axis=1)[deg > 0], 0.0, atol=1e-12)  # I - D^-1 W
+
+
+def _check_search(space, graph, x, gp, run):
+    n = x.shape[0]
+    q = x[n // 2] * 1.03 + 0.001
+    hits1 = run(q, 1.0)
+    cos = x @ q / (np.linalg.norm(x, axis=1) * np.linalg.norm(q))
+    order = sorted(range(n), key=lambda i: (-cos[i], i))[:len(hits1)]
+    gaps = np.diff(np.sort(cos)[::-1][:len(hits1) + 1])
+    if len(gaps) == 0 or np.abs(gaps).min() > 1e-12:                           # tau = 1: pure cosine order
+        assert [i for i, _ in hits1] == order
+    assert len(hits1) == min(gp["topk"], n)
+    hits = run(q, 0.6)
+    sc = [s for _, s in hits]
+    assert sc == sorted(sc, reverse=True), "scores descend"
+    assert all(0.0 <= s <= 1.0 + 1e-12 for s in sc), "tau cos + (1 - tau) / (1 + |dl|) lies in [0, 1] for non-negative data"
+    # scaling the QUERY changes lambda_q (the median tau is not scale invariant, tests/test_0.py) but not the cosine term
+    h2 = run(q * 7.0, 1.0)
+    np.testing.assert_allclose([s for _, s in h2], [s for _, s in hits1], rtol=1e-12)
+
+
+@FAST
+@given(shapes, seeds, params, st.sampled_from([{}, {"symmetrise": "min"}, {"symmetrise": "none"}, {"laplacian": "rw"},
+                                               {"kernel": "gaussian"}, {"k_counts_self": True}]))
+def test_oracle_invariants(oracle_mod, shape, seed, gp, sw):
+    x = _items(shape, seed)
+    s, g = oracle_mod.build(gp, x, **sw)
+    _check_graph(_dense(g), gp, sw)
+    lam = s.lambdas()
+    assert lam.shape == (shape[0],) and np.isfinite(lam).all()
+    if sw.get("laplacian", "combinatorial") == "combinatorial" and sw.get("symmetrise", "max") != "none":
+        assert ((lam >= 0.0) & (lam < 1.0)).all(), "E >= 0 for a PSD Laplacian, so E / (E + tau) lies in [0, 1)"
+    if g.nnz > g.nnodes and not np.any(lam == 0.0):
+        try:
+            _check_search(s, g, x, gp, lambda q, tau: s.search(q, g, tau))
+        except oracle_mod.OracleError as e:                                    # lambda_q == 0 is the reference's panic, not a bug
+            assert e.code == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_invariants(oracle_mod, seed):
+    """The same invariants on the CUDA path, plus agreement with the oracle on the drawn case."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200._lib import LibraryError
+    rng = np.random.default_rng(1000 + seed)
+    shape = (int(rng.integers(4, 400)), int(rng.integers(3, 70)))
+    gp = {"eps": float(rng.uniform(0.05, 1.0)), "k": int(rng.integers(1, 9)), "topk": int(rng.integers(1, 8)),
+          "p": float(rng.choice([1.0, 2.0, 3.0])), "sigma": None if seed % 3 == 0 else float(rng.uniform(0.05, 1.0))}
+    sw = [{}, {"symmetrise": "min"}, {"symmetrise": "none"}, {"laplacian": "rw"}, {"kernel": "gaussian"}, {"k_counts_self": True}][seed % 6]
+    x = _items(shape, seed)
+    aspace, gl = ArrowSpaceBuilder.build(gp, x, **sw)
+    s, g = oracle_mod.build(gp, x, **sw)
+    assert all(np.array_equal(a, b) for a, b in zip(gl.csr()[:2], g.csr()[:2]))
+    _check_graph(_dense(gl), gp, sw)
+    np.testing.assert_allclose(aspace.lambdas(), s.lambdas(), rtol=1e-9, atol=0)
+    if gl.nnz > gl.nnodes and not np.any(s.lambdas() == 0.0):
+        try:
+            _check_search(aspace, gl, x, gp, lambda q, tau: aspace.search(q, gl, tau))
+        except BaseException as e:                                             # the reference's lambda_q == 0 panic
+            assert "lambdas are zero" in str(e)
