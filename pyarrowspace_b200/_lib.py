@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarrowspace_b200.so")
+LIB_PATH = os.environ.get("ASP_B200_LIB") or os.path.join(_HERE, "libarrowspace_b200.so")   # override: A/B of two builds
 
 ASP_OK = 0
 ASP_ERR_EMPTY = 1

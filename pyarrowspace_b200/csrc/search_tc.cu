@@ -340,7 +340,24 @@ __device__ __forceinline__ uint64_t make_kmajor_narrow_desc(uint32_t smem_addr, 
 constexpr uint32_t IDESC_F16_128x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
 constexpr uint32_t IDESC_F16_256x256 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TQ) >> 4) << 24);   // cta_group::2
 
-// r[j] for a run-time j without local memory: a 5-level select tree (31 SEL)
+// r[j] for a run-time j without local memory.  Called from the rare path, where usually ONE lane of the warp is active.
+#ifdef ASP_PICK_SWITCH
+#define ASP_PICK_CASE(i) case i: v = r[i]; break;
+__device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j)
+{
+    uint32_t v = 0;
+    switch (j) {
+        ASP_PICK_CASE(0) ASP_PICK_CASE(1) ASP_PICK_CASE(2) ASP_PICK_CASE(3) ASP_PICK_CASE(4) ASP_PICK_CASE(5) ASP_PICK_CASE(6)
+        ASP_PICK_CASE(7) ASP_PICK_CASE(8) ASP_PICK_CASE(9) ASP_PICK_CASE(10) ASP_PICK_CASE(11) ASP_PICK_CASE(12) ASP_PICK_CASE(13)
+        ASP_PICK_CASE(14) ASP_PICK_CASE(15) ASP_PICK_CASE(16) ASP_PICK_CASE(17) ASP_PICK_CASE(18) ASP_PICK_CASE(19) ASP_PICK_CASE(20)
+        ASP_PICK_CASE(21) ASP_PICK_CASE(22) ASP_PICK_CASE(23) ASP_PICK_CASE(24) ASP_PICK_CASE(25) ASP_PICK_CASE(26) ASP_PICK_CASE(27)
+        ASP_PICK_CASE(28) ASP_PICK_CASE(29) ASP_PICK_CASE(30) ASP_PICK_CASE(31)
+    }
+    return __uint_as_float(v);
+}
+#undef ASP_PICK_CASE
+#else
+// a 5-level select tree (31 SEL)
 __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j)
 {
     uint32_t a[16], b[8], c[4], d[2];
@@ -354,6 +371,7 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j)
     for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[i + 2] : c[i];
     return __uint_as_float((j & 1) ? d[1] : d[0]);
 }
+#endif
 
 struct TcParams {
     int64_t nq, n_local;
@@ -390,7 +408,7 @@ struct TcParams {
 // pipeline depth.  Barriers: TMA loads of both CTAs complete on the LEADER's full barrier; tcgen05.commit multicasts the
 // "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely on the leader's
 // "accumulator drained" barrier.
-template <bool DUMP, int VARIANT, bool ARES, bool PAIR, int LISTN>   // LISTN: running list per thread (>= topk); VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued, 4 epilogue loads TMEM only
+template <bool DUMP, int VARIANT, bool ARES, bool PAIR, int LISTN>   // LISTN (>= topk): the four column-quarter threads of a query row keep LISTN / 4 scores each; VARIANT (profiling only): 0 normal, 2 epilogue does no work, 3 no MMA issued, 4 epilogue loads TMEM only
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
@@ -409,6 +427,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
     __shared__ uint32_t s_tmem_base;
     __shared__ uint32_t s_theta[TQ];          // per query row: best k-th score seen by its threads / other CTAs (ordered bits)
     __shared__ int s_cnt[TQ];                 // per query row: emission cursor shared by its column-quarter threads
+    __shared__ float s_part[TQ * 4];          // per query row and column quarter: that quarter's ceil(topk/4)-th best score
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, chunk = blockIdx.y;
@@ -437,6 +456,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         asp::fence_barrier_init();
     }
     if (threadIdx.x < TQ) { s_theta[threadIdx.x] = 0u; s_cnt[threadIdx.x] = 0; }
+    if (threadIdx.x < TQ * 4) s_part[threadIdx.x] = -INFINITY;
     if (warp == 1) { if (PAIR) asp::tmem_alloc_pair(&s_tmem_base, 512); else asp::tmem_alloc(&s_tmem_base, 512); }
     asp::tc_fence_before();
     __syncthreads();
@@ -547,9 +567,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
         const int et = threadIdx.x - 64;                                         // 0 .. EPI_WARPS*32-1
         const float inv_tau = 1.0f / p.tau;
         const float delta2 = (qvalid && !DUMP) ? 2.0f * p.delta_q[gq] : 0.f;
-        float lst[LISTN];
+        // Running threshold of a query row: its four threads (column quarters) each keep the best rr = ceil(topk / 4) scores of
+        // THEIR columns; 4 rr >= topk distinct items score at least m = min over the quarters of the rr-th best, so m is a valid
+        // lower bound of the row's topk-th best -- about the (topk + 4)-th best overall, where a full list per quarter would
+        // only give the 4 topk-th.  lst[PL-1] is the rr-th best (the slots in front of the real ones hold +inf and never move).
+        constexpr int PL = LISTN / 4;
+        const int rr = (p.topk + 3) >> 2;
+        float lst[PL];
 #pragma unroll
-        for (int i = 0; i < LISTN; ++i) lst[i] = -INFINITY;
+        for (int i = 0; i < PL; ++i) lst[i] = (i < PL - rr) ? INFINITY : -INFINITY;
+        volatile float *my_part = s_part + row * 4;
         const float floor_row = p.score_floor - 0.5f * delta2;                    // exact-score floor minus the row's band (-inf: none)
         float theta_k = -INFINITY, theta_emit = floor_row;
         const size_t ebase = ((size_t)gq * p.nchunks + chunk) * (size_t)p.capb;
@@ -635,18 +662,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_consta
                             if (sc >= theta_emit && n < p.n_local) {
                                 const int pos = atomicAdd(&s_cnt[row], 1);
                                 if (pos < p.capb) { p.emit_sc[ebase + pos] = sc; p.emit_ix[ebase + pos] = p.perm[n]; }
-                                if (sc > lst[LISTN - 1]) {
-                                    float v = sc;
+                                if (sc > lst[PL - 1]) {
+                                    float v = sc;                                // sorted insertion
 #pragma unroll
-                                    for (int i = 0; i < LISTN; ++i) {
+                                    for (int i = 0; i < PL; ++i) {
                                         const float o = lst[i];
                                         const bool sw = v > o;
                                         lst[i] = sw ? v : o;
                                         v = sw ? o : v;
                                     }
-                                    float kth = lst[0];
-#pragma unroll
-                                    for (int i = 1; i < LISTN; ++i) kth = (i < p.topk) ? lst[i] : kth;
+                                    my_part[part] = lst[PL - 1];                 // a stale (lower) value read by the others is still valid
+                                    const float kth = fminf(fminf(my_part[0], my_part[1]), fminf(my_part[2], my_part[3]));
                                     if (kth > theta_k) {
                                         theta_k = kth;
                                         theta_emit = fmaxf(theta_k - delta2, floor_row);
