@@ -203,6 +203,21 @@ __device__ __forceinline__ double warp_sum_f64(double v)
     return v;
 }
 
+// Sums of FOUR per-lane values over the warp with 12 shuffles instead of 40: the halves of the warp first trade two values,
+// the quarters one, then three plain butterfly steps.  Lanes 8u .. 8u+7 end with the total of value u.
+__device__ __forceinline__ double warp_sum4_transposed(const double (&d)[4], int lane)
+{
+    const bool hi = (lane & 16) != 0;
+    const double k0 = hi ? d[2] : d[0], k1 = hi ? d[3] : d[1];
+    const double s0 = hi ? d[0] : d[2], s1 = hi ? d[1] : d[3];
+    const double e0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), e1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool mid = (lane & 8) != 0;
+    double f = (mid ? e1 : e0) + __shfl_xor_sync(0xffffffffu, mid ? e0 : e1, 8);
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) f += __shfl_xor_sync(0xffffffffu, f, off);
+    return f;
+}
+
 __global__ void __launch_bounds__(KR_WARPS * 32)
 knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pitch, const double *__restrict__ norms,
                       double eps, int kk, int64_t b0, int64_t nq, int nsub, int capb, const float *__restrict__ delta_q,
@@ -258,6 +273,8 @@ knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pi
     unsigned long long nsurv = 0;
     auto flush = [&](int count) {
         Cand mine = asp::cand_empty();
+        double my_dot = 0.0;
+        int my_item = -1;
         for (int s0 = 0; s0 < count; s0 += 4) {
             int ii[4];
             const double *rr[4];
@@ -273,16 +290,18 @@ knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pi
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { d[u] = fma(qq.x, a[u].x, d[u]); d[u] = fma(qq.y, a[u].y, d[u]); }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) d[u] = warp_sum_f64(d[u]);
+            const double tot = warp_sum4_transposed(d, lane);                    // lanes 8u .. 8u+7: the dot of row s0 + u
             const int u_mine = lane - s0;
+            const double dd = __shfl_sync(0xffffffffu, tot, 8 * (u_mine & 3));
             if (u_mine >= 0 && u_mine < 4 && lane < count) {
-                const double dd = (u_mine == 0) ? d[0] : (u_mine == 1) ? d[1] : (u_mine == 2) ? d[2] : d[3];
-                const int it = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
-                const double den = ni * norms[it];
-                mine.s = (den != 0.0) ? dd / den : 0.0;                          // fast cosine
-                mine.i = it;
+                my_dot = dd;
+                my_item = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
             }
+        }
+        if (my_item >= 0) {
+            const double den = ni * norms[my_item];
+            mine.s = (den != 0.0) ? my_dot / den : 0.0;                          // fast cosine
+            mine.i = my_item;
         }
         best[1] = mine;
         asp::warp_sort_best_first<2>(best, lane);

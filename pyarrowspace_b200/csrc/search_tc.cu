@@ -737,6 +737,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Sums of FOUR per-lane values over the warp with 12 shuffles instead of 40: the halves of the warp first trade two values,
+// the quarters one, then three plain butterfly steps.  Lanes 8u .. 8u+7 end with the total of value u.
+__device__ __forceinline__ double warp_sum4_transposed(const double (&d)[4], int lane)
+{
+    const bool hi = (lane & 16) != 0;
+    const double k0 = hi ? d[2] : d[0], k1 = hi ? d[3] : d[1];
+    const double s0 = hi ? d[0] : d[2], s1 = hi ? d[1] : d[3];
+    const double e0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), e1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool mid = (lane & 8) != 0;
+    double f = (mid ? e1 : e0) + __shfl_xor_sync(0xffffffffu, mid ? e0 : e1, 8);
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) f += __shfl_xor_sync(0xffffffffu, f, off);
+    return f;
+}
+
 constexpr int TR_WARPS = 4;
 constexpr int TR_MIN_CTAS = 8;    // throughput shape: 32 resident warps per SM (64 registers per thread)
 constexpr int TR_QUEUE = 96;       // survivor queue per warp (flushed in batches of 32)
@@ -851,6 +866,8 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
     // (A): `count` queued survivors, four rows at a time, every lane a slice of the features (coalesced 16 B loads)
     auto flush = [&](int count) {
         Cand mine = asp::cand_empty();
+        double my_dot = 0.0;
+        int my_item = -1;
         for (int s0 = 0; s0 < count; s0 += 4) {
             int ii[4];
             const double *rr[4];
@@ -866,15 +883,17 @@ tc_rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const do
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { d[u] = fma(qq.x, a[u].x, d[u]); d[u] = fma(qq.y, a[u].y, d[u]); }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) d[u] = warp_sum(d[u]);
+            const double tot = warp_sum4_transposed(d, lane);                    // lanes 8u .. 8u+7: the dot of row s0 + u
             const int u_mine = lane - s0;                                        // lanes s0 .. s0+3 keep one result each
+            const double dd = __shfl_sync(0xffffffffu, tot, 8 * (u_mine & 3));
             if (u_mine >= 0 && u_mine < 4 && lane < count) {
-                const double dd = (u_mine == 0) ? d[0] : (u_mine == 1) ? d[1] : (u_mine == 2) ? d[2] : d[3];
-                const int it = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
-                mine.s = exact_score_tc(dd, nqv, norm_x[it], tau, lqv, lam_x[it]);
-                mine.i = it;
+                my_dot = dd;
+                my_item = (u_mine == 0) ? ii[0] : (u_mine == 1) ? ii[1] : (u_mine == 2) ? ii[2] : ii[3];
             }
+        }
+        if (my_item >= 0) {                                                      // one score per lane, all lanes at once
+            mine.s = exact_score_tc(my_dot, nqv, norm_x[my_item], tau, lqv, lam_x[my_item]);
+            mine.i = my_item;
         }
         best[1] = mine;
         asp::warp_sort_best_first<2>(best, lane);
