@@ -545,6 +545,12 @@ def main():
     except Exception:
         pass
 
+    def profiled(kernel, key):
+        e = prof.get(kernel)
+        if isinstance(e, dict) and e.get("n_items") == n_shard and e.get("n_queries") == q_rank and e.get("n_features") == f:
+            return e.get(key)
+        return None
+
     def profiled_traffic(kernel):
         """dram__bytes_read + write of one launch from the committed `ncu --set full` capture -- only when that capture was
         taken at THIS launch shape (items per rank, queries per rank, features); otherwise null, never a stale constant."""
@@ -561,7 +567,11 @@ def main():
         burst = peaks.get("bf16_tflops", sustained)
         achieved = gemm_flop / (stage1_ms * 1e-3) / 1e12
         executed_tflops = executed / (stage1_ms * 1e-3) / 1e12
-        peak = sustained if executed_tflops <= sustained else burst
+        # the kernel is timed inside a long step: the sustained figure is the prescribed denominator.  The figure was
+        # measured (cuBLAS bf16, 4 s back to back) at the clocks THAT workload reached under the power cap; this kernel draws
+        # less power per FLOP and can clock higher, so its executed FLOP rate can exceed it -- the burst fraction is printed
+        # next to it, and profiles/ holds the clock-independent figure (ncu sm__pipe_tensor_cycles_active)
+        peak = sustained
         roofline = {"kernel": "tc_gemm_kernel (tcgen05.mma kind::f16, fp16 operands, f32 TMEM accumulators, TMA SWIZZLE_128B; items in "
                               "lambda order, rank-1 mean-direction term + %s of the residuals; single-compare epilogue, thresholds "
                               "shared across CTAs); exact f64 stage 2 follows"
@@ -573,6 +583,9 @@ def main():
                                    "2*Q_rank*N_shard*16*%d = %.3e fp16 tensor FLOP (K padded to 16%s)"
                                    % (q_rank, n_shard, f, gemm_flop, ksteps, executed, ", three split terms" if terms == 3 else ""),
                     "executed_tflops": executed_tflops, "executed_frac": executed_tflops / peak,
+                    "peak_burst": burst, "frac_of_burst": achieved / burst, "executed_frac_of_burst": executed_tflops / burst,
+                    # clock-independent evidence from the committed capture of this launch shape (profiles/ncu_full_r02.json)
+                    "ncu_tensor_pipe_active_pct": profiled("tc_gemm_kernel", "tensor_pipe_active_pct"),
                     "fp64_tensor_peak_tflops": fp64_peak_tflops,
                     "kernel_ms": stage1_ms, "share_of_step": stage1_ms / step_ms,
                     "stage2_ms": sstat["search_stage2_ms"],
@@ -581,8 +594,10 @@ def main():
                     "residual_norms": {"rho_q_max": sstat["search_rho_q_max"], "rho_x_max": sstat["search_rho_x_max"]},
                     "rescored_candidates_per_query": rescored,
                     "reference_order_rescored_per_query": sstat["search_exact_per_query"],
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peak == sustained
-                                    else "MEASURED_PEAKS.json bf16_tflops (burst): the kernel ran above the sustained figure %.1f" % sustained)
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                                    + ("; executed FLOP rate above it: this kernel held higher clocks under the power cap than the "
+                                       "cuBLAS run that set the figure -- see frac_of_burst and the ncu tensor-pipe activity in profiles/"
+                                       if executed_tflops > sustained else ""))
                                    if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
     else:
         achieved = gemm_flop / (stage1_ms * 1e-3) / 1e12
