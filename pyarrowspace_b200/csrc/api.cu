@@ -743,7 +743,7 @@ static int search_device_batch(const asp_space *s, const asp_graph *g, const dou
     return rc;
 }
 
-// Large host batches are pipelined in TWO pieces: a short head (1/32 of the batch) and the rest.  The head's kernels run
+// Large host batches are pipelined in TWO pieces: a short head (3/64 of the batch) and the rest.  The head's kernels run
 // under the H2D copy of the rest (copy stream `up`), the head's D2H copy (copy stream `down`) under the kernels of the
 // rest.  The head is sized so that its kernels last about as long as the rest's upload: more or larger pieces were
 // measured and lose, because every piece pays its own host synchronisations, GEMM tail and threshold warm-up (an 8k-query
@@ -784,7 +784,7 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     const char *nopipe = getenv("ASP_NO_PIPELINE");
     const bool host_io = !asp_is_device_ptr(queries) && !asp_is_device_ptr(out_idx) && !asp_is_device_ptr(out_score) &&
                          (!out_lambda_q || !asp_is_device_ptr(out_lambda_q));
-    int64_t head = std::max<int64_t>(1024, (nq / 32 + 127) / 128 * 128);
+    int64_t head = std::max<int64_t>(1024, (nq * 3 / 64 + 127) / 128 * 128);   // 3072 of 65536: its kernels (~2.5 ms) cover most of the rest's upload
     if (const char *e = getenv("ASP_PIPE_HEAD")) { const long v = atol(e); if (v >= 128 && v < nq) head = v; }   // tuning knob
     int rc = ASP_OK;
     auto prefault = [=](int64_t q0, int64_t qn) {                 // first touch of the caller's result pages
