@@ -193,10 +193,11 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, c
  * in the reference order (left-to-right f64 dot); the candidate set is proven complete against the
  * rounding band of the tensor-core pass, otherwise the query is re-scanned exactly.
  * Stage 1 runs on tcgen05 (fp16 operands: exact rank-1 mean-direction term + one or two fp16 terms of the residuals)
- * for topk <= 16 when nq >= 256 or the shard has >= 131072 items -- which includes the reference's ONE query per call:
+ * for topk <= 31 when nq >= 256 or the shard has >= 131072 items -- which includes the reference's ONE query per call:
  * the candidate pass then streams the fp16 operands instead of the f64 rows -- and on FP64 DMMA / the HBM-bound GEMV
  * kernel (nq <= 8) otherwise; env ASP_SEARCH_STAGE1=fp64|tc forces one.  The answers are bit-identical whichever
- * stage 1 produced the candidates.
+ * stage 1 produced the candidates.  topk >= 32 is answered by the exact scan of every query (correct, ~130 queries/s at 1M x 384:
+ * the completeness test needs one kept candidate beyond the k-th and the kernels keep 32).
  * queries / outputs may be host or device memory.  Host batches of >= 32768 queries are processed in two pieces so that
  * the PCIe copies run under the kernels (env ASP_NO_PIPELINE=1: single shot); the result is the same either way.
  * One caller per ctx at a time (the reference holds the GIL for the whole call, src/lib.rs:132).
