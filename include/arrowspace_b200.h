@@ -196,8 +196,8 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, c
  * for topk <= 31 when nq >= 256 or the shard has >= 131072 items -- which includes the reference's ONE query per call:
  * the candidate pass then streams the fp16 operands instead of the f64 rows -- and on FP64 DMMA / the HBM-bound GEMV
  * kernel (nq <= 8) otherwise; env ASP_SEARCH_STAGE1=fp64|tc forces one.  The answers are bit-identical whichever
- * stage 1 produced the candidates.  topk >= 32 is answered by the exact scan of every query (correct, ~130 queries/s at 1M x 384:
- * the completeness test needs one kept candidate beyond the k-th and the kernels keep 32).
+ * stage 1 produced the candidates.  topk >= 32 is answered by the batched exact scan of every query (reference-order score of
+ * every item; ~3300 queries/s at 1M x 384: the completeness test needs one kept candidate beyond the k-th and the kernels keep 32).
  * queries / outputs may be host or device memory.  Host batches of >= 32768 queries are processed in two pieces so that
  * the PCIe copies run under the kernels (env ASP_NO_PIPELINE=1: single shot); the result is the same either way.
  * One caller per ctx at a time (the reference holds the GIL for the whole call, src/lib.rs:132).

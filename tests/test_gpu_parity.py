@@ -1032,3 +1032,27 @@ def test_save_and_load_keep_the_reduction(tmp_path):
     i1, s1 = aspace.search_batch(q, gl, 0.62)
     i2, s2 = a2.search_batch(q, g2, 0.62)
     assert np.array_equal(i1, i2) and np.array_equal(s1, s2)
+
+
+@pytest.mark.parametrize("n,f,topk,nq", [(5000, 64, 32, 300), (3000, 130, 40, 300), (20, 16, 33, 7), (9000, 48, 100, 64), (400, 4800, 33, 40)])
+def test_topk_beyond_the_kept_lists_takes_the_exact_scan(oracle_mod, n, f, topk, nq):
+    """topk >= 32: the candidate kernels keep 32 entries, so every query is answered by the batched exact scan (reference-order
+    score of every item, top-k by (score desc, index asc)); duplicated rows make exact ties.  The last case is wide enough for
+    the one-query-per-block variant of the scan."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api
+    rng = np.random.default_rng(n + topk)
+    x = _clustered(n, f, 3 * n + f, n_clusters=6)
+    if n > 100:
+        x[n // 2:n // 2 + 60] = x[:60]                        # exact duplicates: ties across the k-th place
+    gp = {"eps": 0.6, "k": 5, "topk": topk, "p": 2.0, "sigma": 0.3}
+    aspace, gl = ArrowSpaceBuilder.build(gp, x)
+    s, g = oracle_mod.build(gp, x)
+    q = x[rng.integers(0, n, nq)] * 1.02
+    idx, sc = aspace.search_batch(q, gl, 0.62)
+    if n > 64:                                                # (a shard no larger than the kept lists is complete as it is)
+        assert api.stat("search_slow_queries") == nq
+    oidx, osc, _ = s.search_batch(q, g, 0.62)
+    _assert_hits_equal(idx, sc, oidx, osc)
+    idx1, sc1 = aspace.search_batch(q[:3], gl, 0.62)            # the small-batch route ends in the same scan
+    _assert_hits_equal(idx1, sc1, oidx[:3], osc[:3])
