@@ -10,9 +10,10 @@
 //   stage 2  knn_rescore_kernel: the candidates' distances are recomputed in the oracle's order
 //            (left-to-right dot, d = 1 - max(0, dot/(|a||b|))), d <= eps is decided on those values, the k
 //            smallest by (d, index) are kept.  Complete iff s~(LIST) < s~(k) - 2 band; otherwise the row takes
-//            the exact scan (knn_exact_scan_kernel + knn_exact_select_kernel).
+//            the exact scan (exact_scan.cuh, KnnScanPolicy).
 // Output: neighbour lists for csr.cu (K2).
 #include "gemm_topk.cuh"
+#include "exact_scan.cuh"
 
 namespace {
 
@@ -107,83 +108,30 @@ knn_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pitch
     if (lane == 0) out_cnt[i] = keep;
 }
 
-// slow path: score[j] = -d(i,j) for valid neighbours, -inf otherwise
-__global__ void knn_exact_scan_kernel(const double *__restrict__ items, int64_t n, int f, int pitch,
-                                      const double *__restrict__ norms, double eps, const int32_t *__restrict__ slow_list,
-                                      int slot, double *__restrict__ scores)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *xs = reinterpret_cast<double *>(smem_raw);
-    const int64_t i = slow_list[slot];
-    for (int j = threadIdx.x; j < f; j += blockDim.x) xs[j] = items[i * pitch + j];
-    __syncthreads();
-    const double ni = norms[i];
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        const double d = exact_dist(seq_dot_row(xs, items + j * pitch, f), ni, norms[j]);
-        scores[j] = (j != i && d <= eps) ? -d : -INFINITY;
+// slow path (exact_scan.cuh): value = -d(i, j), admissible = another item within eps; the k best by (d asc, index asc)
+struct KnnScanPolicy {
+    const double *items; int pitch; const double *norms; double eps; const int32_t *slow_list;
+    int kk; int32_t *out_idx; double *out_dist; int32_t *out_cnt;
+    struct Row { double ni; int64_t self; };
+    struct Item { double nj; };
+    __device__ const double *query(int slot) const { return items + (int64_t)slow_list[slot] * pitch; }
+    __device__ Row row(int slot) const { const int64_t i = slow_list[slot]; return Row{norms[i], i}; }
+    __device__ Item item(int64_t j) const { return Item{norms[j]}; }
+    __device__ double value(const Row &r, const Item &it, double dot, int64_t j, bool &valid) const
+    {
+        const double d = exact_dist(dot, r.ni, it.nj);
+        valid = (j != r.self) && (d <= eps);                                    // GRAPH_VARIABLES.md:7
+        return -d;
     }
-}
-
-// single block: kk rounds of "best element strictly after the previous winner" in (score desc, index asc)
-__global__ void knn_exact_select_kernel(const double *__restrict__ scores, int64_t n, int kk,
-                                        const int32_t *__restrict__ slow_list, int slot, int32_t *__restrict__ out_idx,
-                                        double *__restrict__ out_dist, int32_t *__restrict__ out_cnt)
-{
-    __shared__ double s_s[32];
-    __shared__ int64_t s_i[32];
-    __shared__ double prev_s;
-    __shared__ int64_t prev_i;
-    __shared__ int s_keep;
-    const int64_t row = slow_list[slot];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { prev_s = INFINITY; prev_i = -1; s_keep = 0; }
-    __syncthreads();
-    for (int r = 0; r < kk; ++r) {
-        const double ps = prev_s;
-        const int64_t pi = prev_i;
-        double bs = -INFINITY;
-        int64_t bi = INT64_MAX;
-        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-            const double s = scores[j];
-            if (s == -INFINITY) continue;
-            const bool after_prev = (s < ps) || (s == ps && j > pi);
-            if (after_prev && ((s > bs) || (s == bs && j < bi))) { bs = s; bi = j; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (oi != INT64_MAX && ((os > bs) || (os == bs && oi < bi) || bi == INT64_MAX)) { bs = os; bi = oi; }
-        }
-        if (lane == 0) { s_s[warp] = bs; s_i[warp] = bi; }
-        __syncthreads();
-        if (warp == 0) {
-            bs = (lane < (int)(blockDim.x >> 5)) ? s_s[lane] : -INFINITY;
-            bi = (lane < (int)(blockDim.x >> 5)) ? s_i[lane] : INT64_MAX;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (oi != INT64_MAX && ((os > bs) || (os == bs && oi < bi) || bi == INT64_MAX)) { bs = os; bi = oi; }
-            }
-            if (lane == 0) {
-                if (bi != INT64_MAX) {
-                    out_idx[row * kk + r] = (int32_t)bi;
-                    out_dist[row * kk + r] = -bs;
-                    s_keep = r + 1;
-                    prev_s = bs;
-                    prev_i = bi;
-                } else {
-                    prev_s = -INFINITY;
-                    prev_i = INT64_MAX;
-                }
-            }
-        }
-        __syncthreads();
-        if (prev_i == INT64_MAX) break;
+    __device__ void emit(int slot, int r, bool ok, double v, int64_t j) const
+    {
+        if (!ok) return;
+        const int64_t row = slow_list[slot];
+        out_idx[row * kk + r] = (int32_t)j;
+        out_dist[row * kk + r] = -v;
     }
-    if (threadIdx.x == 0) out_cnt[row] = s_keep;
-}
+    __device__ void finish(int slot, int count) const { out_cnt[slow_list[slot]] = count; }
+};
 
 // ---------------------------------------------------------------- tcgen05 candidate pass (search_tc.cu) + exact stage 2
 // Stage 1 is the search's tensor-core kernel with tau = 1 (score = cosine), the items themselves as queries, lists of
@@ -353,22 +301,16 @@ knn_tc_rescore_kernel(const double *__restrict__ items, int64_t n, int f, int pi
 
 }  // namespace
 
-// exact scan of the rows listed in slow_list (device), one row at a time
+// exact scan of the rows listed in slow_list (device)
 static int knn_slow_rows(asp_space *s, const asp_graph_params *gp, int64_t kk, const int32_t *slow_list, int nslow, asp_knn_lists *lists)
 {
     asp_ctx *ctx = s->ctx;
-    cudaStream_t st = ctx->stream;
-    const int64_t n = s->n_local;
-    const int f = s->f;
-    double *scores = nullptr;
-    ASP_CUDA(cudaMallocAsync(&scores, sizeof(double) * n, st));
-    for (int i = 0; i < nslow; ++i) {
-        knn_exact_scan_kernel<<<ctx->num_sms * 4, 256, (size_t)f * 8, st>>>(s->items, n, f, s->fp, s->norms, gp->eps, slow_list, i, scores);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        knn_exact_select_kernel<<<1, 1024, 0, st>>>(scores, n, (int)kk, slow_list, i, lists->idx, lists->dist, lists->cnt);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    }
-    ASP_CUDA(cudaFreeAsync(scores, st));
+    const KnnScanPolicy pol{s->items, s->fp, s->norms, gp->eps, slow_list, (int)kk, lists->idx, lists->dist, lists->cnt};
+    const int rc = asp_xs::run(ctx->stream, ctx->num_sms, pol, nslow, s->items, s->n_local, s->f, s->fp, kk,
+                               [&](int k) { ctx->launches += k; });
+    if (rc == 3) ASP_FAIL(ASP_ERR_NOMEM, "out of device memory in the exact scan of the item graph");
+    if (rc == 1 || rc == 2) ASP_FAIL(ASP_ERR_UNSUPPORTED, "item graph: exact scan does not fit (k = %lld, %d features)", (long long)kk, s->f);
+    if (rc != 0) ASP_FAIL(ASP_ERR_CUDA, "item graph: exact scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return ASP_OK;
 }
 
@@ -598,7 +540,7 @@ static int item_knn_tc(asp_space *s, const asp_graph_params *gp, int64_t kk, int
         ctx->stats["knn_slow_rows"] = n_final;
         ctx->stats["knn_stage1_is_tc"] = 1.0;
         ctx->stats["knn_rescored_per_row"] = (double)nsurv / (double)(rows > 0 ? rows : 1);
-        if (n_final > 8192) {
+        if (n_final > 262144) {                                          // the batched scan does ~3000 rows/s at 1M x 384
             asp_set_error("item graph: %d rows need the exact scan even after the two-term pass (long runs of ties around the "
                           "k-th neighbour?); use ASP_KNN_STAGE1=fp64", n_final);
             rc = ASP_ERR_UNSUPPORTED;

@@ -14,9 +14,10 @@
 //   stage 2  rescore_kernel.  The LIST candidates of a query are re-scored in the reference order
 //            (sequential dot, the oracle's exact expression), sorted, top-k emitted.  The candidate set is
 //            complete iff  s~(LIST) < s~(k) - 2 DELTA  (or the shard has <= LIST items); otherwise the
-//            query takes the exact full scan (exact_scan_kernel + exact_select_kernel).
+//            query takes the exact full scan (exact_scan.cuh, SearchScanPolicy).
 //   K5       topk_merge_kernel: merge of per-shard results (cross-GPU), (score desc, index asc).
 #include "gemm_topk.cuh"
+#include "exact_scan.cuh"
 
 #include <math.h>
 
@@ -236,175 +237,30 @@ rescore_kernel(const double *__restrict__ q, int qpitch, int64_t nq, const doubl
     }
 }
 
-// ============================================================================ slow path: exact full scan
-// Queries whose candidate set could not be proven complete (ties around the k-th score, emission overflow, topk >= 32) are
-// answered from the reference-order score of EVERY item.  All such queries of a batch go through two launches:
-//   exact_scan_topk_kernel  block (x, y) = item range x of XS_QPB queries: a thread owns an item row at a time and carries the
-//                           XS_QPB ordered dot products together (the row is read once for all of them); the scores of a
-//                           chunk land in shared memory, one warp per query folds them into that query's running top-k
-//                           (k rounds of "best entry strictly after the previous winner": exact ties by index);
-//   exact_merge_kernel      one block per query: the same k rounds over the ranges' top-k lists.
-constexpr int XS_THREADS = 256, XS_CHUNK = 1024, XS_TOPK_MAX = 1024;   // XS_QPB (template): 4 queries per block, 1 for very wide rows
-
-// (score desc, index asc): does (s, i) come strictly after (ps, pi), and before (bs, bi)?
-__device__ __forceinline__ bool xs_after(double s, int64_t i, double ps, int64_t pi) { return (s < ps) || (s == ps && i > pi); }
-__device__ __forceinline__ bool xs_before(double s, int64_t i, double bs, int64_t bi) { return (s > bs) || (s == bs && i < bi); }
-
-template <int XS_QPB>
-__global__ void __launch_bounds__(XS_THREADS)
-exact_scan_topk_kernel(const double *__restrict__ q, int qpitch, const int32_t *__restrict__ slow_list, int nslow,
-                       const double *__restrict__ items, int64_t n_local, int f, int pitch,
-                       const double *__restrict__ norm_x, const double *__restrict__ lam_x,
-                       const double *__restrict__ norm_q, const double *__restrict__ lam_q, double tau, int topk,
-                       double *__restrict__ part_score, int64_t *__restrict__ part_idx)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *qs = reinterpret_cast<double *>(smem_raw);                        // [XS_QPB][f]
-    double *sc = qs + (size_t)XS_QPB * f;                                    // [XS_QPB][2 topk + XS_CHUNK]: top | chunk | new top
-    int64_t *ix = reinterpret_cast<int64_t *>(sc + (size_t)XS_QPB * (2 * topk + XS_CHUNK));
-    const int stride = 2 * topk + XS_CHUNK;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.y * XS_QPB;
-    int64_t qi[XS_QPB];
-    double nqv[XS_QPB], lqv[XS_QPB];
-#pragma unroll
-    for (int u = 0; u < XS_QPB; ++u) {
-        qi[u] = (q0 + u < nslow) ? slow_list[q0 + u] : -1;
-        nqv[u] = qi[u] >= 0 ? norm_q[qi[u]] : 1.0;
-        lqv[u] = qi[u] >= 0 ? lam_q[qi[u]] : 0.0;
+// ============================================================================ slow path: exact full scan (exact_scan.cuh)
+// value = the reference-order score; every item is admissible
+struct SearchScanPolicy {
+    const double *q; int qpitch; const int32_t *slow_list;
+    const double *norm_x, *lam_x, *norm_q, *lam_q; double tau;
+    int64_t row0; int topk; int64_t *out_idx; double *out_score;
+    struct Row { double nq, lq; };
+    struct Item { double nx, lx; };
+    __device__ const double *query(int slot) const { return q + (int64_t)slow_list[slot] * qpitch; }
+    __device__ Row row(int slot) const { const int64_t qi = slow_list[slot]; return Row{norm_q[qi], lam_q[qi]}; }
+    __device__ Item item(int64_t it) const { return Item{norm_x[it], lam_x[it]}; }
+    __device__ double value(const Row &r, const Item &i, double dot, int64_t, bool &valid) const
+    {
+        valid = true;
+        return exact_score(dot, r.nq, i.nx, tau, r.lq, i.lx);
     }
-    for (int j = threadIdx.x; j < XS_QPB * f; j += XS_THREADS) {
-        const int u = j / f, t = j - u * f;
-        const int64_t src = (q0 + u < nslow) ? slow_list[q0 + u] : -1;
-        qs[j] = src >= 0 ? q[src * qpitch + t] : 0.0;
+    __device__ void emit(int slot, int r, bool ok, double v, int64_t it) const
+    {
+        const int64_t qi = slow_list[slot];
+        out_idx[qi * topk + r] = ok ? row0 + it : -1;
+        out_score[qi * topk + r] = ok ? v : NAN;
     }
-    for (int j = threadIdx.x; j < XS_QPB * topk; j += XS_THREADS) {
-        const int u = j / topk, t = j - u * topk;
-        sc[u * stride + t] = -INFINITY;
-        ix[u * stride + t] = INT64_MAX;
-    }
-    __syncthreads();
-    const int64_t per = (n_local + gridDim.x - 1) / gridDim.x;
-    const int64_t r0 = blockIdx.x * per, r1 = (r0 + per < n_local) ? r0 + per : n_local;
-    for (int64_t c0 = r0; c0 < r1; c0 += XS_CHUNK) {
-        const int len = (int)((r1 - c0 < XS_CHUNK) ? r1 - c0 : XS_CHUNK);
-        for (int e = threadIdx.x; e < len; e += XS_THREADS) {
-            const int64_t it = c0 + e;
-            const double *row = items + it * pitch;
-            double d[XS_QPB];
-#pragma unroll
-            for (int u = 0; u < XS_QPB; ++u) d[u] = 0.0;
-            int j = 0;
-            for (; j + 2 <= f; j += 2) {                                      // one load of the row for the XS_QPB ordered sums
-                const double2 xv = *reinterpret_cast<const double2 *>(row + j);
-#pragma unroll
-                for (int u = 0; u < XS_QPB; ++u) {
-                    d[u] = __dadd_rn(d[u], __dmul_rn(qs[u * f + j], xv.x));
-                    d[u] = __dadd_rn(d[u], __dmul_rn(qs[u * f + j + 1], xv.y));
-                }
-            }
-            for (; j < f; ++j)
-#pragma unroll
-                for (int u = 0; u < XS_QPB; ++u) d[u] = __dadd_rn(d[u], __dmul_rn(qs[u * f + j], row[j]));
-            const double nx = norm_x[it], lx = lam_x[it];
-#pragma unroll
-            for (int u = 0; u < XS_QPB; ++u) {
-                sc[u * stride + topk + e] = exact_score(d[u], nqv[u], nx, tau, lqv[u], lx);
-                ix[u * stride + topk + e] = it;
-            }
-        }
-        __syncthreads();
-        if (warp < XS_QPB && qi[warp] >= 0) {                                 // warp u folds the chunk into query u's top-k
-            double *s_u = sc + warp * stride;
-            int64_t *i_u = ix + warp * stride;
-            const int total = topk + len;
-            double ps = INFINITY;
-            int64_t pi = -1;
-            for (int r = 0; r < topk; ++r) {
-                double bs = -INFINITY;
-                int64_t bi = INT64_MAX;
-                for (int e = lane; e < total; e += 32) {
-                    const double v = s_u[e];
-                    const int64_t vi = i_u[e];
-                    if (vi != INT64_MAX && xs_after(v, vi, ps, pi) && xs_before(v, vi, bs, bi)) { bs = v; bi = vi; }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-                    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (xs_before(os, oi, bs, bi)) { bs = os; bi = oi; }
-                }
-                if (lane == 0) { s_u[topk + XS_CHUNK + r] = bs; i_u[topk + XS_CHUNK + r] = bi; }
-                if (bi == INT64_MAX) { ps = -INFINITY; pi = INT64_MAX; } else { ps = bs; pi = bi; }
-            }
-            __syncwarp();
-            for (int r = lane; r < topk; r += 32) { s_u[r] = s_u[topk + XS_CHUNK + r]; i_u[r] = i_u[topk + XS_CHUNK + r]; }
-        }
-        __syncthreads();
-    }
-    for (int j = threadIdx.x; j < XS_QPB * topk; j += XS_THREADS) {
-        const int u = j / topk, t = j - u * topk;
-        if (q0 + u < nslow) {
-            const size_t o = ((size_t)(q0 + u) * gridDim.x + blockIdx.x) * topk + t;
-            part_score[o] = sc[u * stride + t];
-            part_idx[o] = ix[u * stride + t];
-        }
-    }
-}
-
-// one block per slow query: top-k of its nparts x topk range winners
-__global__ void __launch_bounds__(XS_THREADS)
-exact_merge_kernel(const double *__restrict__ part_score, const int64_t *__restrict__ part_idx, int nparts, int topk,
-                   int64_t row0, const int32_t *__restrict__ slow_list, int64_t *__restrict__ out_idx, double *__restrict__ out_score)
-{
-    __shared__ double s_s[XS_THREADS / 32];
-    __shared__ int64_t s_i[XS_THREADS / 32];
-    __shared__ double prev_s;
-    __shared__ int64_t prev_i;
-    const int64_t qi = slow_list[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t base = (size_t)blockIdx.x * nparts * topk;
-    const int total = nparts * topk;
-    if (threadIdx.x == 0) { prev_s = INFINITY; prev_i = -1; }
-    __syncthreads();
-    for (int r = 0; r < topk; ++r) {
-        const double ps = prev_s;
-        const int64_t pi = prev_i;
-        double bs = -INFINITY;
-        int64_t bi = INT64_MAX;
-        for (int e = threadIdx.x; e < total; e += XS_THREADS) {
-            const double v = part_score[base + e];
-            const int64_t vi = part_idx[base + e];
-            if (vi != INT64_MAX && xs_after(v, vi, ps, pi) && xs_before(v, vi, bs, bi)) { bs = v; bi = vi; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (xs_before(os, oi, bs, bi)) { bs = os; bi = oi; }
-        }
-        if (lane == 0) { s_s[warp] = bs; s_i[warp] = bi; }
-        __syncthreads();
-        if (warp == 0) {
-            bs = (lane < XS_THREADS / 32) ? s_s[lane] : -INFINITY;
-            bi = (lane < XS_THREADS / 32) ? s_i[lane] : INT64_MAX;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double os = __shfl_xor_sync(0xffffffffu, bs, off);
-                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (xs_before(os, oi, bs, bi)) { bs = os; bi = oi; }
-            }
-            if (lane == 0) {
-                const bool ok = (bi != INT64_MAX);
-                out_idx[qi * topk + r] = ok ? row0 + bi : -1;
-                out_score[qi * topk + r] = ok ? bs : NAN;
-                prev_s = ok ? bs : -INFINITY;
-                prev_i = ok ? bi : INT64_MAX;
-            }
-        }
-        __syncthreads();
-    }
-}
+    __device__ void finish(int, int) const {}
+};
 
 // ============================================================================ K5: cross-shard merge
 
@@ -520,45 +376,14 @@ int asp_search_slow_path(const asp_space *s, const double *q_dev, int32_t qpitch
                          int64_t *out_idx_dev, double *out_score_dev)
 {
     asp_ctx *ctx = s->ctx;
-    cudaStream_t st = ctx->stream;
-    const int f = s->f;
-    if (nslow <= 0) return ASP_OK;
-    if (topk > XS_TOPK_MAX) ASP_FAIL(ASP_ERR_UNSUPPORTED, "exact scan supports topk <= %d (got %lld)", XS_TOPK_MAX, (long long)topk);
-    auto smem_for = [&](int qpb) { return sizeof(double) * (size_t)qpb * f + (size_t)qpb * (2 * topk + XS_CHUNK) * 16; };
-    const int qpb = (smem_for(4) <= 200 * 1024) ? 4 : 1;
-    const size_t smem = smem_for(qpb);
-    if (smem > 220 * 1024) ASP_FAIL(ASP_ERR_UNSUPPORTED, "exact scan: %d features x topk %lld do not fit in shared memory", f, (long long)topk);
-    // item ranges: enough blocks to fill the device a few times over per query group, at least one chunk each
-    int64_t nparts = std::min<int64_t>(asp_ceil_div(s->n_local, XS_CHUNK), (int64_t)ctx->num_sms * 2);
-    if (nparts < 1) nparts = 1;
-    const int64_t ngroups = asp_ceil_div(nslow, qpb);
-    double *part_score = nullptr;
-    int64_t *part_idx = nullptr;
-    if (qpb == 4) ASP_CUDA(cudaFuncSetAttribute(exact_scan_topk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else ASP_CUDA(cudaFuncSetAttribute(exact_scan_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // groups of queries per launch: bounded scratch (nslow can be the whole batch when topk >= 32) and grid.y <= 65535
-    const int64_t max_groups = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t)(1u << 28) / (nparts * topk * 16 * qpb)));
-    ASP_CUDA(cudaMallocAsync(&part_score, sizeof(double) * (size_t)std::min(ngroups, max_groups) * qpb * nparts * topk, st));
-    ASP_CUDA(cudaMallocAsync(&part_idx, sizeof(int64_t) * (size_t)std::min(ngroups, max_groups) * qpb * nparts * topk, st));
-    for (int64_t g0 = 0; g0 < ngroups; g0 += max_groups) {
-        const int64_t ng = std::min(max_groups, ngroups - g0);
-        const int first = (int)(g0 * qpb), count = (int)std::min<int64_t>(ng * qpb, nslow - first);
-        const dim3 grid((unsigned)nparts, (unsigned)ng);
-        if (qpb == 4)
-            exact_scan_topk_kernel<4><<<grid, XS_THREADS, smem, st>>>(q_dev, qpitch, slow_list + first, count, s->items, s->n_local, f,
-                                                                      s->fp, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-                                                                      (int)topk, part_score, part_idx);
-        else
-            exact_scan_topk_kernel<1><<<grid, XS_THREADS, smem, st>>>(q_dev, qpitch, slow_list + first, count, s->items, s->n_local, f,
-                                                                      s->fp, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
-                                                                      (int)topk, part_score, part_idx);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-        exact_merge_kernel<<<(unsigned)count, XS_THREADS, 0, st>>>(part_score, part_idx, (int)nparts, (int)topk, s->row0,
-                                                                  slow_list + first, out_idx_dev, out_score_dev);
-        ASP_CUDA(cudaGetLastError()); ASP_LAUNCHED(ctx);
-    }
-    ASP_CUDA(cudaFreeAsync(part_score, st));
-    ASP_CUDA(cudaFreeAsync(part_idx, st));
+    const SearchScanPolicy pol{q_dev, qpitch, slow_list, s->norms, s->lambdas, qnorm_dev, lambda_q_dev, tau,
+                               s->row0, (int)topk, out_idx_dev, out_score_dev};
+    const int rc = asp_xs::run(ctx->stream, ctx->num_sms, pol, nslow, s->items, s->n_local, s->f, s->fp, topk,
+                               [&](int k) { ctx->launches += k; });
+    if (rc == 1) ASP_FAIL(ASP_ERR_UNSUPPORTED, "exact scan supports topk <= %d (got %lld)", asp_xs::TOPK_MAX, (long long)topk);
+    if (rc == 2) ASP_FAIL(ASP_ERR_UNSUPPORTED, "exact scan: %d features x topk %lld do not fit in shared memory", s->f, (long long)topk);
+    if (rc == 3) ASP_FAIL(ASP_ERR_NOMEM, "out of device memory in the exact scan");
+    if (rc != 0) ASP_FAIL(ASP_ERR_CUDA, "exact scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return ASP_OK;
 }
 
