@@ -1,5 +1,5 @@
 """Regenerates tests/golden/oracle_vectors.npz: oracle outputs on the reference's two KAT inputs and on
-two small seeded synthetic cases (+ the item graph of a third).  kat.json itself is transcribed from the reference's README.md:37-69
+two small seeded synthetic cases (+ the item graph of a third, + the pre-graph reduction of a fourth).  kat.json itself is transcribed from the reference's README.md:37-69
 and tests/test_0.py:4-61 (the reference engine -- crate arrowspace 0.18.0 -- is not vendored and cannot
 be imported here, so there is no reference run to record).
 
@@ -47,6 +47,14 @@ def main():
     s, g = oracle.build({"eps": 0.5, "k": 8, "topk": 3, "p": 2.0, "sigma": 0.2}, x, nodes="items")
     indptr, indices, data = g.csr()
     out.update(itemsC_indptr=indptr, itemsC_indices=indices.astype(np.int32), itemsC_data=data)
+    # pre-graph reduction: centroids, statistics, the centroid graph and the lambdas it gives every item
+    x = synth.make_items(3000, 40, 8, scale=100.0, n_clusters=10)
+    s, g, cent, info = oracle.build_reduced({"eps": 0.6, "k": 5, "topk": 5, "p": 2.0, "sigma": 0.3}, x, reduction={"max_iters": 6})
+    indptr, indices, data = g.csr()
+    out.update(reducedD_centroids=cent, reducedD_indptr=indptr, reducedD_indices=indices.astype(np.int32), reducedD_data=data,
+               reducedD_lambdas=s.lambdas(),
+               reducedD_info=np.array([info["n_sampled"], info["n_probes"], info["two_nn_mean_ratio"], info["intrinsic_dim"],
+                                       info["n_clusters"], info["iters"], info["converged"]], dtype=np.float64))
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

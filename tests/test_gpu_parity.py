@@ -93,6 +93,22 @@ def test_golden_fixture(golden):
     _assert_hits_equal(idx, sc, golden["synthB_idx"], golden["synthB_score"])
 
 
+def test_golden_reduction_gpu(golden):
+    """The committed reduction fixture (tests/golden/make_kat.py, case reducedD) through the CUDA path."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(3000, 40, 8, scale=100.0, n_clusters=10)
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 0.6, "k": 5, "topk": 5, "p": 2.0, "sigma": 0.3}, x, reduction={"max_iters": 6})
+    assert np.array_equal(gl.centroids(), golden["reducedD_centroids"])
+    ip, ix, dt = gl.csr()
+    assert np.array_equal(ip, golden["reducedD_indptr"]) and np.array_equal(ix, golden["reducedD_indices"])
+    np.testing.assert_allclose(dt, golden["reducedD_data"], rtol=RTOL)
+    np.testing.assert_allclose(aspace.lambdas(), golden["reducedD_lambdas"], rtol=RTOL)
+    info = gl.reduction
+    got = [info[k] for k in ("n_sampled", "n_probes", "two_nn_mean_ratio", "intrinsic_dim", "n_clusters", "iters", "converged")]
+    assert np.array_equal(np.array(got, dtype=np.float64), golden["reducedD_info"])
+
+
 @pytest.mark.parametrize("stage1", ["fp64", "tc"])
 def test_golden_item_graph(golden, stage1):
     """Item graph (nodes = items) against the committed fixture, both candidate passes."""

@@ -151,6 +151,20 @@ GRAPH_SWITCH_CASES = [
 ]
 
 
+def test_golden_reduction(oracle_mod, golden):
+    """Drift guard of the pre-graph reduction (tests/golden/make_kat.py, case reducedD)."""
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(3000, 40, 8, scale=100.0, n_clusters=10)
+    s, g, cent, info = oracle_mod.build_reduced({"eps": 0.6, "k": 5, "topk": 5, "p": 2.0, "sigma": 0.3}, x, reduction={"max_iters": 6})
+    assert np.array_equal(cent, golden["reducedD_centroids"])
+    ip, ix, dt = g.csr()
+    assert (ip == golden["reducedD_indptr"]).all() and (ix == golden["reducedD_indices"]).all() and (dt == golden["reducedD_data"]).all()
+    assert (s.lambdas() == golden["reducedD_lambdas"]).all()
+    want = golden["reducedD_info"]
+    got = [info[k] for k in ("n_sampled", "n_probes", "two_nn_mean_ratio", "intrinsic_dim", "n_clusters", "iters", "converged")]
+    assert np.array_equal(np.array(got, dtype=np.float64), want)
+
+
 @pytest.mark.parametrize("case", GRAPH_SWITCH_CASES, ids=lambda c: ",".join("%s=%s" % kv for kv in c.items()))
 def test_graph_switches_match_mirror(oracle_mod, case):
     """Every unpinned graph switch: C oracle == independent numpy restatement (L entry by entry, lambdas 1e-12)."""
