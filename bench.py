@@ -318,7 +318,7 @@ def main():
             launches = lib.asp_ctx_launch_count(ctx) - l0
             st = {k: api.stat(k, local) for k in ("search_slow_queries", "search_stage1_is_tc", "search_rescored_per_query", "search_terms",
                                                  "search_stage2_ms", "search_a_resident", "search_delta_cos_max", "search_rho_q_max",
-                                                 "search_rho_x_max", "search_exact_per_query")}
+                                                 "search_rho_x_max", "search_exact_per_query", "search_retry_queries")}
             # the caller's result buffers: pinned host memory reused from step to step (search_batch(out=...))
             out_h = (torch.empty((q_host[0].shape[0], topk), dtype=torch.int64).pin_memory().numpy(),
                      torch.empty((q_host[0].shape[0], topk), dtype=torch.float64).pin_memory().numpy())
@@ -434,6 +434,7 @@ def main():
                   "e2e": {"value": Q / (mz["e2e_ms"] * 1e-3), "unit": "queries/s", "ms_per_step": mz["e2e_ms"]},
                   "stage1_ms": mz["stage1_ms"], "stage2_ms": mz["stats"]["search_stage2_ms"], "mma_terms": int(mz["stats"]["search_terms"]),
                   "query_operand_resident": mz["stats"]["search_a_resident"] == 1.0,
+                  "three_term_retry_queries_last_step": mz["stats"].get("search_retry_queries"),
                   "survivors_per_query": mz["stats"]["search_rescored_per_query"], "exact_rescan_queries_last_step": mz["stats"]["search_slow_queries"],
                   "band_cos_max": mz["stats"]["search_delta_cos_max"],
                   "residual_norms": {"rho_q_max": mz["stats"]["search_rho_q_max"], "rho_x_max": mz["stats"]["search_rho_x_max"]},

@@ -1072,3 +1072,37 @@ def test_topk_beyond_the_kept_lists_takes_the_exact_scan(oracle_mod, n, f, topk,
     _assert_hits_equal(idx, sc, oidx, osc)
     idx1, sc1 = aspace.search_batch(q[:3], gl, 0.62)            # the small-batch route ends in the same scan
     _assert_hits_equal(idx1, sc1, oidx[:3], osc[:3])
+
+
+def test_wide_band_one_term_first_then_three_term_retry(oracle_mod):
+    """Mean-zero embeddings: residual norms ~1, so ONE fp16 term has a wide band (2e-3 in cosine).  The search still tries it
+    first (a wide band only costs survivors); queries whose emission buffers overflow are redone with the three-term split, what
+    is still undecided takes the exact scan.  Answers equal the oracle's whichever route a query took."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import api, synth
+    n, f = 20000, 96
+    x = synth.make_items(n, f, 21, 100.0, n_clusters=8, shift=0.0)
+    gp = {"eps": 0.5, "k": 6, "topk": 10, "p": 2.0, "sigma": 0.25}
+    sw = {"tau_mode": "median_abs"}
+    aspace, gl = ArrowSpaceBuilder.build(gp, x, **sw)
+    s, g = oracle_mod.build(gp, x, **sw)
+    q, _ = synth.make_fresh_queries(f, 600, 121, n_clusters=8)
+    oidx, osc, _ = s.search_batch(q, g, 0.62)
+    try:
+        _force_stage1("tc")
+        idx, sc = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_terms") == 1.0 and api.stat("search_delta_cos_max") > 2.5e-4      # the wide band, one term
+        _assert_hits_equal(idx, sc, oidx, osc)
+        os.environ["ASP_TC_CAPB"] = "16"                      # emission buffers that overflow under the wide band
+        idx, sc = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_retry_queries") >= 1          # ... those queries were redone with the three-term split
+        _assert_hits_equal(idx, sc, oidx, osc)
+        os.environ["ASP_TC_FIRST_TERMS"] = "auto"             # the earlier rule (band decides): three terms straight away
+        os.environ.pop("ASP_TC_CAPB")
+        idx, sc = aspace.search_batch(q, gl, 0.62)
+        assert api.stat("search_terms") == 3.0
+        _assert_hits_equal(idx, sc, oidx, osc)
+    finally:
+        _force_stage1(None)
+        for k in ("ASP_TC_CAPB", "ASP_TC_FIRST_TERMS"):
+            os.environ.pop(k, None)
