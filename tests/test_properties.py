@@ -104,3 +104,25 @@ def test_gpu_invariants(oracle_mod, seed):
             _check_search(aspace, gl, x, gp, lambda q, tau: aspace.search(q, gl, tau))
         except BaseException as e:                                             # the reference's lambda_q == 0 panic
             assert "lambdas are zero" in str(e)
+
+
+@FAST
+@given(st.integers(1, 32), st.integers(0, 400), seeds)
+def test_shared_row_threshold_is_a_lower_bound_of_the_kth_best(topk, n_scores, seed):
+    """The candidate kernel's running threshold (csrc/search_tc.cu epilogue): the four threads of a query row each keep the
+    best rr = ceil(topk / 4) scores of THEIR quarter of the columns and the row's threshold is the minimum over the quarters of the
+    rr-th best (minus infinity while a quarter has seen fewer).  Whatever the split, it never exceeds the row's topk-th best
+    score, so no true top-k item is ever filtered."""
+    rng = np.random.default_rng(seed)
+    scores = np.round(rng.normal(size=n_scores), 1)                  # rounding makes ties
+    quarter = rng.integers(0, 4, size=n_scores)                      # any assignment of columns to the four threads
+    rr = (topk + 3) // 4
+    published = []
+    for t in range(4):
+        mine = np.sort(scores[quarter == t])[::-1]
+        published.append(mine[rr - 1] if len(mine) >= rr else -np.inf)
+    threshold = min(published)
+    kth = np.sort(scores)[::-1][topk - 1] if n_scores >= topk else -np.inf
+    assert threshold <= kth
+    if threshold > -np.inf:
+        assert (scores >= threshold).sum() >= topk
