@@ -206,6 +206,21 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw, c
 int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq,
                      double tau, int64_t *out_idx, double *out_score, double *out_lambda_q);
 
+/* Hybrid search, batched.  Replaces prepare_query_item + search_lambda_aware_hybrid(&query,
+ * gl.graph_params.topk, tau) of ArrowSpace.search_hybrid (src/lib.rs:182-219).  The crate function's body is not in the
+ * reference and nothing there documents or tests it, so this is a restatement (PARITY UNPINNED against the crate; GPU ==
+ * oracle: indices identical, scores bit for bit) of the two-stage reading of "hybrid", the shortlist length an argument:
+ *   H1 lambda_q as in asp_search_batch, WITHOUT the lambda_q != 0 assertion (search_hybrid has none);
+ *   H2 shortlist = the `pool` items of largest cosine, ties -> smaller index (pool <= 0: 4 * topk; raised to topk, cut to n):
+ *      asp_search_batch's own path at tau = 1 with topk = pool (tcgen05 candidates + exact stage 2 for pool <= 31, the
+ *      batched exact scan beyond);
+ *   H3 score_i = tau*cos_i + (1-tau)/(1+|lambda_q-lambda_i|) over the shortlist, evaluated in the reference order; the best
+ *      min(topk, n) by (score desc, index asc).
+ * Output layout as asp_search_batch.  Needs every item on this GPU (world-1 space or a replicated item shard);
+ * ASP_ERR_UNSUPPORTED on a row shard. */
+int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq, double tau,
+                            int64_t pool, int64_t *out_idx, double *out_score, double *out_lambda_q);
+
 /* Test hook of the tcgen05 candidate pass: the approximate cosines (unit-scaled operands, bf16 two-term split,
  * f32 accumulation in TMEM) of nq queries against every item of the shard, out[nq][n_local] f32 (host or device). */
 int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, float *out);

@@ -115,6 +115,7 @@ def lib():
             fn.restype = res
         L.orc_taumode.argtypes = [vp, C.POINTER(_Switches), vp, C.c_int64, vp, vp, vp]
         L.orc_search.argtypes = [vp, vp, C.POINTER(_Switches), vp, C.c_int64, C.c_double, vp, vp, vp]
+        L.orc_search_hybrid.argtypes = [vp, vp, C.POINTER(_Switches), vp, C.c_int64, C.c_double, C.c_int64, vp, vp, vp]
         L.orc_gram_columns.argtypes = [vp, C.c_int64, C.c_int64, vp]
         L.orc_gram_columns.restype = None
         L.orc_scores.argtypes = [vp, vp, C.c_double, C.c_double, vp]
@@ -257,6 +258,24 @@ class Space:
 
     def search(self, query, graph, tau):
         idx, sc, _ = self.search_batch(np.asarray(query, dtype=np.float64).reshape(1, -1), graph, tau)
+        return [(int(i), float(s)) for i, s in zip(idx[0], sc[0]) if i >= 0]
+
+    def search_hybrid_batch(self, queries, graph, tau, pool=0):
+        """orc_search_hybrid (src/lib.rs:182-219 restated, PARITY UNPINNED): cosine shortlist of `pool` items (0: 4 * topk),
+        re-ranked by the lambda-aware score; no lambda_q != 0 assertion."""
+        q = _f64(queries, 2)
+        if q.shape[1] != self.nfeatures:
+            raise ValueError("query length %d must match nfeatures %d" % (q.shape[1], self.nfeatures))
+        nq, topk = q.shape[0], graph.params.topk
+        idx = np.empty((nq, topk), dtype=np.int64)
+        sc = np.empty((nq, topk), dtype=np.float64)
+        lq = np.empty(nq, dtype=np.float64)
+        _check(lib().orc_search_hybrid(self._h, graph._h, C.byref(self.switches), q.ctypes.data, nq, float(tau), int(pool),
+                                       idx.ctypes.data, sc.ctypes.data, lq.ctypes.data))
+        return idx, sc, lq
+
+    def search_hybrid(self, query, graph, tau, pool=0):
+        idx, sc, _ = self.search_hybrid_batch(np.asarray(query, dtype=np.float64).reshape(1, -1), graph, tau, pool)
         return [(int(i), float(s)) for i, s in zip(idx[0], sc[0]) if i >= 0]
 
     def scores(self, query, lambda_q, tau):

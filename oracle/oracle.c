@@ -820,6 +820,67 @@ int orc_search(const orc_space *s, const orc_graph *g, const orc_switches *sw_in
     return rc;
 }
 
+/* ---------------------------------------------------------------- hybrid search
+ *
+ * ArrowSpace.search_hybrid (src/lib.rs:182-219): lambda_q = prepare_query_item (lib.rs:205), k = gl.graph_params.topk
+ * (lib.rs:214), then the crate's search_lambda_aware_hybrid(&query, k, tau) (lib.rs:218).  That function's body is in the
+ * un-vendored crate and nothing under /root/reference documents or tests it: PARITY UNPINNED.  Restated as the two-stage
+ * reading of "hybrid" -- a cosine shortlist re-ranked by the lambda-aware score -- with the shortlist length an explicit
+ * argument:
+ *   H1  lambda_q as in search; NO lambda_q != 0 assertion (search_hybrid has none, unlike lib.rs:156-159);
+ *   H2  shortlist = the `pool` items of largest cosine (README arithmetic), ties -> smaller index; pool <= 0 means 4 * topk,
+ *       and pool is raised to topk and cut to n;
+ *   H3  score_i = tau * cos_i + (1 - tau) / (1 + |lambda_q - lambda_i|) (TAUMODE.md:33) over the shortlist; the best
+ *       min(topk, n) by (score desc, index asc).
+ * With pool >= n it is search without the assertion. */
+int orc_search_hybrid(const orc_space *s, const orc_graph *g, const orc_switches *sw_in, const double *q, int64_t nq,
+                      double tau, int64_t pool, int64_t *out_idx, double *out_score, double *out_lambda_q)
+{
+    if (!s || !g || !q || nq < 0 || !out_idx || !out_score) return ORC_ERR_ARG;
+    if (g->nnodes != s->f) return ORC_ERR_ARG;
+    orc_switches sw = sw_in ? *sw_in : g->sw;
+    const int64_t n = s->n, f = s->f;
+    const int64_t topk = g->gp.topk;                      /* lib.rs:214 */
+    const int64_t kk = topk < n ? topk : n;
+    int64_t m = pool > 0 ? pool : 4 * topk;
+    if (m < topk) m = topk;
+    if (m > n) m = n;
+    int rc = ORC_OK;
+#pragma omp parallel
+    {
+        double *scratch = (double *)malloc((size_t)f * sizeof(double));
+        hit_t *all = (hit_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(hit_t));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            const double *qv = q + qi * f;
+            for (int64_t j = 0; j < topk; ++j) { out_idx[qi * topk + j] = -1; out_score[qi * topk + j] = NAN; }
+            double lq = NAN;
+            int r = taumode_one(g, &sw, qv, scratch, NULL, NULL, &lq);   /* lib.rs:205 */
+            if (out_lambda_q) out_lambda_q[qi] = lq;
+            if (r != ORC_OK) {
+#pragma omp atomic write
+                rc = r;
+                continue;
+            }
+            const double nrm = sqrt(seq_dot(qv, qv, f));
+            for (int64_t i = 0; i < n; ++i) {                            /* H2: cosine of every item */
+                const double den = nrm * s->norms[i];
+                all[i].s = (den == 0.0) ? 0.0 : seq_dot(qv, s->items + i * f, f) / den;
+                all[i].i = i;
+            }
+            qsort(all, (size_t)n, sizeof(hit_t), hit_cmp);
+            for (int64_t j = 0; j < m; ++j) {                            /* H3: re-rank the shortlist */
+                const int64_t i = all[j].i;
+                all[j].s = tau * all[j].s + (1.0 - tau) * (1.0 / (1.0 + fabs(lq - s->lambdas[i])));
+            }
+            qsort(all, (size_t)m, sizeof(hit_t), hit_cmp);
+            for (int64_t j = 0; j < kk; ++j) { out_idx[qi * topk + j] = all[j].i; out_score[qi * topk + j] = all[j].s; }
+        }
+        free(scratch); free(all);
+    }
+    return rc;
+}
+
 /* ---------------------------------------------------------------- accessors */
 
 int64_t orc_space_nitems(const orc_space *s) { return s->n; }

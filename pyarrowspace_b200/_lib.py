@@ -112,6 +112,7 @@ SYMBOLS = {
     "asp_graph_switches": (_int, [_vp, C.POINTER(Switches)]),
     "asp_query_lambda": (_int, [_vp, _vp, C.POINTER(Switches), _vp, _i64, _vp, _vp, _vp]),
     "asp_search_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp]),
+    "asp_search_hybrid_batch": (_int, [_vp, _vp, _vp, _i64, _dbl, _i64, _vp, _vp, _vp]),
     "asp_debug_tc_dots": (_int, [_vp, _vp, _i64, _vp]),
     "asp_topk_merge": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _vp, _vp]),
     "asp_peer_exchange_bytes": (C.c_size_t, [_int, _i64, _i64]),

@@ -408,9 +408,54 @@ class ArrowSpace:
         from . import persist
         return persist.save(path, self, gl, items)
 
+    # ------------------------------------------------------------------ hybrid search
+    def search_hybrid(self, item, gl, tau, *, pool=None):
+        """list[(index, score)], best first -- src/lib.rs:182-219: same argument checks and lambda_q as `search`, no
+        lambda_q != 0 assertion, k = gl.graph_params.topk, then the crate's search_lambda_aware_hybrid.  That function is not
+        in the reference (PARITY UNPINNED): restated as a cosine shortlist of `pool` items (keyword-only extra, default
+        4 * topk) re-ranked by the lambda-aware score (include/arrowspace_b200.h, asp_search_hybrid_batch)."""
+        if not isinstance(gl, GraphLaplacian):
+            raise TypeError("argument 'gl': 'GraphLaplacian' object expected")
+        if not isinstance(item, np.ndarray) or item.dtype != np.float64 or item.ndim != 1:
+            raise TypeError("argument 'item': expected 1-D numpy.ndarray of float64")
+        if not item.flags.c_contiguous:
+            raise ValueError("The given array is not contiguous")           # as_slice()? src/lib.rs:189
+        if item.shape[0] != self.nfeatures:
+            raise ValueError("query length %d must match nfeatures %d" % (item.shape[0], self.nfeatures))   # src/lib.rs:190-196
+        idx, score, lam_q = self.search_hybrid_batch(item.reshape(1, -1), gl, float(tau), pool=pool, want_lambda=True)
+        dbg_println("search: qlen=%d, lambda_q=%.6f" % (item.shape[0], lam_q[0]))     # src/lib.rs:207-211 (same text as search)
+        return [(int(i), float(s)) for i, s in zip(idx[0], score[0]) if i >= 0]
+
+    def search_hybrid_batch(self, queries, gl, tau, *, pool=None, want_lambda=False):
+        """Extension: search_hybrid for a host batch; (idx int64[Q, topk], score f64[Q, topk]) padded with -1 / NaN
+        (+ lambda_q with want_lambda).  Every item must be on this GPU: one GPU, or the replicated layout of
+        build_sharded (item_shards = 1), where each rank answers on its own."""
+        if not isinstance(gl, GraphLaplacian):
+            raise TypeError("argument 'gl': 'GraphLaplacian' object expected")
+        n_local, f, _, n_total = self._dims()
+        if n_local != n_total:
+            raise NotImplementedError("search_hybrid needs every item on this GPU (this rank holds %d of %d rows); build with "
+                                      "item_shards=1" % (n_local, n_total))
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        if q.ndim != 2 or q.shape[1] != f:
+            raise ValueError("query length %d must match nfeatures %d" % (q.shape[-1], f))
+        if pool is not None and (isinstance(pool, bool) or not isinstance(pool, (int, np.integer)) or pool < 1):
+            raise ValueError("pool must be a positive integer (the shortlist length; default 4 * topk)")
+        topk = gl.graph_params["topk"]
+        nq = q.shape[0]
+        idx = np.empty((nq, topk), dtype=np.int64)
+        score = np.empty((nq, topk), dtype=np.float64)
+        lam = np.empty(nq, dtype=np.float64)
+        try:
+            _lib.check(_lib.load().asp_search_hybrid_batch(self._h, gl._h, q.ctypes.data, nq, float(tau), int(pool or 0),
+                                                           idx.ctypes.data, score.ctypes.data, lam.ctypes.data))
+        except LibraryError as e:
+            if e.code == _lib.ASP_ERR_ZERO_VECTOR:
+                raise PanicException(e.message)
+            raise
+        return (idx, score, lam) if want_lambda else (idx, score)
+
     # ------------------------------------------------------------------ out of scope (SURVEY.md 8(f))
-    def search_hybrid(self, item, gl, tau):
-        raise NotImplementedError("search_hybrid is outside the build-and-search hot path (src/lib.rs:182-219)")
 
     def search_energy(self, item, gl, k, w_lambda=None, w_dirichlet=None):
         raise NotImplementedError("search_energy belongs to the energy pipeline (src/lib.rs:232-262)")

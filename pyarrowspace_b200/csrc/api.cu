@@ -2,6 +2,7 @@
 // Host-side orchestration only; every numeric step is a kernel in gram.cu / graph_select.cu /
 // csr.cu / taumode.cu / search.cu / knn.cu.  There is no CPU fallback anywhere in this file.
 #include "common.cuh"
+#include "hybrid.cuh"
 
 #include <algorithm>
 #include <math.h>
@@ -711,7 +712,8 @@ int asp_query_lambda(asp_ctx *ctx, const asp_graph *g, const asp_switches *sw_in
 // One device-resident batch: lambda_q (src/lib.rs:154), the lambda_q != 0 guard (src/lib.rs:156-159), candidate pass +
 // exact stage 2.  `flags` is a 2-int device scratch.  Synchronises ctx->stream before returning.
 static int search_device_batch(const asp_space *s, const asp_graph *g, const double *dq, int64_t nq, double tau, int64_t topk,
-                               double *dlam, double *dnorm, int *flags, int64_t *didx, double *dscore)
+                               double *dlam, double *dnorm, int *flags, int64_t *didx, double *dscore,
+                               bool assert_lambda_nonzero = true)
 {
     asp_ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -725,7 +727,8 @@ static int search_device_batch(const asp_space *s, const asp_graph *g, const dou
     ASP_CUDA(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
     ASP_CUDA(cudaStreamSynchronize(st));
     if (h[0]) ASP_FAIL(ASP_ERR_ZERO_VECTOR, "a query vector is all zeros: its Rayleigh quotient is undefined");
-    if (h[1]) ASP_FAIL(ASP_ERR_LAMBDA_ZERO, "The lambdas are zero, check the magnitude of items and eps.");   // src/lib.rs:156-159
+    if (h[1] && assert_lambda_nonzero)
+        ASP_FAIL(ASP_ERR_LAMBDA_ZERO, "The lambdas are zero, check the magnitude of items and eps.");   // src/lib.rs:156-159
     ctx->stats["search_host_lambda_us"] = asp_now_us() - t_in;
     if (topk <= 0) return ASP_OK;
     // stage 1 on tcgen05 (fp16 split) for batches, FP64 DMMA / GEMV otherwise; same exact stage 2, same answers
@@ -872,6 +875,79 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     cudaFreeAsync(dlam, st);
     cudaFreeAsync(dnorm, st);
     cudaFreeAsync(flags, st);
+    if (didx) cudaFreeAsync(didx, st);
+    if (dscore) cudaFreeAsync(dscore, st);
+    return rc;
+}
+
+// Hybrid search (src/lib.rs:182-219 -> the crate's search_lambda_aware_hybrid; restatement H1-H3 of the header): the cosine
+// shortlist is the search above at tau = 1 with topk = pool (same candidate passes, same exact stage 2), the re-ranking is
+// hybrid.cuh.  No lambda_q != 0 assertion (search_hybrid has none).
+int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq, double tau, int64_t pool,
+                            int64_t *out_idx, double *out_score, double *out_lambda_q)
+{
+    if (!s || !g || (nq > 0 && (!queries || !out_idx || !out_score)))
+        ASP_FAIL(ASP_ERR_ARG, "asp_search_hybrid_batch: NULL argument");
+    if (!s->have_lambdas) ASP_FAIL(ASP_ERR_ARG, "asp_search_hybrid_batch: item lambdas have not been computed");
+    if (g->nnodes != s->f)
+        ASP_FAIL(ASP_ERR_ARG, "graph has %lld nodes but items have %d features", (long long)g->nnodes, s->f);
+    if (s->n_local != s->n_total)
+        ASP_FAIL(ASP_ERR_UNSUPPORTED, "asp_search_hybrid_batch needs every item on this GPU (rows [%lld, %lld) of %lld are here): "
+                 "the shortlist is a property of the whole item set", (long long)s->row0, (long long)(s->row0 + s->n_local),
+                 (long long)s->n_total);
+    if (nq == 0) return ASP_OK;
+    if (s->f > 6144) ASP_FAIL(ASP_ERR_UNSUPPORTED, "search supports at most 6144 features (got %d)", s->f);
+    asp_ctx *ctx = s->ctx;
+    ASP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t topk = g->gp.topk;                              // src/lib.rs:214
+    const int32_t f = s->f, fp = s->fp;
+    int64_t m = pool > 0 ? pool : 4 * topk;                       // H2: shortlist length
+    if (m < topk) m = topk;
+    if (m > s->n_local) m = s->n_local;
+
+    double *dq = nullptr, *dlam = nullptr, *dnorm = nullptr, *pscore = nullptr, *dscore = nullptr;
+    int64_t *pidx = nullptr, *didx = nullptr;
+    int *flags = nullptr;
+    ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * fp, st));
+    ASP_CUDA(cudaMallocAsync(&dlam, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&dnorm, sizeof(double) * nq, st));
+    ASP_CUDA(cudaMallocAsync(&flags, sizeof(int) * 2, st));
+    if (topk > 0) {
+        ASP_CUDA(cudaMallocAsync(&pidx, sizeof(int64_t) * (size_t)nq * m, st));
+        ASP_CUDA(cudaMallocAsync(&pscore, sizeof(double) * (size_t)nq * m, st));
+        ASP_CUDA(cudaMallocAsync(&didx, sizeof(int64_t) * (size_t)nq * topk, st));
+        ASP_CUDA(cudaMallocAsync(&dscore, sizeof(double) * (size_t)nq * topk, st));
+    }
+    int rc = upload_pitched(st, queries, nq, f, fp, dq);
+    // H1 + H2: lambda_q, then the m largest cosines per query (score at tau = 1 is the cosine), ties by the smaller index
+    if (rc == ASP_OK) rc = search_device_batch(s, g, dq, nq, 1.0, topk > 0 ? m : 0, dlam, dnorm, flags, pidx, pscore, false);
+    if (rc == ASP_OK && topk > 0) {
+        // H3: reference-order scores of the shortlist, best topk by (score desc, index asc)
+        const int64_t total = nq * m;
+        const unsigned blocks_r = (unsigned)std::min<int64_t>(asp_ceil_div(total, 256), (int64_t)ctx->num_sms * 8);
+        asp_hybrid::hybrid_rescore_kernel<<<blocks_r, 256, 0, st>>>(total, m, dq, fp, s->items, fp, f, s->row0, s->norms, s->lambdas,
+                                                                     dnorm, dlam, tau, pidx, pscore);
+        ASP_LAUNCHED(ctx);
+        const unsigned blocks_s = (unsigned)std::min<int64_t>(asp_ceil_div(nq, 128), (int64_t)ctx->num_sms * 8);
+        asp_hybrid::hybrid_select_kernel<<<blocks_s, 128, 0, st>>>(nq, m, topk, pidx, pscore, didx, dscore);
+        ASP_LAUNCHED(ctx);
+        if (cudaGetLastError() != cudaSuccess) { asp_set_error("hybrid re-ranking kernels failed to launch"); rc = ASP_ERR_CUDA; }
+    }
+    if (rc == ASP_OK && out_lambda_q) rc = asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq);
+    if (rc == ASP_OK && topk > 0) {
+        rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
+        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
+    }
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (rc == ASP_OK && es != cudaSuccess) { asp_set_error("hybrid search: %s", cudaGetErrorString(es)); rc = ASP_ERR_CUDA; }
+    ctx->stats["hybrid_pool"] = (double)m;
+    cudaFreeAsync(dq, st);
+    cudaFreeAsync(dlam, st);
+    cudaFreeAsync(dnorm, st);
+    cudaFreeAsync(flags, st);
+    if (pidx) cudaFreeAsync(pidx, st);
+    if (pscore) cudaFreeAsync(pscore, st);
     if (didx) cudaFreeAsync(didx, st);
     if (dscore) cudaFreeAsync(dscore, st);
     return rc;
