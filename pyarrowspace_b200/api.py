@@ -88,6 +88,51 @@ def parse_graph_params(graph_params):
     return out
 
 
+# EnergyParams::default() as documented by the binding (src/lib.rs:311-322); the struct itself is in the crate.
+DEFAULT_ENERGY_PARAMS = {"optical_tokens": None, "trim_quantile": 0.1, "eta": 0.1, "steps": 4, "split_quantile": 0.9,
+                         "neighbor_k": 8, "split_tau": 0.15, "w_lambda": 1.0, "w_disp": 0.5, "w_dirichlet": 0.25,
+                         "candidate_m": 32}
+_ENERGY_INT_KEYS = ("steps", "neighbor_k", "candidate_m")
+
+
+def _extract_usize(v):
+    """pyo3 `extract::<usize>()`: ints only (bool is an int subclass and is accepted by pyo3), negative -> OverflowError."""
+    if not isinstance(v, (int, np.integer)):
+        raise TypeError("'%s' object cannot be interpreted as an integer" % type(v).__name__)
+    if v < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    return int(v)
+
+
+def _extract_f64(v):
+    """pyo3 `extract::<f64>()`: anything float() accepts through __float__ / __index__ (so ints and bools too)."""
+    if isinstance(v, (str, bytes)) or not (hasattr(v, "__float__") or hasattr(v, "__index__")):
+        raise TypeError("must be real number, not %s" % type(v).__name__)
+    return float(v)
+
+
+def parse_energy_params(energy_params):
+    """src/energyparams.rs:6-45: start from EnergyParams::default(), overwrite the keys present in the dict (absent keys
+    keep their default, unknown keys are ignored); optical_tokens is Option<usize> (None allowed), steps / neighbor_k /
+    candidate_m are usize, the rest f64.  Extraction errors surface as the Python exceptions pyo3 raises."""
+    out = dict(DEFAULT_ENERGY_PARAMS)
+    if energy_params is None:
+        return out
+    if not isinstance(energy_params, dict):
+        raise TypeError("argument 'energy_params': 'dict' object expected")
+    for key in DEFAULT_ENERGY_PARAMS:
+        if key not in energy_params:
+            continue
+        v = energy_params[key]
+        if key == "optical_tokens":
+            out[key] = None if v is None else _extract_usize(v)
+        elif key in _ENERGY_INT_KEYS:
+            out[key] = _extract_usize(v)
+        else:
+            out[key] = _extract_f64(v)
+    return out
+
+
 class GraphLaplacian:
     """Opaque handle of the feature-graph Laplacian (CSR on the device) + its parameters."""
 
@@ -458,7 +503,26 @@ class ArrowSpace:
     # ------------------------------------------------------------------ out of scope
 
     def search_energy(self, item, gl, k, w_lambda=None, w_dirichlet=None):
-        raise NotImplementedError("search_energy belongs to the energy pipeline (src/lib.rs:232-262)")
+        """src/lib.rs:232-262.  The binding's own part is here -- argument types, the query-length check (lib.rs:241-247),
+        the defaults w_lambda = 1.0 / w_dirichlet = 0.5 (lib.rs:252-253) and the debug line (lib.rs:255-258).  The scoring
+        is the crate's ArrowSpace::search_energy (lib.rs:260), whose arithmetic (lambda proximity + "Rayleigh-Dirichlet
+        term") exists nowhere under /root/reference -- no formula, no test, no golden output, only retrieval metrics on an
+        absent dataset (tests/output/1761234699_v0_18_energymaps_8_sweep) -- so the call ends in NotImplementedError
+        rather than in numbers nothing can check."""
+        if not isinstance(gl, GraphLaplacian):
+            raise TypeError("argument 'gl': 'GraphLaplacian' object expected")
+        if not isinstance(item, np.ndarray) or item.dtype != np.float64 or item.ndim != 1:
+            raise TypeError("argument 'item': expected 1-D numpy.ndarray of float64")
+        if not item.flags.c_contiguous:
+            raise ValueError("The given array is not contiguous")
+        if item.shape[0] != self.nfeatures:
+            raise ValueError("query length %d must match nfeatures %d" % (item.shape[0], self.nfeatures))
+        k = _extract_usize(k)
+        w_l = 1.0 if w_lambda is None else _extract_f64(w_lambda)
+        w_d = 0.5 if w_dirichlet is None else _extract_f64(w_dirichlet)
+        dbg_println("search_energy: qlen=%d, k=%d, w_λ=%.2f, w_D=%.2f" % (item.shape[0], k, w_l, w_d))
+        raise NotImplementedError("search_energy: the energy score is defined only inside the crate arrowspace 0.18.0 "
+                                  "(src/lib.rs:260); there is no specification to build it against")
 
 
 def persist_items(space):
@@ -684,7 +748,29 @@ class ArrowSpaceBuilder:
 
     @staticmethod
     def build_energy(items, energy_params=None, graph_params=None):
-        raise NotImplementedError("build_energy belongs to the energy pipeline (src/lib.rs:333-376)")
+        """src/lib.rs:333-376.  The binding's own part is here: the marshalling check (`pyarray2_to_vecvec(items)?`,
+        lib.rs:341 -- a ValueError, not a panic, because this entry point propagates with `?`), parse_energy_params
+        (src/energyparams.rs:6-45) and parse_graph_params, the debug lines.  The pipeline itself (optical compression,
+        diffusion, sub-centroid splitting, energy-distance graph: RustBuilder::build_energy, lib.rs:362) is documented only
+        by its parameter names (lib.rs:309-322); nothing under /root/reference states its arithmetic or holds an output
+        that could check a restatement, so the call ends in NotImplementedError."""
+        dbg_println("build_energy: Converting pyarray2 to Vec<Vec>")
+        if _is_device_tensor(items):
+            n, f = (items.shape + (0, 0))[:2] if items.dim() == 2 else (0, 0)
+        else:
+            if not isinstance(items, np.ndarray) or items.dtype != np.float64 or items.ndim != 2:
+                raise TypeError("argument 'items': expected 2-D numpy.ndarray of float64")
+            n, f = items.shape
+        if n == 0 or f == 0:
+            raise ValueError("items must be non-empty 2D array")                 # src/helpers.rs:27-29 through `?`
+        e = parse_energy_params(energy_params)
+        dbg_println("build_energy: optical_tokens=%s, w_λ=%.2f, w_G=%.2f, w_D=%.2f"
+                    % ("None" if e["optical_tokens"] is None else "Some(%d)" % e["optical_tokens"], e["w_lambda"], e["w_disp"],
+                       e["w_dirichlet"]))
+        parse_graph_params(graph_params)                                          # lib.rs:351 `?`: errors propagate as they are
+        dbg_println("build_energy: Starting energy pipeline")
+        raise NotImplementedError("build_energy: the energy pipeline is defined only inside the crate arrowspace 0.18.0 "
+                                  "(src/lib.rs:362); there is no specification to build it against")
 
 
 def shard_rows(n_total, world, rank):

@@ -101,6 +101,69 @@ def test_build_argument_errors_surface_as_panics():
         ArrowSpaceBuilder.build_energy(np.ones((2, 2)))
 
 
+def test_parse_energy_params():
+    """src/energyparams.rs:6-45: defaults (src/lib.rs:311-322), present keys overwrite, unknown keys ignored, pyo3's
+    extraction errors."""
+    from pyarrowspace_b200.api import DEFAULT_ENERGY_PARAMS, parse_energy_params
+    assert parse_energy_params(None) == DEFAULT_ENERGY_PARAMS
+    assert parse_energy_params({}) == DEFAULT_ENERGY_PARAMS
+    assert DEFAULT_ENERGY_PARAMS == {"optical_tokens": None, "trim_quantile": 0.1, "eta": 0.1, "steps": 4, "split_quantile": 0.9,
+                                     "neighbor_k": 8, "split_tau": 0.15, "w_lambda": 1.0, "w_disp": 0.5, "w_dirichlet": 0.25,
+                                     "candidate_m": 32}
+    # the dict of tests/test_8_CVE_db_sweep.py:164-176
+    got = parse_energy_params({"optical_tokens": 40, "trim_quantile": 0.1, "eta": 0.05, "steps": 2, "split_quantile": 0.9,
+                               "neighbor_k": 8, "split_tau": 0.15, "w_lambda": 1.0, "w_disp": 0.5, "w_dirichlet": 0.25,
+                               "candidate_m": 32, "not_a_key": "ignored"})
+    assert got["optical_tokens"] == 40 and got["eta"] == 0.05 and got["steps"] == 2 and "not_a_key" not in got
+    assert parse_energy_params({"optical_tokens": None})["optical_tokens"] is None
+    assert parse_energy_params({"eta": 1})["eta"] == 1.0 and isinstance(parse_energy_params({"eta": 1})["eta"], float)
+    assert parse_energy_params({"steps": np.int64(6)})["steps"] == 6
+    with pytest.raises(TypeError, match="cannot be interpreted as an integer"):
+        parse_energy_params({"steps": 2.5})
+    with pytest.raises(OverflowError):
+        parse_energy_params({"neighbor_k": -1})
+    with pytest.raises(TypeError, match="must be real number, not str"):
+        parse_energy_params({"eta": "0.1"})
+    with pytest.raises(TypeError):
+        parse_energy_params({"eta": None})                                 # f64, not Option<f64>
+    with pytest.raises(TypeError):
+        parse_energy_params([("eta", 0.1)])
+
+
+def test_energy_entry_points_do_the_bindings_part_then_stop(capsys):
+    """build_energy / search_energy (src/lib.rs:232-262,333-376): argument handling and debug lines of the binding are
+    reproduced; the crate-internal arithmetic has no specification under /root/reference, so they stop with
+    NotImplementedError instead of returning numbers nothing can check."""
+    from arrowspace import ArrowSpaceBuilder, set_debug
+    with pytest.raises(ValueError, match="items must be non-empty 2D array"):     # `?`, not .unwrap(): a plain ValueError
+        ArrowSpaceBuilder.build_energy(np.zeros((0, 4)))
+    with pytest.raises(TypeError):
+        ArrowSpaceBuilder.build_energy(np.ones((2, 2), dtype=np.float32))
+    with pytest.raises(TypeError, match="must be real number"):
+        ArrowSpaceBuilder.build_energy(np.ones((2, 2)), {"eta": "x"})
+    with pytest.raises(ValueError, match=r"graph_params\['k'\] is required"):
+        ArrowSpaceBuilder.build_energy(np.ones((2, 2)), None, {"eps": 1.0, "topk": 1, "p": 2.0})
+    set_debug(True)
+    try:
+        with pytest.raises(NotImplementedError, match="src/lib.rs:362"):
+            ArrowSpaceBuilder.build_energy(np.ones((2, 2)), {"optical_tokens": 40})
+    finally:
+        set_debug(False)
+    err = capsys.readouterr().err
+    assert "[pyarrowspace] build_energy: optical_tokens=Some(40), w_λ=1.00, w_G=0.50, w_D=0.25" in err   # src/lib.rs:344-347
+    assert "[pyarrowspace] build_energy: Starting energy pipeline" in err
+
+
+def test_search_hybrid_signature():
+    """src/lib.rs:182-188: (item, gl, tau) positionally; the shortlist length is a keyword-only extra."""
+    import inspect
+    from arrowspace import ArrowSpace
+    params = inspect.signature(ArrowSpace.search_hybrid).parameters
+    assert list(params)[1:4] == ["item", "gl", "tau"]
+    assert params["pool"].kind is inspect.Parameter.KEYWORD_ONLY and params["pool"].default is None
+    assert list(inspect.signature(ArrowSpace.search_energy).parameters)[1:] == ["item", "gl", "k", "w_lambda", "w_dirichlet"]
+
+
 def test_set_debug_prefix(capsys):
     from pyarrowspace_b200 import api
     api.set_debug(True)
