@@ -94,6 +94,25 @@ int upload_pitched(cudaStream_t st, const double *src, int64_t n, int32_t f, int
     return ASP_OK;
 }
 
+// stream-ordered scratch of asp_search_hybrid_batch, released on every exit path
+struct HybridScratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    template <typename T> int get(T **out, size_t count)
+    {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), st) != cudaSuccess) {
+            cudaGetLastError();
+            asp_set_error("out of device memory in the hybrid search (%zu bytes)", sizeof(T) * count);
+            return ASP_ERR_NOMEM;
+        }
+        ptrs.push_back(p);
+        *out = static_cast<T *>(p);
+        return ASP_OK;
+    }
+    ~HybridScratch() { for (void *p : ptrs) cudaFreeAsync(p, st); }
+};
+
 }  // namespace
 
 extern "C" {
@@ -906,51 +925,44 @@ int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double
     if (m < topk) m = topk;
     if (m > s->n_local) m = s->n_local;
 
+    HybridScratch scratch{st, {}};
     double *dq = nullptr, *dlam = nullptr, *dnorm = nullptr, *pscore = nullptr, *dscore = nullptr;
     int64_t *pidx = nullptr, *didx = nullptr;
     int *flags = nullptr;
-    ASP_CUDA(cudaMallocAsync(&dq, sizeof(double) * (size_t)nq * fp, st));
-    ASP_CUDA(cudaMallocAsync(&dlam, sizeof(double) * nq, st));
-    ASP_CUDA(cudaMallocAsync(&dnorm, sizeof(double) * nq, st));
-    ASP_CUDA(cudaMallocAsync(&flags, sizeof(int) * 2, st));
+    ASP_CHECK(scratch.get(&dq, (size_t)nq * fp));
+    ASP_CHECK(scratch.get(&dlam, (size_t)nq));
+    ASP_CHECK(scratch.get(&dnorm, (size_t)nq));
+    ASP_CHECK(scratch.get(&flags, 2));
     if (topk > 0) {
-        ASP_CUDA(cudaMallocAsync(&pidx, sizeof(int64_t) * (size_t)nq * m, st));
-        ASP_CUDA(cudaMallocAsync(&pscore, sizeof(double) * (size_t)nq * m, st));
-        ASP_CUDA(cudaMallocAsync(&didx, sizeof(int64_t) * (size_t)nq * topk, st));
-        ASP_CUDA(cudaMallocAsync(&dscore, sizeof(double) * (size_t)nq * topk, st));
+        ASP_CHECK(scratch.get(&pidx, (size_t)nq * m));
+        ASP_CHECK(scratch.get(&pscore, (size_t)nq * m));
+        ASP_CHECK(scratch.get(&didx, (size_t)nq * topk));
+        ASP_CHECK(scratch.get(&dscore, (size_t)nq * topk));
     }
-    int rc = upload_pitched(st, queries, nq, f, fp, dq);
-    // H1 + H2: lambda_q, then the m largest cosines per query (score at tau = 1 is the cosine), ties by the smaller index
-    if (rc == ASP_OK) rc = search_device_batch(s, g, dq, nq, 1.0, topk > 0 ? m : 0, dlam, dnorm, flags, pidx, pscore, false);
-    if (rc == ASP_OK && topk > 0) {
+    ASP_CHECK(upload_pitched(st, queries, nq, f, fp, dq));
+    // H1 + H2: lambda_q, then the m largest cosines per query (the score at tau = 1 is the cosine), ties by the smaller index
+    ASP_CHECK(search_device_batch(s, g, dq, nq, 1.0, topk > 0 ? m : 0, dlam, dnorm, flags, pidx, pscore, false));
+    if (topk > 0) {
         // H3: reference-order scores of the shortlist, best topk by (score desc, index asc)
         const int64_t total = nq * m;
         const unsigned blocks_r = (unsigned)std::min<int64_t>(asp_ceil_div(total, 256), (int64_t)ctx->num_sms * 8);
         asp_hybrid::hybrid_rescore_kernel<<<blocks_r, 256, 0, st>>>(total, m, dq, fp, s->items, fp, f, s->row0, s->norms, s->lambdas,
                                                                      dnorm, dlam, tau, pidx, pscore);
+        ASP_CUDA(cudaGetLastError());
         ASP_LAUNCHED(ctx);
         const unsigned blocks_s = (unsigned)std::min<int64_t>(asp_ceil_div(nq, 128), (int64_t)ctx->num_sms * 8);
         asp_hybrid::hybrid_select_kernel<<<blocks_s, 128, 0, st>>>(nq, m, topk, pidx, pscore, didx, dscore);
+        ASP_CUDA(cudaGetLastError());
         ASP_LAUNCHED(ctx);
-        if (cudaGetLastError() != cudaSuccess) { asp_set_error("hybrid re-ranking kernels failed to launch"); rc = ASP_ERR_CUDA; }
     }
-    if (rc == ASP_OK && out_lambda_q) rc = asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq);
-    if (rc == ASP_OK && topk > 0) {
-        rc = asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk);
-        if (rc == ASP_OK) rc = asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk);
+    if (out_lambda_q) ASP_CHECK(asp_copy_out(ctx, out_lambda_q, dlam, sizeof(double) * nq));
+    if (topk > 0) {
+        ASP_CHECK(asp_copy_out(ctx, out_idx, didx, sizeof(int64_t) * (size_t)nq * topk));
+        ASP_CHECK(asp_copy_out(ctx, out_score, dscore, sizeof(double) * (size_t)nq * topk));
     }
-    const cudaError_t es = cudaStreamSynchronize(st);
-    if (rc == ASP_OK && es != cudaSuccess) { asp_set_error("hybrid search: %s", cudaGetErrorString(es)); rc = ASP_ERR_CUDA; }
+    ASP_CUDA(cudaStreamSynchronize(st));
     ctx->stats["hybrid_pool"] = (double)m;
-    cudaFreeAsync(dq, st);
-    cudaFreeAsync(dlam, st);
-    cudaFreeAsync(dnorm, st);
-    cudaFreeAsync(flags, st);
-    if (pidx) cudaFreeAsync(pidx, st);
-    if (pscore) cudaFreeAsync(pscore, st);
-    if (didx) cudaFreeAsync(didx, st);
-    if (dscore) cudaFreeAsync(dscore, st);
-    return rc;
+    return ASP_OK;
 }
 
 int asp_debug_tc_dots(const asp_space *s, const double *queries, int64_t nq, float *out)
