@@ -921,7 +921,7 @@ int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double
     cudaStream_t st = ctx->stream;
     const int64_t topk = g->gp.topk;                              // src/lib.rs:214
     const int32_t f = s->f, fp = s->fp;
-    int64_t m = pool > 0 ? pool : 4 * topk;                       // H2: shortlist length
+    int64_t m = pool > 0 ? pool : 2 * topk;                       // H2: shortlist length
     if (m < topk) m = topk;
     if (m > s->n_local) m = s->n_local;
 

@@ -23,7 +23,7 @@ def _data(n, f, seed, dup=True):
 
 def _numpy_hybrid(x, lam, nrm, q, lq, tau, topk, pool):
     n = x.shape[0]
-    m = min(n, max(topk, pool if pool > 0 else 4 * topk))
+    m = min(n, max(topk, pool if pool > 0 else 2 * topk))
     out_i = np.full((q.shape[0], topk), -1, dtype=np.int64)
     out_s = np.full((q.shape[0], topk), np.nan)
     for qi in range(q.shape[0]):
@@ -92,8 +92,8 @@ def test_rerank_kernel_bodies_on_the_cpu_equal_the_oracle(oracle_mod, emul, n, f
     gp = {"eps": 0.7, "k": 4, "topk": topk, "p": 2.0, "sigma": 0.3}
     s, g = oracle_mod.build(gp, x)
     oidx, osc, lq = s.search_hybrid_batch(q, g, tau, pool)
-    m = min(n, max(topk, pool if pool > 0 else 4 * topk))
-    m_dev = max(topk, pool if pool > 0 else 4 * topk)
+    m = min(n, max(topk, pool if pool > 0 else 2 * topk))
+    m_dev = max(topk, pool if pool > 0 else 2 * topk)
     m_dev = min(m_dev, n)
     assert m_dev == m
     s2, g2 = oracle_mod.build(dict(gp, topk=m), x)                          # same graph, shortlist-sized result lists

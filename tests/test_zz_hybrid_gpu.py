@@ -27,11 +27,11 @@ def _assert_hits_equal(idx, sc, oidx, osc):
 
 
 @pytest.mark.parametrize("n,f,topk,pool,nq,dup", [
-    (3000, 96, 5, None, 300, 0),        # shortlist 20: tensor-core candidates (batch >= 256)
-    (3000, 96, 5, None, 7, 0),          # the same through the FP64 candidate pass (small batch)
+    (3000, 96, 10, None, 300, 0),       # shortlist 20: tensor-core candidates (batch >= 256)
+    (3000, 96, 10, None, 7, 0),         # the same through the FP64 candidate pass (small batch)
     (5000, 64, 3, 24, 257, 12),         # 32-entry lists of the tensor-core pass, duplicated rows
-    (2000, 130, 10, None, 64, 0),       # shortlist 40: the batched exact scan
-    (40, 16, 6, None, 9, 0),            # shortlist cut to n
+    (2000, 130, 20, None, 64, 0),       # shortlist 40: the batched exact scan
+    (10, 16, 6, None, 9, 0),            # shortlist (12) cut to n
     (1500, 48, 4, 5000, 33, 0),         # pool >= n: search without the assertion
 ])
 def test_hybrid_search_gpu_equals_oracle(oracle_mod, n, f, topk, pool, nq, dup):
