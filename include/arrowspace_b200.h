@@ -216,6 +216,7 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
  *      batched exact scan beyond -- the default 2 * topk keeps the reference scripts' topk = 15 on the tensor cores);
  *   H3 score_i = tau*cos_i + (1-tau)/(1+|lambda_q-lambda_i|) over the shortlist, evaluated in the reference order; the best
  *      min(topk, n) by (score desc, index asc).
+ * pool >= n: no shortlist, i.e. asp_search_batch without the assertion; otherwise pool <= 1024 (what the exact scan keeps).
  * Output layout as asp_search_batch.  Needs every item on this GPU (world-1 space or a replicated item shard);
  * ASP_ERR_UNSUPPORTED on a row shard. */
 int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double *queries, int64_t nq, double tau,

@@ -924,6 +924,10 @@ int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double
     int64_t m = pool > 0 ? pool : 2 * topk;                       // H2: shortlist length
     if (m < topk) m = topk;
     if (m > s->n_local) m = s->n_local;
+    const bool whole_set = (m >= s->n_local);                     // the shortlist is every item: H3 is the plain search
+    if (!whole_set && m > 1024)
+        ASP_FAIL(ASP_ERR_UNSUPPORTED, "hybrid search: a shortlist of %lld items is beyond the 1024 the exact scan keeps per query "
+                 "(use pool >= nitems = %lld for no shortlist at all)", (long long)m, (long long)s->n_local);
 
     HybridScratch scratch{st, {}};
     double *dq = nullptr, *dlam = nullptr, *dnorm = nullptr, *pscore = nullptr, *dscore = nullptr;
@@ -934,15 +938,20 @@ int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double
     ASP_CHECK(scratch.get(&dnorm, (size_t)nq));
     ASP_CHECK(scratch.get(&flags, 2));
     if (topk > 0) {
-        ASP_CHECK(scratch.get(&pidx, (size_t)nq * m));
-        ASP_CHECK(scratch.get(&pscore, (size_t)nq * m));
+        if (!whole_set) {
+            ASP_CHECK(scratch.get(&pidx, (size_t)nq * m));
+            ASP_CHECK(scratch.get(&pscore, (size_t)nq * m));
+        }
         ASP_CHECK(scratch.get(&didx, (size_t)nq * topk));
         ASP_CHECK(scratch.get(&dscore, (size_t)nq * topk));
     }
     ASP_CHECK(upload_pitched(st, queries, nq, f, fp, dq));
     // H1 + H2: lambda_q, then the m largest cosines per query (the score at tau = 1 is the cosine), ties by the smaller index
-    ASP_CHECK(search_device_batch(s, g, dq, nq, 1.0, topk > 0 ? m : 0, dlam, dnorm, flags, pidx, pscore, false));
-    if (topk > 0) {
+    if (whole_set)
+        ASP_CHECK(search_device_batch(s, g, dq, nq, tau, topk, dlam, dnorm, flags, didx, dscore, false));
+    else
+        ASP_CHECK(search_device_batch(s, g, dq, nq, 1.0, topk > 0 ? m : 0, dlam, dnorm, flags, pidx, pscore, false));
+    if (topk > 0 && !whole_set) {
         // H3: reference-order scores of the shortlist, best topk by (score desc, index asc)
         const int64_t total = nq * m;
         const unsigned blocks_r = (unsigned)std::min<int64_t>(asp_ceil_div(total, 256), (int64_t)ctx->num_sms * 8);
