@@ -186,6 +186,7 @@ void asp_ctx_destroy(asp_ctx *ctx)
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
     if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
+    for (auto &e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -818,18 +819,18 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
     };
     const bool touch = host_io && (size_t)nq * (topk + 1) * 16 >= (1u << 18);
     if (host_io && nq >= ASP_PIPE_MIN_BATCH && !(nopipe && nopipe[0] == '1')) {
-        if (!ctx->up_stream) {
+        if (!ctx->up_stream) {                                     // streams and events live as long as the context
             ASP_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
             ASP_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
         }
+        for (auto &e : ctx->pipe_ev)
+            if (!e) ASP_CUDA(cudaEventCreate(&e));
         const int nch = 2;
         const int64_t bounds[3] = {0, head, nq};
-        cudaEvent_t up[nch], done[nch], alloc_ready;
-        for (auto &e : up) cudaEventCreate(&e);
-        for (auto &e : done) cudaEventCreate(&e);
-        cudaEventCreate(&alloc_ready);
-        cudaEvent_t start_c[nch];                                  // timeline diagnostics (search_pipe_* stats)
-        for (auto &e : start_c) cudaEventCreate(&e);
+        // every call ends with both copy streams and the compute stream drained, so the events are free again
+        cudaEvent_t *const up = ctx->pipe_ev, *const done = ctx->pipe_ev + 2;
+        cudaEvent_t *const start_c = ctx->pipe_ev + 4;             // timeline diagnostics (search_pipe_* stats)
+        const cudaEvent_t alloc_ready = ctx->pipe_ev[6];
         // the copy stream may touch dq only once the allocation is ordered on st
         cudaEventRecord(alloc_ready, st);
         cudaStreamWaitEvent(ctx->up_stream, alloc_ready, 0);
@@ -872,10 +873,6 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
             for (int i = 0; i < 6; ++i)
                 if (cudaEventElapsedTime(&ms, alloc_ready, evs[i]) == cudaSuccess) ctx->stats[names[i]] = ms; else cudaGetLastError();
         }
-        for (auto &e : up) cudaEventDestroy(e);
-        for (auto &e : done) cudaEventDestroy(e);
-        for (auto &e : start_c) cudaEventDestroy(e);
-        cudaEventDestroy(alloc_ready);
         ctx->stats["search_pipeline_chunks"] = nch;
     } else {
         rc = upload_pitched(st, queries, nq, f, fp, dq);

@@ -48,6 +48,7 @@ struct asp_ctx {
     std::map<std::string, double> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;   // copy streams of the pipelined host search (lazily created)
+    cudaEvent_t pipe_ev[7] = {};         // its events (uploads, piece done, piece start, allocation ready), created with the streams
     std::function<void()> on_wait;       // host work the search runs once, right before its long wait for the kernels
 };
 
