@@ -140,3 +140,54 @@ def test_rerank_kernel_bodies_with_a_row_offset_and_padding(emul):
         assert list(out_idx[qi, :n]) == list(row0 + order) and out_idx[qi, n] == -1
         np.testing.assert_allclose(out_score[qi, :n], sc[order], rtol=1e-13)
         assert np.isnan(out_score[qi, n])
+
+
+# ----------------------------------------------------------------------------- properties (hypothesis, CPU)
+
+from hypothesis import HealthCheck, given, settings              # noqa: E402
+from hypothesis import strategies as st                           # noqa: E402
+
+FAST = settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+
+
+@FAST
+@given(st.integers(1, 40), st.integers(1, 9), st.integers(1, 12), st.integers(0, 60), st.sampled_from([0.0, 0.3, 0.62, 1.0]),
+       st.integers(0, 2 ** 31 - 1))
+def test_select_and_rescore_bodies_on_random_shapes(emul, n, f, topk, pool, tau, seed):
+    """Ragged shapes, heavy ties (values rounded to one decimal), shortlists shorter and longer than the item count: the
+    kernel bodies against a direct numpy evaluation of H3 on the same shortlist."""
+    rng = np.random.default_rng(seed)
+    nq = int(rng.integers(1, 6))
+    fp = (f + 3) // 4 * 4
+    x = np.zeros((n, fp)); x[:, :f] = np.round(rng.normal(size=(n, f)), 1)
+    x[x[:, :f].any(axis=1) == 0, 0] = 1.0                                       # no zero rows
+    q = np.zeros((nq, fp)); q[:, :f] = np.round(rng.normal(size=(nq, f)), 1) + 0.05
+    nrm = np.array([np.sqrt(sum(v * v for v in row[:f])) for row in x])
+    nrq = np.array([np.sqrt(sum(v * v for v in row[:f])) for row in q])
+    lam = np.round(rng.uniform(0, 1, n), 1); lq = np.round(rng.uniform(0, 1, nq), 1)
+    m = max(topk, pool if pool > 0 else 2 * topk)                               # slots (may exceed n: padded with -1)
+    pool_idx = np.full((nq, m), -1, dtype=np.int64)
+    for qi in range(nq):
+        take = rng.permutation(n)[:min(n, m)]
+        pool_idx[qi, :len(take)] = take
+    want_idx = np.full((nq, topk), -1, dtype=np.int64); want_sc = np.full((nq, topk), np.nan)
+    for qi in range(nq):
+        ids = pool_idx[qi][pool_idx[qi] >= 0]
+        sc = []
+        for i in ids:
+            d = 0.0
+            for a, b in zip(q[qi, :f], x[i, :f]):
+                d += a * b
+            den = nrq[qi] * nrm[i]
+            c = 0.0 if den == 0.0 else d / den
+            sc.append(tau * c + (1.0 - tau) * (1.0 / (1.0 + abs(lq[qi] - lam[i]))))
+        sc = np.array(sc)
+        order = np.lexsort((ids, -sc))[:topk]
+        want_idx[qi, :len(order)] = ids[order]; want_sc[qi, :len(order)] = sc[order]
+    pool_score = np.zeros((nq, m)); out_idx = np.zeros((nq, topk), dtype=np.int64); out_sc = np.zeros((nq, topk))
+    work = pool_idx.copy()
+    emul.hyb_emulate(nq, m, topk, q.ctypes.data, fp, x.ctypes.data, fp, f, 0, nrm.ctypes.data, lam.ctypes.data, nrq.ctypes.data,
+                     lq.ctypes.data, tau, work.ctypes.data, pool_score.ctypes.data, out_idx.ctypes.data, out_sc.ctypes.data)
+    assert np.array_equal(out_idx, want_idx)
+    ok = want_idx >= 0
+    assert np.array_equal(out_sc[ok], want_sc[ok]) and np.isnan(out_sc[~ok]).all()
