@@ -211,9 +211,10 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
  * reference and nothing there documents or tests it, so this is a restatement (PARITY UNPINNED against the crate; GPU ==
  * oracle: indices identical, scores bit for bit) of the two-stage reading of "hybrid", the shortlist length an argument:
  *   H1 lambda_q as in asp_search_batch, WITHOUT the lambda_q != 0 assertion (search_hybrid has none);
- *   H2 shortlist = the `pool` items of largest cosine, ties -> smaller index (pool <= 0: 2 * topk; raised to topk, cut to n):
+ *   H2 shortlist = the `pool` items of largest cosine, ties -> smaller index (pool <= 0: min(2 * topk, 31); raised to topk, cut to n):
  *      asp_search_batch's own path at tau = 1 with topk = pool (tcgen05 candidates + exact stage 2 for pool <= 31, the
- *      batched exact scan beyond -- the default 2 * topk keeps the reference scripts' topk = 15 on the tensor cores);
+ *      batched exact scan beyond -- the default keeps every topk <= 31, the reference scripts' 15 and 25 included, on the
+ *      tensor cores);
  *   H3 score_i = tau*cos_i + (1-tau)/(1+|lambda_q-lambda_i|) over the shortlist, evaluated in the reference order; the best
  *      min(topk, n) by (score desc, index asc).
  * pool >= n: no shortlist, i.e. asp_search_batch without the assertion; otherwise pool <= 1024 (what the exact scan keeps).

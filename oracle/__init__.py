@@ -261,7 +261,7 @@ class Space:
         return [(int(i), float(s)) for i, s in zip(idx[0], sc[0]) if i >= 0]
 
     def search_hybrid_batch(self, queries, graph, tau, pool=0):
-        """orc_search_hybrid (src/lib.rs:182-219 restated, PARITY UNPINNED): cosine shortlist of `pool` items (0: 2 * topk),
+        """orc_search_hybrid (src/lib.rs:182-219 restated, PARITY UNPINNED): cosine shortlist of `pool` items (0: min(2 * topk, 31)),
         re-ranked by the lambda-aware score; no lambda_q != 0 assertion."""
         q = _f64(queries, 2)
         if q.shape[1] != self.nfeatures:

@@ -828,7 +828,7 @@ int orc_search(const orc_space *s, const orc_graph *g, const orc_switches *sw_in
  * reading of "hybrid" -- a cosine shortlist re-ranked by the lambda-aware score -- with the shortlist length an explicit
  * argument:
  *   H1  lambda_q as in search; NO lambda_q != 0 assertion (search_hybrid has none, unlike lib.rs:156-159);
- *   H2  shortlist = the `pool` items of largest cosine (README arithmetic), ties -> smaller index; pool <= 0 means 2 * topk,
+ *   H2  shortlist = the `pool` items of largest cosine (README arithmetic), ties -> smaller index; pool <= 0 means min(2 * topk, 31),
  *       and pool is raised to topk and cut to n;
  *   H3  score_i = tau * cos_i + (1 - tau) / (1 + |lambda_q - lambda_i|) (TAUMODE.md:33) over the shortlist; the best
  *       min(topk, n) by (score desc, index asc).
@@ -842,7 +842,7 @@ int orc_search_hybrid(const orc_space *s, const orc_graph *g, const orc_switches
     const int64_t n = s->n, f = s->f;
     const int64_t topk = g->gp.topk;                      /* lib.rs:214 */
     const int64_t kk = topk < n ? topk : n;
-    int64_t m = pool > 0 ? pool : 2 * topk;
+    int64_t m = pool > 0 ? pool : (2 * topk < 31 ? 2 * topk : 31);   /* 31: the longest list the GPU's tensor-core pass keeps */
     if (m < topk) m = topk;
     if (m > n) m = n;
     int rc = ORC_OK;

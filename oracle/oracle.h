@@ -120,7 +120,7 @@ int orc_search(const orc_space *s, const orc_graph *g, const orc_switches *sw, c
 
 /* Hybrid search (src/lib.rs:182-219).  The crate function behind it, search_lambda_aware_hybrid, is not
  * in the reference and has no test or golden output there: PARITY UNPINNED.  Restatement H1-H3 (oracle.c): lambda_q without the
- * zero assertion, shortlist of the `pool` largest cosines (<= 0: 2 * topk; raised to topk, cut to n; ties -> smaller index),
+ * zero assertion, shortlist of the `pool` largest cosines (<= 0: min(2 * topk, 31); raised to topk, cut to n; ties -> smaller index),
  * lambda-aware score over the shortlist, best topk by (score desc, index asc).  Output layout as orc_search. */
 int orc_search_hybrid(const orc_space *s, const orc_graph *g, const orc_switches *sw, const double *q, int64_t nq,
                       double tau, int64_t pool, int64_t *out_idx, double *out_score, double *out_lambda_q);

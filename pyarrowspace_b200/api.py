@@ -458,7 +458,7 @@ class ArrowSpace:
         """list[(index, score)], best first -- src/lib.rs:182-219: same argument checks and lambda_q as `search`, no
         lambda_q != 0 assertion, k = gl.graph_params.topk, then the crate's search_lambda_aware_hybrid.  That function is not
         in the reference (PARITY UNPINNED): restated as a cosine shortlist of `pool` items (keyword-only extra, default
-        2 * topk) re-ranked by the lambda-aware score (include/arrowspace_b200.h, asp_search_hybrid_batch)."""
+        min(2 * topk, 31)) re-ranked by the lambda-aware score (include/arrowspace_b200.h, asp_search_hybrid_batch)."""
         if not isinstance(gl, GraphLaplacian):
             raise TypeError("argument 'gl': 'GraphLaplacian' object expected")
         if not isinstance(item, np.ndarray) or item.dtype != np.float64 or item.ndim != 1:
@@ -485,7 +485,7 @@ class ArrowSpace:
         if q.ndim != 2 or q.shape[1] != f:
             raise ValueError("query length %d must match nfeatures %d" % (q.shape[-1], f))
         if pool is not None and (isinstance(pool, bool) or not isinstance(pool, (int, np.integer)) or pool < 1):
-            raise ValueError("pool must be a positive integer (the shortlist length; default 2 * topk)")
+            raise ValueError("pool must be a positive integer (the shortlist length; default min(2 * topk, 31))")
         topk = gl.graph_params["topk"]
         nq = q.shape[0]
         idx = np.empty((nq, topk), dtype=np.int64)

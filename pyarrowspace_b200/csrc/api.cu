@@ -918,7 +918,7 @@ int asp_search_hybrid_batch(const asp_space *s, const asp_graph *g, const double
     cudaStream_t st = ctx->stream;
     const int64_t topk = g->gp.topk;                              // src/lib.rs:214
     const int32_t f = s->f, fp = s->fp;
-    int64_t m = pool > 0 ? pool : 2 * topk;                       // H2: shortlist length
+    int64_t m = pool > 0 ? pool : std::min<int64_t>(2 * topk, 31);   // H2: shortlist length (31: the longest tensor-core list)
     if (m < topk) m = topk;
     if (m > s->n_local) m = s->n_local;
     const bool whole_set = (m >= s->n_local);                     // the shortlist is every item: H3 is the plain search

@@ -23,7 +23,7 @@ def _data(n, f, seed, dup=True):
 
 def _numpy_hybrid(x, lam, nrm, q, lq, tau, topk, pool):
     n = x.shape[0]
-    m = min(n, max(topk, pool if pool > 0 else 2 * topk))
+    m = min(n, max(topk, pool if pool > 0 else min(2 * topk, 31)))
     out_i = np.full((q.shape[0], topk), -1, dtype=np.int64)
     out_s = np.full((q.shape[0], topk), np.nan)
     for qi in range(q.shape[0]):
@@ -92,8 +92,8 @@ def test_rerank_kernel_bodies_on_the_cpu_equal_the_oracle(oracle_mod, emul, n, f
     gp = {"eps": 0.7, "k": 4, "topk": topk, "p": 2.0, "sigma": 0.3}
     s, g = oracle_mod.build(gp, x)
     oidx, osc, lq = s.search_hybrid_batch(q, g, tau, pool)
-    m = min(n, max(topk, pool if pool > 0 else 2 * topk))
-    m_dev = max(topk, pool if pool > 0 else 2 * topk)
+    m = min(n, max(topk, pool if pool > 0 else min(2 * topk, 31)))
+    m_dev = max(topk, pool if pool > 0 else min(2 * topk, 31))
     m_dev = min(m_dev, n)
     assert m_dev == m
     s2, g2 = oracle_mod.build(dict(gp, topk=m), x)                          # same graph, shortlist-sized result lists
@@ -165,7 +165,7 @@ def test_select_and_rescore_bodies_on_random_shapes(emul, n, f, topk, pool, tau,
     nrm = np.array([np.sqrt(sum(v * v for v in row[:f])) for row in x])
     nrq = np.array([np.sqrt(sum(v * v for v in row[:f])) for row in q])
     lam = np.round(rng.uniform(0, 1, n), 1); lq = np.round(rng.uniform(0, 1, nq), 1)
-    m = max(topk, pool if pool > 0 else 2 * topk)                               # slots (may exceed n: padded with -1)
+    m = max(topk, pool if pool > 0 else min(2 * topk, 31))                               # slots (may exceed n: padded with -1)
     pool_idx = np.full((nq, m), -1, dtype=np.int64)
     for qi in range(nq):
         take = rng.permutation(n)[:min(n, m)]

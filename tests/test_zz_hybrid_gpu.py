@@ -30,7 +30,7 @@ def _assert_hits_equal(idx, sc, oidx, osc):
     (3000, 96, 10, None, 300, 0),       # shortlist 20: tensor-core candidates (batch >= 256)
     (3000, 96, 10, None, 7, 0),         # the same through the FP64 candidate pass (small batch)
     (5000, 64, 3, 24, 257, 12),         # 32-entry lists of the tensor-core pass, duplicated rows
-    (2000, 130, 20, None, 64, 0),       # shortlist 40: the batched exact scan
+    (2000, 130, 20, 40, 64, 0),         # shortlist 40: the batched exact scan
     (10, 16, 6, None, 9, 0),            # shortlist (12) cut to n
     (1500, 48, 4, 5000, 33, 0),         # pool >= n: search without the assertion
 ])
@@ -40,7 +40,7 @@ def test_hybrid_search_gpu_equals_oracle(oracle_mod, n, f, topk, pool, nq, dup):
     gp = {"eps": 0.6, "k": 5, "topk": topk, "p": 2.0, "sigma": 0.3}
     aspace, gl = ArrowSpaceBuilder.build(gp, x)
     s, g = oracle_mod.build(gp, x)
-    shortlist = min(n, max(topk, pool or 2 * topk))
+    shortlist = min(n, max(topk, pool or min(2 * topk, 31)))
     # below n the shortlist pass always runs at tau = 1 and tau only enters the re-ranking kernel: any tau; a shortlist of
     # every item is the plain search at the caller's tau
     for tau in ((0.62, 1.0, 0.0) if shortlist < n else (0.62, 1.0)):
