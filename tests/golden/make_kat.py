@@ -1,5 +1,5 @@
 """Regenerates tests/golden/oracle_vectors.npz: oracle outputs on the reference's two KAT inputs and on
-two small seeded synthetic cases (+ the item graph of a third, + the pre-graph reduction of a fourth).  kat.json itself is transcribed from the reference's README.md:37-69
+two small seeded synthetic cases (+ the item graph of a third, + the pre-graph reduction of a fourth, + the hybrid search on the first).  kat.json itself is transcribed from the reference's README.md:37-69
 and tests/test_0.py:4-61 (the reference engine -- crate arrowspace 0.18.0 -- is not vendored and cannot
 be imported here, so there is no reference run to record).
 
@@ -55,6 +55,13 @@ def main():
                reducedD_lambdas=s.lambdas(),
                reducedD_info=np.array([info["n_sampled"], info["n_probes"], info["two_nn_mean_ratio"], info["intrinsic_dim"],
                                        info["n_clusters"], info["iters"], info["converged"]], dtype=np.float64))
+    # hybrid search: default shortlist and an explicit one, on the synthA inputs
+    x = synth.make_items(600, 48, 5, scale=100.0, n_clusters=16)
+    qs, _ = synth.make_queries(x, 16, 5)
+    s, g = oracle.build({"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}, x)
+    for tag, pool in (("hybridE", 0), ("hybridE_pool13", 13)):
+        idx, sc, lq = s.search_hybrid_batch(qs, g, 0.3, pool)      # tau 0.3: the lambda term decides places
+        out.update({tag + "_idx": idx, tag + "_score": sc, tag + "_lambda_q": lq})
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

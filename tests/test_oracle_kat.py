@@ -109,6 +109,18 @@ def test_golden_vectors(oracle_mod, kat, golden):
     assert (ip == golden["itemsC_indptr"]).all() and (ix == golden["itemsC_indices"]).all() and (dt == golden["itemsC_data"]).all()
 
 
+def test_golden_hybrid_search(oracle_mod, golden):
+    """Drift guard of the hybrid search (tests/golden/make_kat.py, case hybridE: the synthA inputs, tau 0.3)."""
+    x = synth.make_items(600, 48, 5, scale=100.0, n_clusters=16)
+    q, _ = synth.make_queries(x, 16, 5)
+    s, g = oracle_mod.build({"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}, x)
+    plain, _, _ = s.search_batch(q, g, 0.3)
+    for tag, pool in (("hybridE", 0), ("hybridE_pool13", 13)):
+        idx, sc, lq = s.search_hybrid_batch(q, g, 0.3, pool)
+        assert (idx == golden[tag + "_idx"]).all() and (sc == golden[tag + "_score"]).all() and (lq == golden[tag + "_lambda_q"]).all()
+        assert (idx != plain).any()                     # the shortlist matters on this case: not the plain search again
+
+
 @pytest.mark.parametrize("nodes", ["feature_columns", "items"])
 @pytest.mark.parametrize("kernel", ["inv_power", "gaussian"])
 def test_c_oracle_equals_numpy_mirror(oracle_mod, nodes, kernel):

@@ -78,3 +78,17 @@ def test_search_hybrid_surface_and_errors(oracle_mod):
         a0.search(x[0].copy(), g0, 0.5)
     hits = a0.search_hybrid(x[0].copy(), g0, 0.5)                                         # ... and search_hybrid answers
     assert hits[0][0] == 0 and len(hits) == 2
+
+
+def test_golden_hybrid_search_gpu(golden):
+    """The committed fixture (tests/golden/make_kat.py, case hybridE) through the CUDA path: no oracle call at run time."""
+    from arrowspace import ArrowSpaceBuilder
+    from pyarrowspace_b200 import synth
+    x = synth.make_items(600, 48, 5, scale=100.0, n_clusters=16)
+    q, _ = synth.make_queries(x, 16, 5)
+    aspace, gl = ArrowSpaceBuilder.build({"eps": 0.6, "k": 5, "topk": 10, "p": 2.0, "sigma": 0.3}, x)
+    for tag, pool in (("hybridE", None), ("hybridE_pool13", 13)):
+        idx, sc, lq = aspace.search_hybrid_batch(q, gl, 0.3, pool=pool, want_lambda=True)
+        assert np.array_equal(idx, golden[tag + "_idx"])
+        np.testing.assert_allclose(sc, golden[tag + "_score"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(lq, golden[tag + "_lambda_q"], rtol=RTOL, atol=0)
