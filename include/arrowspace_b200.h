@@ -209,7 +209,8 @@ int asp_search_batch(const asp_space *s, const asp_graph *g, const double *queri
 /* Hybrid search, batched.  Replaces prepare_query_item + search_lambda_aware_hybrid(&query,
  * gl.graph_params.topk, tau) of ArrowSpace.search_hybrid (src/lib.rs:182-219).  The crate function's body is not in the
  * reference and nothing there documents or tests it, so this is a restatement (PARITY UNPINNED against the crate; GPU ==
- * oracle: indices identical, scores bit for bit) of the two-stage reading of "hybrid", the shortlist length an argument:
+ * oracle: indices identical; scores the oracle's bit for bit on the shortlist route, as asp_search_batch's when pool >= n)
+ * of the two-stage reading of "hybrid", the shortlist length an argument:
  *   H1 lambda_q as in asp_search_batch, WITHOUT the lambda_q != 0 assertion (search_hybrid has none);
  *   H2 shortlist = the `pool` items of largest cosine, ties -> smaller index (pool <= 0: min(2 * topk, 31); raised to topk, cut to n):
  *      asp_search_batch's own path at tau = 1 with topk = pool (tcgen05 candidates + exact stage 2 for pool <= 31, the
