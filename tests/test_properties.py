@@ -126,3 +126,34 @@ def test_shared_row_threshold_is_a_lower_bound_of_the_kth_best(topk, n_scores, s
     assert threshold <= kth
     if threshold > -np.inf:
         assert (scores >= threshold).sum() >= topk
+
+
+@FAST
+@given(shapes, seeds, params, st.integers(0, 50), st.sampled_from([0.0, 0.4, 0.62, 1.0]))
+def test_hybrid_search_invariants(oracle_mod, shape, seed, gp, pool, tau):
+    """Properties of the restated hybrid search (orc_search_hybrid) that need no reference value: every hit comes from the
+    cosine shortlist; tau = 1 returns the head of the shortlist; a shortlist of every item is the plain search; a longer
+    shortlist never lowers the k-th score; the score of a hit is the plain search's score of that item."""
+    x = _items(shape, seed)
+    n = shape[0]
+    s, g = oracle_mod.build(gp, x)
+    if np.any(s.lambdas() == 0.0) or g.nnz <= g.nnodes:
+        return
+    q = (x[n // 3] * 1.07 + 0.002).reshape(1, -1)
+    topk = gp["topk"]
+    m = min(n, max(topk, pool if pool > 0 else min(2 * topk, 31)))
+    cos = s.scores(q[0], 0.5, 1.0)                                             # tau = 1: the cosine of every item
+    short = sorted(range(n), key=lambda i: (-cos[i], i))[:m]
+    idx, sc, lq = s.search_hybrid_batch(q, g, tau, pool)
+    hits = [int(i) for i in idx[0] if i >= 0]
+    assert len(hits) == min(topk, n) and set(hits) <= set(short)
+    full = s.scores(q[0], lq[0], tau)
+    assert [full[i] for i in hits] == [v for v in sc[0][:len(hits)]]            # same expression as the plain search
+    assert list(sc[0][:len(hits)]) == sorted(sc[0][:len(hits)], reverse=True)
+    one, _, _ = s.search_hybrid_batch(q, g, 1.0, pool)
+    assert [int(i) for i in one[0] if i >= 0] == short[:min(topk, n)]
+    if lq[0] != 0.0:
+        whole, wsc, _ = s.search_hybrid_batch(q, g, tau, n)
+        plain, psc, _ = s.search_batch(q, g, tau)
+        assert np.array_equal(whole, plain) and np.array_equal(wsc[plain >= 0], psc[plain >= 0])
+        assert wsc[0][len(hits) - 1] >= sc[0][len(hits) - 1]                     # more candidates cannot lower the k-th score
