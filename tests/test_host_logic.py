@@ -32,6 +32,20 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) <= exported
 
 
+def test_entry_points_reject_null_handles_without_a_gpu():
+    """Argument checks come before any CUDA call: the typed ctypes signatures reach the library and NULL handles are refused
+    with ASP_ERR_ARG (no compute, no device needed)."""
+    from pyarrowspace_b200 import _lib
+    lib = _lib.load()
+    q = np.ones((1, 4))
+    idx, sc, lam = np.zeros((1, 3), dtype=np.int64), np.zeros((1, 3)), np.zeros(1)
+    for call in (lambda: lib.asp_search_batch(None, None, q.ctypes.data, 1, 0.5, idx.ctypes.data, sc.ctypes.data, lam.ctypes.data),
+                 lambda: lib.asp_search_hybrid_batch(None, None, q.ctypes.data, 1, 0.5, 0, idx.ctypes.data, sc.ctypes.data,
+                                                     lam.ctypes.data)):
+        assert call() == _lib.ASP_ERR_ARG
+        assert b"NULL argument" in lib.asp_last_error()
+
+
 def test_library_is_built_for_sm_100a_only():
     from pyarrowspace_b200 import _lib
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
