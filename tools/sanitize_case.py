@@ -49,6 +49,10 @@ for n, f in ((700, 48), (300, 130)) if QUICK else ((1500, 48), (600, 130), (400,
     os.environ.pop("ASP_SEARCH_STAGE1")
     idx, sc = a.search_batch(q[:3], g, 0.7)                           # GEMV / small-batch route
     ok &= same(idx, s.search_batch(q[:3], og, 0.7)[0], "search, 3 queries")
+    for pool in (None, 40):                                           # hybrid search: shortlist + re-ranking kernels (csrc/hybrid.cuh)
+        idx, sc = a.search_hybrid_batch(q, g, 0.4, pool=pool)
+        oidx, osc, _ = s.search_hybrid_batch(q, og, 0.4, pool or 0)
+        ok &= same(idx, oidx, "hybrid search, shortlist %s" % (pool or "default")) and same(sc, osc, "hybrid scores bit for bit")
     del a, g
 # unpinned switches (symmetrise / laplacian variants, synthetic lambda, l2 distance)
 x = clustered(500, 40)
