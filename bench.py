@@ -21,6 +21,8 @@ parity_check : UNTIMED, after the timed loops: the CPU oracle builds the same 1M
 regimes  : the same search on MEAN-ZERO embeddings (no positive shift, tau_mode = median_abs) with queries that are fresh
            draws from the clusters, not perturbed copies of items: the regime in which the candidate pass needs the
            two-term fp16 split; throughput, mode, survivors per query and its own parity_check.
+hybrid   : N = 1 only, in a separate process (tools/hybrid_leg.py): ArrowSpace.search_hybrid_batch (restated
+           semantics) on the same items, wall clock of the public call with host buffers, and its own oracle check.
 cpu_baseline / --impl reference : the CPU oracle (oracle/, a restatement: the reference's Rust engine is not
            vendored and cannot be built here) timed on this box's host cores.
 
@@ -83,6 +85,7 @@ def parse_args():
     ap.add_argument("--parity-queries", type=int, default=64, help="queries of the last step checked against the oracle's full scan (0: skip)")
     ap.add_argument("--no-regimes", action="store_true", help="skip the mean-zero regime")
     ap.add_argument("--no-reduction", action="store_true", help="skip the build with the pre-graph reduction (SURVEY.md 8(f)-1)")
+    ap.add_argument("--no-hybrid", action="store_true", help="skip the hybrid-search leg (SURVEY.md 8(f)-2; N = 1 only, separate process)")
     return ap.parse_args()
 
 
@@ -199,6 +202,24 @@ def gram_roofline(n_local, f, ms, peak):
             "achieved_tflops": executed / (ms * 1e-3) / 1e12, "frac": executed / (ms * 1e-3) / 1e12 / peak,
             "symmetry_speedup_vs_algorithmic": algorithmic / executed,
             "note": "ms is the stage time (slice kernel + reduces + scratch allocation), not the kernel alone"}
+
+
+def hybrid_leg(args, n, local):
+    """search_hybrid on the same workload, in a separate process with a timeout: the path was written after
+    the round's GPU budget was spent, so whatever happens in it must not cost this run its JSON line."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "hybrid_leg.py"), "--items", str(n), "--device", str(local)]
+    if args.parity_queries <= 0:
+        cmd += ["--parity-queries", "0"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+        for ln in reversed(r.stdout.splitlines()):
+            if ln.startswith("HYBRID_LEG "):
+                return json.loads(ln[len("HYBRID_LEG "):])
+        return {"error": "exit code %d: %s" % (r.returncode, (r.stderr or r.stdout).strip()[-400:])}
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after 180 s"}
+    except Exception as e:                                             # noqa: BLE001 -- a diagnostic leg never fails the bench
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -653,6 +674,8 @@ def main():
         "single_query": single,
         "clocks": clk,
     }
+    if world == 1 and not args.no_hybrid:
+        line["hybrid"] = hybrid_leg(args, n, local)
     if not args.no_cpu_baseline:
         ns = min(n, args.cpu_sample_items)
         r = cpu_oracle_run(dict(cfg, n=n), ns, args.cpu_sample_queries, 3, "sample")
