@@ -46,6 +46,37 @@ def test_entry_points_reject_null_handles_without_a_gpu():
         assert b"NULL argument" in lib.asp_last_error()
 
 
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The drop-in boundary is a C ABI: include/arrowspace_b200.h compiles as C99 and a C program linked against the library
+    reaches it (entry points that need no device: ABI version, defaults, the row-shard arithmetic, argument checks)."""
+    from pyarrowspace_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "arrowspace_b200.h"
+int main(void)
+{
+    asp_switches sw; asp_reduction red; int64_t r0 = -1, r1 = -1;
+    asp_default_switches(&sw); asp_default_reduction(&red);
+    if (asp_abi_version() != ASP_ABI_VERSION) return 1;
+    if (sw.kernel != ASP_KERNEL_INV_POWER || sw.symmetrise != ASP_SYM_MAX || red.seed != 42) return 2;
+    if (asp_shard_rows(1000000, 8, 3, &r0, &r1) != ASP_OK || r0 >= r1) return 3;
+    if (asp_search_hybrid_batch(NULL, NULL, NULL, 1, 0.5, 0, NULL, NULL, NULL) != ASP_ERR_ARG) return 4;
+    printf("%lld %lld %s\n", (long long)r0, (long long)r1, asp_last_error());
+    return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-larrowspace_b200", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    r0, r1 = (int(v) for v in r.stdout.split()[:2])
+    from pyarrowspace_b200 import shard_rows
+    assert (r0, r1) == shard_rows(1000000, 8, 3) and "NULL argument" in r.stdout
+
+
 def test_library_is_built_for_sm_100a_only():
     from pyarrowspace_b200 import _lib
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
