@@ -30,9 +30,9 @@ def graph(nodes, eps, k, topk, p, sigma, kernel, symmetrise, k_counts_self, topk
     else:
         d2 = np.maximum(0.0, np.add.outer(np.diag(G), np.diag(G)) - 2.0 * G)
         d = np.sqrt(d2) if distance == "l2" else d2
-    keep = k - 1 if k_counts_self else k
-    if topk_prunes:
-        keep = min(keep, topk)
+    keep = min(k, topk) if topk_prunes else k          # the neighbour cap of the library (asp_neighbour_cap): min(k, topk) ...
+    if k_counts_self:
+        keep -= 1                                      # ... minus the node itself when k counts it
     W = np.zeros((M, M))
     for a in range(M):
         cand = sorted((d[a, b], b) for b in range(M) if b != a and d[a, b] <= eps)
