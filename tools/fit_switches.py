@@ -7,7 +7,7 @@ reference's own known-answer data (tests/golden/kat.json, transcribed from /root
 prints, per combination, how many of the 12 expected indices it reproduces and the smallest decisive score margin.
 The README example (README.md:69) is tau = 1, i.e. independent of every switch here.
 
-    python tools/fit_switches.py            # table of the 12/12 combinations, most robust first
+    python tools/fit_switches.py [--no-distance] [--extended]     # table of the 12/12 combinations, most robust first
 """
 import itertools
 import json
@@ -90,17 +90,27 @@ def main():
         tau_mode=["median", "median_abs", "mean"], lambda_form=["bounded", "synthetic"])
     if "--no-distance" in sys.argv:
         space["distance"] = ["cosine"]
+    # --extended: two more hypotheses that are NOT switches of the library, tried to see whether a more natural family than
+    # kat12 exists (it does not: the same structural family, whatever these are set to) -- stored vectors / query scaled to
+    # unit norm before the lambda pass (NORMALISATION.md:9-14; the graph is scale invariant, tau is not), and the shape of the
+    # lambda proximity term (1/(1+d) is TAUMODE.md:33; 1 - d and exp(-d) are the obvious alternatives)
+    space["normalise"] = ["none", "items", "both"] if "--extended" in sys.argv else ["none"]
+    space["prox"] = ["inv", "lin", "exp"] if "--extended" in sys.argv else ["inv"]
     keys = list(space)
     rows = []
     for combo in itertools.product(*[space[k] for k in keys]):
         sw = dict(zip(keys, combo))
-        L = graph(X.T, gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"], sw["kernel"], sw["symmetrise"],
+        Xn = X / np.linalg.norm(X, axis=1, keepdims=True) if sw["normalise"] != "none" else X
+        qn = q / np.linalg.norm(q) if sw["normalise"] == "both" else q
+        L = graph(Xn.T, gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"], sw["kernel"], sw["symmetrise"],
                   sw["k_counts_self"], sw["topk_prunes"], sw["laplacian"], sw["distance"])
-        lam = np.array([lam_of(x, L, sw["tau_mode"], sw["lambda_form"]) for x in X])
-        lq = lam_of(q, L, sw["tau_mode"], sw["lambda_form"])
+        lam = np.array([lam_of(x, L, sw["tau_mode"], sw["lambda_form"]) for x in Xn])
+        lq = lam_of(qn, L, sw["tau_mode"], sw["lambda_form"])
+        dl = np.abs(lq - lam)
+        prox = 1.0 / (1.0 + dl) if sw["prox"] == "inv" else (1.0 - dl if sw["prox"] == "lin" else np.exp(-dl))
         hits, margin = 0, np.inf
         for tau, want in expect.items():
-            s = tau * cosv + (1.0 - tau) / (1.0 + np.abs(lq - lam))
+            s = tau * cosv + (1.0 - tau) * prox
             order = sorted(range(len(s)), key=lambda i: (-s[i], i))
             hits += sum(int(a == b) for a, b in zip(order[:3], want))
             if order[:3] == want:
