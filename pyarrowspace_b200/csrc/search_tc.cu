@@ -730,13 +730,6 @@ __device__ __forceinline__ double seq_dot_row_tc(const double *__restrict__ qv, 
     return d;
 }
 
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-
 // Sums of FOUR per-lane values over the warp with 12 shuffles instead of 40: the halves of the warp first trade two values,
 // the quarters one, then three plain butterfly steps.  Lanes 8u .. 8u+7 end with the total of value u.
 __device__ __forceinline__ double warp_sum4_transposed(const double (&d)[4], int lane)

@@ -187,13 +187,6 @@ __device__ __forceinline__ double warp_min_f64(double v)
     const uint32_t lo = __reduce_min_sync(0xffffffffu, ((uint32_t)(k >> 32) == hi) ? (uint32_t)k : 0xffffffffu);
     return key_f64(((unsigned long long)hi << 32) | lo);
 }
-__device__ __forceinline__ double warp_max_f64(double v)
-{
-    const unsigned long long k = f64_key(v);
-    const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)(k >> 32));
-    const uint32_t lo = __reduce_max_sync(0xffffffffu, ((uint32_t)(k >> 32) == hi) ? (uint32_t)k : 0u);
-    return key_f64(((unsigned long long)hi << 32) | lo);
-}
 
 // Exact selection by INTERPOLATION SEARCH on the empirical distribution, NV rows of one warp in lock step (NV = 2 gives the
 // dependent chain of a pass -- compare, count, interpolate -- a second independent instance to overlap with).
@@ -373,7 +366,6 @@ taumode_kernel(const double *__restrict__ x, int64_t n, int f, int pitch, const 
     }
 
     const int g = threadIdx.x & 15, p = threadIdx.x >> 4;               // compute: lane group / part
-    const int aw = warp - NW;                                           // auxiliary warp index
     int64_t it = 0;                                                     // chunk sequence number (compute warps)
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t item0 = tile * T;
