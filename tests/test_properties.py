@@ -157,3 +157,26 @@ def test_hybrid_search_invariants(oracle_mod, shape, seed, gp, pool, tau):
         plain, psc, _ = s.search_batch(q, g, tau)
         assert np.array_equal(whole, plain) and np.array_equal(wsc[plain >= 0], psc[plain >= 0])
         assert wsc[0][len(hits) - 1] >= sc[0][len(hits) - 1]                     # more candidates cannot lower the k-th score
+
+
+@FAST
+@given(st.integers(2, 60), st.integers(2, 10), st.integers(1, 70), seeds, st.sampled_from([0.0, 0.5, 0.62, 1.0]))
+def test_oracle_topk_selection_with_ties(oracle_mod, n, f, topk, seed, tau):
+    """The arbiter's own top-k (a bounded heap + final sort, oracle.c orc_search) against a full sort of orc_scores on inputs
+    full of exact ties (duplicated rows, values on a coarse grid): indices by (score desc, index asc), padded with -1 / NaN."""
+    rng = np.random.default_rng(seed)
+    x = np.round(np.abs(rng.normal(size=(n, f))), 1) + 0.1
+    x[rng.integers(0, n, n // 2)] = x[rng.integers(0, n, n // 2)]                # duplicated rows: tied scores
+    gp = {"eps": 0.8, "k": 3, "topk": topk, "p": 2.0, "sigma": 0.4}
+    s, g = oracle_mod.build(gp, x)
+    q = np.stack([x[rng.integers(0, n)] * 1.5, np.round(np.abs(rng.normal(size=f)), 1) + 0.1])
+    try:
+        idx, sc, lq = s.search_batch(q, g, tau)
+    except oracle_mod.OracleError as e:
+        assert e.code == 3                                                      # lambda_q == 0: the reference's panic
+        return
+    for qi in range(2):
+        full = s.scores(q[qi], lq[qi], tau)
+        order = np.lexsort((np.arange(n), -full))[:min(topk, n)]
+        assert list(idx[qi][:len(order)]) == list(order) and (idx[qi][len(order):] == -1).all()
+        assert np.array_equal(sc[qi][:len(order)], full[order]) and np.isnan(sc[qi][len(order):]).all()
