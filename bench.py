@@ -214,7 +214,13 @@ def hybrid_leg(args, n, local):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
         for ln in reversed(r.stdout.splitlines()):
             if ln.startswith("HYBRID_LEG "):
-                return json.loads(ln[len("HYBRID_LEG "):])
+                def finite(v):                                         # the bench line must stay strict JSON: no NaN / Infinity
+                    if isinstance(v, dict):
+                        return {k: finite(x) for k, x in v.items()}
+                    if isinstance(v, float) and not np.isfinite(v):
+                        return None
+                    return v
+                return finite(json.loads(ln[len("HYBRID_LEG "):]))
         return {"error": "exit code %d: %s" % (r.returncode, (r.stderr or r.stdout).strip()[-400:])}
     except subprocess.TimeoutExpired:
         return {"error": "timed out after 180 s"}
